@@ -1,0 +1,220 @@
+"""Seeded synthetic LD (R) and XTy (r) generators for tests and benchmarks.
+
+The dense recipe is the reference's own (simulation/sim_gen_phen_mult.py:28-55):
+X ~ Binomial(2, 0.4), column-standardised, sparse beta, y = X beta + noise, X /= sqrt(N),
+r = X^T y, R = X^T X.  The block-diagonal and banded recipes produce genotype-derived LD with
+the structure BASELINE.json's configs name (per-chromosome LD blocks; banded LD), PSD by
+construction: genotypes come from thresholded latent Gaussian haplotypes with short-range
+correlation; the banded matrix is the sample LD restricted to |i-j| <= w and multiplied by a
+Bartlett taper (Schur product of PSD matrices stays PSD).
+
+numpy functions here serve tests and golden vectors (small M).  The ``*_device`` functions use
+torch on the GPU as a data-generation utility only (they are not part of the solver path).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse
+
+
+# ------------------------------------------------------------------------------------------
+# small / host generators
+# ------------------------------------------------------------------------------------------
+def sim_dense(M, N, lam=0.01, h2=0.5, seed=0, K=1, N_list=None):
+    """Reference recipe.  Returns (R_list, r_list, beta, N_list); all cohorts share beta."""
+    rng = np.random.default_rng(seed)
+    cm = max(1, int(M * lam))
+    beta = np.zeros(M)
+    idx = rng.choice(M, cm, replace=False)
+    beta[idx] = rng.normal(0, np.sqrt(h2 / cm), cm)
+    N_list = list(N_list) if N_list is not None else [N] * K
+    Rs, rs = [], []
+    for Nk in N_list:
+        X = rng.binomial(2, 0.4, size=(Nk, M)).astype(np.float64)
+        X = (X - X.mean(axis=0)) / X.std(axis=0)
+        y = X @ beta + rng.normal(0, np.sqrt(1 - h2), Nk)
+        X /= np.sqrt(Nk)
+        rs.append(X.T @ y)
+        Rs.append(X.T @ X)
+    return Rs, rs, beta, N_list
+
+
+def _haplotype_genotypes(n, m, rng, rho=0.97):
+    """n x m standardised genotypes from two thresholded latent AR(1) Gaussian haplotypes."""
+    maf = rng.uniform(0.05, 0.5, m)
+    from scipy.stats import norm as _norm
+    thr = _norm.ppf(maf)
+    G = np.zeros((n, m))
+    for _ in range(2):
+        e = rng.standard_normal((n, m))
+        z = np.empty_like(e)
+        z[:, 0] = e[:, 0]
+        c = np.sqrt(1 - rho * rho)
+        for j in range(1, m):
+            z[:, j] = rho * z[:, j - 1] + c * e[:, j]
+        G += (z < thr[None, :])
+    sd = G.std(axis=0)
+    sd[sd == 0] = 1.0
+    return (G - G.mean(axis=0)) / sd
+
+
+def bartlett_band(M, w):
+    """Sparse Bartlett taper 1-|i-j|/(w+1) on |i-j| <= w (CSR)."""
+    offs = np.arange(-w, w + 1)
+    diags = [np.full(M - abs(o), 1.0 - abs(o) / (w + 1.0)) for o in offs]
+    return scipy.sparse.diags(diags, offs, shape=(M, M), format="csr")
+
+
+def sim_banded(M, w, N_ld=512, N=None, lam=0.01, h2=0.5, seed=0):
+    """Banded LD (CSR, |i-j|<=w, unit diagonal) + r.  Returns (R, r, x0_scaled, N)."""
+    rng = np.random.default_rng(seed)
+    N = N if N is not None else N_ld
+    X = _haplotype_genotypes(N_ld, M, rng) / np.sqrt(N_ld)
+    # banded sample LD, chunked so that M x M is never formed
+    rows, cols, vals = [], [], []
+    step = max(w, 256)
+    for lo in range(0, M, step):
+        hi = min(M, lo + step)
+        clo, chi = max(0, lo - w), min(M, hi + w)
+        B = X[:, lo:hi].T @ X[:, clo:chi]
+        ii, jj = np.meshgrid(np.arange(lo, hi), np.arange(clo, chi), indexing="ij")
+        keep = np.abs(ii - jj) <= w
+        taper = 1.0 - np.abs(ii - jj)[keep] / (w + 1.0)
+        rows.append(ii[keep]); cols.append(jj[keep]); vals.append(B[keep] * taper)
+    R = scipy.sparse.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(M, M))
+    R.setdiag(1.0)
+    R.sort_indices()
+    cm = max(1, int(M * lam))
+    beta = np.zeros(M)
+    beta[rng.choice(M, cm, replace=False)] = rng.normal(0, np.sqrt(h2 / cm), cm)
+    x0 = beta * np.sqrt(N)
+    r = R @ x0 + np.sqrt(1 - h2) * (X.T @ rng.standard_normal(N_ld))
+    return R, r, x0, N
+
+
+def sim_blockdiag(M, block_lo=100, block_hi=400, N_ld=512, N=None, lam=0.01, h2=0.5, seed=0):
+    """Block-diagonal LD (dense inside LD blocks, CSR).  Returns (R, r, x0_scaled, N, block_starts)."""
+    rng = np.random.default_rng(seed)
+    N = N if N is not None else N_ld
+    sizes = []
+    left = M
+    while left > 0:
+        b = int(min(left, rng.integers(block_lo, block_hi)))
+        sizes.append(b)
+        left -= b
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    blocks, Xs = [], []
+    for b in sizes:
+        Xb = _haplotype_genotypes(N_ld, b, rng) / np.sqrt(N_ld)
+        Rb = Xb.T @ Xb
+        np.fill_diagonal(Rb, 1.0)
+        blocks.append(Rb)
+        Xs.append(Xb)
+    R = scipy.sparse.block_diag(blocks, format="csr")
+    R.sort_indices()
+    X = np.concatenate(Xs, axis=1)
+    cm = max(1, int(M * lam))
+    beta = np.zeros(M)
+    beta[rng.choice(M, cm, replace=False)] = rng.normal(0, np.sqrt(h2 / cm), cm)
+    x0 = beta * np.sqrt(N)
+    r = R @ x0 + np.sqrt(1 - h2) * (X.T @ rng.standard_normal(N_ld))
+    return R, r, x0, N, starts
+
+
+def round_to_f32(R):
+    """Round matrix values to fp32-representable fp64 (so fp32 device storage is exact)."""
+    if scipy.sparse.issparse(R):
+        R = R.copy()
+        R.data = R.data.astype(np.float32).astype(np.float64)
+        return R
+    return np.asarray(R).astype(np.float32).astype(np.float64)
+
+
+# ------------------------------------------------------------------------------------------
+# device generators (torch as a data-generation utility; used by bench.py and big GPU tests)
+# ------------------------------------------------------------------------------------------
+def _latent_block(torch, n, lo, hi, seed, hap, B, kern, dev, eps_chunk=8192):
+    """Latent Gaussian field z[:, lo:hi] = sum_i kern[j-i] eps_i, eps generated per fixed
+    chunk of marker indices so that any marker range can be produced independently."""
+    e_lo, e_hi = lo - B, hi
+    c0, c1 = e_lo // eps_chunk, (e_hi - 1) // eps_chunk
+    parts = []
+    for c in range(c0, c1 + 1):
+        g = torch.Generator(device=dev)
+        g.manual_seed((seed * 1000003 + hap * 7919 + (c + 4096)) & 0x7FFFFFFFFFFF)
+        parts.append(torch.randn((n, eps_chunk), generator=g, device=dev, dtype=torch.float32))
+    E = torch.cat(parts, dim=1)[:, e_lo - c0 * eps_chunk: e_hi - c0 * eps_chunk]   # n x (hi-lo+B)
+    # causal FIR filter via unfold-free matmul with a Toeplitz matrix, chunked
+    m = hi - lo
+    z = torch.empty((n, m), device=dev, dtype=torch.float32)
+    T = 2048
+    idx = torch.arange(T, device=dev)
+    # Toep[i_in, j_out] = kern[(j_out + B) - i_in]  for 0 <= (j_out+B-i_in) <= B
+    d = (idx[None, :] + B) - torch.arange(T + B, device=dev)[:, None]
+    Toep = torch.where((d >= 0) & (d <= B), kern[d.clamp(0, B)], torch.zeros((), device=dev))
+    for s in range(0, m, T):
+        t = min(T, m - s)
+        z[:, s:s + t] = E[:, s:s + t + B] @ Toep[:t + B, :t] if t == T else E[:, s:s + t + B] @ Toep[:t + B, :t]
+    return z
+
+
+def genotypes_device(torch, n, lo, hi, seed, dev, rho=0.97, B=256):
+    """Standardised genotype columns [lo, hi) (n x (hi-lo), fp32, already / sqrt(n))."""
+    kern = (rho ** torch.arange(B + 1, device=dev, dtype=torch.float32))
+    kern = kern / kern.norm()
+    j = torch.arange(lo, hi, device=dev, dtype=torch.float64)
+    # deterministic per-marker MAF in [0.05, 0.5] from a hash of the marker index
+    u = torch.frac(torch.sin(j * 12.9898 + seed * 78.233) * 43758.5453).abs()
+    maf = (0.05 + 0.45 * u).to(torch.float32)
+    thr = torch.special.ndtri(maf.to(torch.float64)).to(torch.float32)
+    G = torch.zeros((n, hi - lo), device=dev, dtype=torch.float32)
+    for hap in range(2):
+        z = _latent_block(torch, n, lo, hi, seed, hap, B, kern, dev)
+        G += (z < thr[None, :]).to(torch.float32)
+    mu = G.mean(dim=0, keepdim=True)
+    sd = G.std(dim=0, unbiased=False, keepdim=True)
+    sd = torch.where(sd == 0, torch.ones_like(sd), sd)
+    return (G - mu) / sd / float(np.sqrt(n))
+
+
+def banded_dia_device(torch, M, w, lo, hi, seed, dev, N_ld=4096, chunk=4096):
+    """Rows [lo, hi) of the tapered banded LD in diagonal-major (DIA) layout.
+
+    Returns fp32 tensor band[d, i-lo] = R[i, i+d-w] (zero outside the matrix), shape
+    (2w+1, hi-lo), plus the genotype-noise vector helper (X^T e) for building r.
+    Markers outside [0, M) do not exist.
+    """
+    nloc = hi - lo
+    band = torch.zeros((2 * w + 1, nloc), device=dev, dtype=torch.float32)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed * 31 + 17)
+    e = torch.randn((N_ld,), generator=g, device=dev, dtype=torch.float32)
+    xte = torch.empty((nloc,), device=dev, dtype=torch.float64)
+    dd = torch.arange(2 * w + 1, device=dev)
+    taper = (1.0 - (dd - w).abs().to(torch.float32) / (w + 1.0))
+    for s in range(lo, hi, chunk):
+        t = min(hi, s + chunk)
+        clo, chi = max(0, s - w), min(M, t + w)
+        X = genotypes_device(torch, N_ld, clo, chi, seed, dev)
+        Xi = X[:, s - clo: t - clo]
+        P = Xi.T @ X                                   # (t-s) x (chi-clo), fp32
+        xte[s - lo: t - lo] = (Xi.T @ e).to(torch.float64)
+        ii = torch.arange(s, t, device=dev)
+        col = ii[None, :] + (dd[:, None] - w)          # (2w+1) x (t-s): global column
+        ok = (col >= 0) & (col < M)
+        cidx = (col - clo).clamp(0, chi - clo - 1)
+        vals = P[(ii - s)[None, :].expand_as(cidx), cidx] * taper[:, None]
+        vals = torch.where(ok, vals, torch.zeros((), device=dev))
+        band[:, s - lo: t - lo] = vals
+        del X, P
+    band[w, :] = 1.0
+    return band, xte
+
+
+def causal_effects(M, N, lam, h2, seed):
+    """Sparse true effects scaled by sqrt(N) (the x0 the solver estimates)."""
+    rng = np.random.default_rng(seed + 99)
+    cm = max(1, int(M * lam))
+    beta = np.zeros(M)
+    beta[rng.choice(M, cm, replace=False)] = rng.normal(0, np.sqrt(h2 / cm), cm)
+    return beta * np.sqrt(N)

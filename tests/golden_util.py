@@ -1,0 +1,48 @@
+"""Load the golden fixtures produced by tests/golden/make_golden.py (reference outputs)."""
+import glob
+import os
+
+import numpy as np
+import scipy.sparse
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ALL_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+# regimes where the reference trajectory itself is chaotic (alpha1 -> ~0.9): compared with a
+# looser bar on late iterations, see SURVEY 7.4
+UNSTABLE = {"dense_noprior_fixedgamw_damp", "csr_irregular_L2_em"}
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    c = {k: z[k] for k in z.files}
+    K, M = int(c["K"]), int(c["M"])
+    R = []
+    for k in range(K):
+        if "R%d_dense" % k in c:
+            R.append(c["R%d_dense" % k].astype(np.float64))
+        else:
+            R.append(scipy.sparse.csr_matrix(
+                (c["R%d_data" % k].astype(np.float64), c["R%d_indices" % k], c["R%d_indptr" % k]), shape=(M, M)))
+    c["R"] = R
+    for k in ("K", "M", "iterations", "cg_maxit", "em_prior_maxit", "update_prior_from"):
+        c[k] = int(c[k])
+    for k in ("s", "rho", "gamw", "gam1"):
+        c[k] = float(c[k])
+    for k in ("learn_gamw", "lmmse_damp"):
+        c[k] = bool(c[k])
+    c["prior_update"] = str(c["prior_update"])
+    c["layout"] = str(c["layout"])
+    c["N_list"] = [float(v) for v in c["N_list"]]
+    c["prior_vars"] = [float(v) for v in c["prior_vars"]]
+    c["prior_probs"] = [float(v) for v in c["prior_probs"]]
+    c["probes"] = c["probes"].astype(np.int64)
+    return c
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(np.ravel(a) - np.ravel(b)) / max(np.linalg.norm(np.ravel(b)), 1e-300))
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
