@@ -1,0 +1,140 @@
+/*
+ * sgvamp_b200.h -- C ABI of libsgvamp_b200.so, the B200 (sm_100a) implementation of the
+ * sgVAMP hot path (VAMP.infer and everything it calls, reference src/sgvamp.py:196-389).
+ *
+ * The reference has no FFI layer: the path sits behind the Python class `VAMP`
+ * (src/sgvamp.py:14).  These entry points are what a ctypes binding for that class binds;
+ * `sgvamp-py_b200/sgvamp.py` is that binding and INTEGRATION.md shows the stub a maintainer of
+ * the reference would add.  Each function cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; sgv_last_error() gives the message
+ *     (reference: numerical failures are log-only, bad input raises, src/main.py:90-97).
+ *   - host pointers are owned by the caller for the duration of the call; all device memory is
+ *     owned by the library behind the opaque handle.  One host thread per handle.
+ *   - vectors are fp64; LD values are stored fp32 in HBM (arithmetic: fp32 value x fp64 vector,
+ *     fp64 accumulation).  There is no CPU fallback: without a CUDA device sgv_create fails.
+ *   - a handle owns the marker rows [row_lo,row_hi) of every cohort's LD matrix (the whole
+ *     matrix on one GPU).
+ */
+#ifndef SGVAMP_B200_H
+#define SGVAMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sgv_ctx* sgv_handle;
+
+#define SGV_MAX_K 8   /* cohorts per handle   */
+#define SGV_MAX_L 8   /* mixture components   */
+
+/* LD storage layouts in HBM */
+enum { SGV_LAYOUT_AUTO = 0, SGV_LAYOUT_DENSE = 1, SGV_LAYOUT_DIA = 2, SGV_LAYOUT_BLOCKDIAG = 3, SGV_LAYOUT_CSR = 4 };
+/* element types of host LD values */
+enum { SGV_F32 = 0, SGV_F64 = 1 };
+/* vectors readable / writable through sgv_get_vec / sgv_set_vec (per cohort unless noted) */
+enum { SGV_VEC_XHAT1 = 0 /* shared */, SGV_VEC_R1 = 1, SGV_VEC_XHAT2 = 2, SGV_VEC_SIGMA2U = 3,
+       SGV_VEC_R2 = 4, SGV_VEC_XTY = 5 };
+
+int         sgv_version(void);
+const char* sgv_last_error(void);
+
+/* Library/device lifetime.  `stream` is a cudaStream_t to launch on (NULL: the library creates
+ * its own non-blocking stream). */
+int sgv_create(int device, void* stream, sgv_handle* out);
+int sgv_destroy(sgv_handle h);
+int sgv_sync(sgv_handle h);
+
+/* Problem shape: M markers, K cohorts (reference VAMP.__init__, src/sgvamp.py:15-21).
+ * Allocates all per-cohort state vectors. */
+int sgv_configure(sgv_handle h, int64_t M, int K);
+
+/* ---- LD matrices (reference: R argument of VAMP.infer, src/sgvamp.py:196; Rused formed at
+ * src/main.py:265).  `s` applies Rused = (1-s) R + s I at upload (pass 0 for an R that is
+ * already regularised).  Values are converted to fp32 on the device. ---- */
+int sgv_ld_upload_dense(sgv_handle h, int cohort, const void* R, int dtype, int64_t ld, double s);
+int sgv_ld_upload_csr(sgv_handle h, int cohort, const int64_t* indptr, const int32_t* indices,
+                      const void* data, int dtype, int64_t nnz, double s, int layout_hint);
+/* Adopt LD already resident in HBM (benchmarks: inputs generated on the device).  The library
+ * does not take ownership; the buffers must outlive the handle's use of them.
+ * dia: band[d*ldb + i] = Rused[i][i+d-w], d in [0,2w]; ldb multiple of 4 elements, base 16B aligned.
+ * dense: row-major M x M, ld multiple of 4, base 16B aligned. */
+int sgv_ld_adopt_dia(sgv_handle h, int cohort, const float* band_dev, int64_t w, int64_t ldb);
+int sgv_ld_adopt_dense(sgv_handle h, int cohort, const float* R_dev, int64_t ld);
+/* layout actually chosen + stored bytes + algorithmic bytes of one SpMM pass at nrhs */
+int sgv_ld_info(sgv_handle h, int cohort, int* layout, int64_t* nnz_stored, int64_t* bandwidth,
+                int64_t* nblocks, double* bytes_per_pass_nrhs2);
+
+/* XTy vector r of one cohort (src/sgvamp.py:203) and state reset (src/sgvamp.py:199-217:
+ * r1 <- r, xhat1 = xhat2 = Sigma2_u_prev = 0). */
+int sgv_set_xty(sgv_handle h, int cohort, const double* r);
+int sgv_reset_state(sgv_handle h);
+int sgv_get_vec(sgv_handle h, int cohort, int which, double* dst);
+int sgv_set_vec(sgv_handle h, int cohort, int which, const double* src);
+/* asynchronous variant into pinned memory obtained from sgv_pinned_alloc; completes at the next
+ * sgv_sync / sgv_wait_copies */
+int sgv_get_vec_async(sgv_handle h, int cohort, int which, double scale, double* pinned_dst);
+int sgv_wait_copies(sgv_handle h);
+int sgv_pinned_alloc(sgv_handle h, int64_t bytes, void** out);
+int sgv_pinned_free(sgv_handle h, void* p);
+
+/* ---- prior (src/sgvamp.py:21-28): lam, omegas[L-1], sigmas[L-1] (already times Nt), cohort
+ * weights a[K] (src/main.py:287) ---- */
+int sgv_set_prior(sgv_handle h, int L, double lam, const double* omegas, const double* sigmas);
+int sgv_set_weights(sgv_handle h, const double* a);
+
+/* Denoiser + derivative + damping, one fused kernel over all markers (denoiser_meta /
+ * der_denoiser_meta, src/sgvamp.py:93-114, called at :273,:285; damping :275-276).
+ * xhat1 <- rho*eta(r1s) + (1-rho)*xhat1 if damp else eta(r1s).
+ * *dfac_mean = mean_j d(j) with  d eta/d r_k (j) = a[k]*gam1s[k]*d(j). */
+int sgv_denoise(sgv_handle h, const double* gam1s, double rho, int damp, double* dfac_mean);
+
+/* EM prior learning loop (prior_update_em, src/sgvamp.py:116-136, driver loop :250-257).
+ * Updates the handle's prior; returns lam, omegas, #steps, final relative error. */
+int sgv_prior_em(sgv_handle h, const double* gam1s, int maxit, double tol,
+                 double* lam, double* omegas, int* steps, double* relerr);
+
+/* MLE Lagrangian residual (Lagrangian_der, src/sgvamp.py:139-160); the root finder
+ * (scipy.optimize.fsolve, src/sgvamp.py:180) stays on the host.  x has L+1 entries. */
+int sgv_lagrangian(sgv_handle h, const double* gam1s, const double* x, const double* omega0,
+                   const double* sigma2, double* y);
+
+/* LMMSE step of one cohort (src/sgvamp.py:301-374): r2, mu2, the two CG solves of
+ * (gamw*R + gam2*I) x = b batched as one 2-RHS system with scipy.sparse.linalg.cg semantics
+ * (rtol 1e-5, test at loop top, warm starts), Hutchinson dots and the gamw statistics. */
+typedef struct {
+    double gamw, gam2, alpha1, rho;   /* in */
+    int    cg_maxit, lmmse_damp, learn_gamw, x0_zero;
+} sgv_lmmse_in;
+typedef struct {
+    double u_sigma2u;        /* u^T Sigma2 u            (src/sgvamp.py:338) */
+    double xhat2_r;          /* xhat2^T r               (:352) */
+    double xhat2_R_xhat2;    /* xhat2^T R xhat2         (:352) */
+    double u_R_sigma2u;      /* u^T R Sigma2 u          (:359) */
+    int    cg_iters[2];      /* updates performed by each solve */
+    int    cg_info[2];       /* 0 converged, cg_maxit exhausted (scipy `info`) */
+    int    spmm_passes;      /* SpMM launches that did work */
+} sgv_lmmse_out;
+int sgv_lmmse(sgv_handle h, int cohort, const sgv_lmmse_in* in, const int8_t* probe, sgv_lmmse_out* out);
+/* r1 <- (xhat2 - alpha2*r2)/(1-alpha2)  (src/sgvamp.py:348) */
+int sgv_update_r1(sgv_handle h, int cohort, double alpha2);
+
+/* metrics vs truth (src/sgvamp.py:379-382): dots[0]=xhat1.x0, [1]=xhat1.xhat1, [2]=x0.x0, [3]=|xhat1-x0|^2 */
+int sgv_metrics(sgv_handle h, const double* x0, double* dots);
+
+/* Unit-test / benchmark hook: Y = alpha*(R X) + beta*X for nrhs in {1,2}; X, Y host, column-major M x nrhs */
+int sgv_spmm(sgv_handle h, int cohort, const double* X, double* Y, int nrhs, double alpha, double beta);
+/* Same on device-resident interleaved vectors already inside the handle; launches `reps` times
+ * and returns the average device time per launch in ms (CUDA events on the handle's stream). */
+int sgv_spmm_bench(sgv_handle h, int cohort, int reps, float* ms_per_launch);
+
+/* number of kernels launched by this handle since creation */
+int64_t sgv_launch_count(sgv_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

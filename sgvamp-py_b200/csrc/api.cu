@@ -1,0 +1,301 @@
+// Handle lifetime, state vectors, host<->device transfers and the SpMM test / benchmark hooks of
+// the C ABI (include/sgvamp_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include "sgv_device.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void sgv_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* sgv_last_error(void) { return g_err; }
+extern "C" int sgv_version(void) { return 100; }
+
+extern "C" int sgv_create(int device, void* stream, sgv_handle* out) {
+    SGV_CHECK(out != nullptr, "out is null");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        sgv_set_error("no CUDA device available (%s); libsgvamp_b200 has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return -2;
+    }
+    SGV_CHECK(device >= 0 && device < ndev, "device %d out of range [0,%d)", device, ndev);
+    SGV_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SGV_CUDA(cudaGetDeviceProperties(&prop, device));
+    SGV_CHECK(prop.major >= 10, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+              prop.major, prop.minor);
+    sgv_ctx* c = new sgv_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        SGV_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    SGV_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    SGV_CUDA(cudaMalloc(&c->counter, 64));
+    SGV_CUDA(cudaMemset(c->counter, 0, 64));
+    SGV_CUDA(cudaMalloc(&c->cg, sizeof(CgState)));
+    SGV_CUDA(cudaMemset(c->cg, 0, sizeof(CgState)));
+    SGV_CUDA(cudaMallocHost(&c->cg_host, sizeof(CgState)));
+    memset(c->cg_host, 0, sizeof(CgState));
+    SGV_CUDA(cudaMallocHost(&c->host_scal, 64 * sizeof(double)));
+    SGV_CUDA(cudaEventCreate(&c->ev_a));
+    SGV_CUDA(cudaEventCreate(&c->ev_b));
+    SGV_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    *out = c;
+    return 0;
+}
+
+static void free_vectors(sgv_ctx* c) {
+    for (int k = 0; k < SGV_MAX_K; ++k) {
+        Cohort& co = c->coh[k];
+        sgv_ld_free(co.ld);
+        cudaFree(co.xty);
+        cudaFree(co.r2);
+        cudaFree(co.xhat2);
+        cudaFree(co.sig);
+        cudaFree(co.bb);
+        cudaFree(co.xx);
+        cudaFree(co.rr);
+        cudaFree(co.pp);
+        cudaFree(co.qq);
+        cudaFree(co.probe);
+        co = Cohort();
+    }
+    cudaFree(c->r1_all);
+    cudaFree(c->xhat1);
+    cudaFree(c->truth);
+    c->r1_all = c->xhat1 = c->truth = nullptr;
+}
+
+extern "C" int sgv_destroy(sgv_handle c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
+    free_vectors(c);
+    cudaFree(c->ypart);
+    cudaFree(c->partials);
+    cudaFree(c->counter);
+    cudaFree(c->cg);
+    cudaFree(c->stage);
+    cudaFreeHost(c->cg_host);
+    cudaFreeHost(c->host_scal);
+    cudaEventDestroy(c->ev_a);
+    cudaEventDestroy(c->ev_b);
+    cudaEventDestroy(c->ev_copy);
+    cudaStreamDestroy(c->copy_stream);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int sgv_sync(sgv_handle c) {
+    SGV_CHECK(c != nullptr, "null handle");
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->copy_stream));
+    return 0;
+}
+
+extern "C" int64_t sgv_launch_count(sgv_handle c) { return c ? c->launches : -1; }
+
+extern "C" int sgv_configure(sgv_handle c, int64_t M, int K) {
+    SGV_CHECK(c != nullptr, "null handle");
+    SGV_CHECK(M > 0, "M must be positive");
+    SGV_CHECK(K >= 1 && K <= SGV_MAX_K, "K=%d outside [1,%d]", K, SGV_MAX_K);
+    SGV_CUDA(cudaSetDevice(c->device));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    free_vectors(c);
+    c->M = M;
+    c->K = K;
+    c->prior.K = K;
+    for (int k = 0; k < K; ++k) c->prior.a[k] = 1.0 / K;
+    const size_t vb = (size_t)M * sizeof(double), v2 = (size_t)M * sizeof(double2);
+    SGV_CUDA(cudaMalloc(&c->r1_all, vb * K));
+    SGV_CUDA(cudaMalloc(&c->xhat1, vb));
+    SGV_CUDA(cudaMemsetAsync(c->r1_all, 0, vb * K, c->stream));
+    SGV_CUDA(cudaMemsetAsync(c->xhat1, 0, vb, c->stream));
+    for (int k = 0; k < K; ++k) {
+        Cohort& co = c->coh[k];
+        co.r1 = c->r1_all + (size_t)k * M;
+        SGV_CUDA(cudaMalloc(&co.xty, vb));
+        SGV_CUDA(cudaMalloc(&co.r2, vb));
+        SGV_CUDA(cudaMalloc(&co.xhat2, vb));
+        SGV_CUDA(cudaMalloc(&co.sig, vb));
+        SGV_CUDA(cudaMalloc(&co.bb, v2));
+        SGV_CUDA(cudaMalloc(&co.xx, v2));
+        SGV_CUDA(cudaMalloc(&co.rr, v2));
+        SGV_CUDA(cudaMalloc(&co.pp, v2));
+        SGV_CUDA(cudaMalloc(&co.qq, v2));
+        SGV_CUDA(cudaMalloc(&co.probe, M));
+        double* z[] = {co.xty, co.r2, co.xhat2, co.sig};
+        for (double* p : z) SGV_CUDA(cudaMemsetAsync(p, 0, vb, c->stream));
+        double2* z2[] = {co.bb, co.xx, co.rr, co.pp, co.qq};
+        for (double2* p : z2) SGV_CUDA(cudaMemsetAsync(p, 0, v2, c->stream));
+    }
+    SGV_TRY(sgv_ensure_partials(c, (int64_t)c->sm_count * 16));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int vec_ptr(sgv_ctx* c, int cohort, int which, double** p) {
+    SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
+    SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort index %d out of range [0,%d)", cohort, c->K);
+    Cohort& co = c->coh[cohort];
+    switch (which) {
+        case SGV_VEC_XHAT1: *p = c->xhat1; break;
+        case SGV_VEC_R1: *p = co.r1; break;
+        case SGV_VEC_XHAT2: *p = co.xhat2; break;
+        case SGV_VEC_SIGMA2U: *p = co.sig; break;
+        case SGV_VEC_R2: *p = co.r2; break;
+        case SGV_VEC_XTY: *p = co.xty; break;
+        default: sgv_set_error("unknown vector id %d", which); return -1;
+    }
+    return 0;
+}
+
+extern "C" int sgv_set_xty(sgv_handle c, int cohort, const double* r) {
+    double* p;
+    SGV_TRY(vec_ptr(c, cohort, SGV_VEC_XTY, &p));
+    SGV_CHECK(r != nullptr, "r is null");
+    SGV_CUDA(cudaMemcpyAsync(p, r, c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int sgv_reset_state(sgv_handle c) {
+    SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
+    const size_t vb = (size_t)c->M * sizeof(double);
+    SGV_CUDA(cudaMemsetAsync(c->xhat1, 0, vb, c->stream));
+    for (int k = 0; k < c->K; ++k) {
+        Cohort& co = c->coh[k];
+        SGV_CUDA(cudaMemcpyAsync(co.r1, co.xty, vb, cudaMemcpyDeviceToDevice, c->stream));   // r1 <- r  (:204)
+        SGV_CUDA(cudaMemsetAsync(co.xhat2, 0, vb, c->stream));
+        SGV_CUDA(cudaMemsetAsync(co.sig, 0, vb, c->stream));
+        SGV_CUDA(cudaMemsetAsync(co.r2, 0, vb, c->stream));
+    }
+    return 0;
+}
+
+extern "C" int sgv_get_vec(sgv_handle c, int cohort, int which, double* dst) {
+    double* p;
+    SGV_TRY(vec_ptr(c, cohort, which, &p));
+    SGV_CUDA(cudaMemcpyAsync(dst, p, c->M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int sgv_set_vec(sgv_handle c, int cohort, int which, const double* src) {
+    double* p;
+    SGV_TRY(vec_ptr(c, cohort, which, &p));
+    SGV_CUDA(cudaMemcpyAsync(p, src, c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+__global__ void k_scale_copy(int64_t M, const double* __restrict__ src, double* __restrict__ dst, double scale) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x)
+        dst[j] = src[j] * scale;
+}
+
+// Snapshot (scaled) into a device staging slot on the compute stream, then copy to pinned host
+// memory on the copy stream so that the transfer overlaps the following kernels.
+extern "C" int sgv_get_vec_async(sgv_handle c, int cohort, int which, double scale, double* pinned_dst) {
+    double* p;
+    SGV_TRY(vec_ptr(c, cohort, which, &p));
+    double* snap = nullptr;
+    SGV_CUDA(cudaMallocAsync(&snap, c->M * sizeof(double), c->stream));
+    const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 8);
+    k_scale_copy<<<grid, 256, 0, c->stream>>>(c->M, p, snap, scale);
+    c->launches++;
+    SGV_CUDA(cudaEventRecord(c->ev_copy, c->stream));
+    SGV_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
+    SGV_CUDA(cudaMemcpyAsync(pinned_dst, snap, c->M * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    SGV_CUDA(cudaFreeAsync(snap, c->copy_stream));
+    return 0;
+}
+
+extern "C" int sgv_wait_copies(sgv_handle c) {
+    SGV_CHECK(c != nullptr, "null handle");
+    SGV_CUDA(cudaStreamSynchronize(c->copy_stream));
+    return 0;
+}
+
+extern "C" int sgv_pinned_alloc(sgv_handle c, int64_t bytes, void** out) {
+    SGV_CHECK(c != nullptr && out != nullptr, "null argument");
+    SGV_CUDA(cudaMallocHost(out, bytes));
+    return 0;
+}
+
+extern "C" int sgv_pinned_free(sgv_handle c, void* p) {
+    SGV_CHECK(c != nullptr, "null handle");
+    SGV_CUDA(cudaFreeHost(p));
+    return 0;
+}
+
+extern "C" int sgv_set_prior(sgv_handle c, int L, double lam, const double* omegas, const double* sigmas) {
+    SGV_CHECK(c != nullptr, "null handle");
+    SGV_CHECK(L >= 2 && L <= SGV_MAX_L, "L=%d outside [2,%d]", L, SGV_MAX_L);
+    c->prior.L = L;
+    c->prior.lam = lam;
+    for (int l = 0; l < L - 1; ++l) {
+        c->prior.omegas[l] = omegas[l];
+        c->prior.sigmas[l] = sigmas[l];
+    }
+    return 0;
+}
+
+extern "C" int sgv_set_weights(sgv_handle c, const double* a) {
+    SGV_CHECK(c != nullptr && c->K > 0, "handle not configured");
+    for (int k = 0; k < c->K; ++k) c->prior.a[k] = a[k];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SpMM hooks
+// ---------------------------------------------------------------------------------------------
+extern "C" int sgv_spmm(sgv_handle c, int cohort, const double* X, double* Y, int nrhs, double alpha, double beta) {
+    SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
+    SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
+    SGV_CHECK(nrhs == 1 || nrhs == 2, "nrhs must be 1 or 2");
+    Cohort& co = c->coh[cohort];
+    const int64_t M = c->M;
+    std::vector<double2> h(M);
+    for (int64_t i = 0; i < M; ++i) h[i] = make_double2(X[i], nrhs == 2 ? X[M + i] : 0.0);
+    SGV_CUDA(cudaMemcpyAsync(co.pp, h.data(), M * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    SGV_TRY(sgv_launch_spmm(c, co, EPI_PLAIN, co.pp, co.qq, alpha, beta, 0));
+    SGV_CUDA(cudaMemcpyAsync(h.data(), co.qq, M * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < M; ++i) {
+        Y[i] = h[i].x;
+        if (nrhs == 2) Y[M + i] = h[i].y;
+    }
+    return 0;
+}
+
+extern "C" int sgv_spmm_bench(sgv_handle c, int cohort, int reps, float* ms_per_launch) {
+    SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
+    SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
+    SGV_CHECK(reps > 0 && ms_per_launch, "bad arguments");
+    Cohort& co = c->coh[cohort];
+    // the CG-shaped pass: q = gamw*(R p) + gam2*p with the p.q dots, on whatever the vectors hold
+    for (int i = 0; i < 3; ++i) SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, co.pp, co.qq, 1.5, 0.25, 0));
+    SGV_CUDA(cudaEventRecord(c->ev_a, c->stream));
+    for (int i = 0; i < reps; ++i) SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, co.pp, co.qq, 1.5, 0.25, 0));
+    SGV_CUDA(cudaEventRecord(c->ev_b, c->stream));
+    SGV_CUDA(cudaEventSynchronize(c->ev_b));
+    float ms = 0.f;
+    SGV_CUDA(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+    *ms_per_launch = ms / reps;
+    return 0;
+}

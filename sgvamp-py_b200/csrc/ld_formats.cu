@@ -1,0 +1,457 @@
+// LD matrix ingestion: host CSR / dense -> fp32 HBM layouts (DIA band, dense panels, CSR), with
+// Rused = (1-s) R + s I (reference src/main.py:265) applied in fp64 before rounding to fp32.
+// Layout detection (bandwidth, diagonal blocks, fill) runs on per-row column extents computed on
+// the device, so the host never walks the nnz arrays.
+#include <algorithm>
+#include <climits>
+#include "sgv_device.cuh"
+
+void sgv_ld_free(LdMatrix& ld) {
+    if (ld.owned) {
+        if (ld.band) cudaFree(const_cast<float*>(ld.band));
+        if (ld.panels) cudaFree(const_cast<float*>(ld.panels));
+    }
+    if (ld.items) cudaFree(ld.items);
+    if (ld.indptr) cudaFree(ld.indptr);
+    if (ld.indices) cudaFree(ld.indices);
+    if (ld.vals) cudaFree(ld.vals);
+    ld = LdMatrix();
+}
+
+int sgv_ensure_stage(sgv_ctx* c, int64_t bytes) {
+    if (c->stage_bytes >= bytes) return 0;
+    if (c->stage) cudaFree(c->stage);
+    c->stage = nullptr;
+    c->stage_bytes = 0;
+    SGV_CUDA(cudaMalloc(&c->stage, bytes));
+    c->stage_bytes = bytes;
+    return 0;
+}
+
+int sgv_ensure_partials(sgv_ctx* c, int64_t nblocks) {
+    const int64_t need = nblocks * SGV_MAX_PARTIAL_VALUES;
+    if (c->partials_cap >= need) return 0;
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->partials) cudaFree(c->partials);
+    c->partials = nullptr;
+    c->partials_cap = 0;
+    SGV_CUDA(cudaMalloc(&c->partials, need * sizeof(double)));
+    c->partials_cap = need;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_row_extent(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                             int* __restrict__ lo, int* __restrict__ hi, int* __restrict__ has_diag) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    int mn = INT_MAX, mx = -1, dg = 0;
+    for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
+        const int cidx = indices[k];
+        mn = min(mn, cidx);
+        mx = max(mx, cidx);
+        dg |= (cidx == row);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        dg |= __shfl_xor_sync(0xffffffffu, dg, o);
+    }
+    if (lane == 0) {
+        lo[row] = mn;
+        hi[row] = mx;
+        has_diag[row] = dg;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ float reg_value(T v, bool diag, double s) {
+    return (float)((1.0 - s) * (double)v + (diag ? s : 0.0));
+}
+
+__global__ void k_fill_f32(float* p, int64_t n, float v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+template <typename T>
+__global__ void k_csr_to_dia(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                             const T* __restrict__ data, float* __restrict__ band, int w, int64_t ldb, double s) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
+        const int cidx = indices[k];
+        const int d = cidx - (int)row + w;
+        band[(int64_t)d * ldb + row] = reg_value(data[k], cidx == row, s);
+    }
+}
+
+template <typename T>
+__global__ void k_csr_to_panels(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                const T* __restrict__ data, float* __restrict__ panels,
+                                const int* __restrict__ blk_of_row, const int64_t* __restrict__ blk_start,
+                                const int64_t* __restrict__ blk_off, const int* __restrict__ blk_ld, double s) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    const int b = blk_of_row[row];
+    const int64_t s0 = blk_start[b];
+    float* prow = panels + blk_off[b] + (row - s0) * blk_ld[b];
+    for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
+        const int cidx = indices[k];
+        prow[cidx - s0] = reg_value(data[k], cidx == row, s);
+    }
+}
+
+__global__ void k_panel_diag(int64_t M, float* __restrict__ panels, const int* __restrict__ blk_of_row,
+                             const int64_t* __restrict__ blk_start, const int64_t* __restrict__ blk_off,
+                             const int* __restrict__ blk_ld, float v) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= M) return;
+    const int b = blk_of_row[row];
+    const int64_t r = row - blk_start[b];
+    panels[blk_off[b] + r * blk_ld[b] + r] = v;
+}
+
+template <typename T>
+__global__ void k_csr_vals(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                           const T* __restrict__ data, float* __restrict__ vals, double s) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32)
+        vals[k] = reg_value(data[k], indices[k] == row, s);
+}
+
+// dense chunk: src rows [r0, r0+nr) of an M-column row-major matrix with leading dimension ld_src
+template <typename T>
+__global__ void k_dense_convert(const T* __restrict__ src, int64_t ld_src, float* __restrict__ dst, int64_t ld_dst,
+                                int64_t r0, int64_t nr, int64_t M, double s) {
+    const int64_t n = nr * ld_dst;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t / ld_dst, cidx = t - r * ld_dst;
+        float v = 0.f;
+        if (cidx < M) v = reg_value(src[r * ld_src + cidx], (r0 + r) == cidx, s);
+        dst[(r0 + r) * ld_dst + cidx] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// panel work items
+// ---------------------------------------------------------------------------------------------
+int sgv_build_panel_items(sgv_ctx* c, LdMatrix& ld, const std::vector<int64_t>& starts,
+                          const std::vector<int64_t>& offs, const std::vector<int>& lds) {
+    const int TI = 128 * ld.panel_rw;
+    const int nb = (int)starts.size() - 1;
+    int64_t tiles = 0;
+    for (int b = 0; b < nb; ++b) tiles += (starts[b + 1] - starts[b] + TI - 1) / TI;
+    const int64_t target = (int64_t)c->sm_count * 4;
+    int s_cross = (int)std::min<int64_t>(64, std::max<int64_t>(1, (target + tiles - 1) / tiles));
+    // do not cut segments shorter than 64 stored rows for the largest block
+    int64_t mmax = 0;
+    for (int b = 0; b < nb; ++b) mmax = std::max(mmax, starts[b + 1] - starts[b]);
+    while (s_cross > 1 && mmax / s_cross < 64) --s_cross;
+    std::vector<PanelItem> items;
+    items.reserve((size_t)tiles * s_cross);
+    for (int b = 0; b < nb; ++b) {
+        const int64_t s0 = starts[b], m = starts[b + 1] - s0;
+        const int64_t per = (m + s_cross - 1) / s_cross;
+        for (int64_t i0 = 0; i0 < m; i0 += TI) {
+            for (int sl = 0; sl < s_cross; ++sl) {
+                PanelItem it;
+                const int64_t j0 = std::min<int64_t>(m, (int64_t)sl * per);
+                const int64_t nj = std::max<int64_t>(0, std::min<int64_t>(per, m - j0));
+                it.ld = lds[b];
+                it.off = offs[b] + j0 * lds[b] + i0;
+                it.i0 = (int)(s0 + i0);
+                it.ni = (int)std::min<int64_t>(TI, m - i0);
+                it.j0 = (int)(s0 + j0);
+                it.nj = (int)nj;
+                it.navail = (int)std::min<int64_t>(TI, lds[b] - i0);
+                it.slot = sl;
+                items.push_back(it);
+            }
+        }
+    }
+    // heavier items first: better tail balance
+    std::stable_sort(items.begin(), items.end(), [](const PanelItem& x, const PanelItem& y) {
+        return (int64_t)x.ni * x.nj > (int64_t)y.ni * y.nj;
+    });
+    if (ld.items) cudaFree(ld.items);
+    ld.items = nullptr;
+    SGV_CUDA(cudaMalloc(&ld.items, items.size() * sizeof(PanelItem)));
+    SGV_CUDA(cudaMemcpy(ld.items, items.data(), items.size() * sizeof(PanelItem), cudaMemcpyHostToDevice));
+    ld.n_items = (int)items.size();
+    ld.s_cross = s_cross;
+    ld.nblocks = nb;
+    const int64_t need = (int64_t)s_cross * c->M;
+    if (c->ypart_cap < need) {
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->ypart) cudaFree(c->ypart);
+        c->ypart = nullptr;
+        c->ypart_cap = 0;
+        SGV_CUDA(cudaMalloc(&c->ypart, need * sizeof(double2)));
+        c->ypart_cap = need;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+static int check_cohort(sgv_ctx* c, int cohort) {
+    SGV_CHECK(c != nullptr, "null handle");
+    SGV_CHECK(c->M > 0, "sgv_configure has not been called");
+    SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort index %d out of range [0,%d)", cohort, c->K);
+    return 0;
+}
+
+extern "C" int sgv_ld_upload_dense(sgv_handle c, int cohort, const void* R, int dtype, int64_t ld_src, double s) {
+    SGV_TRY(check_cohort(c, cohort));
+    SGV_CHECK(R != nullptr, "R is null");
+    SGV_CHECK(dtype == SGV_F32 || dtype == SGV_F64, "bad dtype %d", dtype);
+    SGV_CHECK(ld_src >= c->M, "leading dimension %lld < M", (long long)ld_src);
+    SGV_CUDA(cudaSetDevice(c->device));
+    LdMatrix& ld = c->coh[cohort].ld;
+    sgv_ld_free(ld);
+    const int64_t M = c->M, ldd = round_up(M, 4);
+    float* P = nullptr;
+    SGV_CUDA(cudaMalloc(&P, (size_t)M * ldd * sizeof(float)));
+    ld.panels = P;
+    ld.owned = true;
+    ld.layout = SGV_LAYOUT_DENSE;
+    ld.nnz_stored = M * M;
+    const size_t esz = dtype == SGV_F64 ? 8 : 4;
+    const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(M, (int64_t)(256 << 20) / (int64_t)(ld_src * esz)));
+    SGV_TRY(sgv_ensure_stage(c, chunk_rows * ld_src * esz));
+    for (int64_t r0 = 0; r0 < M; r0 += chunk_rows) {
+        const int64_t nr = std::min(chunk_rows, M - r0);
+        SGV_CUDA(cudaMemcpyAsync(c->stage, (const char*)R + (size_t)r0 * ld_src * esz, (size_t)nr * ld_src * esz,
+                                 cudaMemcpyHostToDevice, c->stream));
+        if (dtype == SGV_F64)
+            k_dense_convert<double><<<1184, 256, 0, c->stream>>>((const double*)c->stage, ld_src, P, ldd, r0, nr, M, s);
+        else
+            k_dense_convert<float><<<1184, 256, 0, c->stream>>>((const float*)c->stage, ld_src, P, ldd, r0, nr, M, s);
+        c->launches++;
+        SGV_CUDA(cudaStreamSynchronize(c->stream));   // the staging buffer is reused
+    }
+    SGV_CUDA(cudaGetLastError());
+    return sgv_build_panel_items(c, ld, {0, M}, {0}, {(int)ldd});
+}
+
+extern "C" int sgv_ld_adopt_dense(sgv_handle c, int cohort, const float* R_dev, int64_t ldd) {
+    SGV_TRY(check_cohort(c, cohort));
+    SGV_CHECK(R_dev != nullptr && ((uintptr_t)R_dev & 15) == 0, "device pointer must be 16-byte aligned");
+    SGV_CHECK(ldd >= c->M && ldd % 4 == 0, "ld must be >= M and a multiple of 4");
+    LdMatrix& ld = c->coh[cohort].ld;
+    sgv_ld_free(ld);
+    ld.panels = R_dev;
+    ld.owned = false;
+    ld.layout = SGV_LAYOUT_DENSE;
+    ld.nnz_stored = c->M * c->M;
+    return sgv_build_panel_items(c, ld, {0, c->M}, {0}, {(int)ldd});
+}
+
+extern "C" int sgv_ld_adopt_dia(sgv_handle c, int cohort, const float* band_dev, int64_t w, int64_t ldb) {
+    SGV_TRY(check_cohort(c, cohort));
+    SGV_CHECK(band_dev != nullptr && ((uintptr_t)band_dev & 15) == 0, "device pointer must be 16-byte aligned");
+    SGV_CHECK(ldb >= c->M && ldb % 4 == 0, "ldb must be >= M and a multiple of 4");
+    SGV_CHECK(w >= 0 && sgv_dia_feasible(w), "half-bandwidth %lld not supported by the DIA kernel", (long long)w);
+    LdMatrix& ld = c->coh[cohort].ld;
+    sgv_ld_free(ld);
+    ld.band = band_dev;
+    ld.owned = false;
+    ld.layout = SGV_LAYOUT_DIA;
+    ld.w = w;
+    ld.ldb = ldb;
+    ld.nnz_stored = (2 * w + 1) * c->M;
+    return 0;
+}
+
+template <typename T>
+static int convert_csr(sgv_ctx* c, LdMatrix& ld, int layout, const int64_t* d_indptr, const int32_t* d_indices,
+                       const T* d_data, int64_t nnz, double s, int64_t w, const std::vector<int64_t>& starts) {
+    const int64_t M = c->M;
+    const unsigned wgrid = (unsigned)((M * 32 + 255) / 256);
+    if (layout == SGV_LAYOUT_DIA) {
+        const int64_t ldb = round_up(M, 32);
+        float* band = nullptr;
+        SGV_CUDA(cudaMalloc(&band, (size_t)(2 * w + 1) * ldb * sizeof(float)));
+        ld.band = band;
+        ld.owned = true;
+        ld.w = w;
+        ld.ldb = ldb;
+        ld.nnz_stored = (2 * w + 1) * M;
+        SGV_CUDA(cudaMemsetAsync(band, 0, (size_t)(2 * w + 1) * ldb * sizeof(float), c->stream));
+        k_fill_f32<<<592, 256, 0, c->stream>>>(band + w * ldb, M, (float)s);   // value of an absent diagonal entry
+        k_csr_to_dia<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, band, (int)w, ldb, s);
+        c->launches += 2;
+    } else if (layout == SGV_LAYOUT_DENSE || layout == SGV_LAYOUT_BLOCKDIAG) {
+        const int nb = (int)starts.size() - 1;
+        std::vector<int64_t> offs(nb);
+        std::vector<int> lds(nb), blk_of_row(M);
+        int64_t total = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int64_t m = starts[b + 1] - starts[b];
+            lds[b] = (int)round_up(m, 4);
+            offs[b] = total;
+            total += m * lds[b];
+            for (int64_t i = starts[b]; i < starts[b + 1]; ++i) blk_of_row[i] = b;
+        }
+        float* P = nullptr;
+        SGV_CUDA(cudaMalloc(&P, (size_t)total * sizeof(float)));
+        ld.panels = P;
+        ld.owned = true;
+        ld.nnz_stored = 0;
+        for (int b = 0; b < nb; ++b) ld.nnz_stored += (starts[b + 1] - starts[b]) * (starts[b + 1] - starts[b]);
+        int *d_bor = nullptr, *d_ld = nullptr;
+        int64_t *d_start = nullptr, *d_off = nullptr;
+        SGV_CUDA(cudaMalloc(&d_bor, M * sizeof(int)));
+        SGV_CUDA(cudaMalloc(&d_ld, nb * sizeof(int)));
+        SGV_CUDA(cudaMalloc(&d_start, (nb + 1) * sizeof(int64_t)));
+        SGV_CUDA(cudaMalloc(&d_off, nb * sizeof(int64_t)));
+        SGV_CUDA(cudaMemcpyAsync(d_bor, blk_of_row.data(), M * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        SGV_CUDA(cudaMemcpyAsync(d_ld, lds.data(), nb * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        SGV_CUDA(cudaMemcpyAsync(d_start, starts.data(), (nb + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        SGV_CUDA(cudaMemcpyAsync(d_off, offs.data(), nb * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        SGV_CUDA(cudaMemsetAsync(P, 0, (size_t)total * sizeof(float), c->stream));
+        k_panel_diag<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(M, P, d_bor, d_start, d_off, d_ld, (float)s);
+        k_csr_to_panels<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, P, d_bor, d_start, d_off, d_ld, s);
+        c->launches += 2;
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(d_bor);
+        cudaFree(d_ld);
+        cudaFree(d_start);
+        cudaFree(d_off);
+        SGV_TRY(sgv_build_panel_items(c, ld, starts, offs, lds));
+    } else {
+        float* vals = nullptr;
+        SGV_CUDA(cudaMalloc(&vals, (size_t)std::max<int64_t>(nnz, 1) * sizeof(float)));
+        ld.vals = vals;
+        ld.nnz = nnz;
+        ld.nnz_stored = nnz;
+        k_csr_vals<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, vals, s);
+        c->launches++;
+    }
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    SGV_CUDA(cudaGetLastError());
+    ld.layout = layout;
+    return 0;
+}
+
+extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr, const int32_t* indices,
+                                 const void* data, int dtype, int64_t nnz, double s, int layout_hint) {
+    SGV_TRY(check_cohort(c, cohort));
+    SGV_CHECK(indptr && (nnz == 0 || (indices && data)), "null CSR arrays");
+    SGV_CHECK(dtype == SGV_F32 || dtype == SGV_F64, "bad dtype %d", dtype);
+    SGV_CHECK(c->M < INT_MAX, "M too large for int32 column indices");
+    SGV_CUDA(cudaSetDevice(c->device));
+    const int64_t M = c->M;
+    SGV_CHECK(indptr[0] == 0 && indptr[M] == nnz, "indptr[0]=%lld indptr[M]=%lld inconsistent with nnz=%lld",
+              (long long)indptr[0], (long long)indptr[M], (long long)nnz);
+    LdMatrix& ld = c->coh[cohort].ld;
+    sgv_ld_free(ld);
+    const size_t esz = dtype == SGV_F64 ? 8 : 4;
+    int64_t* d_indptr = nullptr;
+    int32_t* d_indices = nullptr;
+    void* d_data = nullptr;
+    int *d_lo = nullptr, *d_hi = nullptr, *d_dg = nullptr;
+    SGV_CUDA(cudaMalloc(&d_indptr, (M + 1) * sizeof(int64_t)));
+    SGV_CUDA(cudaMalloc(&d_indices, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+    SGV_CUDA(cudaMalloc(&d_data, std::max<int64_t>(nnz, 1) * esz));
+    SGV_CUDA(cudaMalloc(&d_lo, 3 * M * sizeof(int)));
+    d_hi = d_lo + M;
+    d_dg = d_hi + M;
+    SGV_CUDA(cudaMemcpyAsync(d_indptr, indptr, (M + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    SGV_CUDA(cudaMemcpyAsync(d_indices, indices, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    SGV_CUDA(cudaMemcpyAsync(d_data, data, nnz * esz, cudaMemcpyHostToDevice, c->stream));
+    const unsigned wgrid = (unsigned)((M * 32 + 255) / 256);
+    k_row_extent<<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_lo, d_hi, d_dg);
+    c->launches++;
+    std::vector<int> ext(3 * M);
+    SGV_CUDA(cudaMemcpyAsync(ext.data(), d_lo, 3 * M * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    const int *lo = ext.data(), *hi = lo + M, *dg = hi + M;
+
+    // ---- structure analysis on M-length arrays ----
+    int64_t w = 0;
+    bool all_diag = true;
+    for (int64_t i = 0; i < M; ++i) {
+        if (hi[i] < 0) { all_diag = false; continue; }
+        SGV_CHECK(lo[i] >= 0 && hi[i] < M, "column index out of range in row %lld", (long long)i);
+        w = std::max<int64_t>(w, std::max<int64_t>(i - lo[i], hi[i] - i));
+        all_diag = all_diag && dg[i];
+    }
+    std::vector<int> sufmin(M + 1);
+    sufmin[M] = INT_MAX;
+    for (int64_t i = M - 1; i >= 0; --i) sufmin[i] = std::min(sufmin[i + 1], lo[i]);
+    std::vector<int64_t> starts;
+    starts.push_back(0);
+    int runmax = -1;
+    for (int64_t i = 0; i < M; ++i) {
+        if (i > 0 && runmax < i && sufmin[i] >= i) starts.push_back(i);
+        runmax = std::max(runmax, hi[i]);
+    }
+    starts.push_back(M);
+    const int64_t nb = (int64_t)starts.size() - 1;
+    double dense_cells = 0;
+    for (int64_t b = 0; b < nb; ++b) dense_cells += (double)(starts[b + 1] - starts[b]) * (double)(starts[b + 1] - starts[b]);
+    const double dia_cells = (double)M * (2 * w + 1) - (double)w * (w + 1);
+    const double fill_blk = nnz / std::max(dense_cells, 1.0), fill_dia = nnz / std::max(dia_cells, 1.0);
+    size_t free_b = 0, total_b = 0;
+    SGV_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const bool blk_fits = dense_cells * 4.0 < 0.8 * (double)free_b;
+    const bool dia_ok = sgv_dia_feasible(w) && dia_cells * 4.0 < 0.8 * (double)free_b;
+
+    int layout = layout_hint;
+    if (layout == SGV_LAYOUT_AUTO) {
+        layout = SGV_LAYOUT_CSR;
+        const bool blk_good = blk_fits && fill_blk >= (nb == 1 ? 0.25 : 0.5);
+        const bool dia_good = dia_ok && fill_dia >= 0.35;
+        if (blk_good && dia_good) layout = (dense_cells <= dia_cells) ? SGV_LAYOUT_BLOCKDIAG : SGV_LAYOUT_DIA;
+        else if (blk_good) layout = SGV_LAYOUT_BLOCKDIAG;
+        else if (dia_good) layout = SGV_LAYOUT_DIA;
+        if (layout == SGV_LAYOUT_BLOCKDIAG && nb == 1) layout = SGV_LAYOUT_DENSE;
+    }
+    int rc = 0;
+    if (layout == SGV_LAYOUT_DIA && !dia_ok) { sgv_set_error("DIA layout infeasible for half-bandwidth %lld", (long long)w); rc = -1; }
+    if ((layout == SGV_LAYOUT_DENSE || layout == SGV_LAYOUT_BLOCKDIAG) && !blk_fits) { sgv_set_error("dense blocks do not fit in device memory"); rc = -1; }
+    if (layout == SGV_LAYOUT_CSR && s != 0.0 && !all_diag) { sgv_set_error("CSR layout with s != 0 needs every diagonal entry stored"); rc = -3; }
+    if (layout == SGV_LAYOUT_DENSE) starts = {0, M};
+    if (rc == 0) {
+        if (dtype == SGV_F64) rc = convert_csr<double>(c, ld, layout, d_indptr, d_indices, (const double*)d_data, nnz, s, w, starts);
+        else rc = convert_csr<float>(c, ld, layout, d_indptr, d_indices, (const float*)d_data, nnz, s, w, starts);
+    }
+    cudaFree(d_data);
+    cudaFree(d_lo);
+    if (rc == 0 && layout == SGV_LAYOUT_CSR) {
+        ld.indptr = d_indptr;
+        ld.indices = d_indices;
+    } else {
+        cudaFree(d_indptr);
+        cudaFree(d_indices);
+    }
+    if (rc != 0) sgv_ld_free(ld);
+    return rc;
+}
+
+extern "C" int sgv_ld_info(sgv_handle c, int cohort, int* layout, int64_t* nnz_stored, int64_t* bandwidth,
+                           int64_t* nblocks, double* bytes_per_pass_nrhs2) {
+    SGV_TRY(check_cohort(c, cohort));
+    const LdMatrix& ld = c->coh[cohort].ld;
+    if (layout) *layout = ld.layout;
+    if (nnz_stored) *nnz_stored = ld.nnz_stored;
+    if (bandwidth) *bandwidth = ld.w;
+    if (nblocks) *nblocks = ld.nblocks;
+    if (bytes_per_pass_nrhs2) {
+        // algorithmic bytes of one 2-RHS pass: matrix once + vector pair in + vector pair out
+        double b = 32.0 * (double)c->M;
+        if (ld.layout == SGV_LAYOUT_CSR) b += 8.0 * (double)ld.nnz + 8.0 * (double)(c->M + 1);
+        else b += 4.0 * (double)ld.nnz_stored;
+        *bytes_per_pass_nrhs2 = b;
+    }
+    return 0;
+}

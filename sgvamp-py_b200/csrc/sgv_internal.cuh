@@ -1,0 +1,145 @@
+// Internal declarations shared by the translation units of libsgvamp_b200.so.
+// sm_100a only; fp32 LD values, fp64 vectors / accumulation.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/sgvamp_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------------------------
+void sgv_set_error(const char* fmt, ...);
+#define SGV_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            sgv_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return -2;                                                                         \
+        }                                                                                      \
+    } while (0)
+#define SGV_CHECK(cond, ...)                                                                   \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            sgv_set_error(__VA_ARGS__);                                                        \
+            return -1;                                                                         \
+        }                                                                                      \
+    } while (0)
+#define SGV_TRY(expr)                                                                          \
+    do {                                                                                       \
+        int rc_ = (expr);                                                                      \
+        if (rc_ != 0) return rc_;                                                              \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device-resident CG / reduction state (one per handle, reused by every cohort in turn)
+// ---------------------------------------------------------------------------------------------
+struct CgState {
+    double rho[2], rho_prev[2], pq[2], bnorm2[2];
+    double stats[16];      // results of non-CG reductions (read back by the host)
+    int    done[2], iters[2], info[2], zero_b[2];
+    int    step;           // p-updates performed (0 -> p = r)
+    int    maxit;
+};
+
+// Work item of the dense-panel kernel: out_part[slot][i] = sum_{j in [j0,j0+nj)} P[j][i] v[j]
+struct PanelItem {
+    int64_t off;   // element offset of P[j0][i0] inside the panel store (multiple of 4)
+    int     ld;    // leading dimension of the panel (multiple of 4)
+    int     i0, ni;   // output rows [i0, i0+ni)  (global marker index)
+    int     j0, nj;   // input  rows [j0, j0+nj)
+    int     navail;   // readable floats from column i0 to the end of the padded row (multiple of 4)
+    int     slot;
+};
+
+struct LdMatrix {
+    int      layout = 0;
+    bool     owned = false;
+    int64_t  nnz_stored = 0;   // fp32 values read by one pass
+    // DIA
+    const float* band = nullptr;
+    int64_t  w = 0, ldb = 0;
+    // dense panels (DENSE: one block; BLOCKDIAG: one per LD block)
+    const float* panels = nullptr;
+    PanelItem*   items = nullptr;
+    int      n_items = 0, s_cross = 1, panel_rw = 4;
+    int64_t  nblocks = 0;
+    // CSR
+    int64_t* indptr = nullptr;
+    int32_t* indices = nullptr;
+    float*   vals = nullptr;
+    int64_t  nnz = 0;
+};
+
+struct Cohort {
+    LdMatrix ld;
+    double *xty = nullptr, *r1 = nullptr, *r2 = nullptr, *xhat2 = nullptr, *sig = nullptr;
+    double2 *bb = nullptr, *xx = nullptr, *rr = nullptr, *pp = nullptr, *qq = nullptr;
+    int8_t* probe = nullptr;
+};
+
+struct PriorParams {
+    int    K, L;
+    double lam;
+    double omegas[SGV_MAX_L];   // L-1 used
+    double sigmas[SGV_MAX_L];   // L-1 used
+    double a[SGV_MAX_K];
+    double gam1s[SGV_MAX_K];
+};
+
+struct sgv_ctx {
+    int          device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool         own_stream = false;
+    int          sm_count = 148;
+    int64_t      M = 0;
+    int          K = 0;
+    Cohort       coh[SGV_MAX_K];
+    double*      r1_all = nullptr;   // K x M, cohort k's r1 at r1_all + k*M (coh[k].r1 aliases it)
+    double*      xhat1 = nullptr;
+    double*      truth = nullptr;
+    double2*     ypart = nullptr;    // cross-CTA partial outputs of the panel kernel
+    int64_t      ypart_cap = 0;      // in double2 elements
+    PriorParams  prior{};
+    // reductions
+    double*      partials = nullptr;   // per-block partial sums
+    int64_t      partials_cap = 0;     // in doubles
+    unsigned*    counter = nullptr;    // ticket for "last block finalises"
+    CgState*     cg = nullptr;         // device
+    CgState*     cg_host = nullptr;    // pinned mirror
+    double*      host_scal = nullptr;  // pinned scratch (64 doubles)
+    void*        stage = nullptr;      // device staging buffer for uploads
+    int64_t      stage_bytes = 0;
+    cudaEvent_t  ev_a = nullptr, ev_b = nullptr, ev_copy = nullptr;
+    int64_t      launches = 0;
+};
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// epilogues of the SpMM kernels
+enum { EPI_Q = 0, EPI_RESID = 1, EPI_STATS = 2, EPI_PLAIN = 3 };
+
+struct SpmmArgs {
+    const double2* v;      // input vector pair, indexed by global marker
+    double2*       out;    // EPI_Q: qq ; EPI_RESID: rr ; EPI_PLAIN: y
+    const double2* bb;     // EPI_RESID: right-hand sides ; EPI_STATS: col1 = probe u
+    double         gamw, gam2;
+    int64_t        M;
+    CgState*       cg;
+    double*        partials;
+    unsigned*      counter;
+    int            check_done;   // 1: exit immediately when both CG columns are done
+};
+
+// spmm.cu
+int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, const double2* v, double2* out, double gamw, double gam2,
+                    int check_done);
+size_t sgv_dia_smem_bytes(int64_t w, int rw, int s);
+bool   sgv_dia_feasible(int64_t w);
+// ld_formats.cu
+void sgv_ld_free(LdMatrix& ld);
+int  sgv_build_panel_items(sgv_ctx* c, LdMatrix& ld, const std::vector<int64_t>& starts,
+                           const std::vector<int64_t>& offs, const std::vector<int>& lds);
+int  sgv_ensure_stage(sgv_ctx* c, int64_t bytes);
+int  sgv_ensure_partials(sgv_ctx* c, int64_t nblocks);

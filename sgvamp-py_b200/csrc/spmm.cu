@@ -1,0 +1,434 @@
+// Fused shifted SpMM kernels:  out = gamw * (R v) + gam2 * v  for a pair of fp64 vectors (the
+// xhat2 system and the Hutchinson probe system of the LMMSE step share the matrix, reference
+// src/sgvamp.py:312-332), with the CG dot products / residual fused into the epilogue.
+//
+// R is stored fp32 in one of three layouts (DESIGN.md "Data layout in HBM"):
+//   DIA        diagonal-major band, band[d*ldb + i] = R[i][i+d-w]        4 B / stored value
+//   panels     row-major dense blocks (whole matrix, or one per LD block) 4 B / stored value
+//   CSR        fp32 value + int32 column                                  8 B / stored value
+// All three are HBM-bound streaming kernels (0.5 - 1 flop/B): 128-bit coalesced loads of the
+// matrix, vector operands in shared memory / registers, fp64 FMA accumulation.
+#include "sgv_device.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// epilogues
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epi_row(const SpmmArgs& a, int64_t i, double2 acc, double2 vi, double (&dots)[2]) {
+    double2 o;
+    o.x = a.gamw * acc.x + a.gam2 * vi.x;
+    o.y = a.gamw * acc.y + a.gam2 * vi.y;
+    if (EPI == EPI_Q) {
+        a.out[i] = o;
+        dots[0] += vi.x * o.x;
+        dots[1] += vi.y * o.y;
+    } else if (EPI == EPI_RESID) {
+        double2 b = a.bb[i];
+        double2 r = make_double2(b.x - o.x, b.y - o.y);
+        a.out[i] = r;
+        dots[0] += r.x * r.x;
+        dots[1] += r.y * r.y;
+    } else if (EPI == EPI_STATS) {
+        double2 b = a.bb[i];
+        dots[0] += vi.x * o.x;   // xhat2^T R xhat2
+        dots[1] += b.y * o.y;    // u^T R Sigma2_u
+    } else {
+        a.out[i] = o;
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void spmm_finalize(const SpmmArgs& a, double (&t)[2]) {
+    CgState* s = a.cg;
+    if (EPI == EPI_Q) {
+        s->pq[0] = t[0];
+        s->pq[1] = t[1];
+    } else if (EPI == EPI_RESID) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            if (!s->done[c]) {
+                s->rho[c] = t[c];
+                cg_top_test(s, c);
+            }
+        }
+    } else if (EPI == EPI_STATS) {
+        s->stats[0] = t[0];
+        s->stats[1] = t[1];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DIA (banded) kernel
+//   CTA = RW row-warps x S diagonal-segments; a thread owns 4 consecutive rows (one float4 per
+//   diagonal) and a contiguous range of diagonals; the x window [r0-w, r0+TR+w) sits in shared
+//   memory split into 4 planes by (index mod 4) so that the stride-4 access of consecutive lanes
+//   is bank-conflict free; each thread slides a 4-entry register window along the diagonals, so a
+//   step of 4 rows x 1 diagonal x 2 RHS costs 1 LDG.128 + 1 LDS.128 + 4 cvt + 8 DFMA.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline int dia_plane_len(int W) {
+    int pl = (W + 3) / 4 + 1;
+    while ((pl & 7) != 1) ++pl;
+    return pl;
+}
+
+size_t sgv_dia_smem_bytes(int64_t w, int rw, int s) {
+    int TR = 128 * rw;
+    int W = TR + 2 * (int)w;
+    size_t b = (size_t)4 * dia_plane_len(W) * sizeof(double2);
+    b += (size_t)(s > 1 ? (s - 1) : 0) * 8 * (TR / 4) * sizeof(double);
+    b += 2 * 32 * sizeof(double);
+    return b;
+}
+bool sgv_dia_feasible(int64_t w) { return sgv_dia_smem_bytes(w, 1, 8) <= 200 * 1024; }
+
+#define FMA4(C, XA, XB, XC, XD)                                       \
+    do {                                                              \
+        double v0 = (double)(C).x, v1 = (double)(C).y, v2 = (double)(C).z, v3 = (double)(C).w; \
+        acc0.x = fma(v0, (XA).x, acc0.x); acc0.y = fma(v0, (XA).y, acc0.y); \
+        acc1.x = fma(v1, (XB).x, acc1.x); acc1.y = fma(v1, (XB).y, acc1.y); \
+        acc2.x = fma(v2, (XC).x, acc2.x); acc2.y = fma(v2, (XC).y, acc2.y); \
+        acc3.x = fma(v3, (XD).x, acc3.x); acc3.y = fma(v3, (XD).y, acc3.y); \
+    } while (0)
+
+template <int RW, int S, int EPI>
+__global__ void __launch_bounds__(32 * RW * S, 2)
+k_spmm_dia(SpmmArgs a, const float* __restrict__ band, int w, int64_t ldb) {
+    if (a.check_done && a.cg->done[0] && a.cg->done[1]) return;
+    constexpr int TR = 128 * RW;
+    constexpr int NT = 32 * RW * S;
+    extern __shared__ double2 smem2[];
+    const int W = TR + 2 * w;
+    const int PL = dia_plane_len(W);
+    double2* xw = smem2;
+    double* redseg = reinterpret_cast<double*>(xw + 4 * PL);
+    double* red = redseg + (S > 1 ? (S - 1) : 0) * 8 * (TR / 4);
+
+    const int64_t r0 = (int64_t)blockIdx.x * TR;
+    // stage the x window (zero outside the matrix and in the plane padding)
+    for (int j = threadIdx.x; j < 4 * PL; j += NT) {
+        const int64_t col = r0 - w + j;
+        double2 val = make_double2(0.0, 0.0);
+        if (j < W && col >= 0 && col < a.M) val = a.v[col];
+        xw[(j & 3) * PL + (j >> 2)] = val;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int rw = wid % RW, s = wid / RW;
+    const int g = rw * 32 + lane;
+    const int64_t row4 = r0 + 4 * g;
+    const bool active = row4 < ldb;
+
+    const int Dtot = 2 * w + 1;
+    const int per = (((Dtot + S - 1) / S) + 3) & ~3;
+    const int d0 = s * per;
+    const int d1 = min(Dtot, d0 + per);
+
+    double2 acc0 = make_double2(0, 0), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+    if (active && d0 < d1) {
+        const float* bp = band + (int64_t)d0 * ldb + row4;
+        const int nfull = (d1 - d0) >> 2;
+        int xi = g + (d0 >> 2);
+        double2 X0 = xw[xi], X1 = xw[PL + xi], X2 = xw[2 * PL + xi], X3 = xw[3 * PL + xi];
+        float4 c0, c1, c2, c3;
+        if (nfull > 0) {
+            c0 = ldg_stream_f4(bp);
+            c1 = ldg_stream_f4(bp + ldb);
+            c2 = ldg_stream_f4(bp + 2 * ldb);
+            c3 = ldg_stream_f4(bp + 3 * ldb);
+        }
+        for (int m = 0; m < nfull; ++m) {
+            float4 n0 = c0, n1 = c1, n2 = c2, n3 = c3;
+            if (m + 1 < nfull) {
+                const float* np_ = bp + (int64_t)(4 * (m + 1)) * ldb;
+                n0 = ldg_stream_f4(np_);
+                n1 = ldg_stream_f4(np_ + ldb);
+                n2 = ldg_stream_f4(np_ + 2 * ldb);
+                n3 = ldg_stream_f4(np_ + 3 * ldb);
+            }
+            const double2 N0 = xw[xi + 1], N1 = xw[PL + xi + 1], N2 = xw[2 * PL + xi + 1], N3 = xw[3 * PL + xi + 1];
+            FMA4(c0, X0, X1, X2, X3);
+            FMA4(c1, X1, X2, X3, N0);
+            FMA4(c2, X2, X3, N0, N1);
+            FMA4(c3, X3, N0, N1, N2);
+            X0 = N0; X1 = N1; X2 = N2; X3 = N3;
+            ++xi;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        }
+        for (int d = d0 + 4 * nfull; d < d1; ++d) {   // < 4 leftover diagonals
+            const float4 c = ldg_stream_f4(band + (int64_t)d * ldb + row4);
+            const int j = 4 * g + d;
+            const double2 xa = xw[((j) & 3) * PL + ((j) >> 2)];
+            const double2 xb = xw[((j + 1) & 3) * PL + ((j + 1) >> 2)];
+            const double2 xc = xw[((j + 2) & 3) * PL + ((j + 2) >> 2)];
+            const double2 xd = xw[((j + 3) & 3) * PL + ((j + 3) >> 2)];
+            FMA4(c, xa, xb, xc, xd);
+        }
+    }
+    // cross-segment reduction (fixed order)
+    if (S > 1) {
+        constexpr int G = TR / 4;
+        if (s > 0) {
+            double* rp = redseg + (size_t)(s - 1) * 8 * G + g;
+            rp[0 * G] = acc0.x; rp[1 * G] = acc0.y; rp[2 * G] = acc1.x; rp[3 * G] = acc1.y;
+            rp[4 * G] = acc2.x; rp[5 * G] = acc2.y; rp[6 * G] = acc3.x; rp[7 * G] = acc3.y;
+        }
+        __syncthreads();
+        if (s == 0) {
+#pragma unroll
+            for (int ss = 1; ss < S; ++ss) {
+                const double* rp = redseg + (size_t)(ss - 1) * 8 * G + g;
+                acc0.x += rp[0 * G]; acc0.y += rp[1 * G]; acc1.x += rp[2 * G]; acc1.y += rp[3 * G];
+                acc2.x += rp[4 * G]; acc2.y += rp[5 * G]; acc3.x += rp[6 * G]; acc3.y += rp[7 * G];
+            }
+        }
+    }
+    double dots[2] = {0.0, 0.0};
+    if (s == 0 && active) {
+        const int jw = 4 * g + w;   // window index of row4
+        double2 accs[4] = {acc0, acc1, acc2, acc3};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int64_t i = row4 + e;
+            if (i < a.M) {
+                const int j = jw + e;
+                epi_row<EPI>(a, i, accs[e], xw[(j & 3) * PL + (j >> 2)], dots);
+            }
+        }
+    }
+    if (EPI != EPI_PLAIN) {
+        grid_reduce<2>(dots, a.partials, a.counter, red, [&](double (&t)[2]) { spmm_finalize<EPI>(a, t); });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense-panel kernel (DENSE and BLOCKDIAG layouts).  R is symmetric, so the stored row j of a
+// panel is also column j: the kernel sweeps stored rows ("columns") j and accumulates
+// y[i..i+3] += P[j][i..i+3] * v[j] with y in registers and v[j] a shared-memory broadcast;
+// no shared-memory traffic per matrix element, fully coalesced 128-bit loads.
+// Cross-CTA partial sums over j-segments go to ypart[slot][i]; k_panel_finish adds the slots in
+// fixed order and applies the epilogue.
+// ---------------------------------------------------------------------------------------------
+#define PANEL_JC 1024
+
+#define PFMA(C, X)                                                                            \
+    do {                                                                                      \
+        double v0 = (double)(C).x, v1 = (double)(C).y, v2 = (double)(C).z, v3 = (double)(C).w; \
+        acc0.x = fma(v0, (X).x, acc0.x); acc0.y = fma(v0, (X).y, acc0.y);                     \
+        acc1.x = fma(v1, (X).x, acc1.x); acc1.y = fma(v1, (X).y, acc1.y);                     \
+        acc2.x = fma(v2, (X).x, acc2.x); acc2.y = fma(v2, (X).y, acc2.y);                     \
+        acc3.x = fma(v3, (X).x, acc3.x); acc3.y = fma(v3, (X).y, acc3.y);                     \
+    } while (0)
+
+template <int RW, int S>
+__global__ void __launch_bounds__(32 * RW * S, 2)
+k_spmm_panel(SpmmArgs a, const float* __restrict__ panels, const PanelItem* __restrict__ items, double2* ypart) {
+    if (a.check_done && a.cg->done[0] && a.cg->done[1]) return;
+    constexpr int TI = 128 * RW;
+    constexpr int NT = 32 * RW * S;
+    constexpr int G = TI / 4;
+    __shared__ double2 xs[PANEL_JC];
+    __shared__ double redseg[(S > 1 ? (S - 1) : 1) * 8 * G];
+    const PanelItem it = items[blockIdx.x];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int rw = wid % RW, s = wid / RW;
+    const int g = rw * 32 + lane;
+    const bool active = 4 * g < it.navail;
+    const float* base = panels + it.off + 4 * g;
+
+    double2 acc0 = make_double2(0, 0), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+    for (int jb = 0; jb < it.nj; jb += PANEL_JC) {
+        const int cnt = min(PANEL_JC, it.nj - jb);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cnt; t += NT) xs[t] = a.v[(int64_t)it.j0 + jb + t];
+        __syncthreads();
+        const int per = (cnt + S - 1) / S;
+        const int lo = s * per, hi = min(cnt, lo + per);
+        if (active && lo < hi) {
+            const float* p = base + (int64_t)(jb + lo) * it.ld;
+            int jj = lo;
+            for (; jj + 4 <= hi; jj += 4) {
+                const float4 c0 = ldg_stream_f4(p);
+                const float4 c1 = ldg_stream_f4(p + it.ld);
+                const float4 c2 = ldg_stream_f4(p + 2 * (int64_t)it.ld);
+                const float4 c3 = ldg_stream_f4(p + 3 * (int64_t)it.ld);
+                const double2 x0 = xs[jj], x1 = xs[jj + 1], x2 = xs[jj + 2], x3 = xs[jj + 3];
+                PFMA(c0, x0);
+                PFMA(c1, x1);
+                PFMA(c2, x2);
+                PFMA(c3, x3);
+                p += 4 * (int64_t)it.ld;
+            }
+            for (; jj < hi; ++jj) {
+                const float4 c0 = ldg_stream_f4(p);
+                const double2 x0 = xs[jj];
+                PFMA(c0, x0);
+                p += it.ld;
+            }
+        }
+    }
+    if (S > 1) {
+        __syncthreads();
+        if (s > 0) {
+            double* rp = redseg + (size_t)(s - 1) * 8 * G + g;
+            rp[0 * G] = acc0.x; rp[1 * G] = acc0.y; rp[2 * G] = acc1.x; rp[3 * G] = acc1.y;
+            rp[4 * G] = acc2.x; rp[5 * G] = acc2.y; rp[6 * G] = acc3.x; rp[7 * G] = acc3.y;
+        }
+        __syncthreads();
+        if (s == 0) {
+#pragma unroll
+            for (int ss = 1; ss < S; ++ss) {
+                const double* rp = redseg + (size_t)(ss - 1) * 8 * G + g;
+                acc0.x += rp[0 * G]; acc0.y += rp[1 * G]; acc1.x += rp[2 * G]; acc1.y += rp[3 * G];
+                acc2.x += rp[4 * G]; acc2.y += rp[5 * G]; acc3.x += rp[6 * G]; acc3.y += rp[7 * G];
+            }
+        }
+    }
+    if (s == 0) {
+        double2* yp = ypart + (int64_t)it.slot * a.M + it.i0 + 4 * g;
+        const int left = it.ni - 4 * g;
+        if (left > 0) yp[0] = acc0;
+        if (left > 1) yp[1] = acc1;
+        if (left > 2) yp[2] = acc2;
+        if (left > 3) yp[3] = acc3;
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(256) k_panel_finish(SpmmArgs a, const double2* __restrict__ ypart, int nslots) {
+    if (a.check_done && a.cg->done[0] && a.cg->done[1]) return;
+    __shared__ double red[2 * 32];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double dots[2] = {0.0, 0.0};
+    if (i < a.M) {
+        double2 acc = ypart[i];
+        for (int sl = 1; sl < nslots; ++sl) {
+            const double2 t = ypart[(int64_t)sl * a.M + i];
+            acc.x += t.x;
+            acc.y += t.y;
+        }
+        epi_row<EPI>(a, i, acc, a.v[i], dots);
+    }
+    if (EPI != EPI_PLAIN) {
+        grid_reduce<2>(dots, a.partials, a.counter, red, [&](double (&t)[2]) { spmm_finalize<EPI>(a, t); });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSR kernel (general sparsity): one warp per row, coalesced value / index loads, 16-byte gathers
+// of the vector pair through the read-only path (the vectors stay L2 resident).
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(256)
+k_spmm_csr(SpmmArgs a, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+           const float* __restrict__ vals) {
+    if (a.check_done && a.cg->done[0] && a.cg->done[1]) return;
+    __shared__ double red[2 * 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * 8 + wid;
+    double dots[2] = {0.0, 0.0};
+    if (row < a.M) {
+        const int64_t beg = indptr[row], end = indptr[row + 1];
+        double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+        int64_t k = beg + lane;
+        for (; k + 32 < end; k += 64) {
+            const float v0 = ldg_stream_f1(vals + k), v1 = ldg_stream_f1(vals + k + 32);
+            const int c0 = ldg_stream_i1(indices + k), c1 = ldg_stream_i1(indices + k + 32);
+            const double2 x0 = __ldg(&a.v[c0]);
+            const double2 x1 = __ldg(&a.v[c1]);
+            ax = fma((double)v0, x0.x, ax); ay = fma((double)v0, x0.y, ay);
+            bx = fma((double)v1, x1.x, bx); by = fma((double)v1, x1.y, by);
+        }
+        if (k < end) {
+            const float v0 = ldg_stream_f1(vals + k);
+            const int c0 = ldg_stream_i1(indices + k);
+            const double2 x0 = __ldg(&a.v[c0]);
+            ax = fma((double)v0, x0.x, ax); ay = fma((double)v0, x0.y, ay);
+        }
+        ax = warp_sum(ax + bx);
+        ay = warp_sum(ay + by);
+        if (lane == 0) epi_row<EPI>(a, row, make_double2(ax, ay), a.v[row], dots);
+    }
+    if (EPI != EPI_PLAIN) {
+        grid_reduce<2>(dots, a.partials, a.counter, red, [&](double (&t)[2]) { spmm_finalize<EPI>(a, t); });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------------
+template <int RW, int S, int EPI>
+static int launch_dia(sgv_ctx* c, const LdMatrix& ld, const SpmmArgs& a) {
+    constexpr int TR = 128 * RW;
+    const size_t smem = sgv_dia_smem_bytes(ld.w, RW, S);
+    static size_t configured = 0;
+    if (smem > configured) {
+        SGV_CUDA(cudaFuncSetAttribute(k_spmm_dia<RW, S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const unsigned grid = (unsigned)((ld.ldb + TR - 1) / TR);
+    SGV_TRY(sgv_ensure_partials(c, grid));
+    SpmmArgs aa = a;
+    aa.partials = c->partials;
+    k_spmm_dia<RW, S, EPI><<<grid, 32 * RW * S, smem, c->stream>>>(aa, ld.band, (int)ld.w, ld.ldb);
+    c->launches++;
+    return 0;
+}
+
+template <int EPI>
+static int launch_epi(sgv_ctx* c, Cohort& co, const SpmmArgs& a) {
+    const LdMatrix& ld = co.ld;
+    if (ld.layout == SGV_LAYOUT_DIA) {
+        // wide tiles when there are enough rows to fill the machine, narrow ones otherwise
+        const bool big = ld.ldb >= (int64_t)c->sm_count * 2 * 256 * 2;
+        if (big && sgv_dia_smem_bytes(ld.w, 2, 4) <= 100 * 1024) return launch_dia<2, 4, EPI>(c, ld, a);
+        return launch_dia<1, 8, EPI>(c, ld, a);
+    }
+    if (ld.layout == SGV_LAYOUT_DENSE || ld.layout == SGV_LAYOUT_BLOCKDIAG) {
+        SpmmArgs aa = a;
+        k_spmm_panel<4, 2><<<ld.n_items, 256, 0, c->stream>>>(aa, ld.panels, ld.items, c->ypart);
+        c->launches++;
+        const unsigned grid = (unsigned)((c->M + 255) / 256);
+        SGV_TRY(sgv_ensure_partials(c, grid));
+        aa.partials = c->partials;
+        k_panel_finish<EPI><<<grid, 256, 0, c->stream>>>(aa, c->ypart, ld.s_cross);
+        c->launches++;
+        return 0;
+    }
+    if (ld.layout == SGV_LAYOUT_CSR) {
+        const unsigned grid = (unsigned)((c->M + 7) / 8);
+        SGV_TRY(sgv_ensure_partials(c, grid));
+        SpmmArgs aa = a;
+        aa.partials = c->partials;
+        k_spmm_csr<EPI><<<grid, 256, 0, c->stream>>>(aa, ld.indptr, ld.indices, ld.vals);
+        c->launches++;
+        return 0;
+    }
+    sgv_set_error("cohort has no LD matrix uploaded");
+    return -1;
+}
+
+int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, const double2* v, double2* out, double gamw, double gam2,
+                    int check_done) {
+    SpmmArgs a;
+    a.v = v;
+    a.out = out;
+    a.bb = co.bb;
+    a.gamw = gamw;
+    a.gam2 = gam2;
+    a.M = c->M;
+    a.cg = c->cg;
+    a.partials = c->partials;
+    a.counter = c->counter;
+    a.check_done = check_done;
+    int rc;
+    switch (epi) {
+        case EPI_Q: rc = launch_epi<EPI_Q>(c, co, a); break;
+        case EPI_RESID: rc = launch_epi<EPI_RESID>(c, co, a); break;
+        case EPI_STATS: rc = launch_epi<EPI_STATS>(c, co, a); break;
+        default: rc = launch_epi<EPI_PLAIN>(c, co, a); break;
+    }
+    if (rc) return rc;
+    SGV_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,539 @@
+// Per-iteration VAMP kernels: denoiser (+derivative, damping), EM / MLE prior reductions,
+// LMMSE set-up, the 2-RHS conjugate-gradient driver with scipy semantics, and the post-CG
+// Hutchinson / gamw statistics.  Reference: src/sgvamp.py:93-160 and :196-389.
+#include <cmath>
+#include <cstring>
+#include "sgv_device.cuh"
+
+static int check_ready(sgv_ctx* c) {
+    SGV_CHECK(c != nullptr, "null handle");
+    SGV_CHECK(c->M > 0, "sgv_configure has not been called");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// denoiser: posterior mean + derivative factor + damping (src/sgvamp.py:93-114, :273-276, :285)
+// ---------------------------------------------------------------------------------------------
+struct DenoiseConsts {
+    int    K, Lm1;
+    double w[SGV_MAX_K];
+    double s2[SGV_MAX_L], sq[SGV_MAX_L], lw[SGV_MAX_L];   // sigma2_meta, sqrt(s2/sigma), lam*omega
+    double one_minus_lam;
+};
+
+__global__ void __launch_bounds__(256)
+k_denoise(int64_t M, const double* __restrict__ r1_all, double* __restrict__ xhat1, DenoiseConsts k, double rho,
+          int damp, double* partials, unsigned* counter, CgState* st) {
+    __shared__ double red[32];
+    double dsum[1] = {0.0};
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        double sw = 0.0;
+        for (int q = 0; q < k.K; ++q) sw += r1_all[(int64_t)q * M + j] * k.w[q];   // np.inner(rs, a*gam1s)  :96
+        double mu[SGV_MAX_L];
+        int mi = 0;
+        double best = -1.0;
+        for (int l = 0; l < k.Lm1; ++l) {
+            mu[l] = sw * k.s2[l];
+            const double score = mu[l] * mu[l] / k.s2[l];                              // :97
+            if (l == 0 || score > best) { best = score; mi = l; }
+        }
+        const double mum = mu[mi], s2m = k.s2[mi];
+        double num = 0.0, den = 0.0, dnum = 0.0, dden = 0.0;
+        for (int l = 0; l < k.Lm1; ++l) {
+            const double e = exp(0.5 * (mu[l] * mu[l] * s2m - mum * mum * k.s2[l]) / (k.s2[l] * s2m));   // :98
+            const double t = k.lw[l] * e * k.sq[l];
+            num += t * mu[l];                          // :99
+            den += t;                                  // :101
+            dnum += t * (mu[l] * mu[l] + k.s2[l]);     // :112 (without a_k*gam1_k)
+            dden += t * mu[l];                         // :113 (without a_k*gam1_k)
+        }
+        den += k.one_minus_lam * exp(-0.5 * (mum * mum / s2m));                        // :100-101
+        double xh = num / den;
+        dsum[0] += (dnum * den - dden * num) / (den * den);                            // :114
+        if (damp) xh = rho * xh + (1.0 - rho) * xhat1[j];                              // :276
+        xhat1[j] = xh;
+    }
+    grid_reduce<1>(dsum, partials, counter, red, [&](double (&t)[1]) { st->stats[0] = t[0]; });
+}
+
+static void fill_denoise_consts(const sgv_ctx* c, const double* gam1s, DenoiseConsts& k) {
+    const PriorParams& p = c->prior;
+    k.K = p.K;
+    k.Lm1 = p.L - 1;
+    double W = 0.0;
+    for (int q = 0; q < p.K; ++q) {
+        k.w[q] = p.a[q] * gam1s[q];
+        W += k.w[q];                                   // sum(self.a * gam1s), left to right
+    }
+    for (int l = 0; l < k.Lm1; ++l) {
+        k.s2[l] = 1.0 / (W + 1.0 / p.sigmas[l]);       // :95
+        k.sq[l] = std::sqrt(k.s2[l] / p.sigmas[l]);
+        k.lw[l] = p.lam * p.omegas[l];
+    }
+    k.one_minus_lam = 1.0 - p.lam;
+}
+
+extern "C" int sgv_denoise(sgv_handle c, const double* gam1s, double rho, int damp, double* dfac_mean) {
+    SGV_TRY(check_ready(c));
+    SGV_CHECK(c->prior.L >= 2, "prior not set");
+    DenoiseConsts k;
+    fill_denoise_consts(c, gam1s, k);
+    const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 8);
+    SGV_TRY(sgv_ensure_partials(c, grid));
+    k_denoise<<<grid, 256, 0, c->stream>>>(c->M, c->r1_all, c->xhat1, k, rho, damp, c->partials, c->counter, c->cg);
+    c->launches++;
+    SGV_CUDA(cudaGetLastError());
+    SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    *dfac_mean = c->host_scal[0] / (double)c->M;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// EM prior update (src/sgvamp.py:116-136): one pass = one grid reduction of K + (L-1) + 1 sums
+// ---------------------------------------------------------------------------------------------
+struct EmConsts {
+    int    K, Lm1;
+    double lam, one_minus_lam;
+    double a[SGV_MAX_K], g[SGV_MAX_K], ginv[SGV_MAX_K], sqginv[SGV_MAX_K];
+    double lo[SGV_MAX_L];                      // lam * omega_l
+    double den[SGV_MAX_K][SGV_MAX_L];          // sigma_l + 1/gam_k
+    double sqden[SGV_MAX_K][SGV_MAX_L];        // sqrt(1/gam_k + sigma_l)
+};
+
+__global__ void __launch_bounds__(256)
+k_em(int64_t M, const double* __restrict__ r1_all, EmConsts k, double* partials, unsigned* counter, CgState* st) {
+    __shared__ double red[16 * 32];
+    double acc[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) acc[t] = 0.0;
+    // acc[0..K-1] = sum_j pi_kj ; acc[8..8+Lm1-1] = sum a_k pi xi~_l ; acc[15] = sum a_k pi
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        for (int q = 0; q < k.K; ++q) {
+            const double r = r1_all[(int64_t)q * M + j];
+            const double r2 = r * r;
+            double e[SGV_MAX_L], emax = 0.0;
+            for (int l = 0; l < k.Lm1; ++l) {
+                e[l] = -r2 / 2 / k.den[q][l];                                       // :127
+                if (l == 0 || e[l] > emax) emax = e[l];
+            }
+            double xi[SGV_MAX_L], sum_xi = 0.0;
+            for (int l = 0; l < k.Lm1; ++l) {
+                xi[l] = k.lo[l] * exp(e[l] - emax) / k.sqden[q][l];                 // :128
+                sum_xi += xi[l];
+            }
+            const double pi = 1.0 / (1.0 + k.one_minus_lam * exp(-r2 / 2 * k.g[q] - emax) / k.sqginv[q] / sum_xi);   // :131
+            const double api = k.a[q] * pi;
+#pragma unroll
+            for (int t = 0; t < SGV_MAX_K; ++t)
+                if (t == q) acc[t] += pi;
+#pragma unroll
+            for (int l = 0; l < SGV_MAX_L - 1; ++l)
+                if (l < k.Lm1) acc[8 + l] += api * (xi[l] / sum_xi);                // :130,:136
+            acc[15] += api;
+        }
+    }
+    grid_reduce<16>(acc, partials, counter, red, [&](double (&t)[16]) {
+        for (int i = 0; i < 16; ++i) st->stats[i] = t[i];
+    });
+}
+
+extern "C" int sgv_prior_em(sgv_handle c, const double* gam1s, int maxit, double tol, double* lam_out,
+                            double* omegas_out, int* steps_out, double* relerr_out) {
+    SGV_TRY(check_ready(c));
+    PriorParams& p = c->prior;
+    SGV_CHECK(p.L >= 2, "prior not set");
+    const int Lm1 = p.L - 1;
+    const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 4);
+    SGV_TRY(sgv_ensure_partials(c, grid + 1));
+    int steps = 0;
+    double rel = 0.0;
+    double asum = 0.0;
+    for (int q = 0; q < p.K; ++q) asum += p.a[q];
+    for (int it = 0; it < maxit; ++it) {
+        EmConsts k;
+        k.K = p.K;
+        k.Lm1 = Lm1;
+        k.lam = p.lam;
+        k.one_minus_lam = 1.0 - p.lam;
+        for (int q = 0; q < p.K; ++q) {
+            k.a[q] = p.a[q];
+            k.g[q] = gam1s[q];
+            k.ginv[q] = 1.0 / gam1s[q];
+            k.sqginv[q] = std::sqrt(k.ginv[q]);
+            for (int l = 0; l < Lm1; ++l) {
+                k.den[q][l] = p.sigmas[l] + k.ginv[q];
+                k.sqden[q][l] = std::sqrt(k.ginv[q] + p.sigmas[l]);
+            }
+        }
+        for (int l = 0; l < Lm1; ++l) k.lo[l] = p.lam * p.omegas[l];
+        k_em<<<grid, 256, 0, c->stream>>>(c->M, c->r1_all, k, c->partials, c->counter, c->cg);
+        c->launches++;
+        SGV_CUDA(cudaGetLastError());
+        SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+        const double* t = c->host_scal;
+        double wsum = 0.0;
+        for (int q = 0; q < p.K; ++q) wsum += p.a[q] * t[q];
+        const double lam_new = wsum / asum / (double)c->M;                          // :134
+        double om_new[SGV_MAX_L], dn = 0.0, on = 0.0;
+        for (int l = 0; l < Lm1; ++l) {
+            om_new[l] = t[8 + l] / t[15];                                            // :136
+            dn += (om_new[l] - p.omegas[l]) * (om_new[l] - p.omegas[l]);
+            on += p.omegas[l] * p.omegas[l];
+        }
+        const double om_err = std::sqrt(dn) / std::sqrt(on);                        // :254
+        const double lam_err = std::fabs(lam_new - p.lam) / lam_new;                // :255
+        p.lam = lam_new;
+        for (int l = 0; l < Lm1; ++l) p.omegas[l] = om_new[l];
+        steps = it + 1;
+        rel = std::max(om_err, lam_err);
+        if (om_err < tol && lam_err < tol) break;                                   // :256
+    }
+    *lam_out = p.lam;
+    for (int l = 0; l < Lm1; ++l) omegas_out[l] = p.omegas[l];
+    if (steps_out) *steps_out = steps;
+    if (relerr_out) *relerr_out = rel;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MLE Lagrangian residual (src/sgvamp.py:139-160)
+// ---------------------------------------------------------------------------------------------
+struct LagConsts {
+    int    K, L;
+    double a[SGV_MAX_K];
+    double den[SGV_MAX_K][SGV_MAX_L];     // sigma2_l + 1/gam_k
+    double sqden[SGV_MAX_K][SGV_MAX_L];
+    double omega[SGV_MAX_L];
+};
+
+__global__ void __launch_bounds__(256)
+k_min_r2(int64_t M, int K, const double* __restrict__ r1_all, double* partials, unsigned* counter, CgState* st) {
+    __shared__ double red[8 * 32];
+    double mn[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mn[q] = __longlong_as_double(0x7ff0000000000000LL);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q < K) {
+                const double r = r1_all[(int64_t)q * M + j];
+                mn[q] = fmin(mn[q], r * r);
+            }
+    }
+    grid_reduce<8, true>(mn, partials, counter, red, [&](double (&t)[8]) {
+        for (int q = 0; q < 8; ++q) st->stats[q] = t[q];
+    });
+}
+
+__global__ void __launch_bounds__(256)
+k_lagrangian(int64_t M, const double* __restrict__ r1_all, LagConsts k, double* partials, unsigned* counter,
+             CgState* st) {
+    __shared__ double red[8 * 32];
+    // global shift exp_max = max_{k,j,l} -r^2/2/(sigma2_l + 1/gam_k)  (:153); e is monotone in r^2, so
+    // the maximum over j is attained at min_j r^2 (st->stats[k], from k_min_r2).
+    double exp_max = -__longlong_as_double(0x7ff0000000000000LL);
+    for (int q = 0; q < k.K; ++q)
+        for (int l = 0; l < k.L; ++l) exp_max = fmax(exp_max, -st->stats[q] / 2 / k.den[q][l]);
+    double acc[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc[l] = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        for (int q = 0; q < k.K; ++q) {
+            const double r = r1_all[(int64_t)q * M + j];
+            const double r2 = r * r;
+            double pr[SGV_MAX_L], den = 0.0;
+            for (int l = 0; l < k.L; ++l) {
+                pr[l] = exp(-r2 / 2 / k.den[q][l] - exp_max) / k.sqden[q][l];       // :154
+                den += pr[l] * k.omega[l];                                           // :156
+            }
+#pragma unroll
+            for (int l = 0; l < 8; ++l)
+                if (l < k.L) acc[l] += k.a[q] * pr[l] / den;                         // :155,:158
+        }
+    }
+    grid_reduce<8>(acc, partials, counter, red, [&](double (&t)[8]) {
+        for (int l = 0; l < 8; ++l) st->stats[8 + l] = t[l];
+    });
+}
+
+extern "C" int sgv_lagrangian(sgv_handle c, const double* gam1s, const double* x, const double* omega0,
+                              const double* sigma2, double* y) {
+    SGV_TRY(check_ready(c));
+    const PriorParams& p = c->prior;
+    const int L = p.L;
+    SGV_CHECK(L >= 2, "prior not set");
+    LagConsts k;
+    k.K = p.K;
+    k.L = L;
+    for (int q = 0; q < p.K; ++q) {
+        k.a[q] = p.a[q];
+        const double ginv = 1.0 / gam1s[q];
+        for (int l = 0; l < L; ++l) {
+            k.den[q][l] = sigma2[l] + ginv;
+            k.sqden[q][l] = std::sqrt(sigma2[l] + ginv);
+        }
+    }
+    for (int l = 0; l < L; ++l) k.omega[l] = x[l];
+    const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 4);
+    SGV_TRY(sgv_ensure_partials(c, grid + 1));
+    k_min_r2<<<grid, 256, 0, c->stream>>>(c->M, p.K, c->r1_all, c->partials, c->counter, c->cg);
+    k_lagrangian<<<grid, 256, 0, c->stream>>>(c->M, c->r1_all, k, c->partials, c->counter, c->cg);
+    c->launches += 2;
+    SGV_CUDA(cudaGetLastError());
+    SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats + 8, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    double osum = 0.0;
+    for (int l = 0; l < L; ++l) {
+        y[l] = c->host_scal[l] + (omega0[l] - 1) / x[l] + x[L];                     // :158
+        osum += x[l];
+    }
+    y[L] = osum - 1.0;                                                               // :159
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// metrics vs truth (src/sgvamp.py:379-382)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_metrics(int64_t M, const double* __restrict__ xhat1, const double* __restrict__ x0, double* partials,
+          unsigned* counter, CgState* st) {
+    __shared__ double red[4 * 32];
+    double acc[4] = {0, 0, 0, 0};
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        const double a = xhat1[j], b = x0[j];
+        acc[0] += a * b;
+        acc[1] += a * a;
+        acc[2] += b * b;
+        acc[3] += (a - b) * (a - b);
+    }
+    grid_reduce<4>(acc, partials, counter, red, [&](double (&t)[4]) {
+        for (int l = 0; l < 4; ++l) st->stats[l] = t[l];
+    });
+}
+
+extern "C" int sgv_metrics(sgv_handle c, const double* x0, double* dots) {
+    SGV_TRY(check_ready(c));
+    if (x0 != nullptr) {
+        if (!c->truth) SGV_CUDA(cudaMalloc(&c->truth, c->M * sizeof(double)));
+        SGV_CUDA(cudaMemcpyAsync(c->truth, x0, c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    SGV_CHECK(c->truth != nullptr, "truth vector not uploaded yet");
+    const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 4);
+    SGV_TRY(sgv_ensure_partials(c, grid + 1));
+    k_metrics<<<grid, 256, 0, c->stream>>>(c->M, c->xhat1, c->truth, c->partials, c->counter, c->cg);
+    c->launches++;
+    SGV_CUDA(cudaGetLastError());
+    SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 4; ++i) dots[i] = c->host_scal[i];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LMMSE: set-up, CG vector kernels, post-processing
+// ---------------------------------------------------------------------------------------------
+// r2 = (xhat1 - alpha1 r1)/(1-alpha1) (:310); b0 = mu2 = gamw r + gam2 r2 (:313); b1 = u (:326);
+// x0 = (xhat2_prev, Sigma2_u_prev) (:316,:332); |b|^2 per column; initialise the CG state.
+__global__ void __launch_bounds__(256)
+k_lmmse_setup(int64_t M, const double* __restrict__ xhat1, const double* __restrict__ r1,
+              const double* __restrict__ xty, const int8_t* __restrict__ probe, const double* __restrict__ xhat2,
+              const double* __restrict__ sig, double* __restrict__ r2, double2* __restrict__ bb,
+              double2* __restrict__ xx, double2* __restrict__ rr, double alpha1, double gamw, double gam2,
+              int maxit, int x0_zero, double* partials, unsigned* counter, CgState* st) {
+    __shared__ double red[2 * 32];
+    double acc[2] = {0.0, 0.0};
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        const double r2j = (xhat1[j] - alpha1 * r1[j]) / (1.0 - alpha1);
+        r2[j] = r2j;
+        const double2 b = make_double2(gamw * xty[j] + gam2 * r2j, (double)probe[j]);
+        bb[j] = b;
+        xx[j] = make_double2(xhat2[j], sig[j]);
+        if (x0_zero) rr[j] = b;
+        acc[0] += b.x * b.x;
+        acc[1] += b.y * b.y;
+    }
+    grid_reduce<2>(acc, partials, counter, red, [&](double (&t)[2]) {
+        st->maxit = maxit;
+        st->step = 0;
+        for (int c = 0; c < 2; ++c) {
+            st->bnorm2[c] = t[c];
+            st->rho[c] = 0.0;
+            st->rho_prev[c] = 0.0;
+            st->pq[c] = 0.0;
+            st->iters[c] = 0;
+            st->info[c] = 0;
+            st->done[c] = 0;
+            st->zero_b[c] = 0;
+            if (t[c] == 0.0) {          // scipy: `if bnrm2 == 0: return b, 0`
+                st->done[c] = 1;
+                st->zero_b[c] = 1;
+            } else if (x0_zero) {       // r = b.copy(); loop-top test of iteration 0
+                st->rho[c] = t[c];
+                cg_top_test(st, c);
+            }
+        }
+    });
+}
+
+// p = r (first step) or p = r + (rho/rho_prev) p
+__global__ void __launch_bounds__(256)
+k_p_update(int64_t M, const double2* __restrict__ rr, double2* __restrict__ pp, const CgState* __restrict__ st) {
+    const int d0 = st->done[0], d1 = st->done[1];
+    if (d0 && d1) return;
+    const bool first = st->step == 0;
+    const double b0 = first ? 0.0 : st->rho[0] / st->rho_prev[0];
+    const double b1 = first ? 0.0 : st->rho[1] / st->rho_prev[1];
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        const double2 r = rr[j];
+        double2 p = first ? make_double2(0.0, 0.0) : pp[j];
+        // scipy: p *= beta; p += z
+        if (!d0) p.x = first ? r.x : (p.x * b0 + r.x);
+        if (!d1) p.y = first ? r.y : (p.y * b1 + r.y);
+        pp[j] = p;
+    }
+}
+
+// alpha = rho/(p.q); x += alpha p; r -= alpha q; rho_prev = rho; rho = r.r; loop-top test
+__global__ void __launch_bounds__(256)
+k_cg_update(int64_t M, double2* __restrict__ xx, double2* __restrict__ rr, const double2* __restrict__ pp,
+            const double2* __restrict__ qq, double* partials, unsigned* counter, CgState* st) {
+    __shared__ double red[2 * 32];
+    const int d0 = st->done[0], d1 = st->done[1];
+    if (d0 && d1) return;
+    const double a0 = d0 ? 0.0 : st->rho[0] / st->pq[0];
+    const double a1 = d1 ? 0.0 : st->rho[1] / st->pq[1];
+    double acc[2] = {0.0, 0.0};
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        double2 x = xx[j], r = rr[j];
+        const double2 p = pp[j], q = qq[j];
+        if (!d0) { x.x += a0 * p.x; r.x -= a0 * q.x; }
+        if (!d1) { x.y += a1 * p.y; r.y -= a1 * q.y; }
+        xx[j] = x;
+        rr[j] = r;
+        acc[0] += r.x * r.x;
+        acc[1] += r.y * r.y;
+    }
+    grid_reduce<2>(acc, partials, counter, red, [&](double (&t)[2]) {
+        for (int c = 0; c < 2; ++c) {
+            if (st->done[c]) continue;
+            st->rho_prev[c] = st->rho[c];
+            st->rho[c] = t[c];
+            st->iters[c] += 1;
+            cg_top_test(st, c);
+        }
+        st->step += 1;
+    });
+}
+
+// xhat2 <- CG col 0 (damped with the previous xhat2 if lmmse_damp, :322-323); Sigma2_u_prev <- col 1
+// (:333); dots u.Sigma2_u (:338) and xhat2.r (:352).  xx col 0 is overwritten with the final xhat2 so
+// that the statistics SpMM can read (xhat2, Sigma2_u) as one vector pair.
+__global__ void __launch_bounds__(256)
+k_lmmse_post(int64_t M, double2* __restrict__ xx, const double2* __restrict__ bb, const double* __restrict__ xty,
+             double* __restrict__ xhat2, double* __restrict__ sig, double rho, int damp, double* partials,
+             unsigned* counter, CgState* st) {
+    __shared__ double red[2 * 32];
+    const int z0 = st->zero_b[0], z1 = st->zero_b[1];
+    double acc[2] = {0.0, 0.0};
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        double2 x = xx[j];
+        const double2 b = bb[j];
+        if (z0) x.x = b.x;
+        if (z1) x.y = b.y;
+        if (damp) x.x = rho * x.x + (1.0 - rho) * xhat2[j];
+        xhat2[j] = x.x;
+        sig[j] = x.y;
+        xx[j] = x;
+        acc[0] += b.y * x.y;
+        acc[1] += x.x * xty[j];
+    }
+    grid_reduce<2>(acc, partials, counter, red, [&](double (&t)[2]) {
+        st->stats[2] = t[0];
+        st->stats[3] = t[1];
+    });
+}
+
+__global__ void __launch_bounds__(256)
+k_update_r1(int64_t M, const double* __restrict__ xhat2, const double* __restrict__ r2, double* __restrict__ r1,
+            double alpha2) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x)
+        r1[j] = (xhat2[j] - alpha2 * r2[j]) / (1.0 - alpha2);                       // :348
+}
+
+extern "C" int sgv_update_r1(sgv_handle c, int cohort, double alpha2) {
+    SGV_TRY(check_ready(c));
+    SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
+    Cohort& co = c->coh[cohort];
+    const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 8);
+    k_update_r1<<<grid, 256, 0, c->stream>>>(c->M, co.xhat2, co.r2, co.r1, alpha2);
+    c->launches++;
+    SGV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const int8_t* probe, sgv_lmmse_out* out) {
+    SGV_TRY(check_ready(c));
+    SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
+    SGV_CHECK(in && probe && out, "null argument");
+    Cohort& co = c->coh[cohort];
+    SGV_CHECK(co.ld.layout != 0, "cohort %d has no LD matrix", cohort);
+    const int64_t M = c->M;
+    const unsigned vgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 8);
+    SGV_TRY(sgv_ensure_partials(c, vgrid + 1));
+    SGV_CUDA(cudaMemcpyAsync(co.probe, probe, M, cudaMemcpyHostToDevice, c->stream));
+    k_lmmse_setup<<<vgrid, 256, 0, c->stream>>>(M, c->xhat1, co.r1, co.xty, co.probe, co.xhat2, co.sig, co.r2, co.bb,
+                                               co.xx, co.rr, in->alpha1, in->gamw, in->gam2, in->cg_maxit,
+                                               in->x0_zero, c->partials, c->counter, c->cg);
+    c->launches++;
+    int passes = 0;
+    if (!in->x0_zero) {   // r = b - A x0  and the loop-top test of iteration 0
+        SGV_TRY(sgv_launch_spmm(c, co, EPI_RESID, co.xx, co.rr, in->gamw, in->gam2, 1));
+        passes++;
+    }
+    int launched = 0;
+    int batch = 4;
+    CgState* hs = c->cg_host;
+    while (launched < in->cg_maxit) {
+        const int nb = std::min(batch, in->cg_maxit - launched);
+        for (int b = 0; b < nb; ++b) {
+            k_p_update<<<vgrid, 256, 0, c->stream>>>(M, co.rr, co.pp, c->cg);
+            SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, co.pp, co.qq, in->gamw, in->gam2, 1));
+            k_cg_update<<<vgrid, 256, 0, c->stream>>>(M, co.xx, co.rr, co.pp, co.qq, c->partials, c->counter, c->cg);
+            c->launches += 2;
+        }
+        launched += nb;
+        SGV_CUDA(cudaMemcpyAsync(hs, c->cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+        if (hs->done[0] && hs->done[1]) break;
+        batch = std::min(16, batch * 2);
+    }
+    if (in->cg_maxit == 0 || launched == 0) {
+        SGV_CUDA(cudaMemcpyAsync(hs, c->cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    out->cg_iters[0] = hs->iters[0];
+    out->cg_iters[1] = hs->iters[1];
+    // a column that ran out of iterations without ever passing the test reports maxiter (scipy)
+    out->cg_info[0] = hs->done[0] ? hs->info[0] : in->cg_maxit;
+    out->cg_info[1] = hs->done[1] ? hs->info[1] : in->cg_maxit;
+    passes += std::max(hs->iters[0], hs->iters[1]);
+
+    k_lmmse_post<<<vgrid, 256, 0, c->stream>>>(M, co.xx, co.bb, co.xty, co.xhat2, co.sig, in->rho, in->lmmse_damp,
+                                              c->partials, c->counter, c->cg);
+    c->launches++;
+    if (in->learn_gamw) {   // R xhat2 and R Sigma2_u in one pass (:352,:359)
+        SGV_TRY(sgv_launch_spmm(c, co, EPI_STATS, co.xx, nullptr, 1.0, 0.0, 0));
+        passes++;
+    }
+    SGV_CUDA(cudaGetLastError());
+    SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    out->xhat2_R_xhat2 = in->learn_gamw ? c->host_scal[0] : 0.0;
+    out->u_R_sigma2u = in->learn_gamw ? c->host_scal[1] : 0.0;
+    out->u_sigma2u = c->host_scal[2];
+    out->xhat2_r = c->host_scal[3];
+    out->spmm_passes = passes;
+    return 0;
+}

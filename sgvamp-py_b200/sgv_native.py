@@ -1,0 +1,251 @@
+"""ctypes binding of libsgvamp_b200.so (C ABI declared in include/sgvamp_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no B200 is present, loading /
+creating a handle raises.  Nothing in this module imports the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsgvamp_b200.so")
+
+LAYOUT_AUTO, LAYOUT_DENSE, LAYOUT_DIA, LAYOUT_BLOCKDIAG, LAYOUT_CSR = 0, 1, 2, 3, 4
+LAYOUT_NAMES = {0: "auto", 1: "dense", 2: "dia", 3: "blockdiag", 4: "csr"}
+F32, F64 = 0, 1
+VEC_XHAT1, VEC_R1, VEC_XHAT2, VEC_SIGMA2U, VEC_R2, VEC_XTY = 0, 1, 2, 3, 4, 5
+
+# every symbol the header declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "sgv_version", "sgv_last_error", "sgv_create", "sgv_destroy", "sgv_sync", "sgv_configure",
+    "sgv_ld_upload_dense", "sgv_ld_upload_csr", "sgv_ld_adopt_dia", "sgv_ld_adopt_dense", "sgv_ld_info",
+    "sgv_set_xty", "sgv_reset_state", "sgv_get_vec", "sgv_set_vec", "sgv_get_vec_async", "sgv_wait_copies",
+    "sgv_pinned_alloc", "sgv_pinned_free", "sgv_set_prior", "sgv_set_weights", "sgv_denoise", "sgv_prior_em",
+    "sgv_lagrangian", "sgv_lmmse", "sgv_update_r1", "sgv_metrics", "sgv_spmm", "sgv_spmm_bench",
+    "sgv_launch_count",
+]
+
+
+class LmmseIn(C.Structure):
+    _fields_ = [("gamw", C.c_double), ("gam2", C.c_double), ("alpha1", C.c_double), ("rho", C.c_double),
+                ("cg_maxit", C.c_int), ("lmmse_damp", C.c_int), ("learn_gamw", C.c_int), ("x0_zero", C.c_int)]
+
+
+class LmmseOut(C.Structure):
+    _fields_ = [("u_sigma2u", C.c_double), ("xhat2_r", C.c_double), ("xhat2_R_xhat2", C.c_double),
+                ("u_R_sigma2u", C.c_double), ("cg_iters", C.c_int * 2), ("cg_info", C.c_int * 2),
+                ("spmm_passes", C.c_int)]
+
+
+class SgvError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (raises if it has not been built: no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SgvError("%s not found - build it with `python sgvamp-py_b200/build_native.py` "
+                       "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.sgv_last_error.restype = C.c_char_p
+    lib.sgv_launch_count.restype = C.c_int64
+    lib.sgv_launch_count.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Handle:
+    """One GPU's worth of solver state (opaque sgv_handle)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load()
+        self.h = C.c_void_p()
+        self._ck(self.lib.sgv_create(C.c_int(device), C.c_void_p(stream or 0), C.byref(self.h)))
+        self.M = 0
+        self.K = 0
+        self._pinned = []
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SgvError("libsgvamp_b200 error %d: %s" % (rc, self.lib.sgv_last_error().decode()))
+
+    def close(self):
+        if self.h:
+            for p in self._pinned:
+                self.lib.sgv_pinned_free(self.h, C.c_void_p(p))
+            self._pinned = []
+            self.lib.sgv_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- setup ---------------------------------------------------------------------------------
+    def configure(self, M, K):
+        self._ck(self.lib.sgv_configure(self.h, C.c_int64(M), C.c_int(K)))
+        self.M, self.K = int(M), int(K)
+
+    def sync(self):
+        self._ck(self.lib.sgv_sync(self.h))
+
+    def upload_dense(self, cohort, R, s=0.0):
+        R = np.asarray(R)
+        if R.dtype not in (np.float32, np.float64):
+            R = R.astype(np.float64)
+        if not R.flags.c_contiguous:
+            R = np.ascontiguousarray(R)
+        assert R.shape == (self.M, self.M), R.shape
+        self._ck(self.lib.sgv_ld_upload_dense(self.h, C.c_int(cohort), R.ctypes.data_as(C.c_void_p),
+                                              C.c_int(F64 if R.dtype == np.float64 else F32),
+                                              C.c_int64(R.shape[1]), C.c_double(s)))
+
+    def upload_csr(self, cohort, indptr, indices, data, s=0.0, layout=LAYOUT_AUTO):
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        data = np.ascontiguousarray(data)
+        if data.dtype not in (np.float32, np.float64):
+            data = data.astype(np.float64)
+        rc = self.lib.sgv_ld_upload_csr(self.h, C.c_int(cohort), indptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                        indices.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        data.ctypes.data_as(C.c_void_p),
+                                        C.c_int(F64 if data.dtype == np.float64 else F32),
+                                        C.c_int64(data.shape[0]), C.c_double(s), C.c_int(layout))
+        return rc
+
+    def adopt_dia(self, cohort, band_ptr, w, ldb):
+        self._ck(self.lib.sgv_ld_adopt_dia(self.h, C.c_int(cohort), C.c_void_p(band_ptr), C.c_int64(w), C.c_int64(ldb)))
+
+    def adopt_dense(self, cohort, ptr, ld):
+        self._ck(self.lib.sgv_ld_adopt_dense(self.h, C.c_int(cohort), C.c_void_p(ptr), C.c_int64(ld)))
+
+    def ld_info(self, cohort):
+        layout = C.c_int()
+        nnz = C.c_int64()
+        bw = C.c_int64()
+        nb = C.c_int64()
+        bpp = C.c_double()
+        self._ck(self.lib.sgv_ld_info(self.h, C.c_int(cohort), C.byref(layout), C.byref(nnz), C.byref(bw),
+                                      C.byref(nb), C.byref(bpp)))
+        return dict(layout=LAYOUT_NAMES[layout.value], nnz_stored=nnz.value, bandwidth=bw.value,
+                    nblocks=nb.value, bytes_per_pass=bpp.value)
+
+    def set_xty(self, cohort, r):
+        r = _f64(r).ravel()
+        assert r.shape[0] == self.M
+        self._ck(self.lib.sgv_set_xty(self.h, C.c_int(cohort), _dp(r)))
+
+    def reset_state(self):
+        self._ck(self.lib.sgv_reset_state(self.h))
+
+    def get_vec(self, cohort, which):
+        out = np.empty(self.M, dtype=np.float64)
+        self._ck(self.lib.sgv_get_vec(self.h, C.c_int(cohort), C.c_int(which), _dp(out)))
+        return out
+
+    def set_vec(self, cohort, which, v):
+        v = _f64(v).ravel()
+        assert v.shape[0] == self.M
+        self._ck(self.lib.sgv_set_vec(self.h, C.c_int(cohort), C.c_int(which), _dp(v)))
+
+    def pinned_array(self, n):
+        p = C.c_void_p()
+        self._ck(self.lib.sgv_pinned_alloc(self.h, C.c_int64(n * 8), C.byref(p)))
+        self._pinned.append(p.value)
+        buf = (C.c_double * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float64)
+
+    def get_vec_async(self, cohort, which, scale, pinned):
+        self._ck(self.lib.sgv_get_vec_async(self.h, C.c_int(cohort), C.c_int(which), C.c_double(scale), _dp(pinned)))
+
+    def wait_copies(self):
+        self._ck(self.lib.sgv_wait_copies(self.h))
+
+    # -- prior ---------------------------------------------------------------------------------
+    def set_prior(self, lam, omegas, sigmas):
+        om, sg = _f64(omegas), _f64(sigmas)
+        self._ck(self.lib.sgv_set_prior(self.h, C.c_int(len(om) + 1), C.c_double(lam), _dp(om), _dp(sg)))
+
+    def set_weights(self, a):
+        a = _f64(a)
+        assert a.shape[0] == self.K
+        self._ck(self.lib.sgv_set_weights(self.h, _dp(a)))
+
+    # -- per-iteration steps -------------------------------------------------------------------
+    def denoise(self, gam1s, rho, damp):
+        g = _f64(gam1s)
+        out = C.c_double()
+        self._ck(self.lib.sgv_denoise(self.h, _dp(g), C.c_double(rho), C.c_int(int(damp)), C.byref(out)))
+        return out.value
+
+    def prior_em(self, gam1s, maxit, tol, Lm1):
+        g = _f64(gam1s)
+        lam = C.c_double()
+        om = np.zeros(max(Lm1, 1))
+        steps = C.c_int()
+        rel = C.c_double()
+        self._ck(self.lib.sgv_prior_em(self.h, _dp(g), C.c_int(maxit), C.c_double(tol), C.byref(lam), _dp(om),
+                                       C.byref(steps), C.byref(rel)))
+        return lam.value, om[:Lm1].copy(), steps.value, rel.value
+
+    def lagrangian(self, gam1s, x, omega0, sigma2):
+        g, x, o, s2 = _f64(gam1s), _f64(x), _f64(omega0), _f64(sigma2)
+        y = np.zeros(x.shape[0])
+        self._ck(self.lib.sgv_lagrangian(self.h, _dp(g), _dp(x), _dp(o), _dp(s2), _dp(y)))
+        return y
+
+    def lmmse(self, cohort, gamw, gam2, alpha1, rho, cg_maxit, lmmse_damp, learn_gamw, x0_zero, probe):
+        pin = LmmseIn(gamw, gam2, alpha1, rho, int(cg_maxit), int(bool(lmmse_damp)), int(bool(learn_gamw)),
+                      int(bool(x0_zero)))
+        out = LmmseOut()
+        probe = np.ascontiguousarray(probe, dtype=np.int8)
+        assert probe.shape[0] == self.M
+        self._ck(self.lib.sgv_lmmse(self.h, C.c_int(cohort), C.byref(pin), probe.ctypes.data_as(C.POINTER(C.c_int8)),
+                                    C.byref(out)))
+        return out
+
+    def update_r1(self, cohort, alpha2):
+        self._ck(self.lib.sgv_update_r1(self.h, C.c_int(cohort), C.c_double(alpha2)))
+
+    def metrics(self, x0=None):
+        d = np.zeros(4)
+        p = _dp(_f64(x0).ravel()) if x0 is not None else None
+        self._ck(self.lib.sgv_metrics(self.h, p, _dp(d)))
+        return d
+
+    # -- hooks ---------------------------------------------------------------------------------
+    def spmm(self, cohort, X, alpha=1.0, beta=0.0):
+        X = _f64(X)
+        nrhs = 1 if X.ndim == 1 else X.shape[1]
+        Xf = np.ascontiguousarray(X.reshape(self.M, nrhs).T)     # column-major M x nrhs
+        Y = np.zeros_like(Xf)
+        self._ck(self.lib.sgv_spmm(self.h, C.c_int(cohort), _dp(Xf), _dp(Y), C.c_int(nrhs), C.c_double(alpha),
+                                   C.c_double(beta)))
+        return Y.T.reshape(X.shape).copy()
+
+    def spmm_bench(self, cohort, reps):
+        ms = C.c_float()
+        self._ck(self.lib.sgv_spmm_bench(self.h, C.c_int(cohort), C.c_int(reps), C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.lib.sgv_launch_count(self.h))

@@ -1,0 +1,422 @@
+"""sgVAMP solver, B200-native.  Drop-in for the reference module ``src/sgvamp.py``.
+
+Same class name, constructor and ``infer`` signature, same output files
+(``{out}_xhat_it_{it}.bin``, ``{out}_r1_cohort_{k}_it_{it}.bin``, ``{out}_cohort_{k}.csv``,
+``{out}_metrics.csv``; reference src/sgvamp.py:33-76).  The numeric hot path - denoiser,
+EM/MLE reductions, the two conjugate-gradient solves of the LMMSE step, the Hutchinson probe and
+the gamw statistics - runs in hand-written sm_100a CUDA kernels behind the C ABI of
+``libsgvamp_b200.so`` (``include/sgvamp_b200.h``).  Scalars (gam1, gam2, alpha1, alpha2, gamw)
+stay on the host in fp64 exactly where the reference keeps them; M-vectors never leave the GPU
+except for the per-iteration output dumps.  There is no CPU fallback.
+
+Differences from the reference that a caller can see:
+  * one process drives all K cohorts (``R``/``r``/``N`` may be length-K lists, ``comm`` may be
+    None); the reference's rank-per-cohort mode is kept when ``comm.Get_size() == K > 1``;
+  * extra keyword-only arguments of ``infer`` (``s``, ``probes``, ``layout``, ``write_outputs``).
+"""
+from __future__ import annotations
+
+import csv
+import logging
+import os
+import queue
+import threading
+
+import numpy as np
+import scipy.optimize
+import scipy.sparse
+
+import sgv_native as nat
+
+
+class DeviceDIA:
+    """LD already resident in HBM in diagonal-major band layout (see sgv_ld_adopt_dia)."""
+
+    def __init__(self, ptr, w, ldb, keepalive=None):
+        self.ptr, self.w, self.ldb, self.keepalive = int(ptr), int(w), int(ldb), keepalive
+
+
+class DeviceDense:
+    """Dense fp32 row-major LD already resident in HBM (see sgv_ld_adopt_dense)."""
+
+    def __init__(self, ptr, ld, keepalive=None):
+        self.ptr, self.ld, self.keepalive = int(ptr), int(ld), keepalive
+
+
+class _SoloComm:
+    def Get_rank(self):
+        return 0
+
+    def Get_size(self):
+        return 1
+
+    def bcast(self, obj, root=0):
+        return obj
+
+
+class _Writer:
+    """Background writer so that output dumps leave the solver loop."""
+
+    def __init__(self):
+        self.q = queue.Queue()
+        self.err = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        while True:
+            job = self.q.get()
+            if job is None:
+                return
+            try:
+                path, arr = job
+                arr.tofile(path)
+            except Exception as e:  # surfaced at close()
+                self.err = e
+
+    def put(self, path, arr):
+        self.q.put((path, arr))
+
+    def close(self):
+        self.q.put(None)
+        self.t.join()
+        if self.err is not None:
+            raise self.err
+
+
+class VAMP:
+    def __init__(self, N, Nt, M, K, rho, gamw, gam1, a, prior_vars, prior_probs, out_dir, out_name, comm=None,
+                 device=0, stream=None):
+        self.eps = 1e-32
+        self.N = N
+        self.Nt = Nt
+        self.M = int(M)
+        self.K = int(K)
+        self.L = len(prior_probs)
+        self.rho = rho
+        self.gamw = gamw
+        self.gam1 = gam1
+        self.a = np.asarray(a, dtype=np.float64)
+        self.lam = 1 - prior_probs[0]
+        self.sigmas = np.array(prior_vars[1:], dtype=np.float64) * Nt       # src/sgvamp.py:27
+        self.omegas = np.array([p / sum(prior_probs[1:]) for p in prior_probs[1:]])
+        self.comm = comm if comm is not None else _SoloComm()
+        self.gam = None
+        size = self.comm.Get_size() if hasattr(self.comm, "Get_size") else 1
+        self.rank_mode = size > 1
+        if self.rank_mode and size != self.K:
+            raise Exception("communicator size must equal the number of cohorts K")
+        self.rank = self.comm.Get_rank() if self.rank_mode else 0
+        self.my_cohorts = [self.rank] if self.rank_mode else list(range(self.K))
+        self.out_dir, self.out_name = out_dir, out_name
+        if out_dir is not None:
+            self.setup_io(out_dir, out_name)
+        self.handle = nat.Handle(device=device, stream=stream)
+        self.handle.configure(self.M, self.K)
+        self.handle.set_weights(self.a)
+        self._ld_loaded = [False] * self.K
+        self._keep = []
+        self.stats = {}
+
+    # ------------------------------------------------------------------------------------------
+    # output files (byte-compatible with src/sgvamp.py:33-76)
+    # ------------------------------------------------------------------------------------------
+    def setup_io(self, out_dir, out_name):
+        self.out_dir = out_dir
+        self.out_name = out_name
+        for i in range(self.K):
+            with open(os.path.join(self.out_dir, "%s_cohort_%d.csv" % (self.out_name, i + 1)), "w", newline="") as f:
+                csv.writer(f, delimiter="\t").writerow(["it", "gamw", "gam1", "gam2", "alpha1", "alpha2", "lam"])
+        with open(os.path.join(self.out_dir, "%s_metrics.csv" % self.out_name), "w", newline="") as f:
+            csv.writer(f, delimiter="\t").writerow(["it", "alignment", "l2"])
+
+    def write_params_to_file(self, params, cohort_idx):
+        with open(os.path.join(self.out_dir, "%s_cohort_%d.csv" % (self.out_name, cohort_idx + 1)), "a", newline="") as f:
+            csv.writer(f, delimiter="\t").writerow(params)
+
+    def write_metrics_to_file(self, metrics):
+        with open(os.path.join(self.out_dir, "%s_metrics.csv" % self.out_name), "a", newline="") as f:
+            csv.writer(f, delimiter="\t").writerow(metrics)
+
+    def write_xhat_to_file(self, it, xhat):
+        np.ascontiguousarray(xhat, dtype=np.float64).ravel().tofile(
+            os.path.join(self.out_dir, "%s_xhat_it_%d.bin" % (self.out_name, it)))
+
+    def write_r1_to_file(self, it, r1, k):
+        np.ascontiguousarray(r1, dtype=np.float64).ravel().tofile(
+            os.path.join(self.out_dir, "%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k, it)))
+
+    # ------------------------------------------------------------------------------------------
+    # LD / XTy ingestion
+    # ------------------------------------------------------------------------------------------
+    def load_ld(self, cohort, R, s=0.0, layout="auto"):
+        """Upload one cohort's LD matrix; Rused = (1-s) R + s I is applied on the device
+        (src/main.py:265).  R: scipy sparse, ndarray / np.matrix, DeviceDIA or DeviceDense."""
+        h = self.handle
+        lay = {"auto": nat.LAYOUT_AUTO, "dense": nat.LAYOUT_DENSE, "dia": nat.LAYOUT_DIA,
+               "blockdiag": nat.LAYOUT_BLOCKDIAG, "csr": nat.LAYOUT_CSR}[layout]
+        if isinstance(R, DeviceDIA):
+            assert s == 0.0, "device-resident LD must already be regularised"
+            h.adopt_dia(cohort, R.ptr, R.w, R.ldb)
+            self._keep.append(R)
+        elif isinstance(R, DeviceDense):
+            assert s == 0.0, "device-resident LD must already be regularised"
+            h.adopt_dense(cohort, R.ptr, R.ld)
+            self._keep.append(R)
+        elif scipy.sparse.issparse(R):
+            R = R.tocsr()
+            if R.shape != (self.M, self.M):
+                raise Exception("LD matrix shape %s does not match M=%d" % (R.shape, self.M))
+            if not R.has_canonical_format:
+                R = R.copy()
+                R.sum_duplicates()
+            rc = h.upload_csr(cohort, R.indptr, R.indices, R.data, s=s, layout=lay)
+            if rc == -3:   # CSR layout needs an explicitly stored diagonal when s != 0
+                R = (R + scipy.sparse.diags(np.zeros(self.M)).tocsr()).tocsr()
+                R.setdiag(R.diagonal())
+                R.sort_indices()
+                rc = h.upload_csr(cohort, R.indptr, R.indices, R.data, s=s, layout=lay)
+            h._ck(rc)
+        else:
+            Rd = np.asarray(R)
+            if Rd.shape != (self.M, self.M):
+                raise Exception("LD matrix shape %s does not match M=%d" % (Rd.shape, self.M))
+            h.upload_dense(cohort, Rd, s=s)
+        self._ld_loaded[cohort] = True
+        return h.ld_info(cohort)
+
+    # ------------------------------------------------------------------------------------------
+    # per-step methods kept for API compatibility (reference src/sgvamp.py:93-194)
+    # ------------------------------------------------------------------------------------------
+    def _push_prior(self, handle=None):
+        (handle or self.handle).set_prior(float(self.lam), self.omegas, self.sigmas)
+
+    def _one_marker(self, rs, gam1s):
+        aux = getattr(self, "_aux", None)
+        if aux is None:
+            aux = self._aux = nat.Handle(device=0)
+            aux.configure(1, self.K)
+        aux.set_weights(self.a)
+        self._push_prior(aux)
+        for k in range(self.K):
+            aux.set_vec(k, nat.VEC_R1, np.array([rs[k]], dtype=np.float64))
+        dfac = aux.denoise(np.asarray(gam1s, dtype=np.float64), 1.0, False)
+        return aux.get_vec(0, nat.VEC_XHAT1)[0], dfac
+
+    def denoiser_meta(self, rs, gam1s):
+        return self._one_marker(rs, gam1s)[0]
+
+    def der_denoiser_meta(self, rs, gam1s):
+        k = self.comm.Get_rank()
+        return self.a[k] * gam1s[k] * self._one_marker(rs, gam1s)[1]
+
+    def _set_r1s(self, r1s):
+        r1s = np.asarray(r1s, dtype=np.float64).reshape(self.K, self.M)
+        for k in range(self.K):
+            self.handle.set_vec(k, nat.VEC_R1, r1s[k])
+
+    def prior_update_em(self, r1s, gam1s):
+        if r1s is not None:
+            self._set_r1s(r1s)
+        self._push_prior()
+        lam, om, _, _ = self.handle.prior_em(gam1s, 1, 0.0, self.L - 1)
+        self.lam, self.omegas = lam, om
+
+    def Lagrangian_der(self, x, omega0, sigma2, r1s, gam1s):
+        if r1s is not None:
+            self._set_r1s(r1s)
+        self._push_prior()
+        return self.handle.lagrangian(gam1s, x, omega0, sigma2)
+
+    def prior_update_mle(self, r1s, gam1s):
+        if r1s is not None:
+            self._set_r1s(r1s)
+        rank = self.comm.Get_rank()
+        omega0 = np.zeros(self.L)
+        omega0[0] = 1 - self.lam
+        omega0[1:] = self.lam * self.omegas
+        sigma2 = np.zeros(self.L)
+        sigma2[0] = 1e-16
+        sigma2[1:] = self.sigmas
+        x0 = np.zeros(self.L + 1)
+        x0[:-1] = omega0
+        x0[-1] = 1 if self.gam is None else self.gam
+        self._push_prior()
+        nev = [0]
+
+        def func(x):
+            nev[0] += 1
+            return self.handle.lagrangian(gam1s, x, omega0, sigma2)
+
+        x, _, ier, _ = scipy.optimize.fsolve(func=func, x0=x0, full_output=True)
+        self.stats["mle_evals"] = self.stats.get("mle_evals", 0) + nev[0]
+        if ier != 1:
+            if rank == 0:
+                logging.info("WARNING: fsolve not converged. No prior update!")
+            return "not_converged"
+        elif any(s_ <= 0 for s_ in x[:-1]):
+            if rank == 0:
+                logging.info("WARNING: Negative values in MLE. No prior update!")
+            return "negative"
+        x[:-1] /= sum(x[:-1])
+        self.lam = 1 - x[0]
+        self.omegas = np.array([w / sum(x[1:-1]) for w in x[1:-1]])
+        self.gam = x[self.L]
+        return "ok"
+
+    # ------------------------------------------------------------------------------------------
+    # the solver loop (reference src/sgvamp.py:196-389)
+    # ------------------------------------------------------------------------------------------
+    def infer(self, R, r, iterations, x0=None, cg_maxit=500, em_prior_maxit=100, learn_gamw=True, lmmse_damp=True,
+              prior_update=None, update_prior_from=1, *, s=0.0, probes=None, layout="auto", write_outputs=True):
+        M, K, Nt, rho = self.M, self.K, self.Nt, self.rho
+        h = self.handle
+        rank = self.rank
+        mine = self.my_cohorts
+        Rs = list(R) if isinstance(R, (list, tuple)) else [R]
+        rs = list(r) if isinstance(r, (list, tuple)) else [r]
+        if isinstance(self.N, (list, tuple, np.ndarray)):
+            Ns = [float(n) for n in np.ravel(self.N)]
+            Ns = Ns if len(Ns) == K else [Ns[0]] * K
+        else:
+            Ns = [float(self.N)] * K
+        if len(Rs) != len(mine) or len(rs) != len(mine):
+            raise Exception("expected %d LD matrices / XTy vectors, got %d / %d" % (len(mine), len(Rs), len(rs)))
+        for idx, k in enumerate(mine):
+            if Rs[idx] is not None:
+                self.load_ld(k, Rs[idx], s=s, layout=layout)
+            elif not self._ld_loaded[k]:
+                raise Exception("no LD matrix for cohort %d" % k)
+            h.set_xty(k, np.asarray(rs[idx], dtype=np.float64).reshape(M))
+        h.reset_state()                                                 # :199-217
+        write = write_outputs and self.out_dir is not None
+        writer = _Writer() if write else None
+        sqrtNt = np.sqrt(Nt)
+        truth = None
+        if x0 is not None:
+            truth = np.asarray(x0, dtype=np.float64).reshape(M)
+            tn = None
+        gam1 = [np.float64(self.gam1)] * K
+        gamw = [self.gamw] * K
+        alpha1 = [np.float64(0.0)] * K
+        alpha2 = [np.float64(0.0)] * K
+        xhat1s = []
+        self.history = dict(rows=[], cg_iters=[], cg_info=[], em_steps=[], spmm_passes=[], lam=[], omegas=[])
+        pin_x = [h.pinned_array(M) for _ in range(2)]
+        pin_r = [[h.pinned_array(M) for _ in mine] for _ in range(2)] if write else None
+
+        if rank == 0:
+            logging.debug(f"a = {self.a}")
+        for it in range(iterations):
+            if rank == 0:
+                logging.info(f"\n -----ITERATION {it} -----")
+            gam1s = np.array(gam1, dtype=np.float64)
+            if self.rank_mode:                                          # :228-233
+                mine_r1 = h.get_vec(rank, nat.VEC_R1)
+                for i in range(K):
+                    gam1s[i] = self.comm.bcast(gam1s[i], root=i)
+                    got = self.comm.bcast(mine_r1 if i == rank else None, root=i)
+                    if i != rank:
+                        h.set_vec(i, nat.VEC_R1, got)
+            # prior update :242-259
+            em_steps = 0
+            if it >= update_prior_from:
+                if prior_update == "mle":
+                    if rank == 0:
+                        logging.info("...Updating prior parameters using MLE")
+                    self.prior_update_mle(None, gam1s)
+                elif prior_update == "em":
+                    if rank == 0:
+                        logging.info("...Updating prior parameters using EM")
+                    self._push_prior()
+                    self.lam, self.omegas, em_steps, rel = h.prior_em(gam1s, em_prior_maxit, 1e-6, self.L - 1)
+                    if rank == 0:
+                        logging.info(f"... prior-learning EM algorithm performed {em_steps} steps and had final relative error = {rel:0.9f}")
+            self._push_prior()
+            # denoising :270-293
+            if rank == 0:
+                logging.info("...Denoising")
+            dmean = np.float64(h.denoise(gam1s, rho, it > 0))
+            slot = it & 1
+            h.get_vec_async(0, nat.VEC_XHAT1, 1.0, pin_x[slot])
+            if write:
+                for idx, k in enumerate(mine):
+                    h.get_vec_async(k, nat.VEC_R1, 1.0, pin_r[slot][idx])
+            rows_it, iters_it, info_it, passes_it = {}, {}, {}, 0
+            for k in mine:
+                a1 = self.a[k] * gam1s[k] * dmean                        # :285
+                if it > 0:
+                    a1 = rho * a1 + (1 - rho) * alpha1[k]                # :290-291
+                alpha1[k] = a1
+                logging.info(f"...LMMSE cohort {k}")
+                alpha2_prev = alpha2[k]
+                gam2 = gam1[k] * (1 - a1) / a1                           # :305
+                if probes is None:
+                    u = np.random.binomial(p=1 / 2, n=1, size=M) * 2 - 1  # :326 (same RNG call, same position)
+                elif callable(probes):
+                    u = probes(k, it, M)
+                else:
+                    u = np.asarray(probes)[k, it]
+                out = h.lmmse(k, float(gamw[k]), float(gam2), float(a1), float(rho), cg_maxit, lmmse_damp, learn_gamw,
+                              it == 0, u)
+                for c in range(2):
+                    if out.cg_info[c] > 0:
+                        logging.info(f"Rank {k} WARNING: CG {c + 1} convergence after {out.cg_info[c]} iterations not achieved!")
+                a2 = gam2 * np.float64(out.u_sigma2u) / M                # :338-340
+                if lmmse_damp:
+                    a2 = rho * a2 + (1 - rho) * alpha2_prev              # :345-346
+                alpha2[k] = a2
+                gam1[k] = gam2 * (1 - a2) / a2                           # :347
+                h.update_r1(k, float(a2))                                # :348
+                gw = gamw[k]
+                if learn_gamw:                                           # :350-364
+                    N = Ns[k]
+                    z = N - 2 * out.xhat2_r + out.xhat2_R_xhat2
+                    if z < 0:
+                        z = 0
+                    gw = float(1 / (z / N + out.u_R_sigma2u / N))
+                gw = max(gw, 1.0)                                        # :374
+                gamw[k] = gw
+                row = [it, gw, gam1[k], gam2, a1, a2, self.lam]
+                rows_it[k] = row
+                iters_it[k] = (out.cg_iters[0], out.cg_iters[1])
+                info_it[k] = (out.cg_info[0], out.cg_info[1])
+                passes_it += out.spmm_passes
+                if self.out_dir is not None and write_outputs:
+                    self.write_params_to_file(row, k)                    # :377
+            h.wait_copies()
+            xh = pin_x[slot].copy()
+            xhat1s.append(xh.reshape(M, 1))
+            if write:
+                if rank == 0:
+                    writer.put(os.path.join(self.out_dir, "%s_xhat_it_%d.bin" % (self.out_name, it)), xh / sqrtNt)
+                for idx, k in enumerate(mine):
+                    writer.put(os.path.join(self.out_dir, "%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k + 1, it)),
+                               pin_r[slot][idx] / sqrtNt)
+            if truth is not None:                                        # :379-387
+                d = h.metrics(truth if it == 0 else None)
+                alignment = d[0] / np.sqrt(d[1]) / np.sqrt(d[2])
+                l2 = np.sqrt(d[3]) / np.sqrt(d[2])
+                if rank == 0:
+                    logging.debug(f"Alignment(xhat1, x0) = {alignment:0.9f} \n")
+                    logging.debug(f"L2_error(xhat1, x0) = {l2:0.9f} \n")
+                    if self.out_dir is not None and write_outputs:
+                        self.write_metrics_to_file([it, alignment, l2])
+                self.history.setdefault("metrics", []).append((it, alignment, l2))
+            self.history["rows"].append(rows_it)
+            self.history["cg_iters"].append(iters_it)
+            self.history["cg_info"].append(info_it)
+            self.history["em_steps"].append(em_steps)
+            self.history["spmm_passes"].append(passes_it)
+            self.history["lam"].append(float(self.lam))
+            self.history["omegas"].append(np.array(self.omegas, dtype=np.float64).copy())
+        h.sync()
+        if writer is not None:
+            writer.close()
+        self.gam1_final, self.gamw_final = gam1, gamw
+        return xhat1s
+
+    def close(self):
+        self.handle.close()
+        if getattr(self, "_aux", None) is not None:
+            self._aux.close()
