@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the sgVAMP hot path: VAMP iterations / second at M markers with banded LD
+(BASELINE.json metric; configs[4]: M=1M banded LD row-partitioned over 1/2/4/8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--M M] [--w W]
+
+A "step" is one VAMP iteration (denoiser -> prior EM -> 2-RHS CG LMMSE -> Hutchinson -> gamw)
+on synthetic genotype-derived banded LD.  The run performs W warm-up iterations followed by K
+timed iterations of one continuing VAMP trajectory; the timed region is bracketed by CUDA events
+on the solver's stream (max over ranks).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, "sgvamp-py_b200")
+for p in (REPO, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+H2, LAM_TRUE, S_REG, N_GWAS, N_LD = 0.5, 0.01, 0.1, 500_000, 4096
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--M", type=int, default=1_000_000)
+    ap.add_argument("--w", type=int, default=500)
+    ap.add_argument("--cpu-sample-M", type=int, default=60_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--seed", type=int, default=5)
+    return ap.parse_args()
+
+
+def vamp_params(M):
+    cm = max(1, int(M * LAM_TRUE))
+    return dict(prior_vars=[0.0, H2 / cm], prior_probs=[0.99, 0.01], rho=0.5, gamw=2.0, gam1=1e-6,
+                cg_maxit=500, em_prior_maxit=100, learn_gamw=True, lmmse_damp=False, prior_update="em",
+                update_prior_from=1)
+
+
+def make_probes(iterations, M, seed):
+    rng = np.random.RandomState(1234 + seed)
+    return (rng.binomial(p=0.5, n=1, size=(1, iterations, M)) * 2 - 1).astype(np.int8)
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic banded LD + XTy on the device (torch as a data-generation utility)
+# ------------------------------------------------------------------------------------------------
+def build_problem(torch, M, w, seed, dev):
+    import ldgen
+    t0 = time.time()
+    ldb = (M + 31) // 32 * 32
+    band = torch.zeros((2 * w + 1, ldb), device=dev, dtype=torch.float32)
+    b, xte = ldgen.banded_dia_device(torch, M, w, 0, M, seed, dev, N_ld=N_LD)
+    band[:, :M] = b
+    del b
+    band *= (1.0 - S_REG)                       # Rused = (1-s) R + s I  (src/main.py:265)
+    band[w, :M] += S_REG
+    x0 = torch.from_numpy(ldgen.causal_effects(M, N_GWAS, LAM_TRUE, H2, seed)).to(dev)
+    # r = Rused x0 + sqrt(1-h2) X^T e  (the recipe of simulation/sim_gen_phen_mult.py:39-55 in summary form)
+    xp = torch.zeros(M + 2 * w, device=dev, dtype=torch.float64)
+    xp[w:w + M] = x0
+    r = torch.zeros(M, device=dev, dtype=torch.float64)
+    for d in range(2 * w + 1):
+        r += band[d, :M].to(torch.float64) * xp[d:d + M]
+    r += float(np.sqrt(1.0 - H2)) * xte
+    torch.cuda.synchronize()
+    return band, ldb, r.cpu().numpy(), x0.cpu().numpy(), time.time() - t0
+
+
+def band_to_host_csr(torch, band, M, w, pinned=True):
+    """CSR (fp32 data, int32 indices) of the banded matrix in (pinned) host memory - the host-side
+    input of the end-to-end leg."""
+    nnz = M * (2 * w + 1) - w * (w + 1)
+    data = torch.empty(nnz, dtype=torch.float32, pin_memory=pinned)
+    idx = torch.empty(nnz, dtype=torch.int32, pin_memory=pinned)
+    indptr = np.zeros(M + 1, dtype=np.int64)
+    dd = torch.arange(2 * w + 1, device=band.device)
+    pos = 0
+    step = 32768
+    for i0 in range(0, M, step):
+        i1 = min(M, i0 + step)
+        rows = torch.arange(i0, i1, device=band.device)
+        cols = rows[:, None] + (dd[None, :] - w)
+        ok = (cols >= 0) & (cols < M)
+        vals = band[:, i0:i1].t()[ok]
+        cc = cols[ok].to(torch.int32)
+        n = vals.numel()
+        data[pos:pos + n].copy_(vals)
+        idx[pos:pos + n].copy_(cc)
+        indptr[i0 + 1:i1 + 1] = pos + torch.cumsum(ok.sum(dim=1), 0).cpu().numpy()
+        pos += n
+    assert pos == nnz
+    torch.cuda.synchronize()
+    import scipy.sparse
+    R = scipy.sparse.csr_matrix((data.numpy(), idx.numpy(), indptr.astype(np.int32) if nnz < 2**31 else indptr),
+                                shape=(M, M))
+    R.has_canonical_format = True
+    return R, (data, idx)
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.stop, self.index = [], False, index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        self.t.start()
+
+    def finish(self):
+        self.stop = True
+        self.t.join(timeout=10)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]),
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port of the reference on the host cores, on a bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(M_full, w, sample_M, iterations, seed, threads):
+    """Time the CPU oracle (numpy/scipy restatement of src/sgvamp.py, same algorithm, same scipy CG)
+    on the leading sample_M x sample_M principal sub-band of the same kind of workload; scale the
+    per-iteration time linearly in M (every per-iteration cost is O(M w))."""
+    import ldgen
+    from oracle import sgvamp_oracle as orc
+    Ms = int(min(sample_M, M_full))
+    R, r, x0, N = ldgen.sim_banded(M=Ms, w=w, N_ld=256, N=N_GWAS, lam=LAM_TRUE, h2=H2, seed=seed)
+    R = orc.regularise(R, S_REG)
+    p = vamp_params(Ms)
+    o = orc.VAMPOracle([N_GWAS], Ms, p["rho"], p["gamw"], p["gam1"], p["prior_vars"], p["prior_probs"])
+    probes = make_probes(iterations, Ms, seed)
+    tm = {}
+    t0 = time.perf_counter()
+    out = o.infer([R], [r], iterations, cg_maxit=p["cg_maxit"], em_prior_maxit=p["em_prior_maxit"],
+                  learn_gamw=True, lmmse_damp=False, prior_update="em", update_prior_from=1,
+                  probe_fn=lambda k, it, M_: probes[k, it], timers=tm, threads=threads)
+    dt = time.perf_counter() - t0
+    its_per_s_sample = iterations / dt
+    return dict(value=its_per_s_sample * Ms / M_full, sample_its_per_s=its_per_s_sample, sample_M=Ms,
+                seconds=dt, cg_iters=[list(x[0]) for x in out["cg_iters"]], timers=tm)
+
+
+def main():
+    a = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = len(os.sched_getaffinity(0))
+    workload = "banded LD M=%d w=%d (DIA fp32 in HBM), K=1, L=2, EM prior, learn gamw, s=%.1f, cg_maxit=500" % (
+        a.M, a.w, S_REG)
+
+    # -------------------------------------------------------------------------------------------
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        its = max(2, min(a.steps + a.warmup, 3))
+        res = cpu_reference_run(a.M, a.w, a.cpu_sample_M, its, a.seed, threads=ncores)
+        line = {"impl": "reference", "metric": "VAMP iterations/s", "value": res["value"], "unit": "it/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1000.0 / res["value"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload},
+                "cpu_baseline": {"value": res["value"], "unit": "it/s", "cores": ncores, "kind": "port",
+                                 "sample": "oracle port of src/sgvamp.py (scipy CG, threaded row-split csr_matvec), "
+                                           "%d VAMP iterations from it=0 on an M=%d w=%d banded sample, "
+                                           "scaled by M_sample/M (all per-iteration costs are O(M w))" % (
+                                               its, res["sample_M"], a.w),
+                                 "sample_its_per_s": res["sample_its_per_s"], "cg_iters": res["cg_iters"]},
+                "e2e": {"value": res["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # -------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import build_native
+    if rank == 0:
+        build_native.build()
+    if world > 1:
+        dist.barrier()
+    import sgvamp
+    import sgv_native as nat
+    if world > 1:
+        raise SystemExit("multi-GPU row-partitioned path: not wired into bench.py yet")
+
+    M, w = a.M, a.w
+    iterations = a.warmup + a.steps
+    band, ldb, r, x0, t_gen = build_problem(torch, M, w, a.seed, dev)
+    p = vamp_params(M)
+    probes = make_probes(iterations, M, a.seed)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def new_solver():
+        return sgvamp.VAMP(N=N_GWAS, Nt=N_GWAS, M=M, K=1, rho=p["rho"], gamw=p["gamw"], gam1=p["gam1"],
+                           a=np.array([1.0]), prior_vars=p["prior_vars"], prior_probs=p["prior_probs"],
+                           out_dir=None, out_name="bench", comm=None, device=local_rank, stream=stream)
+
+    def run(v, R, n_it, hook=None, **kw):
+        return v.infer(R, r, n_it, x0=None, cg_maxit=p["cg_maxit"], em_prior_maxit=p["em_prior_maxit"],
+                       learn_gamw=p["learn_gamw"], lmmse_damp=p["lmmse_damp"], prior_update=p["prior_update"],
+                       update_prior_from=p["update_prior_from"], probes=probes, iter_hook=hook, **kw)
+
+    # ---- device-resident leg: LD already in HBM when the timed region starts ----
+    v = new_solver()
+    dia = sgvamp.DeviceDIA(band.data_ptr(), w, ldb, keepalive=band)
+    run(v, dia, 2)                                     # process-level warm-up (module load, allocations)
+    events = {}
+    launches = {}
+
+    def hook(it):
+        if it == a.warmup:
+            torch.cuda.synchronize()
+            v.handle.profile(True)
+            launches["a"] = v.handle.launch_count()
+            sampler.start()
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        events[it] = e
+
+    sampler = ClockSampler(local_rank)
+    xs = run(v, None, iterations, hook)
+    torch.cuda.synchronize()
+    clocks = sampler.finish()
+    spmm_ms, spmm_launches = v.handle.profile_read()
+    v.handle.profile(False)
+    launches["b"] = v.handle.launch_count()
+    ms_total = events[a.warmup].elapsed_time(events[iterations])
+    ms_from0 = events[0].elapsed_time(events[iterations])
+    hist = v.history
+    passes = sum(hist["spmm_passes"][a.warmup:])
+    info = v.handle.ld_info(0)
+    value = a.steps / (ms_total / 1e3)
+    # roofline of the dominant kernel: algorithmic bytes of one 2-RHS pass / mean launch time
+    # (all SpMM launches of the timed region, early-exit launches included in the time but not in
+    # the count of passes -> conservative)
+    bytes_pass = info["bytes_per_pass"]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+    avg_ms = spmm_ms / max(passes, 1)
+    achieved = bytes_pass / (avg_ms * 1e-3) / 1e9
+    # isolated kernel timing (back-to-back launches, inputs 4 GB >> L2)
+    iso_ms = v.handle.spmm_bench(0, 20)
+    align = float(np.dot(xs[-1].ravel(), x0) / np.linalg.norm(xs[-1]) / np.linalg.norm(x0))
+
+    # ---- end-to-end leg: host CSR in pinned memory -> VAMP.infer -> host xhat ----
+    e2e = None
+    if not a.no_e2e:
+        Rh, keep = band_to_host_csr(torch, band, M, w)
+        v2 = new_solver()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        xs2 = run(v2, Rh, iterations, None, write_outputs=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        h2d = (Rh.data.nbytes + Rh.indices.nbytes + (M + 1) * 8 + M * 8) / iterations + M
+        d2h = M * 8 + 256
+        e2e = {"value": iterations / dt, "unit": "it/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "what": "VAMP.infer(R=scipy CSR fp32 in pinned host memory, r host) for %d iterations from it=0: LD "
+                       "upload + layout conversion + every iteration's probe H2D and xhat D2H inside the timed region" % iterations,
+               "seconds": dt, "max_rel_diff_vs_resident": float(
+                   max(np.linalg.norm(x1 - x2) / np.linalg.norm(x1) for x1, x2 in zip(xs, xs2)))}
+        v2.close()
+        del Rh, keep
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        res = cpu_reference_run(M, w, a.cpu_sample_M, 2, a.seed, threads=ncores)
+        cpu = {"value": res["value"], "unit": "it/s", "cores": ncores, "kind": "port",
+               "sample": "oracle port of src/sgvamp.py, 2 VAMP iterations from it=0 on an M=%d w=%d banded sample "
+                         "(%.1f s), scaled by M_sample/M" % (res["sample_M"], w, res["seconds"])}
+
+    line = {
+        "metric": "VAMP iterations/s", "value": value, "unit": "it/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "M": M, "half_bandwidth": w, "layout": info["layout"],
+                   "nnz_stored": info["nnz_stored"], "l2_policy": "inputs (%.1f GB band) larger than L2" % (info["nnz_stored"] * 4 / 1e9),
+                   "timed_iterations": "VAMP iterations %d..%d of one trajectory" % (a.warmup, iterations - 1),
+                   "cg_iters_timed": [list(hist["cg_iters"][i][0]) for i in range(a.warmup, iterations)],
+                   "spmm_passes_timed": passes, "its_per_s_from_it0": iterations / (ms_from0 / 1e3),
+                   "alignment_with_truth": align, "gen_seconds": t_gen},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "k_spmm_dia (2-RHS fused shifted SpMM + CG dots)",
+                     "bytes_per_launch": bytes_pass, "avg_launch_ms": avg_ms, "launches_timed": spmm_launches,
+                     "isolated_launch_ms": iso_ms, "isolated_gbs": bytes_pass / (iso_ms * 1e-3) / 1e9,
+                     "peak_source": peak_src, "spmm_share_of_step": spmm_ms / ms_total},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["b"] - launches["a"], "clocks": clocks,
+    }
+    print(json.dumps(line))
+    v.close()
+
+
+if __name__ == "__main__":
+    main()

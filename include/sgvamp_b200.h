@@ -131,6 +131,12 @@ int sgv_spmm(sgv_handle h, int cohort, const double* X, double* Y, int nrhs, dou
  * and returns the average device time per launch in ms (CUDA events on the handle's stream). */
 int sgv_spmm_bench(sgv_handle h, int cohort, int reps, float* ms_per_launch);
 
+/* Per-launch device timing of the SpMM kernels: CUDA event pairs recorded on the handle's stream
+ * around every SpMM launch while enabled.  sgv_profile(h,1) resets and enables, (h,0) disables;
+ * sgv_profile_read synchronises and returns the summed device time and the number of launches. */
+int sgv_profile(sgv_handle h, int enable);
+int sgv_profile_read(sgv_handle h, double* total_ms, int64_t* launches);
+
 /* number of kernels launched by this handle since creation */
 int64_t sgv_launch_count(sgv_handle h);
 

@@ -259,7 +259,7 @@ class VAMPOracle:
 
     def infer(self, R_list, r_list, iterations, x0=None, cg_maxit=500, em_prior_maxit=100,
               learn_gamw=True, lmmse_damp=True, prior_update=None, update_prior_from=1,
-              probe_fn=default_probe, per_marker=False, materialise_A=False, timers=None):
+              probe_fn=default_probe, per_marker=False, materialise_A=False, timers=None, threads=1):
         """Follows VAMP.infer, src/sgvamp.py:196-389, for all K cohorts at once.
 
         ``R_list[k]`` is Rused of cohort k (already regularised as in src/main.py:265), as a
@@ -280,6 +280,25 @@ class VAMPOracle:
         out = dict(xhat1=[], r1_in=[], rows=[], cg_iters=[], cg_info=[], lam=[], omegas=[],
                    em_steps=[], mle_status=[], metrics=[], gamw_raw=[])
         tm = timers if timers is not None else {}
+        pool = None
+        if threads > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = ThreadPoolExecutor(threads)
+
+        def split_rows(A):
+            # row-partitioned operator for the thread pool: every row's sum is formed exactly as in
+            # the single-threaded csr_matvec, so results are bit-identical
+            if pool is None or not scipy.sparse.issparse(A):
+                return None
+            b = np.linspace(0, A.shape[0], threads + 1).astype(int)
+            return [A[b[i]:b[i + 1]] for i in range(threads)]
+
+        def apply(A, parts, v):
+            if parts is None:
+                return np.asarray(A @ v).ravel()
+            return np.concatenate(list(pool.map(lambda P: P @ v, parts)))
+
+        R_parts = [split_rows(R) for R in R_list]
 
         def tick(name, t0):
             tm[name] = tm.get(name, 0.0) + (time.perf_counter() - t0)
@@ -333,10 +352,11 @@ class VAMPOracle:
                 gw = gamw[k]
                 if materialise_A:
                     A = gw * R + gam2 * I                            # :312
-                    A = np.asarray(A) if not scipy.sparse.issparse(A) else A
-                    mv = lambda v, A=A: np.asarray(A @ v).ravel()
+                    A = np.asarray(A) if not scipy.sparse.issparse(A) else A.tocsr()
+                    A_parts = split_rows(A)
+                    mv = lambda v, A=A, A_parts=A_parts: apply(A, A_parts, v)
                 else:
-                    mv = lambda v, R=R, gw=gw, gam2=gam2: gw * np.asarray(R @ v).ravel() + gam2 * v
+                    mv = lambda v, R=R, gw=gw, gam2=gam2, P=R_parts[k]: gw * apply(R, P, v) + gam2 * v
                 mu2 = gw * r[k] + gam2 * r2                          # :313
                 tick("lmmse_setup", t0)
                 t0 = time.perf_counter()
@@ -355,10 +375,10 @@ class VAMPOracle:
                 r1[k] = (x2 - a2 * r2) / (1 - a2)                    # :348
                 gw_new = gw
                 if learn_gamw:                                       # :350-364
-                    z = N - 2 * (x2 @ r[k]) + x2 @ np.asarray(R @ x2).ravel()
+                    z = N - 2 * (x2 @ r[k]) + x2 @ apply(R, R_parts[k], x2)
                     if z < 0:
                         z = 0
-                    TrRS = u @ np.asarray(R @ Sig).ravel()
+                    TrRS = u @ apply(R, R_parts[k], Sig)
                     gw_new = float(1 / (z / N + TrRS / N))
                 gamw_raw_it.append(gw_new)
                 gw_new = max(gw_new, 1.0)                            # :374
@@ -381,6 +401,8 @@ class VAMPOracle:
                 out["metrics"].append((it, alignment, l2))
                 if self.out_dir is not None:
                     self._append("%s_metrics.csv" % self.out_name, [it, alignment, l2])
+        if pool is not None:
+            pool.shutdown()
         return out
 
 

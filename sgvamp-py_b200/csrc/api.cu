@@ -94,6 +94,7 @@ extern "C" int sgv_destroy(sgv_handle c) {
     cudaEventDestroy(c->ev_a);
     cudaEventDestroy(c->ev_b);
     cudaEventDestroy(c->ev_copy);
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -108,6 +109,28 @@ extern "C" int sgv_sync(sgv_handle c) {
 }
 
 extern "C" int64_t sgv_launch_count(sgv_handle c) { return c ? c->launches : -1; }
+
+extern "C" int sgv_profile(sgv_handle c, int enable) {
+    SGV_CHECK(c != nullptr, "null handle");
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    c->prof = enable != 0;
+    if (enable) c->prof_n = 0;
+    return 0;
+}
+
+extern "C" int sgv_profile_read(sgv_handle c, double* total_ms, int64_t* launches) {
+    SGV_CHECK(c != nullptr && total_ms && launches, "null argument");
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < c->prof_n; i += 2) {
+        float ms = 0.f;
+        SGV_CUDA(cudaEventElapsedTime(&ms, c->prof_ev[i], c->prof_ev[i + 1]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = (int64_t)(c->prof_n / 2);
+    return 0;
+}
 
 extern "C" int sgv_configure(sgv_handle c, int64_t M, int K) {
     SGV_CHECK(c != nullptr, "null handle");

@@ -113,6 +113,9 @@ struct sgv_ctx {
     int64_t      stage_bytes = 0;
     cudaEvent_t  ev_a = nullptr, ev_b = nullptr, ev_copy = nullptr;
     int64_t      launches = 0;
+    bool         prof = false;
+    std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
+    size_t       prof_n = 0;             // events used
 };
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }

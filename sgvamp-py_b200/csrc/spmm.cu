@@ -422,6 +422,16 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, const double2* v, double2* 
     a.counter = c->counter;
     a.check_done = check_done;
     int rc;
+    if (c->prof) {
+        if (c->prof_n + 2 > c->prof_ev.size()) {
+            for (int i = 0; i < 256; ++i) {
+                cudaEvent_t e;
+                SGV_CUDA(cudaEventCreate(&e));
+                c->prof_ev.push_back(e);
+            }
+        }
+        SGV_CUDA(cudaEventRecord(c->prof_ev[c->prof_n], c->stream));
+    }
     switch (epi) {
         case EPI_Q: rc = launch_epi<EPI_Q>(c, co, a); break;
         case EPI_RESID: rc = launch_epi<EPI_RESID>(c, co, a); break;
@@ -429,6 +439,10 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, const double2* v, double2* 
         default: rc = launch_epi<EPI_PLAIN>(c, co, a); break;
     }
     if (rc) return rc;
+    if (c->prof) {
+        SGV_CUDA(cudaEventRecord(c->prof_ev[c->prof_n + 1], c->stream));
+        c->prof_n += 2;
+    }
     SGV_CUDA(cudaGetLastError());
     return 0;
 }

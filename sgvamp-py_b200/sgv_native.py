@@ -25,7 +25,7 @@ SYMBOLS = [
     "sgv_set_xty", "sgv_reset_state", "sgv_get_vec", "sgv_set_vec", "sgv_get_vec_async", "sgv_wait_copies",
     "sgv_pinned_alloc", "sgv_pinned_free", "sgv_set_prior", "sgv_set_weights", "sgv_denoise", "sgv_prior_em",
     "sgv_lagrangian", "sgv_lmmse", "sgv_update_r1", "sgv_metrics", "sgv_spmm", "sgv_spmm_bench",
-    "sgv_launch_count",
+    "sgv_launch_count", "sgv_profile", "sgv_profile_read",
 ]
 
 
@@ -246,6 +246,15 @@ class Handle:
         ms = C.c_float()
         self._ck(self.lib.sgv_spmm_bench(self.h, C.c_int(cohort), C.c_int(reps), C.byref(ms)))
         return ms.value
+
+    def profile(self, enable):
+        self._ck(self.lib.sgv_profile(self.h, C.c_int(int(enable))))
+
+    def profile_read(self):
+        ms = C.c_double()
+        n = C.c_int64()
+        self._ck(self.lib.sgv_profile_read(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def launch_count(self):
         return int(self.lib.sgv_launch_count(self.h))

@@ -268,7 +268,8 @@ class VAMP:
     # the solver loop (reference src/sgvamp.py:196-389)
     # ------------------------------------------------------------------------------------------
     def infer(self, R, r, iterations, x0=None, cg_maxit=500, em_prior_maxit=100, learn_gamw=True, lmmse_damp=True,
-              prior_update=None, update_prior_from=1, *, s=0.0, probes=None, layout="auto", write_outputs=True):
+              prior_update=None, update_prior_from=1, *, s=0.0, probes=None, layout="auto", write_outputs=True,
+              iter_hook=None):
         M, K, Nt, rho = self.M, self.K, self.Nt, self.rho
         h = self.handle
         rank = self.rank
@@ -308,6 +309,8 @@ class VAMP:
         if rank == 0:
             logging.debug(f"a = {self.a}")
         for it in range(iterations):
+            if iter_hook is not None:
+                iter_hook(it)
             if rank == 0:
                 logging.info(f"\n -----ITERATION {it} -----")
             gam1s = np.array(gam1, dtype=np.float64)
@@ -410,6 +413,8 @@ class VAMP:
             self.history["spmm_passes"].append(passes_it)
             self.history["lam"].append(float(self.lam))
             self.history["omegas"].append(np.array(self.omegas, dtype=np.float64).copy())
+        if iter_hook is not None:
+            iter_hook(iterations)
         h.sync()
         if writer is not None:
             writer.close()
