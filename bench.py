@@ -25,7 +25,13 @@ for p in (REPO, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-H2, LAM_TRUE, S_REG, N_GWAS, N_LD = 0.5, 0.01, 0.1, 500_000, 4096
+H2, LAM_TRUE, S_REG, N_LD = 0.5, 0.01, 0.1, 4096
+
+
+def n_gwas(M):
+    """GWAS sample size of the synthetic cohort.  The gamw update (src/sgvamp.py:352-363) assumes
+    r = X^T y for an N x M design, so N must be at least rank(R) = M for a full-rank banded R."""
+    return 2 * int(M)
 
 
 def parse():
@@ -45,7 +51,7 @@ def parse():
 
 def vamp_params(M):
     cm = max(1, int(M * LAM_TRUE))
-    return dict(prior_vars=[0.0, H2 / cm], prior_probs=[0.99, 0.01], rho=0.5, gamw=2.0, gam1=1e-6,
+    return dict(prior_vars=[0.0, H2 / cm], prior_probs=[0.99, 0.01], rho=0.2, gamw=2.0, gam1=1e-6,
                 cg_maxit=500, em_prior_maxit=100, learn_gamw=True, lmmse_damp=False, prior_update="em",
                 update_prior_from=1)
 
@@ -63,19 +69,23 @@ def build_problem(torch, M, w, seed, dev):
     t0 = time.time()
     ldb = (M + 31) // 32 * 32
     band = torch.zeros((2 * w + 1, ldb), device=dev, dtype=torch.float32)
-    b, xte = ldgen.banded_dia_device(torch, M, w, 0, M, seed, dev, N_ld=N_LD)
+    b, noise = ldgen.banded_dia_device(torch, M, w, 0, M, seed, dev, N_ld=N_LD)
     band[:, :M] = b
     del b
     band *= (1.0 - S_REG)                       # Rused = (1-s) R + s I  (src/main.py:265)
     band[w, :M] += S_REG
-    x0 = torch.from_numpy(ldgen.causal_effects(M, N_GWAS, LAM_TRUE, H2, seed)).to(dev)
-    # r = Rused x0 + sqrt(1-h2) X^T e  (the recipe of simulation/sim_gen_phen_mult.py:39-55 in summary form)
+    x0 = torch.from_numpy(ldgen.causal_effects(M, n_gwas(M), LAM_TRUE, H2, seed)).to(dev)
+    # r = Rused x0 + n,  n ~ N(0, (1-h2) Rused): the summary-statistic form of the reference recipe
+    # (simulation/sim_gen_phen_mult.py:39-55: r = X^T y, R = X^T X  =>  r ~ N(R x0, (1-h2) R))
     xp = torch.zeros(M + 2 * w, device=dev, dtype=torch.float64)
     xp[w:w + M] = x0
     r = torch.zeros(M, device=dev, dtype=torch.float64)
     for d in range(2 * w + 1):
         r += band[d, :M].to(torch.float64) * xp[d:d + M]
-    r += float(np.sqrt(1.0 - H2)) * xte
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed * 31 + 17)
+    z = torch.randn((M,), generator=g, device=dev, dtype=torch.float64)
+    r += float(np.sqrt(1.0 - H2)) * (float(np.sqrt(1.0 - S_REG)) * noise + float(np.sqrt(S_REG)) * z)
     torch.cuda.synchronize()
     return band, ldb, r.cpu().numpy(), x0.cpu().numpy(), time.time() - t0
 
@@ -112,38 +122,44 @@ def band_to_host_csr(torch, band, M, w, pinned=True):
 
 
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """nvidia-smi sampling at 20 ms in a child process for the whole run; samples are selected by
+    wall-clock window afterwards (B200_PROFILING.md clocks line)."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.samples, self.stop, self.index = [], False, index
-        self.t = threading.Thread(target=self._run, daemon=True)
+        self.lines = []
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
 
-    def _run(self):
-        while not self.stop:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            time.sleep(0.05)
+    def _pump(self):
+        for ln in self.p.stdout:
+            self.lines.append((time.time(), ln))
 
-    def start(self):
-        self.t.start()
-
-    def finish(self):
-        self.stop = True
-        self.t.join(timeout=10)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+    def window(self, t0, t1):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.1)
+        rows = [ln.split(",") for (t, ln) in self.lines if t0 - 0.02 <= t <= t1 + 0.04]
+        rows = [[x.strip() for x in r] for r in rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in window"]}
+        sm = sorted(int(float(r[1])) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": int(float(rows[0][2])),
+                "power_w_max": max(float(r[3]) for r in rows), "reasons": reasons, "samples": len(rows)}
+
+    def close(self):
+        if self.p is not None:
+            self.p.terminate()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -156,10 +172,12 @@ def cpu_reference_run(M_full, w, sample_M, iterations, seed, threads):
     import ldgen
     from oracle import sgvamp_oracle as orc
     Ms = int(min(sample_M, M_full))
-    R, r, x0, N = ldgen.sim_banded(M=Ms, w=w, N_ld=256, N=N_GWAS, lam=LAM_TRUE, h2=H2, seed=seed)
+    R, r, x0, N = ldgen.sim_banded(M=Ms, w=w, N_ld=256, N=n_gwas(Ms), lam=LAM_TRUE, h2=H2, seed=seed, exact_noise=True)
+    noise_R = r - R @ x0                                  # sqrt(1-h2) * N(0, R)
     R = orc.regularise(R, S_REG)
+    r = R @ x0 + np.sqrt(1 - S_REG) * noise_R + np.sqrt((1 - H2) * S_REG) * np.random.default_rng(seed).standard_normal(Ms)
     p = vamp_params(Ms)
-    o = orc.VAMPOracle([N_GWAS], Ms, p["rho"], p["gamw"], p["gam1"], p["prior_vars"], p["prior_probs"])
+    o = orc.VAMPOracle([n_gwas(Ms)], Ms, p["rho"], p["gamw"], p["gam1"], p["prior_vars"], p["prior_probs"])
     probes = make_probes(iterations, Ms, seed)
     tm = {}
     t0 = time.perf_counter()
@@ -226,10 +244,13 @@ def main():
     band, ldb, r, x0, t_gen = build_problem(torch, M, w, a.seed, dev)
     p = vamp_params(M)
     probes = make_probes(iterations, M, a.seed)
-    stream = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    solver_stream = torch.cuda.Stream(device=dev)      # the library launches on this stream; torch events
+    torch.cuda.set_stream(solver_stream)               # recorded below are recorded on the same stream
+    stream = solver_stream.cuda_stream
 
     def new_solver():
-        return sgvamp.VAMP(N=N_GWAS, Nt=N_GWAS, M=M, K=1, rho=p["rho"], gamw=p["gamw"], gam1=p["gam1"],
+        return sgvamp.VAMP(N=n_gwas(M), Nt=n_gwas(M), M=M, K=1, rho=p["rho"], gamw=p["gamw"], gam1=p["gam1"],
                            a=np.array([1.0]), prior_vars=p["prior_vars"], prior_probs=p["prior_probs"],
                            out_dir=None, out_name="bench", comm=None, device=local_rank, stream=stream)
 
@@ -239,29 +260,31 @@ def main():
                        update_prior_from=p["update_prior_from"], probes=probes, iter_hook=hook, **kw)
 
     # ---- device-resident leg: LD already in HBM when the timed region starts ----
-    v = new_solver()
+    sampler = ClockSampler(local_rank)
     dia = sgvamp.DeviceDIA(band.data_ptr(), w, ldb, keepalive=band)
-    run(v, dia, 2)                                     # process-level warm-up (module load, allocations)
-    events = {}
-    launches = {}
+    v0 = new_solver()
+    run(v0, dia, 2)                                    # process-level warm-up (module load, allocations)
+    v0.close()
+    v = new_solver()                                   # fresh solver: prior / state as at program start
+    events, launches, wall = {}, {}, {}
 
     def hook(it):
         if it == a.warmup:
             torch.cuda.synchronize()
             v.handle.profile(True)
             launches["a"] = v.handle.launch_count()
-            sampler.start()
+            wall["a"] = time.time()
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         events[it] = e
 
-    sampler = ClockSampler(local_rank)
-    xs = run(v, None, iterations, hook)
+    xs = run(v, dia, iterations, hook)
     torch.cuda.synchronize()
-    clocks = sampler.finish()
+    wall["b"] = time.time()
     spmm_ms, spmm_launches = v.handle.profile_read()
     v.handle.profile(False)
     launches["b"] = v.handle.launch_count()
+    clocks = sampler.window(wall["a"], wall["b"])
     ms_total = events[a.warmup].elapsed_time(events[iterations])
     ms_from0 = events[0].elapsed_time(events[iterations])
     hist = v.history
@@ -283,7 +306,13 @@ def main():
     achieved = bytes_pass / (avg_ms * 1e-3) / 1e9
     # isolated kernel timing (back-to-back launches, inputs 4 GB >> L2)
     iso_ms = v.handle.spmm_bench(0, 20)
-    align = float(np.dot(xs[-1].ravel(), x0) / np.linalg.norm(xs[-1]) / np.linalg.norm(x0))
+    aligns = [float(np.dot(x.ravel(), x0) / max(np.linalg.norm(x) * np.linalg.norm(x0), 1e-300)) for x in xs]
+    rows = [hist["rows"][i][0] for i in range(iterations)]
+    sys.stderr.write("host timers over all %d iterations (s): %s\n" % (iterations, {k: round(x, 4) for k, x in v.timers.items()}))
+    sys.stderr.write("trajectory (it gamw gam1 gam2 alpha1 alpha2 lam | cg | align):\n")
+    for i, rw in enumerate(rows):
+        sys.stderr.write("  %2d %.4g %.4g %.4g %.4g %.4g %.4g | %s em=%d | %.4f\n" % (
+            rw[0], rw[1], rw[2], rw[3], rw[4], rw[5], rw[6], hist["cg_iters"][i][0], hist["em_steps"][i], aligns[i]))
 
     # ---- end-to-end leg: host CSR in pinned memory -> VAMP.infer -> host xhat ----
     e2e = None
@@ -292,15 +321,19 @@ def main():
         v2 = new_solver()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        xs2 = run(v2, Rh, iterations, None, write_outputs=False)
+        v2.load_ld(0, Rh)
+        torch.cuda.synchronize()
+        t_up = time.perf_counter() - t0
+        xs2 = run(v2, None, iterations, None, write_outputs=False)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         h2d = (Rh.data.nbytes + Rh.indices.nbytes + (M + 1) * 8 + M * 8) / iterations + M
         d2h = M * 8 + 256
         e2e = {"value": iterations / dt, "unit": "it/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "what": "VAMP.infer(R=scipy CSR fp32 in pinned host memory, r host) for %d iterations from it=0: LD "
-                       "upload + layout conversion + every iteration's probe H2D and xhat D2H inside the timed region" % iterations,
-               "seconds": dt, "max_rel_diff_vs_resident": float(
+               "what": "VAMP.load_ld(scipy CSR fp32 in pinned host memory) + VAMP.infer(r host) for %d iterations from "
+                       "it=0: LD upload + layout conversion + every iteration's probe H2D and xhat D2H inside the "
+                       "timed region" % iterations,
+               "seconds": dt, "ld_upload_seconds": t_up, "max_rel_diff_vs_resident": float(
                    max(np.linalg.norm(x1 - x2) / np.linalg.norm(x1) for x1, x2 in zip(xs, xs2)))}
         v2.close()
         del Rh, keep
@@ -311,6 +344,8 @@ def main():
         cpu = {"value": res["value"], "unit": "it/s", "cores": ncores, "kind": "port",
                "sample": "oracle port of src/sgvamp.py, 2 VAMP iterations from it=0 on an M=%d w=%d banded sample "
                          "(%.1f s), scaled by M_sample/M" % (res["sample_M"], w, res["seconds"])}
+    sampler.close()
+    align = aligns[-1]
 
     line = {
         "metric": "VAMP iterations/s", "value": value, "unit": "it/s", "n_gpus": world, "steps": a.steps,

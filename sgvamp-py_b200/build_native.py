@@ -31,7 +31,7 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-               "--extended-lambda", "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3",
+               "--extended-lambda", "-Xcompiler", "-fPIC"] + (["-DSGV_EXPERIMENTS"] if os.environ.get("SGV_EXPERIMENTS") else []) + [ "-Xptxas", "-v" if verbose else "-O3",
                "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

@@ -76,6 +76,15 @@ static void free_vectors(sgv_ctx* c) {
     cudaFree(c->xhat1);
     cudaFree(c->truth);
     c->r1_all = c->xhat1 = c->truth = nullptr;
+    for (int i = 0; i < sgv_ctx::NSNAP; ++i) {
+        if (c->snap[i]) {
+            cudaFree(c->snap[i]);
+            cudaEventDestroy(c->snap_ev[i]);
+            c->snap[i] = nullptr;
+            c->snap_ev[i] = nullptr;
+        }
+    }
+    c->snap_next = 0;
 }
 
 extern "C" int sgv_destroy(sgv_handle c) {
@@ -138,6 +147,7 @@ extern "C" int sgv_configure(sgv_handle c, int64_t M, int K) {
     SGV_CHECK(K >= 1 && K <= SGV_MAX_K, "K=%d outside [1,%d]", K, SGV_MAX_K);
     SGV_CUDA(cudaSetDevice(c->device));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->copy_stream));
     free_vectors(c);
     c->M = M;
     c->K = K;
@@ -165,6 +175,10 @@ extern "C" int sgv_configure(sgv_handle c, int64_t M, int K) {
         for (double* p : z) SGV_CUDA(cudaMemsetAsync(p, 0, vb, c->stream));
         double2* z2[] = {co.bb, co.xx, co.rr, co.pp, co.qq};
         for (double2* p : z2) SGV_CUDA(cudaMemsetAsync(p, 0, v2, c->stream));
+    }
+    for (int i = 0; i < sgv_ctx::NSNAP; ++i) {   // allocated up front: cudaMalloc inside the loop would synchronise
+        SGV_CUDA(cudaMalloc(&c->snap[i], vb));
+        SGV_CUDA(cudaEventCreateWithFlags(&c->snap_ev[i], cudaEventDisableTiming));
     }
     SGV_TRY(sgv_ensure_partials(c, (int64_t)c->sm_count * 16));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
@@ -236,15 +250,17 @@ __global__ void k_scale_copy(int64_t M, const double* __restrict__ src, double* 
 extern "C" int sgv_get_vec_async(sgv_handle c, int cohort, int which, double scale, double* pinned_dst) {
     double* p;
     SGV_TRY(vec_ptr(c, cohort, which, &p));
-    double* snap = nullptr;
-    SGV_CUDA(cudaMallocAsync(&snap, c->M * sizeof(double), c->stream));
+    const int slot = c->snap_next;
+    c->snap_next = (c->snap_next + 1) % sgv_ctx::NSNAP;
+    SGV_CUDA(cudaStreamWaitEvent(c->stream, c->snap_ev[slot], 0));   // previous read-back of this slot is done
+    double* snap = c->snap[slot];
     const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 8);
     k_scale_copy<<<grid, 256, 0, c->stream>>>(c->M, p, snap, scale);
     c->launches++;
     SGV_CUDA(cudaEventRecord(c->ev_copy, c->stream));
     SGV_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
     SGV_CUDA(cudaMemcpyAsync(pinned_dst, snap, c->M * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
-    SGV_CUDA(cudaFreeAsync(snap, c->copy_stream));
+    SGV_CUDA(cudaEventRecord(c->snap_ev[slot], c->copy_stream));
     return 0;
 }
 

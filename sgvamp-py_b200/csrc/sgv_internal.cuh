@@ -112,6 +112,11 @@ struct sgv_ctx {
     void*        stage = nullptr;      // device staging buffer for uploads
     int64_t      stage_bytes = 0;
     cudaEvent_t  ev_a = nullptr, ev_b = nullptr, ev_copy = nullptr;
+    // ring of device snapshot buffers for asynchronous vector read-back
+    static const int NSNAP = 8;
+    double*      snap[NSNAP] = {};
+    cudaEvent_t  snap_ev[NSNAP] = {};
+    int          snap_next = 0;
     int64_t      launches = 0;
     bool         prof = false;
     std::vector<cudaEvent_t> prof_ev;   // start/stop pairs

@@ -8,6 +8,7 @@
 //   CSR        fp32 value + int32 column                                  8 B / stored value
 // All three are HBM-bound streaming kernels (0.5 - 1 flop/B): 128-bit coalesced loads of the
 // matrix, vector operands in shared memory / registers, fp64 FMA accumulation.
+#include <cstdlib>
 #include "sgv_device.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -90,8 +91,8 @@ bool sgv_dia_feasible(int64_t w) { return sgv_dia_smem_bytes(w, 1, 8) <= 200 * 1
         acc3.x = fma(v3, (XD).x, acc3.x); acc3.y = fma(v3, (XD).y, acc3.y); \
     } while (0)
 
-template <int RW, int S, int EPI>
-__global__ void __launch_bounds__(32 * RW * S, 2)
+template <int RW, int S, int EPI, int PF, int MINB>
+__global__ void __launch_bounds__(32 * RW * S, MINB)
 k_spmm_dia(SpmmArgs a, const float* __restrict__ band, int w, int64_t ldb) {
     if (a.check_done && a.cg->done[0] && a.cg->done[1]) return;
     constexpr int TR = 128 * RW;
@@ -130,30 +131,38 @@ k_spmm_dia(SpmmArgs a, const float* __restrict__ band, int w, int64_t ldb) {
         const int nfull = (d1 - d0) >> 2;
         int xi = g + (d0 >> 2);
         double2 X0 = xw[xi], X1 = xw[PL + xi], X2 = xw[2 * PL + xi], X3 = xw[3 * PL + xi];
-        float4 c0, c1, c2, c3;
-        if (nfull > 0) {
-            c0 = ldg_stream_f4(bp);
-            c1 = ldg_stream_f4(bp + ldb);
-            c2 = ldg_stream_f4(bp + 2 * ldb);
-            c3 = ldg_stream_f4(bp + 3 * ldb);
-        }
-        for (int m = 0; m < nfull; ++m) {
-            float4 n0 = c0, n1 = c1, n2 = c2, n3 = c3;
-            if (m + 1 < nfull) {
-                const float* np_ = bp + (int64_t)(4 * (m + 1)) * ldb;
-                n0 = ldg_stream_f4(np_);
-                n1 = ldg_stream_f4(np_ + ldb);
-                n2 = ldg_stream_f4(np_ + 2 * ldb);
-                n3 = ldg_stream_f4(np_ + 3 * ldb);
+        // ring of PF groups (4 diagonals each) in flight: a slot is refilled right after it is consumed
+        float4 q[PF][4];
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+            if (j < nfull) {
+                const float* lp = bp + (int64_t)(4 * j) * ldb;
+                q[j][0] = ldg_stream_f4(lp);
+                q[j][1] = ldg_stream_f4(lp + ldb);
+                q[j][2] = ldg_stream_f4(lp + 2 * ldb);
+                q[j][3] = ldg_stream_f4(lp + 3 * ldb);
             }
-            const double2 N0 = xw[xi + 1], N1 = xw[PL + xi + 1], N2 = xw[2 * PL + xi + 1], N3 = xw[3 * PL + xi + 1];
-            FMA4(c0, X0, X1, X2, X3);
-            FMA4(c1, X1, X2, X3, N0);
-            FMA4(c2, X2, X3, N0, N1);
-            FMA4(c3, X3, N0, N1, N2);
-            X0 = N0; X1 = N1; X2 = N2; X3 = N3;
-            ++xi;
-            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        }
+        for (int m = 0; m < nfull; m += PF) {
+#pragma unroll
+            for (int j = 0; j < PF; ++j) {
+                if (m + j < nfull) {
+                    const double2 N0 = xw[xi + 1], N1 = xw[PL + xi + 1], N2 = xw[2 * PL + xi + 1], N3 = xw[3 * PL + xi + 1];
+                    FMA4(q[j][0], X0, X1, X2, X3);
+                    FMA4(q[j][1], X1, X2, X3, N0);
+                    FMA4(q[j][2], X2, X3, N0, N1);
+                    FMA4(q[j][3], X3, N0, N1, N2);
+                    X0 = N0; X1 = N1; X2 = N2; X3 = N3;
+                    ++xi;
+                    if (m + j + PF < nfull) {
+                        const float* lp = bp + (int64_t)(4 * (m + j + PF)) * ldb;
+                        q[j][0] = ldg_stream_f4(lp);
+                        q[j][1] = ldg_stream_f4(lp + ldb);
+                        q[j][2] = ldg_stream_f4(lp + 2 * ldb);
+                        q[j][3] = ldg_stream_f4(lp + 3 * ldb);
+                    }
+                }
+            }
         }
         for (int d = d0 + 4 * nfull; d < d1; ++d) {   // < 4 leftover diagonals
             const float4 c = ldg_stream_f4(band + (int64_t)d * ldb + row4);
@@ -357,32 +366,60 @@ k_spmm_csr(SpmmArgs a, const int64_t* __restrict__ indptr, const int32_t* __rest
 // ---------------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
-template <int RW, int S, int EPI>
+template <int RW, int S, int EPI, int PF, int MINB>
 static int launch_dia(sgv_ctx* c, const LdMatrix& ld, const SpmmArgs& a) {
     constexpr int TR = 128 * RW;
     const size_t smem = sgv_dia_smem_bytes(ld.w, RW, S);
     static size_t configured = 0;
     if (smem > configured) {
-        SGV_CUDA(cudaFuncSetAttribute(k_spmm_dia<RW, S, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SGV_CUDA(cudaFuncSetAttribute(k_spmm_dia<RW, S, EPI, PF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const unsigned grid = (unsigned)((ld.ldb + TR - 1) / TR);
     SGV_TRY(sgv_ensure_partials(c, grid));
     SpmmArgs aa = a;
     aa.partials = c->partials;
-    k_spmm_dia<RW, S, EPI><<<grid, 32 * RW * S, smem, c->stream>>>(aa, ld.band, (int)ld.w, ld.ldb);
+    k_spmm_dia<RW, S, EPI, PF, MINB><<<grid, 32 * RW * S, smem, c->stream>>>(aa, ld.band, (int)ld.w, ld.ldb);
     c->launches++;
     return 0;
 }
+
+// default tile shapes
+#define DIA_BIG_RW 2
+#define DIA_BIG_S 4
+#define DIA_PF 2
+#define DIA_MINB 3
 
 template <int EPI>
 static int launch_epi(sgv_ctx* c, Cohort& co, const SpmmArgs& a) {
     const LdMatrix& ld = co.ld;
     if (ld.layout == SGV_LAYOUT_DIA) {
+#ifdef SGV_EXPERIMENTS
+        if (EPI == EPI_Q) {   // tuning table for scripts_dev/spmm_variants.py (SGV_DIA_CFG=n)
+            static int cfg = getenv("SGV_DIA_CFG") ? atoi(getenv("SGV_DIA_CFG")) : -1;
+            switch (cfg) {
+                case 0: return launch_dia<2, 4, EPI_Q, 2, 3>(c, ld, a);
+                case 1: return launch_dia<2, 4, EPI_Q, 1, 3>(c, ld, a);
+                case 2: return launch_dia<2, 4, EPI_Q, 2, 4>(c, ld, a);
+                case 3: return launch_dia<4, 2, EPI_Q, 2, 3>(c, ld, a);
+                case 4: return launch_dia<1, 8, EPI_Q, 2, 3>(c, ld, a);
+                case 5: return launch_dia<2, 2, EPI_Q, 2, 6>(c, ld, a);
+                case 6: return launch_dia<1, 4, EPI_Q, 2, 6>(c, ld, a);
+                case 7: return launch_dia<4, 1, EPI_Q, 2, 6>(c, ld, a);
+                case 8: return launch_dia<2, 1, EPI_Q, 2, 12>(c, ld, a);
+                case 9: return launch_dia<1, 2, EPI_Q, 2, 12>(c, ld, a);
+                case 10: return launch_dia<3, 2, EPI_Q, 2, 4>(c, ld, a);
+                case 11: return launch_dia<3, 4, EPI_Q, 2, 2>(c, ld, a);
+                case 12: return launch_dia<4, 4, EPI_Q, 2, 1>(c, ld, a);
+                default: break;
+            }
+        }
+#endif
         // wide tiles when there are enough rows to fill the machine, narrow ones otherwise
         const bool big = ld.ldb >= (int64_t)c->sm_count * 2 * 256 * 2;
-        if (big && sgv_dia_smem_bytes(ld.w, 2, 4) <= 100 * 1024) return launch_dia<2, 4, EPI>(c, ld, a);
-        return launch_dia<1, 8, EPI>(c, ld, a);
+        if (big && sgv_dia_smem_bytes(ld.w, DIA_BIG_RW, DIA_BIG_S) <= 100 * 1024)
+            return launch_dia<DIA_BIG_RW, DIA_BIG_S, EPI, DIA_PF, DIA_MINB>(c, ld, a);
+        return launch_dia<1, 8, EPI, DIA_PF, DIA_MINB>(c, ld, a);
     }
     if (ld.layout == SGV_LAYOUT_DENSE || ld.layout == SGV_LAYOUT_BLOCKDIAG) {
         SpmmArgs aa = a;

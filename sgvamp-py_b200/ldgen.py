@@ -65,7 +65,7 @@ def bartlett_band(M, w):
     return scipy.sparse.diags(diags, offs, shape=(M, M), format="csr")
 
 
-def sim_banded(M, w, N_ld=512, N=None, lam=0.01, h2=0.5, seed=0):
+def sim_banded(M, w, N_ld=512, N=None, lam=0.01, h2=0.5, seed=0, exact_noise=False):
     """Banded LD (CSR, |i-j|<=w, unit diagonal) + r.  Returns (R, r, x0_scaled, N)."""
     rng = np.random.default_rng(seed)
     N = N if N is not None else N_ld
@@ -88,7 +88,16 @@ def sim_banded(M, w, N_ld=512, N=None, lam=0.01, h2=0.5, seed=0):
     beta = np.zeros(M)
     beta[rng.choice(M, cm, replace=False)] = rng.normal(0, np.sqrt(h2 / cm), cm)
     x0 = beta * np.sqrt(N)
-    r = R @ x0 + np.sqrt(1 - h2) * (X.T @ rng.standard_normal(N_ld))
+    if exact_noise:
+        # noise ~ N(0, R) exactly: Bartlett kernel = sum of boxcar outer products (see banded_dia_device)
+        E = rng.standard_normal((N_ld, M + w))
+        C = np.cumsum(E, axis=1)
+        F = C[:, w:].copy()
+        F[:, 1:] -= C[:, :M - 1]
+        noise = (X * F).sum(axis=0) / np.sqrt(w + 1.0)
+    else:
+        noise = X.T @ rng.standard_normal(N_ld)
+    r = R @ x0 + np.sqrt(1 - h2) * noise
     return R, r, x0, N
 
 
@@ -133,28 +142,31 @@ def round_to_f32(R):
 # ------------------------------------------------------------------------------------------
 # device generators (torch as a data-generation utility; used by bench.py and big GPU tests)
 # ------------------------------------------------------------------------------------------
-def _latent_block(torch, n, lo, hi, seed, hap, B, kern, dev, eps_chunk=8192):
-    """Latent Gaussian field z[:, lo:hi] = sum_i kern[j-i] eps_i, eps generated per fixed
-    chunk of marker indices so that any marker range can be produced independently."""
-    e_lo, e_hi = lo - B, hi
-    c0, c1 = e_lo // eps_chunk, (e_hi - 1) // eps_chunk
+def _chunked_randn(torch, n, lo, hi, seed, tag, dev, chunk=8192):
+    """n x (hi-lo) standard normals whose column j depends only on (seed, tag, j): any index range
+    (negative indices included) can be generated independently on any rank."""
+    c0, c1 = lo // chunk, (hi - 1) // chunk
     parts = []
     for c in range(c0, c1 + 1):
         g = torch.Generator(device=dev)
-        g.manual_seed((seed * 1000003 + hap * 7919 + (c + 4096)) & 0x7FFFFFFFFFFF)
-        parts.append(torch.randn((n, eps_chunk), generator=g, device=dev, dtype=torch.float32))
-    E = torch.cat(parts, dim=1)[:, e_lo - c0 * eps_chunk: e_hi - c0 * eps_chunk]   # n x (hi-lo+B)
-    # causal FIR filter via unfold-free matmul with a Toeplitz matrix, chunked
+        g.manual_seed((seed * 1000003 + tag * 7919 + (c + 65536) * 104729) & 0x7FFFFFFFFFFF)
+        parts.append(torch.randn((n, chunk), generator=g, device=dev, dtype=torch.float32))
+    return torch.cat(parts, dim=1)[:, lo - c0 * chunk: hi - c0 * chunk]
+
+
+def _latent_block(torch, n, lo, hi, seed, hap, B, kern, dev):
+    """Latent Gaussian field z[:, lo:hi] = sum_i kern[j-i] eps_i (causal FIR filter of white noise,
+    applied as a Toeplitz matmul)."""
+    E = _chunked_randn(torch, n, lo - B, hi, seed, hap, dev)          # n x (hi-lo+B)
     m = hi - lo
     z = torch.empty((n, m), device=dev, dtype=torch.float32)
     T = 2048
     idx = torch.arange(T, device=dev)
-    # Toep[i_in, j_out] = kern[(j_out + B) - i_in]  for 0 <= (j_out+B-i_in) <= B
-    d = (idx[None, :] + B) - torch.arange(T + B, device=dev)[:, None]
+    d = (idx[None, :] + B) - torch.arange(T + B, device=dev)[:, None]   # Toep[i_in, j_out] = kern[j_out + B - i_in]
     Toep = torch.where((d >= 0) & (d <= B), kern[d.clamp(0, B)], torch.zeros((), device=dev))
     for s in range(0, m, T):
         t = min(T, m - s)
-        z[:, s:s + t] = E[:, s:s + t + B] @ Toep[:t + B, :t] if t == T else E[:, s:s + t + B] @ Toep[:t + B, :t]
+        z[:, s:s + t] = E[:, s:s + t + B] @ Toep[:t + B, :t]
     return z
 
 
@@ -178,18 +190,18 @@ def genotypes_device(torch, n, lo, hi, seed, dev, rho=0.97, B=256):
 
 
 def banded_dia_device(torch, M, w, lo, hi, seed, dev, N_ld=4096, chunk=4096):
-    """Rows [lo, hi) of the tapered banded LD in diagonal-major (DIA) layout.
+    """Rows [lo, hi) of the Bartlett-tapered banded sample LD in diagonal-major (DIA) layout.
 
-    Returns fp32 tensor band[d, i-lo] = R[i, i+d-w] (zero outside the matrix), shape
-    (2w+1, hi-lo), plus the genotype-noise vector helper (X^T e) for building r.
-    Markers outside [0, M) do not exist.
+    Returns (band, noise): fp32 band[d, i-lo] = R[i, i+d-w] (zero outside the matrix, unit
+    diagonal), shape (2w+1, hi-lo), and an fp64 vector noise ~ N(0, R) restricted to [lo, hi).
+    R = T o (X^T X) with the Bartlett kernel T[i,j] = max(0, 1-|i-j|/(w+1)) = sum_c t_c t_c^T,
+    t_c = 1[c <= . <= c+w]/sqrt(w+1); hence noise_i = x_i . f_i with f_i = sum_{c=i-w..i} e_c /
+    sqrt(w+1) for iid e_c ~ N(0, I) has covariance exactly R.  Every quantity depends only on
+    (seed, marker index), so ranks can generate their row ranges independently.
     """
     nloc = hi - lo
     band = torch.zeros((2 * w + 1, nloc), device=dev, dtype=torch.float32)
-    g = torch.Generator(device=dev)
-    g.manual_seed(seed * 31 + 17)
-    e = torch.randn((N_ld,), generator=g, device=dev, dtype=torch.float32)
-    xte = torch.empty((nloc,), device=dev, dtype=torch.float64)
+    noise = torch.empty((nloc,), device=dev, dtype=torch.float64)
     dd = torch.arange(2 * w + 1, device=dev)
     taper = (1.0 - (dd - w).abs().to(torch.float32) / (w + 1.0))
     for s in range(lo, hi, chunk):
@@ -198,7 +210,11 @@ def banded_dia_device(torch, M, w, lo, hi, seed, dev, N_ld=4096, chunk=4096):
         X = genotypes_device(torch, N_ld, clo, chi, seed, dev)
         Xi = X[:, s - clo: t - clo]
         P = Xi.T @ X                                   # (t-s) x (chi-clo), fp32
-        xte[s - lo: t - lo] = (Xi.T @ e).to(torch.float64)
+        E = _chunked_randn(torch, N_ld, s - w, t, seed, 5, dev)          # columns c = s-w .. t-1
+        C = torch.cumsum(E.to(torch.float64), dim=1)
+        F = C[:, w:].clone()                                             # sum_{c <= i}
+        F[:, 1:] -= C[:, : t - s - 1]                                    # minus sum_{c < i-w}
+        noise[s - lo: t - lo] = (Xi.to(torch.float64) * F).sum(dim=0) / float(np.sqrt(w + 1.0))
         ii = torch.arange(s, t, device=dev)
         col = ii[None, :] + (dd[:, None] - w)          # (2w+1) x (t-s): global column
         ok = (col >= 0) & (col < M)
@@ -206,9 +222,9 @@ def banded_dia_device(torch, M, w, lo, hi, seed, dev, N_ld=4096, chunk=4096):
         vals = P[(ii - s)[None, :].expand_as(cidx), cidx] * taper[:, None]
         vals = torch.where(ok, vals, torch.zeros((), device=dev))
         band[:, s - lo: t - lo] = vals
-        del X, P
+        del X, P, E, C, F
     band[w, :] = 1.0
-    return band, xte
+    return band, noise
 
 
 def causal_effects(M, N, lam, h2, seed):

@@ -21,6 +21,7 @@ import logging
 import os
 import queue
 import threading
+import time
 
 import numpy as np
 import scipy.optimize
@@ -54,8 +55,8 @@ class _SoloComm:
         return obj
 
 
-class _Writer:
-    """Background writer so that output dumps leave the solver loop."""
+class _Worker:
+    """Ordered background worker: output dumps and host copies leave the solver loop."""
 
     def __init__(self):
         self.q = queue.Queue()
@@ -68,20 +69,46 @@ class _Writer:
             job = self.q.get()
             if job is None:
                 return
+            fn, done = job
             try:
-                path, arr = job
-                arr.tofile(path)
+                if self.err is None:
+                    fn()
             except Exception as e:  # surfaced at close()
                 self.err = e
+            finally:
+                done.set()
 
-    def put(self, path, arr):
-        self.q.put((path, arr))
+    def submit(self, fn):
+        done = threading.Event()
+        self.q.put((fn, done))
+        return done
 
     def close(self):
         self.q.put(None)
         self.t.join()
         if self.err is not None:
             raise self.err
+
+
+class _ProbeSource:
+    """Rademacher probes exactly as the reference draws them (src/sgvamp.py:326: numpy legacy global
+    RNG, one call per cohort per iteration, in iteration order), generated one step ahead on a
+    helper thread so that the ~15 ns/sample host RNG overlaps the GPU work of the previous step."""
+
+    def __init__(self, order, M):
+        self.q = queue.Queue(maxsize=2)
+        self.t = threading.Thread(target=self._run, args=(order, M), daemon=True)
+        self.t.start()
+
+    def _run(self, order, M):
+        for key in order:
+            u = (np.random.binomial(p=1 / 2, n=1, size=M) * 2 - 1).astype(np.int8)
+            self.q.put((key, u))
+
+    def get(self, key):
+        k, u = self.q.get()
+        assert k == key
+        return u
 
 
 class VAMP:
@@ -291,7 +318,12 @@ class VAMP:
             h.set_xty(k, np.asarray(rs[idx], dtype=np.float64).reshape(M))
         h.reset_state()                                                 # :199-217
         write = write_outputs and self.out_dir is not None
-        writer = _Writer() if write else None
+        worker = _Worker()
+        tm = self.timers = dict(prior=0.0, denoise=0.0, lmmse=0.0, host_tail=0.0)
+        pc = time.perf_counter
+        probe_src = None
+        if probes is None:
+            probe_src = _ProbeSource([(it, k) for it in range(iterations) for k in mine], M)
         sqrtNt = np.sqrt(Nt)
         truth = None
         if x0 is not None:
@@ -301,10 +333,12 @@ class VAMP:
         gamw = [self.gamw] * K
         alpha1 = [np.float64(0.0)] * K
         alpha2 = [np.float64(0.0)] * K
-        xhat1s = []
+        xhat1s = [None] * iterations
         self.history = dict(rows=[], cg_iters=[], cg_info=[], em_steps=[], spmm_passes=[], lam=[], omegas=[])
-        pin_x = [h.pinned_array(M) for _ in range(2)]
-        pin_r = [[h.pinned_array(M) for _ in mine] for _ in range(2)] if write else None
+        NS = 3                                                          # host-copy ring depth
+        pin_x = self._pinned_ring("x", NS, 1)
+        pin_r = self._pinned_ring("r", NS, len(mine)) if write else None
+        slot_done = [None] * NS
 
         if rank == 0:
             logging.debug(f"a = {self.a}")
@@ -313,6 +347,7 @@ class VAMP:
                 iter_hook(it)
             if rank == 0:
                 logging.info(f"\n -----ITERATION {it} -----")
+            t_it = pc()
             gam1s = np.array(gam1, dtype=np.float64)
             if self.rank_mode:                                          # :228-233
                 mine_r1 = h.get_vec(rank, nat.VEC_R1)
@@ -336,15 +371,25 @@ class VAMP:
                     if rank == 0:
                         logging.info(f"... prior-learning EM algorithm performed {em_steps} steps and had final relative error = {rel:0.9f}")
             self._push_prior()
+            t_pr = pc()
+            tm["prior"] += t_pr - t_it
             # denoising :270-293
             if rank == 0:
                 logging.info("...Denoising")
             dmean = np.float64(h.denoise(gam1s, rho, it > 0))
-            slot = it & 1
-            h.get_vec_async(0, nat.VEC_XHAT1, 1.0, pin_x[slot])
+            t_a = pc()
+            slot = it % NS
+            if slot_done[slot] is not None:
+                slot_done[slot].wait()                                   # the worker has drained this slot
+            t_b = pc()
+            tm["slot_wait"] = tm.get("slot_wait", 0.0) + (t_b - t_a)
+            tm["denoise_call"] = tm.get("denoise_call", 0.0) + (t_a - t_pr)
+            h.get_vec_async(0, nat.VEC_XHAT1, 1.0, pin_x[slot][0])
             if write:
                 for idx, k in enumerate(mine):
                     h.get_vec_async(k, nat.VEC_R1, 1.0, pin_r[slot][idx])
+            t_dn = pc()
+            tm["denoise"] += t_dn - t_pr
             rows_it, iters_it, info_it, passes_it = {}, {}, {}, 0
             for k in mine:
                 a1 = self.a[k] * gam1s[k] * dmean                        # :285
@@ -355,7 +400,7 @@ class VAMP:
                 alpha2_prev = alpha2[k]
                 gam2 = gam1[k] * (1 - a1) / a1                           # :305
                 if probes is None:
-                    u = np.random.binomial(p=1 / 2, n=1, size=M) * 2 - 1  # :326 (same RNG call, same position)
+                    u = probe_src.get((it, k))                           # :326 (same RNG calls, same order)
                 elif callable(probes):
                     u = probes(k, it, M)
                 else:
@@ -387,15 +432,21 @@ class VAMP:
                 passes_it += out.spmm_passes
                 if self.out_dir is not None and write_outputs:
                     self.write_params_to_file(row, k)                    # :377
-            h.wait_copies()
-            xh = pin_x[slot].copy()
-            xhat1s.append(xh.reshape(M, 1))
-            if write:
-                if rank == 0:
-                    writer.put(os.path.join(self.out_dir, "%s_xhat_it_%d.bin" % (self.out_name, it)), xh / sqrtNt)
-                for idx, k in enumerate(mine):
-                    writer.put(os.path.join(self.out_dir, "%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k + 1, it)),
-                               pin_r[slot][idx] / sqrtNt)
+            t_lm = pc()
+            tm["lmmse"] += t_lm - t_dn
+
+            def drain(it=it, slot=slot):
+                h.wait_copies()
+                xh = pin_x[slot][0].copy()
+                xhat1s[it] = xh.reshape(M, 1)
+                if write:
+                    if rank == 0:
+                        (xh / sqrtNt).tofile(os.path.join(self.out_dir, "%s_xhat_it_%d.bin" % (self.out_name, it)))
+                    for idx, k in enumerate(mine):
+                        (pin_r[slot][idx] / sqrtNt).tofile(
+                            os.path.join(self.out_dir, "%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k + 1, it)))
+
+            slot_done[slot] = worker.submit(drain)
             if truth is not None:                                        # :379-387
                 d = h.metrics(truth if it == 0 else None)
                 alignment = d[0] / np.sqrt(d[1]) / np.sqrt(d[2])
@@ -413,13 +464,20 @@ class VAMP:
             self.history["spmm_passes"].append(passes_it)
             self.history["lam"].append(float(self.lam))
             self.history["omegas"].append(np.array(self.omegas, dtype=np.float64).copy())
+            tm["host_tail"] += pc() - t_lm
         if iter_hook is not None:
             iter_hook(iterations)
         h.sync()
-        if writer is not None:
-            writer.close()
+        worker.close()
         self.gam1_final, self.gamw_final = gam1, gamw
         return xhat1s
+
+    def _pinned_ring(self, tag, depth, width):
+        key = (tag, depth, width)
+        cache = self.__dict__.setdefault("_pinned_cache", {})
+        if key not in cache:
+            cache[key] = [[self.handle.pinned_array(self.M) for _ in range(width)] for _ in range(depth)]
+        return cache[key]
 
     def close(self):
         self.handle.close()
