@@ -52,6 +52,21 @@ int sgv_sync(sgv_handle h);
  * Allocates all per-cohort state vectors. */
 int sgv_configure(sgv_handle h, int64_t M, int K);
 
+/* ---- multi-GPU (no reference counterpart: the reference has one rank per cohort and no data
+ * parallelism).  One handle per GPU owns the marker rows [row_lo,row_hi) of every
+ * cohort; all vectors are local.  Every grid reduction is completed across ranks inside the
+ * kernels: partial sums are written into every rank's inbox through peer memory (NVLink) and
+ * added in rank order, so all ranks obtain identical scalars without host collectives.
+ * halo != 0: banded LD - the SpMM reads the w halo entries of its input vector directly from the
+ * neighbouring ranks' memory.  halo == 0: block-diagonal LD sharded by block (scalar-only exchange).
+ * All ranks must issue the same sequence of calls. ---- */
+int sgv_configure_part(sgv_handle h, int64_t M, int K, int rank, int world, int64_t row_lo, int64_t row_hi, int halo);
+int sgv_ipc_export(sgv_handle h, void* handle64);                                   /* 64-byte CUDA IPC handle of the arena */
+int sgv_ipc_import(sgv_handle h, int peer_rank, const void* handle64, int64_t peer_rows);
+int sgv_peer_attach_local(sgv_handle h, int peer_rank, sgv_handle other);           /* same-process variant */
+int sgv_ld_set_bandwidth_hint(sgv_handle h, int64_t w);   /* common half-bandwidth of the DIA layout across ranks */
+int sgv_partition_info(sgv_handle h, int64_t* M, int64_t* rows, int64_t* row_lo, int* rank, int* world);
+
 /* ---- LD matrices (reference: R argument of VAMP.infer, src/sgvamp.py:196; Rused formed at
  * src/main.py:265).  `s` applies Rused = (1-s) R + s I at upload (pass 0 for an R that is
  * already regularised).  Values are converted to fp32 on the device. ---- */
@@ -127,6 +142,9 @@ int sgv_metrics(sgv_handle h, const double* x0, double* dots);
 
 /* Unit-test / benchmark hook: Y = alpha*(R X) + beta*X for nrhs in {1,2}; X, Y host, column-major M x nrhs */
 int sgv_spmm(sgv_handle h, int cohort, const double* X, double* Y, int nrhs, double alpha, double beta);
+/* two-phase variant for multi-rank runs (upload; the caller synchronises the ranks; multiply) */
+int sgv_spmm_stage(sgv_handle h, const double* X, int nrhs);
+int sgv_spmm_run(sgv_handle h, int cohort, double* Y, int nrhs, double alpha, double beta);
 /* Same on device-resident interleaved vectors already inside the handle; launches `reps` times
  * and returns the average device time per launch in ms (CUDA events on the handle's stream). */
 int sgv_spmm_bench(sgv_handle h, int cohort, int reps, float* ms_per_launch);

@@ -56,6 +56,13 @@ extern "C" int sgv_create(int device, void* stream, sgv_handle* out) {
     return 0;
 }
 
+static void detach_peers(sgv_ctx* c) {
+    for (int q = 0; q < SGV_MAX_RANKS; ++q) {
+        if (c->peer[q].ipc && c->peer[q].base) cudaIpcCloseMemHandle(c->peer[q].base);
+        c->peer[q] = PeerView();
+    }
+}
+
 static void free_vectors(sgv_ctx* c) {
     for (int k = 0; k < SGV_MAX_K; ++k) {
         Cohort& co = c->coh[k];
@@ -64,14 +71,15 @@ static void free_vectors(sgv_ctx* c) {
         cudaFree(co.r2);
         cudaFree(co.xhat2);
         cudaFree(co.sig);
-        cudaFree(co.bb);
-        cudaFree(co.xx);
-        cudaFree(co.rr);
-        cudaFree(co.pp);
-        cudaFree(co.qq);
         cudaFree(co.probe);
         co = Cohort();
     }
+    detach_peers(c);
+    cudaFree(c->arena);
+    cudaFree(c->bb);
+    cudaFree(c->qq);
+    c->arena = nullptr;
+    c->bb = c->qq = c->xx = c->rr = c->pp[0] = c->pp[1] = nullptr;
     cudaFree(c->r1_all);
     cudaFree(c->xhat1);
     cudaFree(c->truth);
@@ -141,47 +149,186 @@ extern "C" int sgv_profile_read(sgv_handle c, double* total_ms, int64_t* launche
     return 0;
 }
 
-extern "C" int sgv_configure(sgv_handle c, int64_t M, int K) {
+// ---------------------------------------------------------------------------------------------
+// cross-rank reduction plumbing
+// ---------------------------------------------------------------------------------------------
+// One warp; lane q waits for rank q's partial sums of reduction `seq`, lane 0 combines the rows in
+// rank order (bit-identical on all ranks) and applies the state transition.  A bounded spin: on
+// time-out the error flag is raised and both CG columns are marked done so that nothing hangs.
+__global__ void k_resolve(RedCtx rc) {
+    Inbox* me = rc.inbox[rc.rank];
+    const int slot = (int)(rc.seq % SGV_INBOX_SLOTS);
+    const int lane = threadIdx.x;
+    bool good = true;
+    if (lane < rc.world) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(&me->flag[slot][lane]) != rc.seq) {
+            if (clock64() - t0 > 40000000000LL) {   // ~20 s: bounded, so a lost rank cannot hang the GPU
+                good = false;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    good = __all_sync(0xffffffffu, good);
+    if (lane == 0) {
+        if (!good) {
+            rc.st->error = 1;
+            rc.st->done[0] = rc.st->done[1] = 1;
+            return;
+        }
+        double t[SGV_MAX_PARTIAL_VALUES];
+        for (int k = 0; k < rc.ap.nv; ++k) t[k] = rc.ap.is_min ? SGV_INF : 0.0;
+        for (int q = 0; q < rc.world; ++q)
+            for (int k = 0; k < rc.ap.nv; ++k) {
+                const double x = __ldcg(&me->vals[slot][q][k]);
+                t[k] = rc.ap.is_min ? fmin(t[k], x) : t[k] + x;
+            }
+        apply_totals(rc.ap, rc.st, t);
+    }
+}
+
+RedCtx sgv_red_begin(sgv_ctx* c, int kind, int nv, int off, int maxit, int x0_zero, int is_min) {
+    RedCtx rc;
+    memset(&rc, 0, sizeof(rc));
+    rc.partials = c->partials;
+    rc.counter = c->counter;
+    rc.st = c->cg;
+    rc.world = c->world;
+    rc.rank = c->rank;
+    rc.seq = ++c->seq;
+    for (int q = 0; q < c->world; ++q) rc.inbox[q] = reinterpret_cast<Inbox*>(c->peer[q].base);
+    rc.ap.kind = kind;
+    rc.ap.nv = nv;
+    rc.ap.off = off;
+    rc.ap.maxit = maxit;
+    rc.ap.x0_zero = x0_zero;
+    rc.ap.is_min = is_min;
+    return rc;
+}
+
+int sgv_red_end(sgv_ctx* c, const RedCtx& rc) {
+    if (c->world > 1) {
+        k_resolve<<<1, 32, 0, c->stream>>>(rc);
+        c->launches++;
+        SGV_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int sgv_configure_part(sgv_handle c, int64_t M, int K, int rank, int world, int64_t row_lo, int64_t row_hi,
+                                  int halo) {
     SGV_CHECK(c != nullptr, "null handle");
     SGV_CHECK(M > 0, "M must be positive");
     SGV_CHECK(K >= 1 && K <= SGV_MAX_K, "K=%d outside [1,%d]", K, SGV_MAX_K);
+    SGV_CHECK(world >= 1 && world <= SGV_MAX_RANKS && rank >= 0 && rank < world, "bad rank/world %d/%d", rank, world);
+    SGV_CHECK(row_lo >= 0 && row_hi > row_lo && row_hi <= M, "bad row range [%lld,%lld)", (long long)row_lo, (long long)row_hi);
     SGV_CUDA(cudaSetDevice(c->device));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
     SGV_CUDA(cudaStreamSynchronize(c->copy_stream));
     free_vectors(c);
     c->M = M;
+    c->Ml = row_hi - row_lo;
+    c->row_lo = row_lo;
+    c->rank = rank;
+    c->world = world;
+    c->halo = halo;
     c->K = K;
+    c->seq = 0;
     c->prior.K = K;
     for (int k = 0; k < K; ++k) c->prior.a[k] = 1.0 / K;
-    const size_t vb = (size_t)M * sizeof(double), v2 = (size_t)M * sizeof(double2);
+    const int64_t Ml = c->Ml;
+    const size_t vb = (size_t)Ml * sizeof(double), v2 = (size_t)Ml * sizeof(double2);
     SGV_CUDA(cudaMalloc(&c->r1_all, vb * K));
     SGV_CUDA(cudaMalloc(&c->xhat1, vb));
     SGV_CUDA(cudaMemsetAsync(c->r1_all, 0, vb * K, c->stream));
     SGV_CUDA(cudaMemsetAsync(c->xhat1, 0, vb, c->stream));
     for (int k = 0; k < K; ++k) {
         Cohort& co = c->coh[k];
-        co.r1 = c->r1_all + (size_t)k * M;
+        co.r1 = c->r1_all + (size_t)k * Ml;
         SGV_CUDA(cudaMalloc(&co.xty, vb));
         SGV_CUDA(cudaMalloc(&co.r2, vb));
         SGV_CUDA(cudaMalloc(&co.xhat2, vb));
         SGV_CUDA(cudaMalloc(&co.sig, vb));
-        SGV_CUDA(cudaMalloc(&co.bb, v2));
-        SGV_CUDA(cudaMalloc(&co.xx, v2));
-        SGV_CUDA(cudaMalloc(&co.rr, v2));
-        SGV_CUDA(cudaMalloc(&co.pp, v2));
-        SGV_CUDA(cudaMalloc(&co.qq, v2));
-        SGV_CUDA(cudaMalloc(&co.probe, M));
+        SGV_CUDA(cudaMalloc(&co.probe, Ml));
         double* z[] = {co.xty, co.r2, co.xhat2, co.sig};
         for (double* p : z) SGV_CUDA(cudaMemsetAsync(p, 0, vb, c->stream));
-        double2* z2[] = {co.bb, co.xx, co.rr, co.pp, co.qq};
-        for (double2* p : z2) SGV_CUDA(cudaMemsetAsync(p, 0, v2, c->stream));
     }
+    // symmetric arena: [Inbox | xx | rr | pp0 | pp1]
+    c->arena_bytes = arena_size(Ml);
+    SGV_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
+    SGV_CUDA(cudaMemsetAsync(c->arena, 0, c->arena_bytes, c->stream));
+    c->xx = reinterpret_cast<double2*>(c->arena + arena_off_xx(Ml));
+    c->rr = reinterpret_cast<double2*>(c->arena + arena_off_rr(Ml));
+    c->pp[0] = reinterpret_cast<double2*>(c->arena + arena_off_pp(Ml, 0));
+    c->pp[1] = reinterpret_cast<double2*>(c->arena + arena_off_pp(Ml, 1));
+    c->peer[rank].base = c->arena;
+    c->peer[rank].Ml = Ml;
+    c->peer[rank].ipc = false;
+    SGV_CUDA(cudaMalloc(&c->bb, v2));
+    SGV_CUDA(cudaMalloc(&c->qq, v2));
+    SGV_CUDA(cudaMemsetAsync(c->bb, 0, v2, c->stream));
+    SGV_CUDA(cudaMemsetAsync(c->qq, 0, v2, c->stream));
+    SGV_CUDA(cudaMemsetAsync(c->cg, 0, sizeof(CgState), c->stream));
     for (int i = 0; i < sgv_ctx::NSNAP; ++i) {   // allocated up front: cudaMalloc inside the loop would synchronise
         SGV_CUDA(cudaMalloc(&c->snap[i], vb));
         SGV_CUDA(cudaEventCreateWithFlags(&c->snap_ev[i], cudaEventDisableTiming));
     }
     SGV_TRY(sgv_ensure_partials(c, (int64_t)c->sm_count * 16));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int sgv_configure(sgv_handle c, int64_t M, int K) { return sgv_configure_part(c, M, K, 0, 1, 0, M, 0); }
+
+// ---- peer attachment: every rank maps every other rank's arena ----
+extern "C" int sgv_ipc_export(sgv_handle c, void* handle64) {
+    SGV_CHECK(c != nullptr && c->arena != nullptr && handle64 != nullptr, "handle not configured");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+    SGV_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), c->arena));
+    return 0;
+}
+
+extern "C" int sgv_ipc_import(sgv_handle c, int peer_rank, const void* handle64, int64_t peer_Ml) {
+    SGV_CHECK(c != nullptr && c->arena != nullptr, "handle not configured");
+    SGV_CHECK(peer_rank >= 0 && peer_rank < c->world && peer_rank != c->rank, "bad peer rank %d", peer_rank);
+    SGV_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t hdl;
+    memcpy(&hdl, handle64, sizeof(hdl));
+    void* p = nullptr;
+    SGV_CUDA(cudaIpcOpenMemHandle(&p, hdl, cudaIpcMemLazyEnablePeerAccess));
+    c->peer[peer_rank].base = static_cast<char*>(p);
+    c->peer[peer_rank].Ml = peer_Ml;
+    c->peer[peer_rank].ipc = true;
+    return 0;
+}
+
+// same-process variant (one host thread per GPU): direct pointers + cudaDeviceEnablePeerAccess
+extern "C" int sgv_peer_attach_local(sgv_handle c, int peer_rank, sgv_handle other) {
+    SGV_CHECK(c != nullptr && other != nullptr && c->arena && other->arena, "handles not configured");
+    SGV_CHECK(peer_rank >= 0 && peer_rank < c->world && peer_rank != c->rank, "bad peer rank %d", peer_rank);
+    SGV_CUDA(cudaSetDevice(c->device));
+    if (other->device != c->device) {
+        int can = 0;
+        SGV_CUDA(cudaDeviceCanAccessPeer(&can, c->device, other->device));
+        SGV_CHECK(can, "device %d cannot access device %d", c->device, other->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(other->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) SGV_CUDA(e);
+        cudaGetLastError();
+    }
+    c->peer[peer_rank].base = other->arena;
+    c->peer[peer_rank].Ml = other->Ml;
+    c->peer[peer_rank].ipc = false;
+    return 0;
+}
+
+extern "C" int sgv_partition_info(sgv_handle c, int64_t* M, int64_t* Ml, int64_t* row_lo, int* rank, int* world) {
+    SGV_CHECK(c != nullptr, "null handle");
+    if (M) *M = c->M;
+    if (Ml) *Ml = c->Ml;
+    if (row_lo) *row_lo = c->row_lo;
+    if (rank) *rank = c->rank;
+    if (world) *world = c->world;
     return 0;
 }
 
@@ -205,14 +352,14 @@ extern "C" int sgv_set_xty(sgv_handle c, int cohort, const double* r) {
     double* p;
     SGV_TRY(vec_ptr(c, cohort, SGV_VEC_XTY, &p));
     SGV_CHECK(r != nullptr, "r is null");
-    SGV_CUDA(cudaMemcpyAsync(p, r, c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SGV_CUDA(cudaMemcpyAsync(p, r, c->Ml * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
 extern "C" int sgv_reset_state(sgv_handle c) {
     SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
-    const size_t vb = (size_t)c->M * sizeof(double);
+    const size_t vb = (size_t)c->Ml * sizeof(double);
     SGV_CUDA(cudaMemsetAsync(c->xhat1, 0, vb, c->stream));
     for (int k = 0; k < c->K; ++k) {
         Cohort& co = c->coh[k];
@@ -227,7 +374,7 @@ extern "C" int sgv_reset_state(sgv_handle c) {
 extern "C" int sgv_get_vec(sgv_handle c, int cohort, int which, double* dst) {
     double* p;
     SGV_TRY(vec_ptr(c, cohort, which, &p));
-    SGV_CUDA(cudaMemcpyAsync(dst, p, c->M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaMemcpyAsync(dst, p, c->Ml * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -235,7 +382,7 @@ extern "C" int sgv_get_vec(sgv_handle c, int cohort, int which, double* dst) {
 extern "C" int sgv_set_vec(sgv_handle c, int cohort, int which, const double* src) {
     double* p;
     SGV_TRY(vec_ptr(c, cohort, which, &p));
-    SGV_CUDA(cudaMemcpyAsync(p, src, c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SGV_CUDA(cudaMemcpyAsync(p, src, c->Ml * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -254,12 +401,12 @@ extern "C" int sgv_get_vec_async(sgv_handle c, int cohort, int which, double sca
     c->snap_next = (c->snap_next + 1) % sgv_ctx::NSNAP;
     SGV_CUDA(cudaStreamWaitEvent(c->stream, c->snap_ev[slot], 0));   // previous read-back of this slot is done
     double* snap = c->snap[slot];
-    const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 8);
-    k_scale_copy<<<grid, 256, 0, c->stream>>>(c->M, p, snap, scale);
+    const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 8);
+    k_scale_copy<<<grid, 256, 0, c->stream>>>(c->Ml, p, snap, scale);
     c->launches++;
     SGV_CUDA(cudaEventRecord(c->ev_copy, c->stream));
     SGV_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_copy, 0));
-    SGV_CUDA(cudaMemcpyAsync(pinned_dst, snap, c->M * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    SGV_CUDA(cudaMemcpyAsync(pinned_dst, snap, c->Ml * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
     SGV_CUDA(cudaEventRecord(c->snap_ev[slot], c->copy_stream));
     return 0;
 }
@@ -308,12 +455,41 @@ extern "C" int sgv_spmm(sgv_handle c, int cohort, const double* X, double* Y, in
     SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
     SGV_CHECK(nrhs == 1 || nrhs == 2, "nrhs must be 1 or 2");
     Cohort& co = c->coh[cohort];
-    const int64_t M = c->M;
+    const int64_t M = c->Ml;
     std::vector<double2> h(M);
     for (int64_t i = 0; i < M; ++i) h[i] = make_double2(X[i], nrhs == 2 ? X[M + i] : 0.0);
-    SGV_CUDA(cudaMemcpyAsync(co.pp, h.data(), M * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
-    SGV_TRY(sgv_launch_spmm(c, co, EPI_PLAIN, co.pp, co.qq, alpha, beta, 0));
-    SGV_CUDA(cudaMemcpyAsync(h.data(), co.qq, M * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaMemcpyAsync(c->pp[0], h.data(), M * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    SGV_TRY(sgv_launch_spmm(c, co, EPI_PLAIN, VEC_PP0, c->qq, alpha, beta, 0, 0));
+    SGV_CUDA(cudaMemcpyAsync(h.data(), c->qq, M * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < M; ++i) {
+        Y[i] = h[i].x;
+        if (nrhs == 2) Y[M + i] = h[i].y;
+    }
+    return 0;
+}
+
+// In multi-rank runs the vector upload of sgv_spmm must be complete on every rank before any rank's
+// kernel reads its neighbours' halos: sgv_spmm_stage uploads, the caller synchronises the ranks
+// (barrier), sgv_spmm_run multiplies.
+extern "C" int sgv_spmm_stage(sgv_handle c, const double* X, int nrhs) {
+    SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
+    const int64_t M = c->Ml;
+    std::vector<double2> h(M);
+    for (int64_t i = 0; i < M; ++i) h[i] = make_double2(X[i], nrhs == 2 ? X[M + i] : 0.0);
+    SGV_CUDA(cudaMemcpyAsync(c->pp[0], h.data(), M * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int sgv_spmm_run(sgv_handle c, int cohort, double* Y, int nrhs, double alpha, double beta) {
+    SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
+    SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
+    Cohort& co = c->coh[cohort];
+    const int64_t M = c->Ml;
+    std::vector<double2> h(M);
+    SGV_TRY(sgv_launch_spmm(c, co, EPI_PLAIN, VEC_PP0, c->qq, alpha, beta, 0, 0));
+    SGV_CUDA(cudaMemcpyAsync(h.data(), c->qq, M * sizeof(double2), cudaMemcpyDeviceToHost, c->stream));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
     for (int64_t i = 0; i < M; ++i) {
         Y[i] = h[i].x;
@@ -326,11 +502,12 @@ extern "C" int sgv_spmm_bench(sgv_handle c, int cohort, int reps, float* ms_per_
     SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
     SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
     SGV_CHECK(reps > 0 && ms_per_launch, "bad arguments");
+    SGV_CHECK(c->world == 1, "sgv_spmm_bench is a single-rank hook");
     Cohort& co = c->coh[cohort];
     // the CG-shaped pass: q = gamw*(R p) + gam2*p with the p.q dots, on whatever the vectors hold
-    for (int i = 0; i < 3; ++i) SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, co.pp, co.qq, 1.5, 0.25, 0));
+    for (int i = 0; i < 3; ++i) SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, VEC_PP0, c->qq, 1.5, 0.25, 0, 0));
     SGV_CUDA(cudaEventRecord(c->ev_a, c->stream));
-    for (int i = 0; i < reps; ++i) SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, co.pp, co.qq, 1.5, 0.25, 0));
+    for (int i = 0; i < reps; ++i) SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, VEC_PP0, c->qq, 1.5, 0.25, 0, 0));
     SGV_CUDA(cudaEventRecord(c->ev_b, c->stream));
     SGV_CUDA(cudaEventSynchronize(c->ev_b));
     float ms = 0.f;

@@ -44,13 +44,13 @@ int sgv_ensure_partials(sgv_ctx* c, int64_t nblocks) {
 // kernels
 // ---------------------------------------------------------------------------------------------
 __global__ void k_row_extent(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                             int* __restrict__ lo, int* __restrict__ hi, int* __restrict__ has_diag) {
+                             int* __restrict__ lo, int* __restrict__ hi, int* __restrict__ has_diag, int col_base) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
     int mn = INT_MAX, mx = -1, dg = 0;
     for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
-        const int cidx = indices[k];
+        const int cidx = indices[k] - col_base;   // local column (may be < 0 or >= M in the halos)
         mn = min(mn, cidx);
         mx = max(mx, cidx);
         dg |= (cidx == row);
@@ -78,12 +78,13 @@ __global__ void k_fill_f32(float* p, int64_t n, float v) {
 
 template <typename T>
 __global__ void k_csr_to_dia(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                             const T* __restrict__ data, float* __restrict__ band, int w, int64_t ldb, double s) {
+                             const T* __restrict__ data, float* __restrict__ band, int w, int64_t ldb, double s,
+                             int col_base) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
     for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
-        const int cidx = indices[k];
+        const int cidx = indices[k] - col_base;
         const int d = cidx - (int)row + w;
         band[(int64_t)d * ldb + row] = reg_value(data[k], cidx == row, s);
     }
@@ -187,7 +188,7 @@ int sgv_build_panel_items(sgv_ctx* c, LdMatrix& ld, const std::vector<int64_t>& 
     ld.n_items = (int)items.size();
     ld.s_cross = s_cross;
     ld.nblocks = nb;
-    const int64_t need = (int64_t)s_cross * c->M;
+    const int64_t need = (int64_t)s_cross * c->Ml;
     if (c->ypart_cap < need) {
         SGV_CUDA(cudaStreamSynchronize(c->stream));
         if (c->ypart) cudaFree(c->ypart);
@@ -213,6 +214,7 @@ extern "C" int sgv_ld_upload_dense(sgv_handle c, int cohort, const void* R, int 
     SGV_TRY(check_cohort(c, cohort));
     SGV_CHECK(R != nullptr, "R is null");
     SGV_CHECK(dtype == SGV_F32 || dtype == SGV_F64, "bad dtype %d", dtype);
+    SGV_CHECK(c->world == 1, "dense LD upload is single-rank (shard dense LD by cohort, not by row)");
     SGV_CHECK(ld_src >= c->M, "leading dimension %lld < M", (long long)ld_src);
     SGV_CUDA(cudaSetDevice(c->device));
     LdMatrix& ld = c->coh[cohort].ld;
@@ -245,6 +247,7 @@ extern "C" int sgv_ld_upload_dense(sgv_handle c, int cohort, const void* R, int 
 extern "C" int sgv_ld_adopt_dense(sgv_handle c, int cohort, const float* R_dev, int64_t ldd) {
     SGV_TRY(check_cohort(c, cohort));
     SGV_CHECK(R_dev != nullptr && ((uintptr_t)R_dev & 15) == 0, "device pointer must be 16-byte aligned");
+    SGV_CHECK(c->world == 1, "dense LD is single-rank");
     SGV_CHECK(ldd >= c->M && ldd % 4 == 0, "ld must be >= M and a multiple of 4");
     LdMatrix& ld = c->coh[cohort].ld;
     sgv_ld_free(ld);
@@ -258,7 +261,7 @@ extern "C" int sgv_ld_adopt_dense(sgv_handle c, int cohort, const float* R_dev, 
 extern "C" int sgv_ld_adopt_dia(sgv_handle c, int cohort, const float* band_dev, int64_t w, int64_t ldb) {
     SGV_TRY(check_cohort(c, cohort));
     SGV_CHECK(band_dev != nullptr && ((uintptr_t)band_dev & 15) == 0, "device pointer must be 16-byte aligned");
-    SGV_CHECK(ldb >= c->M && ldb % 4 == 0, "ldb must be >= M and a multiple of 4");
+    SGV_CHECK(ldb >= c->Ml && ldb % 4 == 0, "ldb must be >= the local row count and a multiple of 4");
     SGV_CHECK(w >= 0 && sgv_dia_feasible(w), "half-bandwidth %lld not supported by the DIA kernel", (long long)w);
     LdMatrix& ld = c->coh[cohort].ld;
     sgv_ld_free(ld);
@@ -267,14 +270,15 @@ extern "C" int sgv_ld_adopt_dia(sgv_handle c, int cohort, const float* band_dev,
     ld.layout = SGV_LAYOUT_DIA;
     ld.w = w;
     ld.ldb = ldb;
-    ld.nnz_stored = (2 * w + 1) * c->M;
+    ld.nnz_stored = (2 * w + 1) * c->Ml;
     return 0;
 }
 
 template <typename T>
 static int convert_csr(sgv_ctx* c, LdMatrix& ld, int layout, const int64_t* d_indptr, const int32_t* d_indices,
                        const T* d_data, int64_t nnz, double s, int64_t w, const std::vector<int64_t>& starts) {
-    const int64_t M = c->M;
+    const int64_t M = c->Ml;
+    const int col_base = c->halo ? (int)c->row_lo : 0;
     const unsigned wgrid = (unsigned)((M * 32 + 255) / 256);
     if (layout == SGV_LAYOUT_DIA) {
         const int64_t ldb = round_up(M, 32);
@@ -287,7 +291,7 @@ static int convert_csr(sgv_ctx* c, LdMatrix& ld, int layout, const int64_t* d_in
         ld.nnz_stored = (2 * w + 1) * M;
         SGV_CUDA(cudaMemsetAsync(band, 0, (size_t)(2 * w + 1) * ldb * sizeof(float), c->stream));
         k_fill_f32<<<592, 256, 0, c->stream>>>(band + w * ldb, M, (float)s);   // value of an absent diagonal entry
-        k_csr_to_dia<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, band, (int)w, ldb, s);
+        k_csr_to_dia<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, band, (int)w, ldb, s, col_base);
         c->launches += 2;
     } else if (layout == SGV_LAYOUT_DENSE || layout == SGV_LAYOUT_BLOCKDIAG) {
         const int nb = (int)starts.size() - 1;
@@ -349,7 +353,8 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
     SGV_CHECK(dtype == SGV_F32 || dtype == SGV_F64, "bad dtype %d", dtype);
     SGV_CHECK(c->M < INT_MAX, "M too large for int32 column indices");
     SGV_CUDA(cudaSetDevice(c->device));
-    const int64_t M = c->M;
+    const int64_t M = c->Ml;   // local rows; columns are global when the partition has halos
+    const int col_base = c->halo ? (int)c->row_lo : 0;
     SGV_CHECK(indptr[0] == 0 && indptr[M] == nnz, "indptr[0]=%lld indptr[M]=%lld inconsistent with nnz=%lld",
               (long long)indptr[0], (long long)indptr[M], (long long)nnz);
     LdMatrix& ld = c->coh[cohort].ld;
@@ -369,7 +374,7 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
     SGV_CUDA(cudaMemcpyAsync(d_indices, indices, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     SGV_CUDA(cudaMemcpyAsync(d_data, data, nnz * esz, cudaMemcpyHostToDevice, c->stream));
     const unsigned wgrid = (unsigned)((M * 32 + 255) / 256);
-    k_row_extent<<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_lo, d_hi, d_dg);
+    k_row_extent<<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_lo, d_hi, d_dg, col_base);
     c->launches++;
     std::vector<int> ext(3 * M);
     SGV_CUDA(cudaMemcpyAsync(ext.data(), d_lo, 3 * M * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -381,7 +386,8 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
     bool all_diag = true;
     for (int64_t i = 0; i < M; ++i) {
         if (hi[i] < 0) { all_diag = false; continue; }
-        SGV_CHECK(lo[i] >= 0 && hi[i] < M, "column index out of range in row %lld", (long long)i);
+        SGV_CHECK(lo[i] + col_base >= 0 && hi[i] + col_base < c->M, "column index out of range in row %lld", (long long)i);
+        SGV_CHECK(c->halo || (lo[i] >= 0 && hi[i] < M), "row %lld has columns outside this rank's shard", (long long)i);
         w = std::max<int64_t>(w, std::max<int64_t>(i - lo[i], hi[i] - i));
         all_diag = all_diag && dg[i];
     }
@@ -406,7 +412,12 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
     const bool blk_fits = dense_cells * 4.0 < 0.8 * (double)free_b;
     const bool dia_ok = sgv_dia_feasible(w) && dia_cells * 4.0 < 0.8 * (double)free_b;
 
+    if (c->bandwidth_hint > w) w = c->bandwidth_hint;
     int layout = layout_hint;
+    if (c->world > 1 && c->halo) {
+        SGV_CHECK(layout == SGV_LAYOUT_AUTO || layout == SGV_LAYOUT_DIA, "a row partition with halos needs the DIA layout");
+        layout = SGV_LAYOUT_DIA;
+    }
     if (layout == SGV_LAYOUT_AUTO) {
         layout = SGV_LAYOUT_CSR;
         const bool blk_good = blk_fits && fill_blk >= (nb == 1 ? 0.25 : 0.5);
@@ -438,6 +449,12 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
     return rc;
 }
 
+extern "C" int sgv_ld_set_bandwidth_hint(sgv_handle c, int64_t w) {
+    SGV_CHECK(c != nullptr, "null handle");
+    c->bandwidth_hint = w;
+    return 0;
+}
+
 extern "C" int sgv_ld_info(sgv_handle c, int cohort, int* layout, int64_t* nnz_stored, int64_t* bandwidth,
                            int64_t* nblocks, double* bytes_per_pass_nrhs2) {
     SGV_TRY(check_cohort(c, cohort));
@@ -448,8 +465,8 @@ extern "C" int sgv_ld_info(sgv_handle c, int cohort, int* layout, int64_t* nnz_s
     if (nblocks) *nblocks = ld.nblocks;
     if (bytes_per_pass_nrhs2) {
         // algorithmic bytes of one 2-RHS pass: matrix once + vector pair in + vector pair out
-        double b = 32.0 * (double)c->M;
-        if (ld.layout == SGV_LAYOUT_CSR) b += 8.0 * (double)ld.nnz + 8.0 * (double)(c->M + 1);
+        double b = 32.0 * (double)c->Ml;
+        if (ld.layout == SGV_LAYOUT_CSR) b += 8.0 * (double)ld.nnz + 8.0 * (double)(c->Ml + 1);
         else b += 4.0 * (double)ld.nnz_stored;
         *bytes_per_pass_nrhs2 = b;
     }

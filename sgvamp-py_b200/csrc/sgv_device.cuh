@@ -1,8 +1,6 @@
-// Device-side helpers: streaming loads, deterministic block / grid reductions.
+// Device-side helpers: streaming loads, deterministic block / grid / cross-rank reductions.
 #pragma once
 #include "sgv_internal.cuh"
-
-#define SGV_MAX_PARTIAL_VALUES 16
 
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
     float4 r;
@@ -21,6 +19,14 @@ __device__ __forceinline__ int ldg_stream_i1(const int* p) {
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
     return r;
 }
+// vectors that a peer GPU (or another CTA's earlier kernel) wrote: bypass the non-coherent path
+__device__ __forceinline__ double2 ld_vec2(const double2* p) {
+    double2 r;
+    asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+#define SGV_INF __longlong_as_double(0x7ff0000000000000LL)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -33,7 +39,7 @@ __device__ __forceinline__ double warp_min(double v) {
     return v;
 }
 
-// Sum NV values over the block in a fixed order.  Result valid in thread 0 (all lanes of warp 0).
+// Sum NV values over the block in a fixed order.  Result valid in warp 0.
 // `red` is shared scratch of at least NV*32 doubles.  Contains __syncthreads().
 template <int NV, bool MIN = false>
 __device__ __forceinline__ void block_reduce(double (&v)[NV], double* red) {
@@ -50,47 +56,9 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], double* red) {
     if (wid == 0) {
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            double x = (lane < nw) ? red[k * 32 + lane] : (MIN ? __longlong_as_double(0x7ff0000000000000LL) : 0.0);
+            double x = (lane < nw) ? red[k * 32 + lane] : (MIN ? SGV_INF : 0.0);
             v[k] = MIN ? warp_min(x) : warp_sum(x);
         }
-    }
-}
-
-// Grid-wide deterministic reduction: every block contributes NV values; the block that takes the
-// last ticket sums the per-block partials in index order and calls fin(totals) from thread 0.
-// Works for any grid shape; `partials` must hold NV * (number of blocks) doubles and *counter must
-// be 0 on entry (it is reset to 0 on exit).
-template <int NV, bool MIN = false, class Fin>
-__device__ __forceinline__ void grid_reduce(double (&v)[NV], double* partials, unsigned* counter, double* red,
-                                            Fin fin) {
-    __shared__ int s_last;
-    const unsigned nblk = gridDim.x * gridDim.y * gridDim.z;
-    const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    block_reduce<NV, MIN>(v, red);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) partials[(size_t)bid * NV + k] = v[k];
-        __threadfence();
-        unsigned t = atomicAdd(counter, 1u);
-        s_last = (t == nblk - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    double acc[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = MIN ? __longlong_as_double(0x7ff0000000000000LL) : 0.0;
-    for (unsigned b = threadIdx.x; b < nblk; b += blockDim.x) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double x = __ldcg(&partials[(size_t)b * NV + k]);
-            acc[k] = MIN ? fmin(acc[k], x) : acc[k] + x;
-        }
-    }
-    block_reduce<NV, MIN>(acc, red);
-    if (threadIdx.x == 0) {
-        fin(acc);
-        *counter = 0u;
     }
 }
 
@@ -107,5 +75,117 @@ __device__ __forceinline__ void cg_top_test(CgState* s, int c) {
     if (sqrt(s->rho[c]) < 1e-5 * sqrt(s->bnorm2[c])) {
         s->done[c] = 1;
         s->info[c] = 0;
+    }
+}
+
+// The state transition that follows a completed reduction.  Executed by exactly one thread per
+// rank: the finaliser of the reducing kernel (world == 1) or the resolve kernel (world > 1).
+__device__ __forceinline__ void apply_totals(const ApplyArgs& ap, CgState* s, const double* t) {
+    switch (ap.kind) {
+        case AP_STATS:
+            for (int k = 0; k < ap.nv; ++k) s->stats[ap.off + k] = t[k];
+            break;
+        case AP_PQ:
+            s->pq[0] = t[0];
+            s->pq[1] = t[1];
+            break;
+        case AP_RESID:   // r = b - A x0 done: rho and the loop-top test of iteration 0
+            for (int c = 0; c < 2; ++c) {
+                if (!s->done[c]) {
+                    s->rho[c] = t[c];
+                    cg_top_test(s, c);
+                }
+            }
+            break;
+        case AP_SETUP:   // |b|^2 known: initialise the CG state of both columns
+            s->maxit = ap.maxit;
+            s->step = 0;
+            for (int c = 0; c < 2; ++c) {
+                s->bnorm2[c] = t[c];
+                s->rho[c] = 0.0;
+                s->rho_prev[c] = 0.0;
+                s->pq[c] = 0.0;
+                s->iters[c] = 0;
+                s->info[c] = 0;
+                s->done[c] = 0;
+                s->zero_b[c] = 0;
+                if (t[c] == 0.0) {          // scipy: `if bnrm2 == 0: return b, 0`
+                    s->done[c] = 1;
+                    s->zero_b[c] = 1;
+                } else if (ap.x0_zero) {    // r = b.copy(); loop-top test of iteration 0
+                    s->rho[c] = t[c];
+                    cg_top_test(s, c);
+                }
+            }
+            break;
+        case AP_CGUPDATE:   // x, r updated: rho_prev <- rho, rho <- r.r, count, loop-top test
+            for (int c = 0; c < 2; ++c) {
+                if (s->done[c]) continue;
+                s->rho_prev[c] = s->rho[c];
+                s->rho[c] = t[c];
+                s->iters[c] += 1;
+                cg_top_test(s, c);
+            }
+            s->step += 1;
+            break;
+    }
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid-wide deterministic reduction: every block contributes NV values; the block that takes the
+// last ticket combines the per-block partials in index order.  world == 1: it applies the state
+// transition directly.  world > 1: it publishes this rank's totals into every rank's inbox (peer
+// stores) followed by the sequence flag; the resolve kernel launched next combines the rows.
+// `partials` must hold NV * (number of blocks) doubles and *counter must be 0 on entry.
+template <int NV, bool MIN = false>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], const RedCtx& rc, double* red) {
+    __shared__ int s_last;
+    const unsigned nblk = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    block_reduce<NV, MIN>(v, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) rc.partials[(size_t)bid * NV + k] = v[k];
+        __threadfence();
+        unsigned t = atomicAdd(rc.counter, 1u);
+        s_last = (t == nblk - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = MIN ? SGV_INF : 0.0;
+    for (unsigned b = threadIdx.x; b < nblk; b += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double x = __ldcg(&rc.partials[(size_t)b * NV + k]);
+            acc[k] = MIN ? fmin(acc[k], x) : acc[k] + x;
+        }
+    }
+    block_reduce<NV, MIN>(acc, red);
+    if (threadIdx.x == 0) {
+        *rc.counter = 0u;
+        if (rc.world == 1) {
+            apply_totals(rc.ap, rc.st, acc);
+        } else {
+            const int slot = (int)(rc.seq % SGV_INBOX_SLOTS);
+            __threadfence_system();   // everything this rank wrote in this kernel is visible before the flag
+            for (int q = 0; q < rc.world; ++q) {
+                Inbox* ib = rc.inbox[q];
+#pragma unroll
+                for (int k = 0; k < NV; ++k) ib->vals[slot][rc.rank][k] = acc[k];
+            }
+            __threadfence_system();
+            for (int q = 0; q < rc.world; ++q) st_release_sys(&rc.inbox[q]->flag[slot][rc.rank], rc.seq);
+        }
     }
 }

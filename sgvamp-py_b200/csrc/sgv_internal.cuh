@@ -32,6 +32,10 @@ void sgv_set_error(const char* fmt, ...);
         if (rc_ != 0) return rc_;                                                              \
     } while (0)
 
+#define SGV_MAX_RANKS 8
+#define SGV_INBOX_SLOTS 4
+#define SGV_MAX_PARTIAL_VALUES 16
+
 // ---------------------------------------------------------------------------------------------
 // device-resident CG / reduction state (one per handle, reused by every cohort in turn)
 // ---------------------------------------------------------------------------------------------
@@ -39,15 +43,43 @@ struct CgState {
     double rho[2], rho_prev[2], pq[2], bnorm2[2];
     double stats[16];      // results of non-CG reductions (read back by the host)
     int    done[2], iters[2], info[2], zero_b[2];
-    int    step;           // p-updates performed (0 -> p = r)
+    int    step;           // CG updates performed (0 -> p = r)
     int    maxit;
+    int    error;          // != 0: a cross-rank wait timed out
+};
+
+// Cross-rank reduction mailbox.  Lives at the start of every rank's symmetric arena; rank r
+// writes its partial sums of reduction `seq` into slot seq % SLOTS, row r, of EVERY rank's inbox
+// (peer stores over NVLink), then the flag.  Consumers add the rows in rank order, so all ranks
+// obtain bit-identical totals.
+struct Inbox {
+    double             vals[SGV_INBOX_SLOTS][SGV_MAX_RANKS][SGV_MAX_PARTIAL_VALUES];
+    unsigned long long flag[SGV_INBOX_SLOTS][SGV_MAX_RANKS];
+};
+
+// What to do with the totals of a grid-wide (and, for world > 1, cross-rank) reduction.
+enum { AP_STATS = 0, AP_PQ = 1, AP_RESID = 2, AP_SETUP = 3, AP_CGUPDATE = 4 };
+struct ApplyArgs {
+    int kind, nv, off;      // AP_STATS: stats[off + k] = total[k]
+    int maxit, x0_zero;     // AP_SETUP
+    int is_min;             // combine with min instead of +
+};
+
+struct RedCtx {
+    double*            partials;   // per-block partial sums (this rank)
+    unsigned*          counter;    // "last block" ticket
+    CgState*           st;
+    Inbox*             inbox[SGV_MAX_RANKS];   // every rank's inbox, mapped into this rank's address space
+    unsigned long long seq;
+    int                world, rank;
+    ApplyArgs          ap;
 };
 
 // Work item of the dense-panel kernel: out_part[slot][i] = sum_{j in [j0,j0+nj)} P[j][i] v[j]
 struct PanelItem {
     int64_t off;   // element offset of P[j0][i0] inside the panel store (multiple of 4)
     int     ld;    // leading dimension of the panel (multiple of 4)
-    int     i0, ni;   // output rows [i0, i0+ni)  (global marker index)
+    int     i0, ni;   // output rows [i0, i0+ni)  (local marker index)
     int     j0, nj;   // input  rows [j0, j0+nj)
     int     navail;   // readable floats from column i0 to the end of the padded row (multiple of 4)
     int     slot;
@@ -75,7 +107,6 @@ struct LdMatrix {
 struct Cohort {
     LdMatrix ld;
     double *xty = nullptr, *r1 = nullptr, *r2 = nullptr, *xhat2 = nullptr, *sig = nullptr;
-    double2 *bb = nullptr, *xx = nullptr, *rr = nullptr, *pp = nullptr, *qq = nullptr;
     int8_t* probe = nullptr;
 };
 
@@ -88,17 +119,37 @@ struct PriorParams {
     double gam1s[SGV_MAX_K];
 };
 
+// One rank's view of a peer's symmetric arena: [Inbox | xx | rr | pp0 | pp1], vectors of the
+// peer's local length.
+struct PeerView {
+    char*    base = nullptr;
+    int64_t  Ml = 0;
+    bool     ipc = false;      // opened with cudaIpcOpenMemHandle (must be closed)
+};
+
 struct sgv_ctx {
     int          device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     bool         own_stream = false;
     int          sm_count = 148;
-    int64_t      M = 0;
+    int64_t      M = 0;              // global number of markers
+    int64_t      Ml = 0;             // markers owned by this rank (rows [row_lo, row_lo+Ml))
+    int64_t      row_lo = 0;
+    int          rank = 0, world = 1;
+    int64_t      bandwidth_hint = 0; // common half-bandwidth agreed by all ranks (0: detect)
+    int          halo = 0;           // banded row partition: SpMM reads w-element halos from the neighbours
     int          K = 0;
     Cohort       coh[SGV_MAX_K];
-    double*      r1_all = nullptr;   // K x M, cohort k's r1 at r1_all + k*M (coh[k].r1 aliases it)
+    double*      r1_all = nullptr;   // K x Ml, cohort k's r1 at r1_all + k*Ml (coh[k].r1 aliases it)
     double*      xhat1 = nullptr;
     double*      truth = nullptr;
+    // symmetric arena (CG work vectors shared by all cohorts + the inbox), peer-mapped for world > 1
+    char*        arena = nullptr;
+    size_t       arena_bytes = 0;
+    double2 *bb = nullptr, *qq = nullptr;             // private
+    double2 *xx = nullptr, *rr = nullptr, *pp[2] = {nullptr, nullptr};   // inside the arena
+    PeerView     peer[SGV_MAX_RANKS];
+    unsigned long long seq = 0;      // reductions issued so far (identical on all ranks)
     double2*     ypart = nullptr;    // cross-CTA partial outputs of the panel kernel
     int64_t      ypart_cap = 0;      // in double2 elements
     PriorParams  prior{};
@@ -125,24 +176,41 @@ struct sgv_ctx {
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// arena layout for a rank with Ml local markers
+static inline size_t arena_vec_bytes(int64_t Ml) { return (size_t)round_up(Ml, 64) * sizeof(double2); }
+static inline size_t arena_off_xx(int64_t) { return (size_t)round_up((int64_t)sizeof(Inbox), 4096); }
+static inline size_t arena_off_rr(int64_t Ml) { return arena_off_xx(Ml) + arena_vec_bytes(Ml); }
+static inline size_t arena_off_pp(int64_t Ml, int i) { return arena_off_rr(Ml) + (size_t)(1 + i) * arena_vec_bytes(Ml); }
+static inline size_t arena_size(int64_t Ml) { return arena_off_pp(Ml, 2); }
+
 // epilogues of the SpMM kernels
 enum { EPI_Q = 0, EPI_RESID = 1, EPI_STATS = 2, EPI_PLAIN = 3 };
+// which symmetric vector an SpMM reads (so that the halos can be fetched from the neighbours)
+enum { VEC_XX = 0, VEC_PP0 = 1, VEC_PP1 = 2 };
 
 struct SpmmArgs {
-    const double2* v;      // input vector pair, indexed by global marker
+    // input vector pair in local coordinates (index 0 = first owned marker); halos come from
+    // v_left (the left neighbour's last entries) / v_right (the right neighbour's first
+    // entries); null = outside the matrix (zeros)
+    const double2* v;
+    const double2* v_left;
+    const double2* v_right;
+    int64_t        n_left;     // local length of the left neighbour
+    // fused CG direction update (DIA layout): v := r + beta * p_old on the fly, written to p_new
+    int            fused_p;
+    const double2 *r, *r_left, *r_right;
+    double2*       p_new;
     double2*       out;    // EPI_Q: qq ; EPI_RESID: rr ; EPI_PLAIN: y
     const double2* bb;     // EPI_RESID: right-hand sides ; EPI_STATS: col1 = probe u
     double         gamw, gam2;
-    int64_t        M;
-    CgState*       cg;
-    double*        partials;
-    unsigned*      counter;
+    int64_t        M;      // local number of markers
     int            check_done;   // 1: exit immediately when both CG columns are done
+    RedCtx         rc;
 };
 
 // spmm.cu
-int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, const double2* v, double2* out, double gamw, double gam2,
-                    int check_done);
+int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, double gamw, double gam2, int check_done,
+                    int fused_p);
 size_t sgv_dia_smem_bytes(int64_t w, int rw, int s);
 bool   sgv_dia_feasible(int64_t w);
 // ld_formats.cu
@@ -151,3 +219,6 @@ int  sgv_build_panel_items(sgv_ctx* c, LdMatrix& ld, const std::vector<int64_t>&
                            const std::vector<int64_t>& offs, const std::vector<int>& lds);
 int  sgv_ensure_stage(sgv_ctx* c, int64_t bytes);
 int  sgv_ensure_partials(sgv_ctx* c, int64_t nblocks);
+// api.cu: reduction plumbing
+RedCtx sgv_red_begin(sgv_ctx* c, int kind, int nv, int off = 0, int maxit = 0, int x0_zero = 0, int is_min = 0);
+int    sgv_red_end(sgv_ctx* c, const RedCtx& rc);   // launches the cross-rank resolve kernel when world > 1

@@ -9,6 +9,7 @@
 // All three are HBM-bound streaming kernels (0.5 - 1 flop/B): 128-bit coalesced loads of the
 // matrix, vector operands in shared memory / registers, fp64 FMA accumulation.
 #include <cstdlib>
+#include <cstring>
 #include "sgv_device.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -35,26 +36,6 @@ __device__ __forceinline__ void epi_row(const SpmmArgs& a, int64_t i, double2 ac
         dots[1] += b.y * o.y;    // u^T R Sigma2_u
     } else {
         a.out[i] = o;
-    }
-}
-
-template <int EPI>
-__device__ __forceinline__ void spmm_finalize(const SpmmArgs& a, double (&t)[2]) {
-    CgState* s = a.cg;
-    if (EPI == EPI_Q) {
-        s->pq[0] = t[0];
-        s->pq[1] = t[1];
-    } else if (EPI == EPI_RESID) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            if (!s->done[c]) {
-                s->rho[c] = t[c];
-                cg_top_test(s, c);
-            }
-        }
-    } else if (EPI == EPI_STATS) {
-        s->stats[0] = t[0];
-        s->stats[1] = t[1];
     }
 }
 
@@ -94,7 +75,7 @@ bool sgv_dia_feasible(int64_t w) { return sgv_dia_smem_bytes(w, 1, 8) <= 200 * 1
 template <int RW, int S, int EPI, int PF, int MINB>
 __global__ void __launch_bounds__(32 * RW * S, MINB)
 k_spmm_dia(SpmmArgs a, const float* __restrict__ band, int w, int64_t ldb) {
-    if (a.check_done && a.cg->done[0] && a.cg->done[1]) return;
+    if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     constexpr int TR = 128 * RW;
     constexpr int NT = 32 * RW * S;
     extern __shared__ double2 smem2[];
@@ -105,15 +86,6 @@ k_spmm_dia(SpmmArgs a, const float* __restrict__ band, int w, int64_t ldb) {
     double* red = redseg + (S > 1 ? (S - 1) : 0) * 8 * (TR / 4);
 
     const int64_t r0 = (int64_t)blockIdx.x * TR;
-    // stage the x window (zero outside the matrix and in the plane padding)
-    for (int j = threadIdx.x; j < 4 * PL; j += NT) {
-        const int64_t col = r0 - w + j;
-        double2 val = make_double2(0.0, 0.0);
-        if (j < W && col >= 0 && col < a.M) val = a.v[col];
-        xw[(j & 3) * PL + (j >> 2)] = val;
-    }
-    __syncthreads();
-
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int rw = wid % RW, s = wid / RW;
     const int g = rw * 32 + lane;
@@ -125,24 +97,81 @@ k_spmm_dia(SpmmArgs a, const float* __restrict__ band, int w, int64_t ldb) {
     const int d0 = s * per;
     const int d1 = min(Dtot, d0 + per);
 
-    double2 acc0 = make_double2(0, 0), acc1 = acc0, acc2 = acc0, acc3 = acc0;
-    if (active && d0 < d1) {
-        const float* bp = band + (int64_t)d0 * ldb + row4;
-        const int nfull = (d1 - d0) >> 2;
-        int xi = g + (d0 >> 2);
-        double2 X0 = xw[xi], X1 = xw[PL + xi], X2 = xw[2 * PL + xi], X3 = xw[3 * PL + xi];
-        // ring of PF groups (4 diagonals each) in flight: a slot is refilled right after it is consumed
-        float4 q[PF][4];
+    // Issue the first PF groups of matrix loads before the x window is staged: the HBM latency of the
+    // ring fill overlaps the staging pass and its barrier.
+    const bool work = active && d0 < d1;
+    const float* bp = band + (int64_t)d0 * ldb + row4;
+    const int nfull = work ? ((d1 - d0) >> 2) : 0;
+    // ring of PF groups (4 diagonals each) in flight: a slot is refilled right after it is consumed
+    float4 q[PF][4];
 #pragma unroll
-        for (int j = 0; j < PF; ++j) {
-            if (j < nfull) {
-                const float* lp = bp + (int64_t)(4 * j) * ldb;
-                q[j][0] = ldg_stream_f4(lp);
-                q[j][1] = ldg_stream_f4(lp + ldb);
-                q[j][2] = ldg_stream_f4(lp + 2 * ldb);
-                q[j][3] = ldg_stream_f4(lp + 3 * ldb);
+    for (int j = 0; j < PF; ++j) {
+        if (j < nfull) {
+            const float* lp = bp + (int64_t)(4 * j) * ldb;
+            q[j][0] = ldg_stream_f4(lp);
+            q[j][1] = ldg_stream_f4(lp + ldb);
+            q[j][2] = ldg_stream_f4(lp + 2 * ldb);
+            q[j][3] = ldg_stream_f4(lp + 3 * ldb);
+        }
+    }
+
+    // stage the x window [r0-w, r0+TR+w) in local coordinates; entries left of 0 / right of M come
+    // from the neighbouring ranks' vectors through peer memory (or are zero at the matrix edge).
+    // In fused mode the window holds the new CG direction p = r + beta*p_old, computed on the fly
+    // (also for the halo entries, from the neighbours' r and p_old), and the owned part is written
+    // to p_new - no separate direction-update kernel and no halo exchange step.
+    double beta0 = 0.0, beta1 = 0.0;
+    bool first = true, fz0 = false, fz1 = false;
+    if (a.fused_p) {
+        const CgState* st = a.rc.st;
+        first = st->step == 0;
+        fz0 = st->done[0] != 0;
+        fz1 = st->done[1] != 0;
+        if (!first) {
+            beta0 = st->rho[0] / st->rho_prev[0];
+            beta1 = st->rho[1] / st->rho_prev[1];
+        }
+    }
+    for (int j = threadIdx.x; j < 4 * PL; j += NT) {
+        const int64_t col = r0 - w + j;
+        double2 val = make_double2(0.0, 0.0);
+        if (j < W) {
+            const double2 *src = nullptr, *rsrc = nullptr;
+            int64_t idx = col;
+            if (col >= 0 && col < a.M) {
+                src = a.v;
+                rsrc = a.r;
+            } else if (col < 0 && a.v_left != nullptr) {
+                src = a.v_left;
+                rsrc = a.r_left;
+                idx = a.n_left + col;
+            } else if (col >= a.M && a.v_right != nullptr) {
+                src = a.v_right;
+                rsrc = a.r_right;
+                idx = col - a.M;
+            }
+            if (src != nullptr) {
+                if (!a.fused_p) {
+                    val = ld_vec2(src + idx);
+                } else {
+                    const double2 rv = ld_vec2(rsrc + idx);
+                    double2 po = make_double2(0.0, 0.0);
+                    if (!first || fz0 || fz1) po = ld_vec2(src + idx);
+                    // scipy: p *= beta; p += z   (first step: p = z)
+                    val.x = fz0 ? po.x : (first ? rv.x : po.x * beta0 + rv.x);
+                    val.y = fz1 ? po.y : (first ? rv.y : po.y * beta1 + rv.y);
+                    if (j >= w && j < w + TR && col < a.M) a.p_new[col] = val;
+                }
             }
         }
+        xw[(j & 3) * PL + (j >> 2)] = val;
+    }
+    __syncthreads();
+
+    double2 acc0 = make_double2(0, 0), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+    if (work) {
+        int xi = g + (d0 >> 2);
+        double2 X0 = xw[xi], X1 = xw[PL + xi], X2 = xw[2 * PL + xi], X3 = xw[3 * PL + xi];
         for (int m = 0; m < nfull; m += PF) {
 #pragma unroll
             for (int j = 0; j < PF; ++j) {
@@ -205,9 +234,7 @@ k_spmm_dia(SpmmArgs a, const float* __restrict__ band, int w, int64_t ldb) {
             }
         }
     }
-    if (EPI != EPI_PLAIN) {
-        grid_reduce<2>(dots, a.partials, a.counter, red, [&](double (&t)[2]) { spmm_finalize<EPI>(a, t); });
-    }
+    if (EPI != EPI_PLAIN) grid_reduce<2>(dots, a.rc, red);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -232,7 +259,7 @@ k_spmm_dia(SpmmArgs a, const float* __restrict__ band, int w, int64_t ldb) {
 template <int RW, int S>
 __global__ void __launch_bounds__(32 * RW * S, 2)
 k_spmm_panel(SpmmArgs a, const float* __restrict__ panels, const PanelItem* __restrict__ items, double2* ypart) {
-    if (a.check_done && a.cg->done[0] && a.cg->done[1]) return;
+    if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     constexpr int TI = 128 * RW;
     constexpr int NT = 32 * RW * S;
     constexpr int G = TI / 4;
@@ -305,7 +332,7 @@ k_spmm_panel(SpmmArgs a, const float* __restrict__ panels, const PanelItem* __re
 
 template <int EPI>
 __global__ void __launch_bounds__(256) k_panel_finish(SpmmArgs a, const double2* __restrict__ ypart, int nslots) {
-    if (a.check_done && a.cg->done[0] && a.cg->done[1]) return;
+    if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     __shared__ double red[2 * 32];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double dots[2] = {0.0, 0.0};
@@ -318,9 +345,7 @@ __global__ void __launch_bounds__(256) k_panel_finish(SpmmArgs a, const double2*
         }
         epi_row<EPI>(a, i, acc, a.v[i], dots);
     }
-    if (EPI != EPI_PLAIN) {
-        grid_reduce<2>(dots, a.partials, a.counter, red, [&](double (&t)[2]) { spmm_finalize<EPI>(a, t); });
-    }
+    if (EPI != EPI_PLAIN) grid_reduce<2>(dots, a.rc, red);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -331,7 +356,7 @@ template <int EPI>
 __global__ void __launch_bounds__(256)
 k_spmm_csr(SpmmArgs a, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
            const float* __restrict__ vals) {
-    if (a.check_done && a.cg->done[0] && a.cg->done[1]) return;
+    if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     __shared__ double red[2 * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t row = (int64_t)blockIdx.x * 8 + wid;
@@ -358,16 +383,14 @@ k_spmm_csr(SpmmArgs a, const int64_t* __restrict__ indptr, const int32_t* __rest
         ay = warp_sum(ay + by);
         if (lane == 0) epi_row<EPI>(a, row, make_double2(ax, ay), a.v[row], dots);
     }
-    if (EPI != EPI_PLAIN) {
-        grid_reduce<2>(dots, a.partials, a.counter, red, [&](double (&t)[2]) { spmm_finalize<EPI>(a, t); });
-    }
+    if (EPI != EPI_PLAIN) grid_reduce<2>(dots, a.rc, red);
 }
 
 // ---------------------------------------------------------------------------------------------
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
 template <int RW, int S, int EPI, int PF, int MINB>
-static int launch_dia(sgv_ctx* c, const LdMatrix& ld, const SpmmArgs& a) {
+static int launch_dia(sgv_ctx* c, const LdMatrix& ld, SpmmArgs& a) {
     constexpr int TR = 128 * RW;
     const size_t smem = sgv_dia_smem_bytes(ld.w, RW, S);
     static size_t configured = 0;
@@ -377,9 +400,8 @@ static int launch_dia(sgv_ctx* c, const LdMatrix& ld, const SpmmArgs& a) {
     }
     const unsigned grid = (unsigned)((ld.ldb + TR - 1) / TR);
     SGV_TRY(sgv_ensure_partials(c, grid));
-    SpmmArgs aa = a;
-    aa.partials = c->partials;
-    k_spmm_dia<RW, S, EPI, PF, MINB><<<grid, 32 * RW * S, smem, c->stream>>>(aa, ld.band, (int)ld.w, ld.ldb);
+    a.rc.partials = c->partials;
+    k_spmm_dia<RW, S, EPI, PF, MINB><<<grid, 32 * RW * S, smem, c->stream>>>(a, ld.band, (int)ld.w, ld.ldb);
     c->launches++;
     return 0;
 }
@@ -391,53 +413,30 @@ static int launch_dia(sgv_ctx* c, const LdMatrix& ld, const SpmmArgs& a) {
 #define DIA_MINB 3
 
 template <int EPI>
-static int launch_epi(sgv_ctx* c, Cohort& co, const SpmmArgs& a) {
+static int launch_epi(sgv_ctx* c, Cohort& co, SpmmArgs& a) {
     const LdMatrix& ld = co.ld;
     if (ld.layout == SGV_LAYOUT_DIA) {
-#ifdef SGV_EXPERIMENTS
-        if (EPI == EPI_Q) {   // tuning table for scripts_dev/spmm_variants.py (SGV_DIA_CFG=n)
-            static int cfg = getenv("SGV_DIA_CFG") ? atoi(getenv("SGV_DIA_CFG")) : -1;
-            switch (cfg) {
-                case 0: return launch_dia<2, 4, EPI_Q, 2, 3>(c, ld, a);
-                case 1: return launch_dia<2, 4, EPI_Q, 1, 3>(c, ld, a);
-                case 2: return launch_dia<2, 4, EPI_Q, 2, 4>(c, ld, a);
-                case 3: return launch_dia<4, 2, EPI_Q, 2, 3>(c, ld, a);
-                case 4: return launch_dia<1, 8, EPI_Q, 2, 3>(c, ld, a);
-                case 5: return launch_dia<2, 2, EPI_Q, 2, 6>(c, ld, a);
-                case 6: return launch_dia<1, 4, EPI_Q, 2, 6>(c, ld, a);
-                case 7: return launch_dia<4, 1, EPI_Q, 2, 6>(c, ld, a);
-                case 8: return launch_dia<2, 1, EPI_Q, 2, 12>(c, ld, a);
-                case 9: return launch_dia<1, 2, EPI_Q, 2, 12>(c, ld, a);
-                case 10: return launch_dia<3, 2, EPI_Q, 2, 4>(c, ld, a);
-                case 11: return launch_dia<3, 4, EPI_Q, 2, 2>(c, ld, a);
-                case 12: return launch_dia<4, 4, EPI_Q, 2, 1>(c, ld, a);
-                default: break;
-            }
-        }
-#endif
         // wide tiles when there are enough rows to fill the machine, narrow ones otherwise
         const bool big = ld.ldb >= (int64_t)c->sm_count * 2 * 256 * 2;
-        if (big && sgv_dia_smem_bytes(ld.w, DIA_BIG_RW, DIA_BIG_S) <= 100 * 1024)
+        if (big && sgv_dia_smem_bytes(ld.w, DIA_BIG_RW, DIA_BIG_S) <= 72 * 1024)
             return launch_dia<DIA_BIG_RW, DIA_BIG_S, EPI, DIA_PF, DIA_MINB>(c, ld, a);
         return launch_dia<1, 8, EPI, DIA_PF, DIA_MINB>(c, ld, a);
     }
     if (ld.layout == SGV_LAYOUT_DENSE || ld.layout == SGV_LAYOUT_BLOCKDIAG) {
-        SpmmArgs aa = a;
-        k_spmm_panel<4, 2><<<ld.n_items, 256, 0, c->stream>>>(aa, ld.panels, ld.items, c->ypart);
+        k_spmm_panel<4, 2><<<ld.n_items, 256, 0, c->stream>>>(a, ld.panels, ld.items, c->ypart);
         c->launches++;
-        const unsigned grid = (unsigned)((c->M + 255) / 256);
+        const unsigned grid = (unsigned)((c->Ml + 255) / 256);
         SGV_TRY(sgv_ensure_partials(c, grid));
-        aa.partials = c->partials;
-        k_panel_finish<EPI><<<grid, 256, 0, c->stream>>>(aa, c->ypart, ld.s_cross);
+        a.rc.partials = c->partials;
+        k_panel_finish<EPI><<<grid, 256, 0, c->stream>>>(a, c->ypart, ld.s_cross);
         c->launches++;
         return 0;
     }
     if (ld.layout == SGV_LAYOUT_CSR) {
-        const unsigned grid = (unsigned)((c->M + 7) / 8);
+        const unsigned grid = (unsigned)((c->Ml + 7) / 8);
         SGV_TRY(sgv_ensure_partials(c, grid));
-        SpmmArgs aa = a;
-        aa.partials = c->partials;
-        k_spmm_csr<EPI><<<grid, 256, 0, c->stream>>>(aa, ld.indptr, ld.indices, ld.vals);
+        a.rc.partials = c->partials;
+        k_spmm_csr<EPI><<<grid, 256, 0, c->stream>>>(a, ld.indptr, ld.indices, ld.vals);
         c->launches++;
         return 0;
     }
@@ -445,19 +444,49 @@ static int launch_epi(sgv_ctx* c, Cohort& co, const SpmmArgs& a) {
     return -1;
 }
 
-int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, const double2* v, double2* out, double gamw, double gam2,
-                    int check_done) {
+static double2* arena_vec(const sgv_ctx* c, int q, int vec) {
+    const PeerView& pv = c->peer[q];
+    const size_t off = vec == VEC_XX ? arena_off_xx(pv.Ml) : arena_off_pp(pv.Ml, vec - VEC_PP0);
+    return reinterpret_cast<double2*>(pv.base + off);
+}
+
+// vec: which symmetric vector is the SpMM input (VEC_XX / VEC_PP0 / VEC_PP1).  With fused_p it names
+// p_old; the new direction r + beta*p_old is written to the other pp buffer.
+int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, double gamw, double gam2, int check_done,
+                    int fused_p) {
     SpmmArgs a;
-    a.v = v;
+    memset(&a, 0, sizeof(a));
+    a.v = vec == VEC_XX ? c->xx : c->pp[vec - VEC_PP0];
+    a.fused_p = fused_p;
+    if (fused_p) {
+        SGV_CHECK(co.ld.layout == SGV_LAYOUT_DIA && vec != VEC_XX, "fused direction update needs the DIA layout");
+        a.r = c->rr;
+        a.p_new = c->pp[1 - (vec - VEC_PP0)];
+    }
+    if (c->world > 1 && c->halo && co.ld.layout == SGV_LAYOUT_DIA) {
+        if (c->rank > 0) {
+            const PeerView& pv = c->peer[c->rank - 1];
+            SGV_CHECK(pv.base != nullptr && pv.Ml >= co.ld.w, "left neighbour not attached or shorter than the half-bandwidth");
+            a.v_left = arena_vec(c, c->rank - 1, vec);
+            a.r_left = reinterpret_cast<double2*>(pv.base + arena_off_rr(pv.Ml));
+            a.n_left = pv.Ml;
+        }
+        if (c->rank + 1 < c->world) {
+            const PeerView& pv = c->peer[c->rank + 1];
+            SGV_CHECK(pv.base != nullptr && pv.Ml >= co.ld.w, "right neighbour not attached or shorter than the half-bandwidth");
+            a.v_right = arena_vec(c, c->rank + 1, vec);
+            a.r_right = reinterpret_cast<double2*>(pv.base + arena_off_rr(pv.Ml));
+        }
+    }
     a.out = out;
-    a.bb = co.bb;
+    a.bb = c->bb;
     a.gamw = gamw;
     a.gam2 = gam2;
-    a.M = c->M;
-    a.cg = c->cg;
-    a.partials = c->partials;
-    a.counter = c->counter;
+    a.M = c->Ml;
     a.check_done = check_done;
+    const int kind = epi == EPI_Q ? AP_PQ : epi == EPI_RESID ? AP_RESID : AP_STATS;
+    if (epi != EPI_PLAIN) a.rc = sgv_red_begin(c, kind, 2, 0);
+    a.rc.st = c->cg;
     int rc;
     if (c->prof) {
         if (c->prof_n + 2 > c->prof_ev.size()) {
@@ -481,5 +510,6 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, const double2* v, double2* 
         c->prof_n += 2;
     }
     SGV_CUDA(cudaGetLastError());
+    if (epi != EPI_PLAIN) SGV_TRY(sgv_red_end(c, a.rc));
     return 0;
 }

@@ -23,7 +23,7 @@ struct DenoiseConsts {
 
 __global__ void __launch_bounds__(256)
 k_denoise(int64_t M, const double* __restrict__ r1_all, double* __restrict__ xhat1, DenoiseConsts k, double rho,
-          int damp, double* partials, unsigned* counter, CgState* st) {
+          int damp, RedCtx rc) {
     __shared__ double red[32];
     double dsum[1] = {0.0};
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
@@ -53,7 +53,7 @@ k_denoise(int64_t M, const double* __restrict__ r1_all, double* __restrict__ xha
         if (damp) xh = rho * xh + (1.0 - rho) * xhat1[j];                              // :276
         xhat1[j] = xh;
     }
-    grid_reduce<1>(dsum, partials, counter, red, [&](double (&t)[1]) { st->stats[0] = t[0]; });
+    grid_reduce<1>(dsum, rc, red);
 }
 
 static void fill_denoise_consts(const sgv_ctx* c, const double* gam1s, DenoiseConsts& k) {
@@ -78,11 +78,13 @@ extern "C" int sgv_denoise(sgv_handle c, const double* gam1s, double rho, int da
     SGV_CHECK(c->prior.L >= 2, "prior not set");
     DenoiseConsts k;
     fill_denoise_consts(c, gam1s, k);
-    const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 8);
+    const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 8);
     SGV_TRY(sgv_ensure_partials(c, grid));
-    k_denoise<<<grid, 256, 0, c->stream>>>(c->M, c->r1_all, c->xhat1, k, rho, damp, c->partials, c->counter, c->cg);
+    RedCtx rc = sgv_red_begin(c, AP_STATS, 1, 0);
+    k_denoise<<<grid, 256, 0, c->stream>>>(c->Ml, c->r1_all, c->xhat1, k, rho, damp, rc);
     c->launches++;
     SGV_CUDA(cudaGetLastError());
+    SGV_TRY(sgv_red_end(c, rc));
     SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
     *dfac_mean = c->host_scal[0] / (double)c->M;
@@ -102,7 +104,7 @@ struct EmConsts {
 };
 
 __global__ void __launch_bounds__(256)
-k_em(int64_t M, const double* __restrict__ r1_all, EmConsts k, double* partials, unsigned* counter, CgState* st) {
+k_em(int64_t M, const double* __restrict__ r1_all, EmConsts k, RedCtx rc) {
     __shared__ double red[16 * 32];
     double acc[16];
 #pragma unroll
@@ -133,9 +135,7 @@ k_em(int64_t M, const double* __restrict__ r1_all, EmConsts k, double* partials,
             acc[15] += api;
         }
     }
-    grid_reduce<16>(acc, partials, counter, red, [&](double (&t)[16]) {
-        for (int i = 0; i < 16; ++i) st->stats[i] = t[i];
-    });
+    grid_reduce<16>(acc, rc, red);
 }
 
 extern "C" int sgv_prior_em(sgv_handle c, const double* gam1s, int maxit, double tol, double* lam_out,
@@ -144,7 +144,7 @@ extern "C" int sgv_prior_em(sgv_handle c, const double* gam1s, int maxit, double
     PriorParams& p = c->prior;
     SGV_CHECK(p.L >= 2, "prior not set");
     const int Lm1 = p.L - 1;
-    const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 4);
+    const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 4);
     SGV_TRY(sgv_ensure_partials(c, grid + 1));
     int steps = 0;
     double rel = 0.0;
@@ -167,9 +167,11 @@ extern "C" int sgv_prior_em(sgv_handle c, const double* gam1s, int maxit, double
             }
         }
         for (int l = 0; l < Lm1; ++l) k.lo[l] = p.lam * p.omegas[l];
-        k_em<<<grid, 256, 0, c->stream>>>(c->M, c->r1_all, k, c->partials, c->counter, c->cg);
+        RedCtx rc = sgv_red_begin(c, AP_STATS, 16, 0);
+        k_em<<<grid, 256, 0, c->stream>>>(c->Ml, c->r1_all, k, rc);
         c->launches++;
         SGV_CUDA(cudaGetLastError());
+        SGV_TRY(sgv_red_end(c, rc));
         SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         SGV_CUDA(cudaStreamSynchronize(c->stream));
         const double* t = c->host_scal;
@@ -209,7 +211,7 @@ struct LagConsts {
 };
 
 __global__ void __launch_bounds__(256)
-k_min_r2(int64_t M, int K, const double* __restrict__ r1_all, double* partials, unsigned* counter, CgState* st) {
+k_min_r2(int64_t M, int K, const double* __restrict__ r1_all, RedCtx rc) {
     __shared__ double red[8 * 32];
     double mn[8];
 #pragma unroll
@@ -222,14 +224,12 @@ k_min_r2(int64_t M, int K, const double* __restrict__ r1_all, double* partials, 
                 mn[q] = fmin(mn[q], r * r);
             }
     }
-    grid_reduce<8, true>(mn, partials, counter, red, [&](double (&t)[8]) {
-        for (int q = 0; q < 8; ++q) st->stats[q] = t[q];
-    });
+    grid_reduce<8, true>(mn, rc, red);
 }
 
 __global__ void __launch_bounds__(256)
-k_lagrangian(int64_t M, const double* __restrict__ r1_all, LagConsts k, double* partials, unsigned* counter,
-             CgState* st) {
+k_lagrangian(int64_t M, const double* __restrict__ r1_all, LagConsts k, RedCtx rc) {
+    const CgState* st = rc.st;
     __shared__ double red[8 * 32];
     // global shift exp_max = max_{k,j,l} -r^2/2/(sigma2_l + 1/gam_k)  (:153); e is monotone in r^2, so
     // the maximum over j is attained at min_j r^2 (st->stats[k], from k_min_r2).
@@ -253,9 +253,7 @@ k_lagrangian(int64_t M, const double* __restrict__ r1_all, LagConsts k, double* 
                 if (l < k.L) acc[l] += k.a[q] * pr[l] / den;                         // :155,:158
         }
     }
-    grid_reduce<8>(acc, partials, counter, red, [&](double (&t)[8]) {
-        for (int l = 0; l < 8; ++l) st->stats[8 + l] = t[l];
-    });
+    grid_reduce<8>(acc, rc, red);
 }
 
 extern "C" int sgv_lagrangian(sgv_handle c, const double* gam1s, const double* x, const double* omega0,
@@ -276,12 +274,16 @@ extern "C" int sgv_lagrangian(sgv_handle c, const double* gam1s, const double* x
         }
     }
     for (int l = 0; l < L; ++l) k.omega[l] = x[l];
-    const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 4);
+    const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 4);
     SGV_TRY(sgv_ensure_partials(c, grid + 1));
-    k_min_r2<<<grid, 256, 0, c->stream>>>(c->M, p.K, c->r1_all, c->partials, c->counter, c->cg);
-    k_lagrangian<<<grid, 256, 0, c->stream>>>(c->M, c->r1_all, k, c->partials, c->counter, c->cg);
+    RedCtx rc1 = sgv_red_begin(c, AP_STATS, 8, 0, 0, 0, 1);
+    k_min_r2<<<grid, 256, 0, c->stream>>>(c->Ml, p.K, c->r1_all, rc1);
+    SGV_TRY(sgv_red_end(c, rc1));
+    RedCtx rc2 = sgv_red_begin(c, AP_STATS, 8, 8);
+    k_lagrangian<<<grid, 256, 0, c->stream>>>(c->Ml, c->r1_all, k, rc2);
     c->launches += 2;
     SGV_CUDA(cudaGetLastError());
+    SGV_TRY(sgv_red_end(c, rc2));
     SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats + 8, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
     double osum = 0.0;
@@ -297,8 +299,7 @@ extern "C" int sgv_lagrangian(sgv_handle c, const double* gam1s, const double* x
 // metrics vs truth (src/sgvamp.py:379-382)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_metrics(int64_t M, const double* __restrict__ xhat1, const double* __restrict__ x0, double* partials,
-          unsigned* counter, CgState* st) {
+k_metrics(int64_t M, const double* __restrict__ xhat1, const double* __restrict__ x0, RedCtx rc) {
     __shared__ double red[4 * 32];
     double acc[4] = {0, 0, 0, 0};
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
@@ -308,23 +309,23 @@ k_metrics(int64_t M, const double* __restrict__ xhat1, const double* __restrict_
         acc[2] += b * b;
         acc[3] += (a - b) * (a - b);
     }
-    grid_reduce<4>(acc, partials, counter, red, [&](double (&t)[4]) {
-        for (int l = 0; l < 4; ++l) st->stats[l] = t[l];
-    });
+    grid_reduce<4>(acc, rc, red);
 }
 
 extern "C" int sgv_metrics(sgv_handle c, const double* x0, double* dots) {
     SGV_TRY(check_ready(c));
     if (x0 != nullptr) {
-        if (!c->truth) SGV_CUDA(cudaMalloc(&c->truth, c->M * sizeof(double)));
-        SGV_CUDA(cudaMemcpyAsync(c->truth, x0, c->M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        if (!c->truth) SGV_CUDA(cudaMalloc(&c->truth, c->Ml * sizeof(double)));
+        SGV_CUDA(cudaMemcpyAsync(c->truth, x0, c->Ml * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     }
     SGV_CHECK(c->truth != nullptr, "truth vector not uploaded yet");
-    const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 4);
+    const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 4);
     SGV_TRY(sgv_ensure_partials(c, grid + 1));
-    k_metrics<<<grid, 256, 0, c->stream>>>(c->M, c->xhat1, c->truth, c->partials, c->counter, c->cg);
+    RedCtx rc = sgv_red_begin(c, AP_STATS, 4, 0);
+    k_metrics<<<grid, 256, 0, c->stream>>>(c->Ml, c->xhat1, c->truth, rc);
     c->launches++;
     SGV_CUDA(cudaGetLastError());
+    SGV_TRY(sgv_red_end(c, rc));
     SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < 4; ++i) dots[i] = c->host_scal[i];
@@ -341,7 +342,7 @@ k_lmmse_setup(int64_t M, const double* __restrict__ xhat1, const double* __restr
               const double* __restrict__ xty, const int8_t* __restrict__ probe, const double* __restrict__ xhat2,
               const double* __restrict__ sig, double* __restrict__ r2, double2* __restrict__ bb,
               double2* __restrict__ xx, double2* __restrict__ rr, double alpha1, double gamw, double gam2,
-              int maxit, int x0_zero, double* partials, unsigned* counter, CgState* st) {
+              int x0_zero, RedCtx rc) {
     __shared__ double red[2 * 32];
     double acc[2] = {0.0, 0.0};
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
@@ -354,30 +355,10 @@ k_lmmse_setup(int64_t M, const double* __restrict__ xhat1, const double* __restr
         acc[0] += b.x * b.x;
         acc[1] += b.y * b.y;
     }
-    grid_reduce<2>(acc, partials, counter, red, [&](double (&t)[2]) {
-        st->maxit = maxit;
-        st->step = 0;
-        for (int c = 0; c < 2; ++c) {
-            st->bnorm2[c] = t[c];
-            st->rho[c] = 0.0;
-            st->rho_prev[c] = 0.0;
-            st->pq[c] = 0.0;
-            st->iters[c] = 0;
-            st->info[c] = 0;
-            st->done[c] = 0;
-            st->zero_b[c] = 0;
-            if (t[c] == 0.0) {          // scipy: `if bnrm2 == 0: return b, 0`
-                st->done[c] = 1;
-                st->zero_b[c] = 1;
-            } else if (x0_zero) {       // r = b.copy(); loop-top test of iteration 0
-                st->rho[c] = t[c];
-                cg_top_test(st, c);
-            }
-        }
-    });
+    grid_reduce<2>(acc, rc, red);
 }
 
-// p = r (first step) or p = r + (rho/rho_prev) p
+// p = r (first step) or p = r + (rho/rho_prev) p      (layouts without the fused update)
 __global__ void __launch_bounds__(256)
 k_p_update(int64_t M, const double2* __restrict__ rr, double2* __restrict__ pp, const CgState* __restrict__ st) {
     const int d0 = st->done[0], d1 = st->done[1];
@@ -395,11 +376,12 @@ k_p_update(int64_t M, const double2* __restrict__ rr, double2* __restrict__ pp, 
     }
 }
 
-// alpha = rho/(p.q); x += alpha p; r -= alpha q; rho_prev = rho; rho = r.r; loop-top test
+// alpha = rho/(p.q); x += alpha p; r -= alpha q; r.r  (state transition: AP_CGUPDATE)
 __global__ void __launch_bounds__(256)
 k_cg_update(int64_t M, double2* __restrict__ xx, double2* __restrict__ rr, const double2* __restrict__ pp,
-            const double2* __restrict__ qq, double* partials, unsigned* counter, CgState* st) {
+            const double2* __restrict__ qq, RedCtx rc) {
     __shared__ double red[2 * 32];
+    const CgState* st = rc.st;
     const int d0 = st->done[0], d1 = st->done[1];
     if (d0 && d1) return;
     const double a0 = d0 ? 0.0 : st->rho[0] / st->pq[0];
@@ -415,16 +397,7 @@ k_cg_update(int64_t M, double2* __restrict__ xx, double2* __restrict__ rr, const
         acc[0] += r.x * r.x;
         acc[1] += r.y * r.y;
     }
-    grid_reduce<2>(acc, partials, counter, red, [&](double (&t)[2]) {
-        for (int c = 0; c < 2; ++c) {
-            if (st->done[c]) continue;
-            st->rho_prev[c] = st->rho[c];
-            st->rho[c] = t[c];
-            st->iters[c] += 1;
-            cg_top_test(st, c);
-        }
-        st->step += 1;
-    });
+    grid_reduce<2>(acc, rc, red);
 }
 
 // xhat2 <- CG col 0 (damped with the previous xhat2 if lmmse_damp, :322-323); Sigma2_u_prev <- col 1
@@ -432,10 +405,9 @@ k_cg_update(int64_t M, double2* __restrict__ xx, double2* __restrict__ rr, const
 // that the statistics SpMM can read (xhat2, Sigma2_u) as one vector pair.
 __global__ void __launch_bounds__(256)
 k_lmmse_post(int64_t M, double2* __restrict__ xx, const double2* __restrict__ bb, const double* __restrict__ xty,
-             double* __restrict__ xhat2, double* __restrict__ sig, double rho, int damp, double* partials,
-             unsigned* counter, CgState* st) {
+             double* __restrict__ xhat2, double* __restrict__ sig, double rho, int damp, RedCtx rc) {
     __shared__ double red[2 * 32];
-    const int z0 = st->zero_b[0], z1 = st->zero_b[1];
+    const int z0 = rc.st->zero_b[0], z1 = rc.st->zero_b[1];
     double acc[2] = {0.0, 0.0};
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
         double2 x = xx[j];
@@ -449,10 +421,7 @@ k_lmmse_post(int64_t M, double2* __restrict__ xx, const double2* __restrict__ bb
         acc[0] += b.y * x.y;
         acc[1] += x.x * xty[j];
     }
-    grid_reduce<2>(acc, partials, counter, red, [&](double (&t)[2]) {
-        st->stats[2] = t[0];
-        st->stats[3] = t[1];
-    });
+    grid_reduce<2>(acc, rc, red);
 }
 
 __global__ void __launch_bounds__(256)
@@ -466,8 +435,8 @@ extern "C" int sgv_update_r1(sgv_handle c, int cohort, double alpha2) {
     SGV_TRY(check_ready(c));
     SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
     Cohort& co = c->coh[cohort];
-    const unsigned grid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 8);
-    k_update_r1<<<grid, 256, 0, c->stream>>>(c->M, co.xhat2, co.r2, co.r1, alpha2);
+    const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 8);
+    k_update_r1<<<grid, 256, 0, c->stream>>>(c->Ml, co.xhat2, co.r2, co.r1, alpha2);
     c->launches++;
     SGV_CUDA(cudaGetLastError());
     return 0;
@@ -479,17 +448,21 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
     SGV_CHECK(in && probe && out, "null argument");
     Cohort& co = c->coh[cohort];
     SGV_CHECK(co.ld.layout != 0, "cohort %d has no LD matrix", cohort);
-    const int64_t M = c->M;
+    const int64_t M = c->Ml;
+    const bool fused = co.ld.layout == SGV_LAYOUT_DIA;   // direction update fused into the SpMM staging
     const unsigned vgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 8);
     SGV_TRY(sgv_ensure_partials(c, vgrid + 1));
     SGV_CUDA(cudaMemcpyAsync(co.probe, probe, M, cudaMemcpyHostToDevice, c->stream));
-    k_lmmse_setup<<<vgrid, 256, 0, c->stream>>>(M, c->xhat1, co.r1, co.xty, co.probe, co.xhat2, co.sig, co.r2, co.bb,
-                                               co.xx, co.rr, in->alpha1, in->gamw, in->gam2, in->cg_maxit,
-                                               in->x0_zero, c->partials, c->counter, c->cg);
-    c->launches++;
+    {
+        RedCtx rc = sgv_red_begin(c, AP_SETUP, 2, 0, in->cg_maxit, in->x0_zero);
+        k_lmmse_setup<<<vgrid, 256, 0, c->stream>>>(M, c->xhat1, co.r1, co.xty, co.probe, co.xhat2, co.sig, co.r2, c->bb,
+                                                   c->xx, c->rr, in->alpha1, in->gamw, in->gam2, in->x0_zero, rc);
+        c->launches++;
+        SGV_TRY(sgv_red_end(c, rc));
+    }
     int passes = 0;
     if (!in->x0_zero) {   // r = b - A x0  and the loop-top test of iteration 0
-        SGV_TRY(sgv_launch_spmm(c, co, EPI_RESID, co.xx, co.rr, in->gamw, in->gam2, 1));
+        SGV_TRY(sgv_launch_spmm(c, co, EPI_RESID, VEC_XX, c->rr, in->gamw, in->gam2, 1, 0));
         passes++;
     }
     int launched = 0;
@@ -498,14 +471,26 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
     while (launched < in->cg_maxit) {
         const int nb = std::min(batch, in->cg_maxit - launched);
         for (int b = 0; b < nb; ++b) {
-            k_p_update<<<vgrid, 256, 0, c->stream>>>(M, co.rr, co.pp, c->cg);
-            SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, co.pp, co.qq, in->gamw, in->gam2, 1));
-            k_cg_update<<<vgrid, 256, 0, c->stream>>>(M, co.xx, co.rr, co.pp, co.qq, c->partials, c->counter, c->cg);
-            c->launches += 2;
+            const int n = launched + b;             // == device step while the solve is active
+            double2* pcur;
+            if (fused) {
+                pcur = c->pp[n & 1];
+                SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, VEC_PP0 + ((n + 1) & 1), c->qq, in->gamw, in->gam2, 1, 1));
+            } else {
+                pcur = c->pp[0];
+                k_p_update<<<vgrid, 256, 0, c->stream>>>(M, c->rr, pcur, c->cg);
+                c->launches++;
+                SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, VEC_PP0, c->qq, in->gamw, in->gam2, 1, 0));
+            }
+            RedCtx rc = sgv_red_begin(c, AP_CGUPDATE, 2, 0);
+            k_cg_update<<<vgrid, 256, 0, c->stream>>>(M, c->xx, c->rr, pcur, c->qq, rc);
+            c->launches++;
+            SGV_TRY(sgv_red_end(c, rc));
         }
         launched += nb;
         SGV_CUDA(cudaMemcpyAsync(hs, c->cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
         SGV_CUDA(cudaStreamSynchronize(c->stream));
+        SGV_CHECK(hs->error == 0, "cross-rank reduction timed out (rank %d of %d)", c->rank, c->world);
         if (hs->done[0] && hs->done[1]) break;
         batch = std::min(16, batch * 2);
     }
@@ -519,21 +504,24 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
     out->cg_info[0] = hs->done[0] ? hs->info[0] : in->cg_maxit;
     out->cg_info[1] = hs->done[1] ? hs->info[1] : in->cg_maxit;
     passes += std::max(hs->iters[0], hs->iters[1]);
-
-    k_lmmse_post<<<vgrid, 256, 0, c->stream>>>(M, co.xx, co.bb, co.xty, co.xhat2, co.sig, in->rho, in->lmmse_damp,
-                                              c->partials, c->counter, c->cg);
-    c->launches++;
+    {
+        RedCtx rc = sgv_red_begin(c, AP_STATS, 2, 2);
+        k_lmmse_post<<<vgrid, 256, 0, c->stream>>>(M, c->xx, c->bb, co.xty, co.xhat2, co.sig, in->rho, in->lmmse_damp, rc);
+        c->launches++;
+        SGV_TRY(sgv_red_end(c, rc));
+    }
     if (in->learn_gamw) {   // R xhat2 and R Sigma2_u in one pass (:352,:359)
-        SGV_TRY(sgv_launch_spmm(c, co, EPI_STATS, co.xx, nullptr, 1.0, 0.0, 0));
+        SGV_TRY(sgv_launch_spmm(c, co, EPI_STATS, VEC_XX, nullptr, 1.0, 0.0, 0, 0));
         passes++;
     }
     SGV_CUDA(cudaGetLastError());
-    SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaMemcpyAsync(hs, c->cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
-    out->xhat2_R_xhat2 = in->learn_gamw ? c->host_scal[0] : 0.0;
-    out->u_R_sigma2u = in->learn_gamw ? c->host_scal[1] : 0.0;
-    out->u_sigma2u = c->host_scal[2];
-    out->xhat2_r = c->host_scal[3];
+    SGV_CHECK(hs->error == 0, "cross-rank reduction timed out (rank %d of %d)", c->rank, c->world);
+    out->xhat2_R_xhat2 = in->learn_gamw ? hs->stats[0] : 0.0;
+    out->u_R_sigma2u = in->learn_gamw ? hs->stats[1] : 0.0;
+    out->u_sigma2u = hs->stats[2];
+    out->xhat2_r = hs->stats[3];
     out->spmm_passes = passes;
     return 0;
 }

@@ -1,0 +1,153 @@
+"""Command-line driver, drop-in for the reference's ``src/main.py``.
+
+Same flags (both the code spellings of src/main.py:28-50 and the README spellings, e.g.
+``--mle-prior-update``), same input formats for r (.txt / .npy / .linear) and R (.npz / .npy),
+same output files.  One process drives all K cohorts on the GPU (the reference starts one MPI
+rank per cohort); ``Rused = (1-s) R + s I`` (src/main.py:265) is applied on the device at upload.
+
+Not built yet (SURVEY 8f "next"): the ``.bim`` reference-order merge with missing SNPs and the
+PLINK ``.ld`` triple loader with its MPI exchange (src/main.py:126-165, 203-257).  ``--bim-files``
+is accepted; if the files list identical SNP sets the run proceeds, otherwise it stops with a
+clear message.
+"""
+import argparse
+import logging
+import os
+import struct
+import sys
+import time
+
+import numpy as np
+import scipy.sparse
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from sgvamp import VAMP  # noqa: E402
+
+
+def build_parser():
+    p = argparse.ArgumentParser()
+    p.add_argument("-ld_files", "--ld-files", help="Path to LD matrices in .npz/.npy files, separated by comma")
+    p.add_argument("-r_files", "--r-files", help="Path to XTy .npy/.txt/.linear files separated by comma")
+    p.add_argument("-true_signal_file", "--true-signal-file", help="Path to true signal .npy/.bin file", default=None)
+    p.add_argument("-out_dir", "--out-dir", help="Output directory")
+    p.add_argument("-out_name", "--out-name", help="Output file name")
+    p.add_argument("-N", "--N", help="Number of samples in each cohort, separated by comma")
+    p.add_argument("-M", "--M", help="Number of markers in each cohort, separated by comma")
+    p.add_argument("-K", "--K", help="Number of cohorts", default=1)
+    p.add_argument("-L", "--L", help="Number of prior mixture components", default=2)
+    p.add_argument("-iterations", "--iterations", help="Number of iterations", default=10)
+    p.add_argument("-prior_vars", "--prior-vars", help="Prior mixture variances", default="0,1")
+    p.add_argument("-prior_probs", "--prior-probs", help="Prior mixture probabilities", default="0.99,0.01")
+    p.add_argument("-gamw", "--gamw", help="Initial noise precision", default=5)
+    p.add_argument("-gam1", "--gam1", help="Initial signal precision", default=0.000001)
+    p.add_argument("-lmmse_damp", "--lmmse-damp", help="Use LMMSE damping", default=False)
+    p.add_argument("-learn_gamw", "--learn-gamw", help="Learn or fix gamw", default=True)
+    p.add_argument("-rho", "--rho", help="Damping factor rho", default=0.5)
+    p.add_argument("-cg_maxit", "--cg-maxit", help="CG max iterations", default=500)
+    p.add_argument("-s", "--s", help="Rused = (1-s) * R + s * Id", default=0.0)
+    p.add_argument("-prior_update", "--prior-update", "--mle-prior-update", dest="prior_update",
+                   help="Learning prior probabilities: 'em' or 'mle'", default="em")
+    p.add_argument("-update_prior_from", "--update-prior-from", help="Learn prior from this iteration onwards", default=1)
+    p.add_argument("-em_prior_maxit", "--em-prior-maxit", help="Max EM prior-learning iterations", default=100)
+    p.add_argument("-bim_files", "--bim-files", help="Path to files containing list of snps", default=None)
+    p.add_argument("--device", help="CUDA device index", default=0)
+    p.add_argument("--layout", help="LD layout in HBM: auto|dense|dia|blockdiag|csr", default="auto")
+    return p
+
+
+def load_r(path, M, N):
+    if path.endswith(".txt"):
+        return np.loadtxt(path).reshape(M)
+    if path.endswith(".npy"):
+        return np.load(path).reshape(M)
+    if path.endswith(".linear"):
+        import pandas as pd
+        df = pd.read_table(path, sep=r"\s+")
+        r = np.array(df["BETA"], dtype=np.float64).reshape(M)
+        r[np.isnan(r)] = 0
+        return r * np.sqrt(N)                                       # src/main.py:183-185
+    raise Exception("Unsupported r vector format!")
+
+
+def load_R(path):
+    if path.endswith(".npz"):
+        return scipy.sparse.load_npz(path)
+    if path.endswith(".npy"):
+        return np.load(path, mmap_mode="r")
+    if path.endswith(".ld"):
+        raise Exception("PLINK .ld input is not supported by the B200 driver yet; convert it with scripts/plink2np.py")
+    raise Exception("Unsupported R matrix format!")
+
+
+def main(argv=None):
+    logging.basicConfig(format="%(message)s", level=logging.INFO)
+    a = build_parser().parse_args(argv)
+    logging.info(" ### VAMP for summary statistics (B200) ###\n")
+    K, L = int(a.K), int(a.L)
+    ld_list, r_list = a.ld_files.split(","), a.r_files.split(",")
+    N_list = [int(n) for n in a.N.split(",")]
+    M_list = [int(m) for m in a.M.split(",")]
+    prior_vars = [float(x) for x in a.prior_vars.split(",")]
+    prior_probs = [float(x) for x in a.prior_probs.split(",")]
+    if len(ld_list) != K:
+        raise Exception("Specified number of cohorts is not equal to number of LD matrices provided!")
+    if len(r_list) != K:
+        raise Exception("Specified number of cohorts is not equal to number of marginal estimates provided!")
+    if len(prior_vars) != L:
+        raise Exception("Number of prior variances must be L!")
+    if len(prior_probs) != L:
+        raise Exception("Number of prior mixture probabilites must be L!")
+    if len(set(M_list)) != 1:
+        raise Exception("cohorts with different marker sets need the .bim merge, which is not built yet")
+    M = M_list[0]
+    if a.bim_files is not None:
+        import pandas as pd
+        sets = [list(pd.read_table(f, sep=r"\s+", header=None)[1]) for f in a.bim_files.split(",")]
+        if any(s_ != sets[0] for s_ in sets[1:]):
+            raise Exception("cohorts with different marker sets need the .bim merge, which is not built yet")
+    Nt = sum(N_list)
+    lmmse_damp, learn_gamw = bool(int(a.lmmse_damp)), bool(int(a.learn_gamw))
+    s = float(a.s)
+
+    ts = time.time()
+    rs = [load_r(r_list[k], M, N_list[k]) for k in range(K)]
+    Rs = [load_R(ld_list[k]) for k in range(K)]
+    logging.info(f"Loading R and r took {time.time() - ts:0.2f} seconds\n")
+    x0 = None
+    if a.true_signal_file is not None:
+        if a.true_signal_file.endswith(".bin"):
+            with open(a.true_signal_file, "rb") as f:
+                x0 = np.array(struct.unpack(str(M) + "d", f.read(M * 8)))
+        elif a.true_signal_file.endswith(".npy"):
+            x0 = np.load(a.true_signal_file).astype(np.float64).ravel()
+        else:
+            raise Exception("Unsupported true signal format!")
+        x0 = x0 * np.sqrt(N_list[0])                                # src/main.py:276 (rank 0 writes the metrics)
+    avec = np.array(N_list) / sum(N_list)                           # src/main.py:287
+    solver = VAMP(N=N_list if K > 1 else N_list[0], Nt=Nt, M=M, K=K, rho=float(a.rho), gam1=float(a.gam1),
+                  gamw=float(a.gamw), a=avec, prior_vars=prior_vars, prior_probs=prior_probs, out_dir=a.out_dir,
+                  out_name=a.out_name, comm=None, device=int(a.device))
+    logging.info("...Running sgVAMP\n")
+    ts = time.time()
+    xhat1 = solver.infer(Rs if K > 1 else Rs[0], rs if K > 1 else rs[0], int(a.iterations), x0=x0,
+                         cg_maxit=int(a.cg_maxit), em_prior_maxit=int(a.em_prior_maxit), learn_gamw=learn_gamw,
+                         lmmse_damp=lmmse_damp, prior_update=a.prior_update,
+                         update_prior_from=int(a.update_prior_from), s=s, layout=a.layout)
+    logging.info(f"sgVAMP inference running time: {(time.time() - ts):0.4f}s\n")
+    # README names the dump {out}__xhat_it_{it}.bin, the code writes {out}_xhat_it_{it}.bin: provide both
+    for it in range(int(a.iterations)):
+        src = os.path.join(a.out_dir, "%s_xhat_it_%d.bin" % (a.out_name, it))
+        dst = os.path.join(a.out_dir, "%s__xhat_it_%d.bin" % (a.out_name, it))
+        if os.path.exists(src) and not os.path.exists(dst):
+            os.symlink(os.path.basename(src), dst)
+    if x0 is not None:
+        al = [float(np.inner(x.squeeze(), x0) / np.linalg.norm(x) / np.linalg.norm(x0)) for x in xhat1]
+        l2 = [float(np.linalg.norm(x.squeeze() - x0) / np.linalg.norm(x0)) for x in xhat1]
+        logging.info(f"Alignment(x1hat, x0) over iterations: \n {al}\n")
+        logging.info(f"L2 error(x1hat, x0) over iterations: \n {l2}\n")
+    solver.close()
+    return xhat1
+
+
+if __name__ == "__main__":
+    main()

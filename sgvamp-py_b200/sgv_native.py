@@ -25,7 +25,8 @@ SYMBOLS = [
     "sgv_set_xty", "sgv_reset_state", "sgv_get_vec", "sgv_set_vec", "sgv_get_vec_async", "sgv_wait_copies",
     "sgv_pinned_alloc", "sgv_pinned_free", "sgv_set_prior", "sgv_set_weights", "sgv_denoise", "sgv_prior_em",
     "sgv_lagrangian", "sgv_lmmse", "sgv_update_r1", "sgv_metrics", "sgv_spmm", "sgv_spmm_bench",
-    "sgv_launch_count", "sgv_profile", "sgv_profile_read",
+    "sgv_launch_count", "sgv_profile", "sgv_profile_read", "sgv_configure_part", "sgv_ipc_export", "sgv_ipc_import",
+    "sgv_peer_attach_local", "sgv_partition_info", "sgv_ld_set_bandwidth_hint", "sgv_spmm_stage", "sgv_spmm_run",
 ]
 
 
@@ -103,7 +104,29 @@ class Handle:
     # -- setup ---------------------------------------------------------------------------------
     def configure(self, M, K):
         self._ck(self.lib.sgv_configure(self.h, C.c_int64(M), C.c_int(K)))
-        self.M, self.K = int(M), int(K)
+        self.M, self.K = int(M), int(K)          # self.M: length of this handle's (local) vectors
+        self.M_global, self.row_lo, self.rank, self.world = int(M), 0, 0, 1
+
+    def configure_part(self, M, K, rank, world, row_lo, row_hi, halo):
+        """Row partition: this handle owns marker rows [row_lo, row_hi) of an M-marker problem."""
+        self._ck(self.lib.sgv_configure_part(self.h, C.c_int64(M), C.c_int(K), C.c_int(rank), C.c_int(world),
+                                             C.c_int64(row_lo), C.c_int64(row_hi), C.c_int(int(halo))))
+        self.M, self.K = int(row_hi - row_lo), int(K)
+        self.M_global, self.row_lo, self.rank, self.world = int(M), int(row_lo), int(rank), int(world)
+
+    def ipc_export(self):
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.sgv_ipc_export(self.h, buf))
+        return bytes(buf.raw)
+
+    def ipc_import(self, peer_rank, handle_bytes, peer_rows):
+        self._ck(self.lib.sgv_ipc_import(self.h, C.c_int(peer_rank), C.c_char_p(handle_bytes), C.c_int64(peer_rows)))
+
+    def peer_attach_local(self, peer_rank, other):
+        self._ck(self.lib.sgv_peer_attach_local(self.h, C.c_int(peer_rank), other.h))
+
+    def set_bandwidth_hint(self, w):
+        self._ck(self.lib.sgv_ld_set_bandwidth_hint(self.h, C.c_int64(int(w))))
 
     def sync(self):
         self._ck(self.lib.sgv_sync(self.h))
@@ -114,7 +137,7 @@ class Handle:
             R = R.astype(np.float64)
         if not R.flags.c_contiguous:
             R = np.ascontiguousarray(R)
-        assert R.shape == (self.M, self.M), R.shape
+        assert R.shape == (self.M_global, self.M_global), R.shape
         self._ck(self.lib.sgv_ld_upload_dense(self.h, C.c_int(cohort), R.ctypes.data_as(C.c_void_p),
                                               C.c_int(F64 if R.dtype == np.float64 else F32),
                                               C.c_int64(R.shape[1]), C.c_double(s)))
@@ -241,6 +264,18 @@ class Handle:
         self._ck(self.lib.sgv_spmm(self.h, C.c_int(cohort), _dp(Xf), _dp(Y), C.c_int(nrhs), C.c_double(alpha),
                                    C.c_double(beta)))
         return Y.T.reshape(X.shape).copy()
+
+    def spmm_stage(self, X):
+        X = _f64(X)
+        nrhs = 1 if X.ndim == 1 else X.shape[1]
+        Xf = np.ascontiguousarray(X.reshape(self.M, nrhs).T)
+        self._ck(self.lib.sgv_spmm_stage(self.h, _dp(Xf), C.c_int(nrhs)))
+        return nrhs
+
+    def spmm_run(self, cohort, nrhs, alpha=1.0, beta=0.0):
+        Y = np.zeros((nrhs, self.M))
+        self._ck(self.lib.sgv_spmm_run(self.h, C.c_int(cohort), _dp(Y), C.c_int(nrhs), C.c_double(alpha), C.c_double(beta)))
+        return Y.T.copy() if nrhs == 2 else Y[0].copy()
 
     def spmm_bench(self, cohort, reps):
         ms = C.c_float()

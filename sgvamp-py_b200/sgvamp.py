@@ -28,6 +28,7 @@ import scipy.optimize
 import scipy.sparse
 
 import sgv_native as nat
+import shard as shd
 
 
 class DeviceDIA:
@@ -113,7 +114,7 @@ class _ProbeSource:
 
 class VAMP:
     def __init__(self, N, Nt, M, K, rho, gamw, gam1, a, prior_vars, prior_probs, out_dir, out_name, comm=None,
-                 device=0, stream=None):
+                 device=0, stream=None, shard=None, shard_rows=None, halo=True):
         self.eps = 1e-32
         self.N = N
         self.Nt = Nt
@@ -135,11 +136,23 @@ class VAMP:
             raise Exception("communicator size must equal the number of cohorts K")
         self.rank = self.comm.Get_rank() if self.rank_mode else 0
         self.my_cohorts = [self.rank] if self.rank_mode else list(range(self.K))
+        # marker-row sharding over GPUs (no reference counterpart): this process owns rows [lo, hi)
+        self.shard = shard if shard is not None else shd.SoloShard()
+        if self.shard.world > 1 and self.rank_mode:
+            raise Exception("row sharding and rank-per-cohort mode cannot be combined")
+        self.bounds = list(shard_rows) if shard_rows is not None else shd.partition_rows(self.M, self.shard.world)
+        self.lo, self.hi = self.bounds[self.shard.rank]
+        self.Ml = self.hi - self.lo
+        self.root = self.shard.rank == 0
         self.out_dir, self.out_name = out_dir, out_name
-        if out_dir is not None:
+        if out_dir is not None and self.root:
             self.setup_io(out_dir, out_name)
         self.handle = nat.Handle(device=device, stream=stream)
-        self.handle.configure(self.M, self.K)
+        if self.shard.world == 1:
+            self.handle.configure(self.M, self.K)
+        else:
+            self.handle.configure_part(self.M, self.K, self.shard.rank, self.shard.world, self.lo, self.hi, halo)
+            shd.attach_peers(self.handle, self.shard)
         self.handle.set_weights(self.a)
         self._ld_loaded = [False] * self.K
         self._keep = []
@@ -190,6 +203,18 @@ class VAMP:
             assert s == 0.0, "device-resident LD must already be regularised"
             h.adopt_dense(cohort, R.ptr, R.ld)
             self._keep.append(R)
+        elif scipy.sparse.issparse(R) and self.shard.world > 1:
+            R = R.tocsr()
+            if R.shape == (self.M, self.M):
+                R = R[self.lo:self.hi]                 # global matrix given: keep this rank's rows
+            if R.shape != (self.Ml, self.M):
+                raise Exception("LD shard shape %s does not match rows [%d,%d) of M=%d" % (R.shape, self.lo, self.hi, self.M))
+            indptr, indices = R.indptr.astype(np.int64), R.indices.astype(np.int32)
+            wmax = max(self.shard.allgather(shd.local_bandwidth(indptr, indices, self.lo)))
+            if min(hi_ - lo_ for lo_, hi_ in self.bounds) < wmax:
+                raise Exception("row shards are shorter than the LD half-bandwidth %d" % wmax)
+            h.set_bandwidth_hint(wmax)
+            h._ck(h.upload_csr(cohort, indptr, indices, R.data, s=s, layout=nat.LAYOUT_DIA))
         elif scipy.sparse.issparse(R):
             R = R.tocsr()
             if R.shape != (self.M, self.M):

@@ -1,0 +1,118 @@
+"""Row-partitioned multi-GPU plumbing (one process or thread per GPU).
+
+The data path needs no host collective: every reduction of the solver is completed across ranks
+inside the CUDA kernels through peer memory (include/sgvamp_b200.h, "multi-GPU").  The host side
+only has to (1) split the marker rows, (2) hand every rank the others' arena handles once, and
+(3) gather the per-rank output slices at the end.  Those three things are what this module does;
+it is pure host logic and is tested on CPU with gloo (tests/test_shard_cpu.py).
+
+A ``Shard`` offers ``rank``, ``world``, ``allgather(obj) -> list`` and ``barrier()``.
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+
+
+def partition_rows(M, world, align=4):
+    """Contiguous, balanced row ranges; interior boundaries are multiples of ``align``."""
+    b = [0]
+    for r in range(1, world):
+        x = (M * r // world) // align * align
+        b.append(max(x, b[-1]))
+    b.append(M)
+    return [(b[r], b[r + 1]) for r in range(world)]
+
+
+def slice_rows_csr(R, lo, hi):
+    """Rows [lo, hi) of a scipy CSR matrix with GLOBAL column indices (what a rank uploads)."""
+    sub = R[lo:hi]
+    return sub.indptr.astype(np.int64), sub.indices.astype(np.int32), sub.data
+
+
+def local_bandwidth(indptr, indices, lo):
+    """max |col - row| over the local rows (global column indices)."""
+    if len(indices) == 0:
+        return 0
+    rows = np.repeat(np.arange(len(indptr) - 1, dtype=np.int64) + lo, np.diff(indptr))
+    return int(np.abs(indices.astype(np.int64) - rows).max())
+
+
+def gather_rows(shard, local, bounds):
+    """Concatenate per-rank row slices (any leading dims, rows last) into the global array."""
+    parts = shard.allgather(np.ascontiguousarray(local))
+    return np.concatenate(parts, axis=-1)
+
+
+class SoloShard:
+    rank, world = 0, 1
+
+    def allgather(self, obj):
+        return [obj]
+
+    def barrier(self):
+        pass
+
+
+class TorchShard:
+    """torch.distributed as the plumbing (NCCL or gloo default group); objects travel pickled."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def allgather(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+
+class ThreadShard:
+    """In-process ranks (one host thread per GPU) for tests: barrier-based allgather."""
+
+    class _Group:
+        def __init__(self, world):
+            self.world = world
+            self.bar = threading.Barrier(world)
+            self.slots = [None] * world
+
+    def __init__(self, group, rank):
+        self.g, self.rank, self.world = group, rank, group.world
+
+    @staticmethod
+    def make(world):
+        g = ThreadShard._Group(world)
+        return [ThreadShard(g, r) for r in range(world)]
+
+    def allgather(self, obj):
+        self.g.slots[self.rank] = obj
+        self.g.bar.wait()
+        out = list(self.g.slots)
+        self.g.bar.wait()
+        return out
+
+    def barrier(self):
+        self.g.bar.wait()
+
+
+def attach_peers(handle, shard):
+    """Give every rank a mapping of every other rank's symmetric arena (CUDA IPC between
+    processes, direct peer access between threads of one process)."""
+    if shard.world == 1:
+        return
+    if isinstance(shard, ThreadShard):
+        peers = shard.allgather((handle, handle.M))
+        for q, (h, _rows) in enumerate(peers):
+            if q != shard.rank:
+                handle.peer_attach_local(q, h)
+    else:
+        peers = shard.allgather((handle.ipc_export(), handle.M))
+        for q, (hb, rows) in enumerate(peers):
+            if q != shard.rank:
+                handle.ipc_import(q, hb, rows)
+    shard.barrier()
