@@ -64,45 +64,55 @@ def make_probes(iterations, M, seed):
 # ------------------------------------------------------------------------------------------------
 # synthetic banded LD + XTy on the device (torch as a data-generation utility)
 # ------------------------------------------------------------------------------------------------
-def build_problem(torch, M, w, seed, dev):
+def build_problem(torch, M, w, seed, dev, lo=0, hi=None):
+    """Rows [lo, hi) of the workload: DIA band of Rused (fp32, device), r (host), x0 (host, global)."""
     import ldgen
     t0 = time.time()
-    ldb = (M + 31) // 32 * 32
+    hi = M if hi is None else hi
+    Ml = hi - lo
+    ldb = (Ml + 31) // 32 * 32
     band = torch.zeros((2 * w + 1, ldb), device=dev, dtype=torch.float32)
-    b, noise = ldgen.banded_dia_device(torch, M, w, 0, M, seed, dev, N_ld=N_LD)
-    band[:, :M] = b
+    b, noise = ldgen.banded_dia_device(torch, M, w, lo, hi, seed, dev, N_ld=N_LD)
+    band[:, :Ml] = b
     del b
     band *= (1.0 - S_REG)                       # Rused = (1-s) R + s I  (src/main.py:265)
-    band[w, :M] += S_REG
-    x0 = torch.from_numpy(ldgen.causal_effects(M, n_gwas(M), LAM_TRUE, H2, seed)).to(dev)
+    band[w, :Ml] += S_REG
+    x0_host = ldgen.causal_effects(M, n_gwas(M), LAM_TRUE, H2, seed)
     # r = Rused x0 + n,  n ~ N(0, (1-h2) Rused): the summary-statistic form of the reference recipe
     # (simulation/sim_gen_phen_mult.py:39-55: r = X^T y, R = X^T X  =>  r ~ N(R x0, (1-h2) R))
-    xp = torch.zeros(M + 2 * w, device=dev, dtype=torch.float64)
-    xp[w:w + M] = x0
-    r = torch.zeros(M, device=dev, dtype=torch.float64)
+    xp_host = np.zeros(Ml + 2 * w)
+    a0, a1 = max(0, lo - w), min(M, hi + w)
+    xp_host[a0 - (lo - w): a1 - (lo - w)] = x0_host[a0:a1]
+    xp = torch.from_numpy(xp_host).to(dev)
+    r = torch.zeros(Ml, device=dev, dtype=torch.float64)
     for d in range(2 * w + 1):
-        r += band[d, :M].to(torch.float64) * xp[d:d + M]
+        r += band[d, :Ml].to(torch.float64) * xp[d:d + Ml]
     g = torch.Generator(device=dev)
     g.manual_seed(seed * 31 + 17)
-    z = torch.randn((M,), generator=g, device=dev, dtype=torch.float64)
+    z = torch.randn((M,), generator=g, device=dev, dtype=torch.float64)[lo:hi]
     r += float(np.sqrt(1.0 - H2)) * (float(np.sqrt(1.0 - S_REG)) * noise + float(np.sqrt(S_REG)) * z)
     torch.cuda.synchronize()
-    return band, ldb, r.cpu().numpy(), x0.cpu().numpy(), time.time() - t0
+    return band, ldb, r.cpu().numpy(), x0_host, time.time() - t0
 
 
-def band_to_host_csr(torch, band, M, w, pinned=True):
-    """CSR (fp32 data, int32 indices) of the banded matrix in (pinned) host memory - the host-side
-    input of the end-to-end leg."""
-    nnz = M * (2 * w + 1) - w * (w + 1)
+def band_to_host_csr(torch, band, M, w, lo=0, hi=None, pinned=True):
+    """CSR (fp32 data, int32 GLOBAL column indices) of rows [lo, hi) of the banded matrix in (pinned)
+    host memory - the host-side input of the end-to-end leg."""
+    hi = M if hi is None else hi
+    Ml = hi - lo
+    rows_all = np.arange(lo, hi, dtype=np.int64)
+    cnt = np.minimum(rows_all + w, M - 1) - np.maximum(rows_all - w, 0) + 1
+    nnz = int(cnt.sum())
     data = torch.empty(nnz, dtype=torch.float32, pin_memory=pinned)
     idx = torch.empty(nnz, dtype=torch.int32, pin_memory=pinned)
-    indptr = np.zeros(M + 1, dtype=np.int64)
+    indptr = np.zeros(Ml + 1, dtype=np.int64)
+    indptr[1:] = np.cumsum(cnt)
     dd = torch.arange(2 * w + 1, device=band.device)
     pos = 0
     step = 32768
-    for i0 in range(0, M, step):
-        i1 = min(M, i0 + step)
-        rows = torch.arange(i0, i1, device=band.device)
+    for i0 in range(0, Ml, step):
+        i1 = min(Ml, i0 + step)
+        rows = torch.arange(lo + i0, lo + i1, device=band.device)
         cols = rows[:, None] + (dd[None, :] - w)
         ok = (cols >= 0) & (cols < M)
         vals = band[:, i0:i1].t()[ok]
@@ -110,13 +120,12 @@ def band_to_host_csr(torch, band, M, w, pinned=True):
         n = vals.numel()
         data[pos:pos + n].copy_(vals)
         idx[pos:pos + n].copy_(cc)
-        indptr[i0 + 1:i1 + 1] = pos + torch.cumsum(ok.sum(dim=1), 0).cpu().numpy()
         pos += n
     assert pos == nnz
     torch.cuda.synchronize()
     import scipy.sparse
     R = scipy.sparse.csr_matrix((data.numpy(), idx.numpy(), indptr.astype(np.int32) if nnz < 2**31 else indptr),
-                                shape=(M, M))
+                                shape=(Ml, M))
     R.has_canonical_format = True
     return R, (data, idx)
 

@@ -17,6 +17,9 @@ void sgv_set_error(const char* fmt, ...) {
 extern "C" const char* sgv_last_error(void) { return g_err; }
 extern "C" int sgv_version(void) { return 100; }
 
+__global__ void k_resolve(RedCtx rc);
+__global__ void k_scale_copy(int64_t M, const double* __restrict__ src, double* __restrict__ dst, double scale);
+
 extern "C" int sgv_create(int device, void* stream, sgv_handle* out) {
     SGV_CHECK(out != nullptr, "out is null");
     int ndev = 0;
@@ -52,6 +55,13 @@ extern "C" int sgv_create(int device, void* stream, sgv_handle* out) {
     SGV_CUDA(cudaEventCreate(&c->ev_a));
     SGV_CUDA(cudaEventCreate(&c->ev_b));
     SGV_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    {   // load every kernel now (lazy loading inside the solver loop synchronises the device)
+        cudaFuncAttributes fa;
+        SGV_CUDA(cudaFuncGetAttributes(&fa, k_resolve));
+        SGV_CUDA(cudaFuncGetAttributes(&fa, k_scale_copy));
+        SGV_TRY(sgv_preload_spmm());
+        SGV_TRY(sgv_preload_vamp());
+    }
     *out = c;
     return 0;
 }
@@ -156,6 +166,7 @@ extern "C" int sgv_profile_read(sgv_handle c, double* total_ms, int64_t* launche
 // rank order (bit-identical on all ranks) and applies the state transition.  A bounded spin: on
 // time-out the error flag is raised and both CG columns are marked done so that nothing hangs.
 __global__ void k_resolve(RedCtx rc) {
+    if (rc.skip_if_done && rc.st->done[0] && rc.st->done[1]) return;   // nobody published: the producers exited early too
     Inbox* me = rc.inbox[rc.rank];
     const int slot = (int)(rc.seq % SGV_INBOX_SLOTS);
     const int lane = threadIdx.x;
@@ -170,10 +181,13 @@ __global__ void k_resolve(RedCtx rc) {
             __nanosleep(64);
         }
     }
-    good = __all_sync(0xffffffffu, good);
+    const unsigned bad = __ballot_sync(0xffffffffu, !good);
     if (lane == 0) {
-        if (!good) {
-            rc.st->error = 1;
+        if (bad) {
+            if (!rc.st->error) {
+                rc.st->error = (int)bad;
+                rc.st->err_seq = rc.seq;
+            }
             rc.st->done[0] = rc.st->done[1] = 1;
             return;
         }
@@ -274,7 +288,13 @@ extern "C" int sgv_configure_part(sgv_handle c, int64_t M, int K, int rank, int 
         SGV_CUDA(cudaMalloc(&c->snap[i], vb));
         SGV_CUDA(cudaEventCreateWithFlags(&c->snap_ev[i], cudaEventDisableTiming));
     }
-    SGV_TRY(sgv_ensure_partials(c, (int64_t)c->sm_count * 16));
+    // Everything the solver loop needs is allocated here: a cudaMalloc / cudaFree inside the loop is a
+    // device-wide synchronisation, which would deadlock against another rank's resolve kernel spinning
+    // on the same device (ranks sharing a GPU) and stall the pipeline otherwise.
+    SGV_CUDA(cudaMalloc(&c->truth, vb));
+    SGV_CUDA(cudaMemsetAsync(c->truth, 0, vb, c->stream));
+    c->truth_set = false;
+    SGV_TRY(sgv_ensure_partials(c, std::max<int64_t>((int64_t)c->sm_count * 16, (Ml + 7) / 8 + 1)));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -335,6 +355,7 @@ extern "C" int sgv_partition_info(sgv_handle c, int64_t* M, int64_t* Ml, int64_t
 static int vec_ptr(sgv_ctx* c, int cohort, int which, double** p) {
     SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
     SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort index %d out of range [0,%d)", cohort, c->K);
+    SGV_CUDA(cudaSetDevice(c->device));
     Cohort& co = c->coh[cohort];
     switch (which) {
         case SGV_VEC_XHAT1: *p = c->xhat1; break;
@@ -359,6 +380,7 @@ extern "C" int sgv_set_xty(sgv_handle c, int cohort, const double* r) {
 
 extern "C" int sgv_reset_state(sgv_handle c) {
     SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
+    SGV_CUDA(cudaSetDevice(c->device));
     const size_t vb = (size_t)c->Ml * sizeof(double);
     SGV_CUDA(cudaMemsetAsync(c->xhat1, 0, vb, c->stream));
     for (int k = 0; k < c->K; ++k) {
@@ -452,6 +474,7 @@ extern "C" int sgv_set_weights(sgv_handle c, const double* a) {
 // ---------------------------------------------------------------------------------------------
 extern "C" int sgv_spmm(sgv_handle c, int cohort, const double* X, double* Y, int nrhs, double alpha, double beta) {
     SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
+    SGV_CUDA(cudaSetDevice(c->device));
     SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
     SGV_CHECK(nrhs == 1 || nrhs == 2, "nrhs must be 1 or 2");
     Cohort& co = c->coh[cohort];
@@ -474,6 +497,7 @@ extern "C" int sgv_spmm(sgv_handle c, int cohort, const double* X, double* Y, in
 // (barrier), sgv_spmm_run multiplies.
 extern "C" int sgv_spmm_stage(sgv_handle c, const double* X, int nrhs) {
     SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
+    SGV_CUDA(cudaSetDevice(c->device));
     const int64_t M = c->Ml;
     std::vector<double2> h(M);
     for (int64_t i = 0; i < M; ++i) h[i] = make_double2(X[i], nrhs == 2 ? X[M + i] : 0.0);
@@ -484,6 +508,7 @@ extern "C" int sgv_spmm_stage(sgv_handle c, const double* X, int nrhs) {
 
 extern "C" int sgv_spmm_run(sgv_handle c, int cohort, double* Y, int nrhs, double alpha, double beta) {
     SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
+    SGV_CUDA(cudaSetDevice(c->device));
     SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
     Cohort& co = c->coh[cohort];
     const int64_t M = c->Ml;

@@ -207,6 +207,7 @@ static int check_cohort(sgv_ctx* c, int cohort) {
     SGV_CHECK(c != nullptr, "null handle");
     SGV_CHECK(c->M > 0, "sgv_configure has not been called");
     SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort index %d out of range [0,%d)", cohort, c->K);
+    SGV_CUDA(cudaSetDevice(c->device));
     return 0;
 }
 

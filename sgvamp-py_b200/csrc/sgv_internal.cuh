@@ -45,7 +45,8 @@ struct CgState {
     int    done[2], iters[2], info[2], zero_b[2];
     int    step;           // CG updates performed (0 -> p = r)
     int    maxit;
-    int    error;          // != 0: a cross-rank wait timed out
+    int    error;          // != 0: a cross-rank wait timed out; bit q set = rank q's partial never arrived
+    unsigned long long err_seq;   // sequence number of the reduction that timed out
 };
 
 // Cross-rank reduction mailbox.  Lives at the start of every rank's symmetric arena; rank r
@@ -72,6 +73,7 @@ struct RedCtx {
     Inbox*             inbox[SGV_MAX_RANKS];   // every rank's inbox, mapped into this rank's address space
     unsigned long long seq;
     int                world, rank;
+    int                skip_if_done;   // the reducing kernel exits early once both CG columns are done: so does the resolve
     ApplyArgs          ap;
 };
 
@@ -143,6 +145,7 @@ struct sgv_ctx {
     double*      r1_all = nullptr;   // K x Ml, cohort k's r1 at r1_all + k*Ml (coh[k].r1 aliases it)
     double*      xhat1 = nullptr;
     double*      truth = nullptr;
+    bool         truth_set = false;
     // symmetric arena (CG work vectors shared by all cohorts + the inbox), peer-mapped for world > 1
     char*        arena = nullptr;
     size_t       arena_bytes = 0;
@@ -212,6 +215,8 @@ struct SpmmArgs {
 int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, double gamw, double gam2, int check_done,
                     int fused_p);
 size_t sgv_dia_smem_bytes(int64_t w, int rw, int s);
+int    sgv_preload_spmm();   // load all kernels of the TU on the current device (see spmm.cu)
+int    sgv_preload_vamp();
 bool   sgv_dia_feasible(int64_t w);
 // ld_formats.cu
 void sgv_ld_free(LdMatrix& ld);

@@ -393,11 +393,6 @@ template <int RW, int S, int EPI, int PF, int MINB>
 static int launch_dia(sgv_ctx* c, const LdMatrix& ld, SpmmArgs& a) {
     constexpr int TR = 128 * RW;
     const size_t smem = sgv_dia_smem_bytes(ld.w, RW, S);
-    static size_t configured = 0;
-    if (smem > configured) {
-        SGV_CUDA(cudaFuncSetAttribute(k_spmm_dia<RW, S, EPI, PF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
     const unsigned grid = (unsigned)((ld.ldb + TR - 1) / TR);
     SGV_TRY(sgv_ensure_partials(c, grid));
     a.rc.partials = c->partials;
@@ -444,6 +439,35 @@ static int launch_epi(sgv_ctx* c, Cohort& co, SpmmArgs& a) {
     return -1;
 }
 
+// Load every SpMM kernel on the current device and raise its dynamic shared-memory limit once, at
+// handle creation.  Lazy module loading and cudaFuncSetAttribute synchronise the device; done inside
+// the solver loop they would deadlock against another rank's resolve kernel spinning on the same GPU.
+#define DIA_SMEM_LIMIT (200 * 1024)
+template <int RW, int S, int EPI>
+static int preload_dia() {
+    SGV_CUDA(cudaFuncSetAttribute(k_spmm_dia<RW, S, EPI, DIA_PF, DIA_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  DIA_SMEM_LIMIT));
+    return 0;
+}
+template <int EPI>
+static int preload_epi() {
+    SGV_TRY((preload_dia<DIA_BIG_RW, DIA_BIG_S, EPI>()));
+    SGV_TRY((preload_dia<1, 8, EPI>()));
+    cudaFuncAttributes fa;
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_panel_finish<EPI>));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_spmm_csr<EPI>));
+    return 0;
+}
+int sgv_preload_spmm() {
+    SGV_TRY(preload_epi<EPI_Q>());
+    SGV_TRY(preload_epi<EPI_RESID>());
+    SGV_TRY(preload_epi<EPI_STATS>());
+    SGV_TRY(preload_epi<EPI_PLAIN>());
+    cudaFuncAttributes fa;
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_spmm_panel<4, 2>));
+    return 0;
+}
+
 static double2* arena_vec(const sgv_ctx* c, int q, int vec) {
     const PeerView& pv = c->peer[q];
     const size_t off = vec == VEC_XX ? arena_off_xx(pv.Ml) : arena_off_pp(pv.Ml, vec - VEC_PP0);
@@ -485,7 +509,10 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, doub
     a.M = c->Ml;
     a.check_done = check_done;
     const int kind = epi == EPI_Q ? AP_PQ : epi == EPI_RESID ? AP_RESID : AP_STATS;
-    if (epi != EPI_PLAIN) a.rc = sgv_red_begin(c, kind, 2, 0);
+    if (epi != EPI_PLAIN) {
+        a.rc = sgv_red_begin(c, kind, 2, 0);
+        a.rc.skip_if_done = check_done;
+    }
     a.rc.st = c->cg;
     int rc;
     if (c->prof) {

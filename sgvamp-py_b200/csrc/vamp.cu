@@ -8,6 +8,18 @@
 static int check_ready(sgv_ctx* c) {
     SGV_CHECK(c != nullptr, "null handle");
     SGV_CHECK(c->M > 0, "sgv_configure has not been called");
+    SGV_CUDA(cudaSetDevice(c->device));   // several handles (one per GPU) may be driven from one process
+    return 0;
+}
+
+// Read the device-resident reduction / CG state back (one small pinned copy) and surface a
+// cross-rank time-out as an error instead of a hang.
+static int fetch_state(sgv_ctx* c) {
+    SGV_CUDA(cudaMemcpyAsync(c->cg_host, c->cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    const CgState* hs = c->cg_host;
+    SGV_CHECK(hs->error == 0, "cross-rank reduction %llu timed out on rank %d of %d (missing-rank mask 0x%x)",
+              (unsigned long long)hs->err_seq, c->rank, c->world, hs->error);
     return 0;
 }
 
@@ -85,9 +97,8 @@ extern "C" int sgv_denoise(sgv_handle c, const double* gam1s, double rho, int da
     c->launches++;
     SGV_CUDA(cudaGetLastError());
     SGV_TRY(sgv_red_end(c, rc));
-    SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    SGV_CUDA(cudaStreamSynchronize(c->stream));
-    *dfac_mean = c->host_scal[0] / (double)c->M;
+    SGV_TRY(fetch_state(c));
+    *dfac_mean = c->cg_host->stats[0] / (double)c->M;
     return 0;
 }
 
@@ -172,9 +183,8 @@ extern "C" int sgv_prior_em(sgv_handle c, const double* gam1s, int maxit, double
         c->launches++;
         SGV_CUDA(cudaGetLastError());
         SGV_TRY(sgv_red_end(c, rc));
-        SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        SGV_CUDA(cudaStreamSynchronize(c->stream));
-        const double* t = c->host_scal;
+        SGV_TRY(fetch_state(c));
+        const double* t = c->cg_host->stats;
         double wsum = 0.0;
         for (int q = 0; q < p.K; ++q) wsum += p.a[q] * t[q];
         const double lam_new = wsum / asum / (double)c->M;                          // :134
@@ -284,11 +294,10 @@ extern "C" int sgv_lagrangian(sgv_handle c, const double* gam1s, const double* x
     c->launches += 2;
     SGV_CUDA(cudaGetLastError());
     SGV_TRY(sgv_red_end(c, rc2));
-    SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats + 8, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    SGV_TRY(fetch_state(c));
     double osum = 0.0;
     for (int l = 0; l < L; ++l) {
-        y[l] = c->host_scal[l] + (omega0[l] - 1) / x[l] + x[L];                     // :158
+        y[l] = c->cg_host->stats[8 + l] + (omega0[l] - 1) / x[l] + x[L];                     // :158
         osum += x[l];
     }
     y[L] = osum - 1.0;                                                               // :159
@@ -315,10 +324,10 @@ k_metrics(int64_t M, const double* __restrict__ xhat1, const double* __restrict_
 extern "C" int sgv_metrics(sgv_handle c, const double* x0, double* dots) {
     SGV_TRY(check_ready(c));
     if (x0 != nullptr) {
-        if (!c->truth) SGV_CUDA(cudaMalloc(&c->truth, c->Ml * sizeof(double)));
         SGV_CUDA(cudaMemcpyAsync(c->truth, x0, c->Ml * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        c->truth_set = true;
     }
-    SGV_CHECK(c->truth != nullptr, "truth vector not uploaded yet");
+    SGV_CHECK(c->truth_set, "truth vector not uploaded yet");
     const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 4);
     SGV_TRY(sgv_ensure_partials(c, grid + 1));
     RedCtx rc = sgv_red_begin(c, AP_STATS, 4, 0);
@@ -326,9 +335,8 @@ extern "C" int sgv_metrics(sgv_handle c, const double* x0, double* dots) {
     c->launches++;
     SGV_CUDA(cudaGetLastError());
     SGV_TRY(sgv_red_end(c, rc));
-    SGV_CUDA(cudaMemcpyAsync(c->host_scal, c->cg->stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    SGV_CUDA(cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < 4; ++i) dots[i] = c->host_scal[i];
+    SGV_TRY(fetch_state(c));
+    for (int i = 0; i < 4; ++i) dots[i] = c->cg_host->stats[i];
     return 0;
 }
 
@@ -442,6 +450,21 @@ extern "C" int sgv_update_r1(sgv_handle c, int cohort, double alpha2) {
     return 0;
 }
 
+int sgv_preload_vamp() {
+    cudaFuncAttributes fa;
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_denoise));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_em));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_min_r2));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_lagrangian));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_metrics));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_lmmse_setup));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_p_update));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_cg_update));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_lmmse_post));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_update_r1));
+    return 0;
+}
+
 extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const int8_t* probe, sgv_lmmse_out* out) {
     SGV_TRY(check_ready(c));
     SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
@@ -483,21 +506,17 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
                 SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, VEC_PP0, c->qq, in->gamw, in->gam2, 1, 0));
             }
             RedCtx rc = sgv_red_begin(c, AP_CGUPDATE, 2, 0);
+            rc.skip_if_done = 1;
             k_cg_update<<<vgrid, 256, 0, c->stream>>>(M, c->xx, c->rr, pcur, c->qq, rc);
             c->launches++;
             SGV_TRY(sgv_red_end(c, rc));
         }
         launched += nb;
-        SGV_CUDA(cudaMemcpyAsync(hs, c->cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
-        SGV_CUDA(cudaStreamSynchronize(c->stream));
-        SGV_CHECK(hs->error == 0, "cross-rank reduction timed out (rank %d of %d)", c->rank, c->world);
+        SGV_TRY(fetch_state(c));
         if (hs->done[0] && hs->done[1]) break;
         batch = std::min(16, batch * 2);
     }
-    if (in->cg_maxit == 0 || launched == 0) {
-        SGV_CUDA(cudaMemcpyAsync(hs, c->cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
-        SGV_CUDA(cudaStreamSynchronize(c->stream));
-    }
+    if (in->cg_maxit == 0 || launched == 0) SGV_TRY(fetch_state(c));
     out->cg_iters[0] = hs->iters[0];
     out->cg_iters[1] = hs->iters[1];
     // a column that ran out of iterations without ever passing the test reports maxiter (scipy)
@@ -515,9 +534,7 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
         passes++;
     }
     SGV_CUDA(cudaGetLastError());
-    SGV_CUDA(cudaMemcpyAsync(hs, c->cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
-    SGV_CUDA(cudaStreamSynchronize(c->stream));
-    SGV_CHECK(hs->error == 0, "cross-rank reduction timed out (rank %d of %d)", c->rank, c->world);
+    SGV_TRY(fetch_state(c));
     out->xhat2_R_xhat2 = in->learn_gamw ? hs->stats[0] : 0.0;
     out->u_R_sigma2u = in->learn_gamw ? hs->stats[1] : 0.0;
     out->u_sigma2u = hs->stats[2];

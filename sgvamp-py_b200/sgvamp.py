@@ -144,6 +144,8 @@ class VAMP:
         self.lo, self.hi = self.bounds[self.shard.rank]
         self.Ml = self.hi - self.lo
         self.root = self.shard.rank == 0
+        self.halo = bool(halo)
+        self.device = device
         self.out_dir, self.out_name = out_dir, out_name
         if out_dir is not None and self.root:
             self.setup_io(out_dir, out_name)
@@ -209,12 +211,30 @@ class VAMP:
                 R = R[self.lo:self.hi]                 # global matrix given: keep this rank's rows
             if R.shape != (self.Ml, self.M):
                 raise Exception("LD shard shape %s does not match rows [%d,%d) of M=%d" % (R.shape, self.lo, self.hi, self.M))
+            if not R.has_canonical_format:
+                R = R.copy()
+                R.sum_duplicates()
             indptr, indices = R.indptr.astype(np.int64), R.indices.astype(np.int32)
-            wmax = max(self.shard.allgather(shd.local_bandwidth(indptr, indices, self.lo)))
-            if min(hi_ - lo_ for lo_, hi_ in self.bounds) < wmax:
-                raise Exception("row shards are shorter than the LD half-bandwidth %d" % wmax)
-            h.set_bandwidth_hint(wmax)
-            h._ck(h.upload_csr(cohort, indptr, indices, R.data, s=s, layout=nat.LAYOUT_DIA))
+            if self.halo:                              # banded: neighbours supply w halo entries of the input vector
+                wmax = max(self.shard.allgather(shd.local_bandwidth(indptr, indices, self.lo)))
+                if min(hi_ - lo_ for lo_, hi_ in self.bounds) < wmax:
+                    raise Exception("row shards are shorter than the LD half-bandwidth %d" % wmax)
+                h.set_bandwidth_hint(wmax)
+                h._ck(h.upload_csr(cohort, indptr, indices, R.data, s=s, layout=nat.LAYOUT_DIA))
+            else:                                      # block-diagonal sharded by block: no coupling across shards
+                Rl = R[:, self.lo:self.hi].tocsr()
+                if Rl.nnz != R.nnz:
+                    raise Exception("LD couples markers across the shard boundary of rank %d; shard block-diagonal LD "
+                                    "at block boundaries (shard.partition_blocks) or use halo=True" % self.shard.rank)
+                Rl.sort_indices()
+                rc = h.upload_csr(cohort, Rl.indptr, Rl.indices, Rl.data, s=s, layout=lay)
+                if rc == -3:
+                    Rl = Rl.tolil()
+                    Rl.setdiag(Rl.diagonal())
+                    Rl = Rl.tocsr()
+                    Rl.sort_indices()
+                    rc = h.upload_csr(cohort, Rl.indptr, Rl.indices, Rl.data, s=s, layout=lay)
+                h._ck(rc)
         elif scipy.sparse.issparse(R):
             R = R.tocsr()
             if R.shape != (self.M, self.M):
@@ -246,7 +266,7 @@ class VAMP:
     def _one_marker(self, rs, gam1s):
         aux = getattr(self, "_aux", None)
         if aux is None:
-            aux = self._aux = nat.Handle(device=0)
+            aux = self._aux = nat.Handle(device=self.device)
             aux.configure(1, self.K)
         aux.set_weights(self.a)
         self._push_prior(aux)
@@ -321,10 +341,10 @@ class VAMP:
     # ------------------------------------------------------------------------------------------
     def infer(self, R, r, iterations, x0=None, cg_maxit=500, em_prior_maxit=100, learn_gamw=True, lmmse_damp=True,
               prior_update=None, update_prior_from=1, *, s=0.0, probes=None, layout="auto", write_outputs=True,
-              iter_hook=None):
+              iter_hook=None, gather_outputs=True):
         M, K, Nt, rho = self.M, self.K, self.Nt, self.rho
         h = self.handle
-        rank = self.rank
+        rank = self.rank if self.shard.world == 1 else self.shard.rank   # only gates logging / rank-per-cohort mode
         mine = self.my_cohorts
         Rs = list(R) if isinstance(R, (list, tuple)) else [R]
         rs = list(r) if isinstance(r, (list, tuple)) else [r]
@@ -340,9 +360,11 @@ class VAMP:
                 self.load_ld(k, Rs[idx], s=s, layout=layout)
             elif not self._ld_loaded[k]:
                 raise Exception("no LD matrix for cohort %d" % k)
-            h.set_xty(k, np.asarray(rs[idx], dtype=np.float64).reshape(M))
+            h.set_xty(k, self._local(rs[idx]))
         h.reset_state()                                                 # :199-217
         write = write_outputs and self.out_dir is not None
+        sharded = self.shard.world > 1
+        r1_keep = {}
         worker = _Worker()
         tm = self.timers = dict(prior=0.0, denoise=0.0, lmmse=0.0, host_tail=0.0)
         pc = time.perf_counter
@@ -352,8 +374,7 @@ class VAMP:
         sqrtNt = np.sqrt(Nt)
         truth = None
         if x0 is not None:
-            truth = np.asarray(x0, dtype=np.float64).reshape(M)
-            tn = None
+            truth = self._local(x0)
         gam1 = [np.float64(self.gam1)] * K
         gamw = [self.gamw] * K
         alpha1 = [np.float64(0.0)] * K
@@ -367,6 +388,8 @@ class VAMP:
 
         if rank == 0:
             logging.debug(f"a = {self.a}")
+        h.sync()
+        self.shard.barrier()       # every rank's state is initialised before any kernel touches peer memory
         for it in range(iterations):
             if iter_hook is not None:
                 iter_hook(it)
@@ -430,6 +453,8 @@ class VAMP:
                     u = probes(k, it, M)
                 else:
                     u = np.asarray(probes)[k, it]
+                if sharded and len(u) == M:
+                    u = u[self.lo:self.hi]                               # every rank draws the same global probe
                 out = h.lmmse(k, float(gamw[k]), float(gam2), float(a1), float(rho), cg_maxit, lmmse_damp, learn_gamw,
                               it == 0, u)
                 for c in range(2):
@@ -455,7 +480,7 @@ class VAMP:
                 iters_it[k] = (out.cg_iters[0], out.cg_iters[1])
                 info_it[k] = (out.cg_info[0], out.cg_info[1])
                 passes_it += out.spmm_passes
-                if self.out_dir is not None and write_outputs:
+                if self.out_dir is not None and write_outputs and self.root:
                     self.write_params_to_file(row, k)                    # :377
             t_lm = pc()
             tm["lmmse"] += t_lm - t_dn
@@ -463,8 +488,10 @@ class VAMP:
             def drain(it=it, slot=slot):
                 h.wait_copies()
                 xh = pin_x[slot][0].copy()
-                xhat1s[it] = xh.reshape(M, 1)
-                if write:
+                xhat1s[it] = xh.reshape(-1, 1)
+                if write and sharded:                                    # dumps are assembled after the loop
+                    r1_keep[it] = [pin_r[slot][idx].copy() for idx in range(len(mine))]
+                elif write:
                     if rank == 0:
                         (xh / sqrtNt).tofile(os.path.join(self.out_dir, "%s_xhat_it_%d.bin" % (self.out_name, it)))
                     for idx, k in enumerate(mine):
@@ -479,7 +506,7 @@ class VAMP:
                 if rank == 0:
                     logging.debug(f"Alignment(xhat1, x0) = {alignment:0.9f} \n")
                     logging.debug(f"L2_error(xhat1, x0) = {l2:0.9f} \n")
-                    if self.out_dir is not None and write_outputs:
+                    if self.out_dir is not None and write_outputs and self.root:
                         self.write_metrics_to_file([it, alignment, l2])
                 self.history.setdefault("metrics", []).append((it, alignment, l2))
             self.history["rows"].append(rows_it)
@@ -495,16 +522,42 @@ class VAMP:
         h.sync()
         worker.close()
         self.gam1_final, self.gamw_final = gam1, gamw
+        if sharded and gather_outputs:
+            # the data path has no host collective; the per-rank output slices are assembled once, here
+            full = shd.gather_rows(self.shard, np.stack([x.ravel() for x in xhat1s]) if iterations else np.zeros((0, self.Ml)),
+                                   self.bounds)
+            xhat1s = [full[it].reshape(M, 1) for it in range(iterations)]
+            if write:
+                r1_full = shd.gather_rows(self.shard, np.array([[r1_keep[it][idx] for idx in range(len(mine))]
+                                                                for it in range(iterations)]).reshape(iterations, len(mine), self.Ml),
+                                          self.bounds)
+                if self.root:
+                    for it in range(iterations):
+                        self.write_xhat_to_file(it, xhat1s[it] / sqrtNt)
+                        for idx, k in enumerate(mine):
+                            self.write_r1_to_file(it, r1_full[it, idx] / sqrtNt, k + 1)
         return xhat1s
+
+    def _local(self, v):
+        """This rank's rows of a marker vector given either globally (length M) or already sliced."""
+        v = np.asarray(v, dtype=np.float64).ravel()
+        if v.shape[0] == self.M and self.shard.world > 1:
+            return np.ascontiguousarray(v[self.lo:self.hi])
+        if v.shape[0] != self.Ml:
+            raise Exception("vector of length %d does not match M=%d (local rows %d)" % (v.shape[0], self.M, self.Ml))
+        return v
 
     def _pinned_ring(self, tag, depth, width):
         key = (tag, depth, width)
         cache = self.__dict__.setdefault("_pinned_cache", {})
         if key not in cache:
-            cache[key] = [[self.handle.pinned_array(self.M) for _ in range(width)] for _ in range(depth)]
+            cache[key] = [[self.handle.pinned_array(self.Ml) for _ in range(width)] for _ in range(depth)]
         return cache[key]
 
     def close(self):
+        if self.shard.world > 1 and self.handle.h:
+            self.handle.sync()
+            self.shard.barrier()   # peers may still be reading this rank's arena
         self.handle.close()
         if getattr(self, "_aux", None) is not None:
             self._aux.close()

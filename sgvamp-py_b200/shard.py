@@ -25,6 +25,51 @@ def partition_rows(M, world, align=4):
     return [(b[r], b[r + 1]) for r in range(world)]
 
 
+def block_starts(indptr, indices):
+    """Start rows of the diagonal blocks of a symmetric block-diagonal CSR matrix (plus M at the end):
+    a new block starts at row i when no earlier row reaches column i or beyond and no later row
+    reaches back before i."""
+    M = len(indptr) - 1
+    indptr = np.asarray(indptr, dtype=np.int64)
+    lo = np.full(M, np.iinfo(np.int64).max, dtype=np.int64)
+    hi = np.full(M, -1, dtype=np.int64)
+    nz = np.diff(indptr) > 0
+    first, last = indptr[:-1][nz], indptr[1:][nz] - 1
+    idx = np.asarray(indices, dtype=np.int64)
+    # rows are not assumed sorted: use reduceat over the row segments
+    if idx.size:
+        lo[nz] = np.minimum.reduceat(idx, first)
+        hi[nz] = np.maximum.reduceat(idx, first)
+    lo = np.minimum(lo, np.arange(M))
+    hi = np.maximum(hi, np.arange(M))
+    runmax = np.maximum.accumulate(hi)
+    sufmin = np.minimum.accumulate(lo[::-1])[::-1]
+    cut = np.ones(M, dtype=bool)
+    cut[1:] = (runmax[:-1] < np.arange(1, M)) & (sufmin[1:] >= np.arange(1, M))
+    return np.concatenate([np.flatnonzero(cut), [M]]).astype(np.int64)
+
+
+def partition_blocks(starts, world):
+    """Contiguous assignment of LD blocks to ranks balanced by stored values (sum of m_b^2): returns
+    the row range of each rank; every boundary is a block boundary (scalar-only exchange)."""
+    starts = np.asarray(starts, dtype=np.int64)
+    m = np.diff(starts).astype(np.float64)
+    cost = np.concatenate([[0.0], np.cumsum(m * m)])
+    nb = len(m)
+    if nb < world:
+        raise Exception("%d LD blocks cannot be sharded over %d ranks" % (nb, world))
+    cuts = [0]
+    for r in range(1, world):
+        b = int(np.searchsorted(cost, cost[-1] * r / world))
+        b = min(max(b, cuts[-1] + 1), nb - (world - r))
+        # pick the nearer of the two neighbouring block boundaries
+        if b - 1 > cuts[-1] and abs(cost[b - 1] - cost[-1] * r / world) < abs(cost[b] - cost[-1] * r / world):
+            b -= 1
+        cuts.append(b)
+    cuts.append(nb)
+    return [(int(starts[cuts[r]]), int(starts[cuts[r + 1]])) for r in range(world)]
+
+
 def slice_rows_csr(R, lo, hi):
     """Rows [lo, hi) of a scipy CSR matrix with GLOBAL column indices (what a rank uploads)."""
     sub = R[lo:hi]
@@ -78,7 +123,7 @@ class ThreadShard:
     class _Group:
         def __init__(self, world):
             self.world = world
-            self.bar = threading.Barrier(world)
+            self.bar = threading.Barrier(world, timeout=180)   # a rank that died must not hang the others
             self.slots = [None] * world
 
     def __init__(self, group, rank):

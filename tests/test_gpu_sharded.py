@@ -1,0 +1,198 @@
+"""Row-partitioned multi-GPU path on the GPU: one rank per host thread (ThreadShard), ranks placed
+round-robin on the visible devices (on a one-GPU box all ranks share cuda:0 - peer memory, the
+in-kernel cross-rank reductions and the halo reads run exactly the same code).
+
+Parity bar as everywhere: xhat rel-L2 <= 1e-4 and scalars <= 1e-4 against the reference goldens;
+against the single-rank run of the same library the sharded run must agree to ~1e-12 (only the
+order of the partial sums differs), with identical CG iteration counts.
+"""
+import os
+import tempfile
+import threading
+
+import numpy as np
+import pytest
+import scipy.sparse
+
+from golden_util import load_case, rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nat():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import sgv_native
+    return sgv_native
+
+
+def ndev():
+    import torch
+    return torch.cuda.device_count()
+
+
+def run_ranks(world, fn):
+    import shard as shd
+    shards = shd.ThreadShard.make(world)
+    out, err = [None] * world, [None] * world
+
+    def body(r):
+        try:
+            out[r] = fn(shards[r], r % ndev())
+        except BaseException as e:   # noqa: BLE001 - re-raised below
+            err[r] = e
+            shards[r].g.bar.abort()
+
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for e in err:
+        if e is not None and not isinstance(e, threading.BrokenBarrierError):
+            raise e
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+def _band(M, w, seed):
+    rng = np.random.default_rng(seed)
+    diags = [rng.standard_normal(M - o).astype(np.float32).astype(np.float64) for o in range(w + 1)]
+    U = scipy.sparse.diags(diags, list(range(w + 1)), shape=(M, M), format="csr")
+    R = (U + scipy.sparse.triu(U, 1).T).tocsr()
+    R.sort_indices()
+    return R
+
+
+@pytest.mark.parametrize("M,w,world", [(5000, 257, 2), (4000, 33, 3), (2048, 500, 4), (40000, 64, 8)])
+def test_sharded_spmm_banded(nat, M, w, world):
+    import shard as shd
+    R = _band(M, w, seed=M + w)
+    X = np.random.default_rng(2).standard_normal((M, 2))
+    bounds = shd.partition_rows(M, world)
+
+    def fn(sh, dev):
+        lo, hi = bounds[sh.rank]
+        h = nat.Handle(device=dev)
+        h.configure_part(M, 1, sh.rank, world, lo, hi, True)
+        shd.attach_peers(h, sh)
+        ip, ix, data = shd.slice_rows_csr(R, lo, hi)
+        h.set_bandwidth_hint(w)
+        h._ck(h.upload_csr(0, ip, ix, data, s=0.0, layout=nat.LAYOUT_DIA))
+        h.spmm_stage(X[lo:hi])
+        sh.barrier()                       # every rank's vector is in place before anyone reads halos
+        Y = h.spmm_run(0, 2, alpha=1.3, beta=-0.7)
+        sh.barrier()
+        h.close()
+        return Y
+
+    Y = np.concatenate(run_ranks(world, fn), axis=0)
+    assert rel_l2(Y, 1.3 * (R @ X) - 0.7 * X) < 1e-13
+
+
+def _run_sharded(c, world, bounds, halo, out_dir=None, iterations=None):
+    import sgvamp
+    M, N = c["M"], c["N_list"][0]
+    its = iterations or c["iterations"]
+
+    def fn(sh, dev):
+        v = sgvamp.VAMP(N=N, Nt=N, M=M, K=1, rho=c["rho"], gamw=c["gamw"], gam1=c["gam1"], a=np.array([1.0]),
+                        prior_vars=c["prior_vars"], prior_probs=c["prior_probs"], out_dir=out_dir, out_name="g",
+                        device=dev, shard=sh, shard_rows=bounds, halo=halo)
+        x0 = c["x0"] * np.sqrt(N) if "x0" in c else None
+        xs = v.infer(c["R"][0], c["r"][0], its, x0=x0, cg_maxit=c["cg_maxit"], em_prior_maxit=c["em_prior_maxit"],
+                     learn_gamw=c["learn_gamw"], lmmse_damp=c["lmmse_damp"], prior_update=c["prior_update"],
+                     update_prior_from=c["update_prior_from"], s=c["s"], probes=c["probes"])
+        res = (xs, v.history, v.handle.ld_info(0), float(v.lam), np.array(v.omegas))
+        sh.barrier()
+        v.close()
+        return res
+
+    return run_ranks(world, fn)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_banded_trajectory_matches_reference(nat, world):
+    import shard as shd
+    from test_gpu_parity import run_gpu
+    c = load_case("banded_L2_em_s01")
+    bounds = shd.partition_rows(c["M"], world)
+    with tempfile.TemporaryDirectory() as d:
+        res = _run_sharded(c, world, bounds, True, out_dir=d)
+        xs1, hist1, _, fin1 = run_gpu(c)
+        for r in range(world):
+            xs, hist, info, lam, om = res[r]
+            assert info["layout"] == "dia"
+            for it in range(c["iterations"]):
+                assert rel_l2(xs[it], c["xhat"][it]) <= 1e-4
+                assert rel_l2(xs[it], xs1[it]) <= 1e-10                       # vs the single-rank run
+                row = hist["rows"][it][0]
+                assert rel_err(row[1:6], c["rows"][it, 0, 1:6]) <= 1e-4
+                assert rel_err(row[1:6], hist1["rows"][it][0][1:6]) <= 1e-9
+                assert tuple(hist["cg_iters"][it][0]) == tuple(c["cg_iters"][it, 0])
+                assert row == res[0][1]["rows"][it][0]                        # bit-identical scalars on all ranks
+            assert abs(lam - c["final_lam"]) <= 1e-4 * c["final_lam"]
+            m = np.array(hist["metrics"])
+            assert rel_err(m[:, 1:], c["metrics"][:, 1:]) <= 1e-4
+        for it in range(c["iterations"]):                                      # dumps assembled by rank 0
+            dump = np.fromfile(os.path.join(d, "g_xhat_it_%d.bin" % it))
+            assert rel_l2(dump, c["xhat_dump"][it]) <= 1e-4
+            r1d = np.fromfile(os.path.join(d, "g_r1_cohort_1_it_%d.bin" % it))
+            assert rel_l2(r1d, c["r1_dump"][it, 0]) <= 1e-4
+        raw = open(os.path.join(d, "g_cohort_1.csv"), "rb").read()
+        assert raw.count(b"\r\n") == c["iterations"] + 1
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_blockdiag_trajectory_matches_reference(nat, world):
+    """Block-diagonal LD sharded by block: SpMM is local, only scalars cross ranks."""
+    import shard as shd
+    c = load_case("blockdiag_L3_em_s01")
+    R = c["R"][0].tocsr()
+    starts = shd.block_starts(R.indptr, R.indices)
+    bounds = shd.partition_blocks(starts, world)
+    res = _run_sharded(c, world, bounds, False)
+    for r in range(world):
+        xs, hist, info, lam, om = res[r]
+        assert info["layout"] in ("blockdiag", "dense")
+        for it in range(c["iterations"]):
+            assert rel_l2(xs[it], c["xhat"][it]) <= 1e-4
+            assert rel_err(hist["rows"][it][0][1:6], c["rows"][it, 0, 1:6]) <= 1e-4
+            assert tuple(hist["cg_iters"][it][0]) == tuple(c["cg_iters"][it, 0])
+        assert rel_err(om, c["final_omegas"]) <= 1e-4
+
+
+def test_sharded_rejects_coupled_blocks_and_short_shards(nat):
+    import sgvamp
+    import shard as shd
+    c = load_case("banded_L2_em_s01")
+    M, N = c["M"], c["N_list"][0]
+
+    def mk(sh, dev, bounds, halo):
+        return sgvamp.VAMP(N=N, Nt=N, M=M, K=1, rho=0.5, gamw=2.0, gam1=1e-6, a=np.array([1.0]),
+                           prior_vars=c["prior_vars"], prior_probs=c["prior_probs"], out_dir=None, out_name="g",
+                           device=dev, shard=sh, shard_rows=bounds, halo=halo)
+
+    def coupled(sh, dev):
+        v = mk(sh, dev, shd.partition_rows(M, 2), False)
+        try:
+            with pytest.raises(Exception, match="couples markers across the shard boundary"):
+                v.load_ld(0, c["R"][0])
+        finally:
+            sh.barrier()
+            v.close()
+
+    run_ranks(2, coupled)
+
+    def short(sh, dev):
+        v = mk(sh, dev, [(0, 1980), (1980, 2000)], True)      # second shard shorter than w = 40
+        try:
+            with pytest.raises(Exception, match="shorter than the LD half-bandwidth"):
+                v.load_ld(0, c["R"][0])
+        finally:
+            sh.barrier()
+            v.close()
+
+    run_ranks(2, short)

@@ -1,0 +1,110 @@
+"""Host-side logic of the row-partitioned multi-GPU path (sgvamp-py_b200/shard.py), no GPU:
+row / block partitioning, bandwidth detection, and the rank plumbing over torch.distributed with
+the gloo backend at world_size 2 (the same code path NCCL runs on the GPU box)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import scipy.sparse
+
+import shard as shd
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_partition_rows_covers_and_aligns():
+    for M, world in [(1, 1), (10, 2), (1000, 3), (1_000_000, 8), (2000, 4), (7, 8)]:
+        b = shd.partition_rows(M, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == M
+        for r in range(world - 1):
+            assert b[r][1] == b[r + 1][0] and b[r][1] % 4 == 0
+        assert all(hi >= lo for lo, hi in b)
+    b = shd.partition_rows(1_000_000, 8)
+    assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 8
+
+
+def test_block_starts_and_partition_blocks():
+    rng = np.random.default_rng(0)
+    sizes = [3, 1, 40, 17, 250, 9, 120, 64, 5, 300, 31]
+    blocks = []
+    for m in sizes:
+        B = rng.standard_normal((m, m))
+        B = B + B.T
+        B[rng.random((m, m)) < 0.3] = 0.0          # holes inside blocks must not split them ...
+        B = np.triu(B) + np.triu(B, 1).T
+        B[0, m - 1] = B[m - 1, 0] = 1.0             # ... as long as the block stays connected at its extent
+        blocks.append(B)
+    R = scipy.sparse.block_diag(blocks, format="csr")
+    starts = shd.block_starts(R.indptr, R.indices)
+    assert list(starts) == list(np.concatenate([[0], np.cumsum(sizes)]))
+    for world in (1, 2, 3, 4):
+        bounds = shd.partition_blocks(starts, world)
+        assert bounds[0][0] == 0 and bounds[-1][1] == R.shape[0]
+        for r in range(world):
+            lo, hi = bounds[r]
+            assert lo in starts and hi in starts and hi > lo
+            assert R[lo:hi].nnz == R[lo:hi, lo:hi].nnz      # no coupling across shard boundaries
+        cost = [sum(m * m for m, s0 in zip(sizes, starts[:-1]) if lo <= s0 < hi) for lo, hi in bounds]
+        assert max(cost) <= 2.2 * sum(cost) / world
+
+
+def test_local_bandwidth_and_slice():
+    M, w = 300, 7
+    R = scipy.sparse.diags([np.ones(M - abs(o)) for o in range(-w, w + 1)], list(range(-w, w + 1)), format="csr")
+    for lo, hi in shd.partition_rows(M, 3):
+        ip, ix, data = shd.slice_rows_csr(R, lo, hi)
+        assert ip[0] == 0 and ip[-1] == len(ix) == len(data)
+        assert shd.local_bandwidth(ip, ix, lo) == w
+    assert shd.local_bandwidth(np.zeros(5, dtype=np.int64), np.zeros(0, dtype=np.int32), 0) == 0
+
+
+def test_thread_shard_allgather_and_gather_rows():
+    import threading
+    world = 3
+    shards = shd.ThreadShard.make(world)
+    bounds = shd.partition_rows(50, world)
+    full = np.arange(100.0).reshape(2, 50)
+    out = [None] * world
+
+    def run(r):
+        lo, hi = bounds[r]
+        assert shards[r].allgather(r * 10) == [0, 10, 20]
+        out[r] = shd.gather_rows(shards[r], full[:, lo:hi], bounds)
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for r in range(world):
+        assert np.array_equal(out[r], full)
+
+
+def test_torch_shard_gloo_world2(tmp_path):
+    """TorchShard over gloo, 2 processes: allgather of python objects, gather_rows, barrier."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent("""
+        import os, sys
+        sys.path.insert(0, %r)
+        import numpy as np
+        import torch.distributed as dist
+        import shard as shd
+        dist.init_process_group("gloo")
+        s = shd.TorchShard()
+        assert s.world == 2 and s.rank == int(os.environ["RANK"])
+        assert s.allgather(("h%%d" %% s.rank, s.rank)) == [("h0", 0), ("h1", 1)]
+        bounds = shd.partition_rows(10, 2)
+        lo, hi = bounds[s.rank]
+        full = np.arange(30.0).reshape(3, 10)
+        got = shd.gather_rows(s, full[:, lo:hi], bounds)
+        assert np.array_equal(got, full)
+        s.barrier()
+        dist.destroy_process_group()
+        print("ok", s.rank)
+    """ % os.path.join(REPO, "sgvamp-py_b200")))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.count("ok") == 2
