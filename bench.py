@@ -64,19 +64,20 @@ def make_probes(iterations, M, seed):
 # ------------------------------------------------------------------------------------------------
 # synthetic banded LD + XTy on the device (torch as a data-generation utility)
 # ------------------------------------------------------------------------------------------------
-def build_problem(torch, M, w, seed, dev, lo=0, hi=None):
-    """Rows [lo, hi) of the workload: DIA band of Rused (fp32, device), r (host), x0 (host, global)."""
+def build_problem(torch, M, w, seed, dev, lo=0, hi=None, ext=0, keep_full=True):
+    """Rows [lo, hi) of the workload.  Returns the symmetric half band of Rused in the DSYM layout
+    (fp32, device; with `ext` leading extension rows for ranks > 0, sgv_ld_adopt_dsym), the full band
+    of the own rows (for the host-CSR leg; None unless keep_full), r (host), x0 (host, global)."""
     import ldgen
     t0 = time.time()
     hi = M if hi is None else hi
     Ml = hi - lo
-    ldb = (Ml + 31) // 32 * 32
-    band = torch.zeros((2 * w + 1, ldb), device=dev, dtype=torch.float32)
-    b, noise = ldgen.banded_dia_device(torch, M, w, lo, hi, seed, dev, N_ld=N_LD)
-    band[:, :Ml] = b
-    del b
-    band *= (1.0 - S_REG)                       # Rused = (1-s) R + s I  (src/main.py:265)
-    band[w, :Ml] += S_REG
+    glo = lo - ext                                  # first generated row (extension rows included)
+    assert glo >= 0
+    n = hi - glo
+    band, noise = ldgen.banded_dia_device(torch, M, w, glo, hi, seed, dev, N_ld=N_LD)   # (2w+1) x n
+    band *= (1.0 - S_REG)                           # Rused = (1-s) R + s I  (src/main.py:265)
+    band[w, :] += S_REG
     x0_host = ldgen.causal_effects(M, n_gwas(M), LAM_TRUE, H2, seed)
     # r = Rused x0 + n,  n ~ N(0, (1-h2) Rused): the summary-statistic form of the reference recipe
     # (simulation/sim_gen_phen_mult.py:39-55: r = X^T y, R = X^T X  =>  r ~ N(R x0, (1-h2) R))
@@ -86,13 +87,25 @@ def build_problem(torch, M, w, seed, dev, lo=0, hi=None):
     xp = torch.from_numpy(xp_host).to(dev)
     r = torch.zeros(Ml, device=dev, dtype=torch.float64)
     for d in range(2 * w + 1):
-        r += band[d, :Ml].to(torch.float64) * xp[d:d + Ml]
+        r += band[d, ext:].to(torch.float64) * xp[d:d + Ml]
     g = torch.Generator(device=dev)
     g.manual_seed(seed * 31 + 17)
     z = torch.randn((M,), generator=g, device=dev, dtype=torch.float64)[lo:hi]
-    r += float(np.sqrt(1.0 - H2)) * (float(np.sqrt(1.0 - S_REG)) * noise + float(np.sqrt(S_REG)) * z)
+    r += float(np.sqrt(1.0 - H2)) * (float(np.sqrt(1.0 - S_REG)) * noise[ext:] + float(np.sqrt(S_REG)) * z)
+    # half band: U[d, j] = Rused[i, i+d], i = glo + j; extension rows keep only their couplings to own rows
+    Dp = (w + 1 + 3) // 4 * 4
+    ldb = (n + 31) // 32 * 32
+    U = torch.zeros((Dp, ldb), device=dev, dtype=torch.float32)
+    U[: w + 1, :n] = band[w:, :]
+    U[0] *= 0.5                                     # DSYM convention: the diagonal is stored halved
+    if ext:
+        jj = torch.arange(ext, device=dev)[None, :]
+        dd = torch.arange(Dp, device=dev)[:, None]
+        U[:, :ext] *= (jj + dd >= ext).to(torch.float32)
+    full = band[:, ext:].contiguous() if keep_full else None
+    del band
     torch.cuda.synchronize()
-    return band, ldb, r.cpu().numpy(), x0_host, time.time() - t0
+    return U, ldb, full, r.cpu().numpy(), x0_host, time.time() - t0
 
 
 def band_to_host_csr(torch, band, M, w, lo=0, hi=None, pinned=True):
@@ -205,7 +218,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = len(os.sched_getaffinity(0))
-    workload = "banded LD M=%d w=%d (DIA fp32 in HBM), K=1, L=2, EM prior, learn gamw, s=%.1f, cg_maxit=500" % (
+    workload = "banded LD M=%d w=%d (symmetric half band fp32 in HBM), K=1, L=2, EM prior, learn gamw, s=%.1f, cg_maxit=500" % (
         a.M, a.w, S_REG)
 
     # -------------------------------------------------------------------------------------------
@@ -244,15 +257,36 @@ def main():
     if world > 1:
         dist.barrier()
     import sgvamp
-    import sgv_native as nat
-    if world > 1:
-        raise SystemExit("multi-GPU row-partitioned path: not wired into bench.py yet")
+    import shard as shd
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        t = torch.tensor(np.asarray(v, dtype=np.float64), device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
 
     M, w = a.M, a.w
     iterations = a.warmup + a.steps
-    band, ldb, r, x0, t_gen = build_problem(torch, M, w, a.seed, dev)
+    shard = shd.TorchShard() if world > 1 else shd.SoloShard()
+    bounds = shd.partition_rows(M, world)          # contiguous marker rows per GPU; halo of w entries from the neighbours
+    lo, hi = bounds[rank]
+    Ml = hi - lo
+    ext = (w + 255) // 256 * 256 if rank > 0 else 0   # == sgv_dsym_extension (checked again by sgv_ld_adopt_dsym)
+    U, ldb, band, r, x0, t_gen = build_problem(torch, M, w, a.seed, dev, lo, hi, ext, keep_full=not a.no_e2e)
     p = vamp_params(M)
-    probes = make_probes(iterations, M, a.seed)
+    probes = make_probes(iterations, M, a.seed)     # global probes: every rank uses its own rows
     torch.cuda.synchronize()
     solver_stream = torch.cuda.Stream(device=dev)      # the library launches on this stream; torch events
     torch.cuda.set_stream(solver_stream)               # recorded below are recorded on the same stream
@@ -261,16 +295,18 @@ def main():
     def new_solver():
         return sgvamp.VAMP(N=n_gwas(M), Nt=n_gwas(M), M=M, K=1, rho=p["rho"], gamw=p["gamw"], gam1=p["gam1"],
                            a=np.array([1.0]), prior_vars=p["prior_vars"], prior_probs=p["prior_probs"],
-                           out_dir=None, out_name="bench", comm=None, device=local_rank, stream=stream)
+                           out_dir=None, out_name="bench", comm=None, device=local_rank, stream=stream,
+                           shard=shard, shard_rows=bounds, halo=True)
 
     def run(v, R, n_it, hook=None, **kw):
         return v.infer(R, r, n_it, x0=None, cg_maxit=p["cg_maxit"], em_prior_maxit=p["em_prior_maxit"],
                        learn_gamw=p["learn_gamw"], lmmse_damp=p["lmmse_damp"], prior_update=p["prior_update"],
-                       update_prior_from=p["update_prior_from"], probes=probes, iter_hook=hook, **kw)
+                       update_prior_from=p["update_prior_from"], probes=probes, iter_hook=hook,
+                       gather_outputs=False, **kw)
 
     # ---- device-resident leg: LD already in HBM when the timed region starts ----
     sampler = ClockSampler(local_rank)
-    dia = sgvamp.DeviceDIA(band.data_ptr(), w, ldb, keepalive=band)
+    dia = sgvamp.DeviceDSYM(U.data_ptr(), w, ldb, ext, keepalive=U)   # symmetric half band resident in HBM
     v0 = new_solver()
     run(v0, dia, 2)                                    # process-level warm-up (module load, allocations)
     v0.close()
@@ -279,7 +315,7 @@ def main():
 
     def hook(it):
         if it == a.warmup:
-            torch.cuda.synchronize()
+            barrier()                                  # all ranks enter the timed region together
             v.handle.profile(True)
             launches["a"] = v.handle.launch_count()
             wall["a"] = time.time()
@@ -288,21 +324,21 @@ def main():
         events[it] = e
 
     xs = run(v, dia, iterations, hook)
-    torch.cuda.synchronize()
+    barrier()
     wall["b"] = time.time()
     spmm_ms, spmm_launches = v.handle.profile_read()
     v.handle.profile(False)
     launches["b"] = v.handle.launch_count()
     clocks = sampler.window(wall["a"], wall["b"])
-    ms_total = events[a.warmup].elapsed_time(events[iterations])
-    ms_from0 = events[0].elapsed_time(events[iterations])
+    ms_total = max_over_ranks(events[a.warmup].elapsed_time(events[iterations]))     # device time, max over ranks
+    ms_from0 = max_over_ranks(events[0].elapsed_time(events[iterations]))
     hist = v.history
     passes = sum(hist["spmm_passes"][a.warmup:])
     info = v.handle.ld_info(0)
     value = a.steps / (ms_total / 1e3)
-    # roofline of the dominant kernel: algorithmic bytes of one 2-RHS pass / mean launch time
-    # (all SpMM launches of the timed region, early-exit launches included in the time but not in
-    # the count of passes -> conservative)
+    # roofline of the dominant kernel (per GPU): algorithmic bytes of one 2-RHS pass over this rank's rows /
+    # mean launch time (all SpMM launches of the timed region, early-exit launches included in the time but
+    # not in the count of passes -> conservative); the slowest rank is reported
     bytes_pass = info["bytes_per_pass"]
     peaks = {}
     try:
@@ -310,71 +346,91 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     avg_ms = spmm_ms / max(passes, 1)
-    achieved = bytes_pass / (avg_ms * 1e-3) / 1e9
-    # isolated kernel timing (back-to-back launches, inputs 4 GB >> L2)
-    iso_ms = v.handle.spmm_bench(0, 20)
-    aligns = [float(np.dot(x.ravel(), x0) / max(np.linalg.norm(x) * np.linalg.norm(x0), 1e-300)) for x in xs]
+    achieved = -max_over_ranks(-(bytes_pass / (avg_ms * 1e-3) / 1e9))               # min over ranks
+    avg_ms_max = max_over_ranks(avg_ms)
+    spmm_share = max_over_ranks(spmm_ms) / ms_total
+    # isolated kernel timing (back-to-back launches, inputs >> L2); single-rank hook
+    iso_ms = v.handle.spmm_bench(0, 20) if world == 1 else None
+    xl = x0[lo:hi]
+    dots = sum_over_ranks([[float(np.dot(x.ravel(), xl)), float(np.dot(x.ravel(), x.ravel()))] for x in xs] +
+                          [[float(np.dot(xl, xl)), 0.0]])
+    aligns = [float(dots[i, 0] / max(np.sqrt(dots[i, 1] * dots[-1, 0]), 1e-300)) for i in range(iterations)]
     rows = [hist["rows"][i][0] for i in range(iterations)]
-    sys.stderr.write("host timers over all %d iterations (s): %s\n" % (iterations, {k: round(x, 4) for k, x in v.timers.items()}))
-    sys.stderr.write("trajectory (it gamw gam1 gam2 alpha1 alpha2 lam | cg | align):\n")
-    for i, rw in enumerate(rows):
-        sys.stderr.write("  %2d %.4g %.4g %.4g %.4g %.4g %.4g | %s em=%d | %.4f\n" % (
-            rw[0], rw[1], rw[2], rw[3], rw[4], rw[5], rw[6], hist["cg_iters"][i][0], hist["em_steps"][i], aligns[i]))
+    if rank == 0:
+        sys.stderr.write("host timers over all %d iterations (s): %s\n" % (iterations, {k: round(x, 4) for k, x in v.timers.items()}))
+        sys.stderr.write("trajectory (it gamw gam1 gam2 alpha1 alpha2 lam | cg | align):\n")
+        for i, rw in enumerate(rows):
+            sys.stderr.write("  %2d %.4g %.4g %.4g %.4g %.4g %.4g | %s em=%d | %.4f\n" % (
+                rw[0], rw[1], rw[2], rw[3], rw[4], rw[5], rw[6], hist["cg_iters"][i][0], hist["em_steps"][i], aligns[i]))
 
     # ---- end-to-end leg: host CSR in pinned memory -> VAMP.infer -> host xhat ----
     e2e = None
     if not a.no_e2e:
-        Rh, keep = band_to_host_csr(torch, band, M, w)
+        Rh, keep = band_to_host_csr(torch, band, M, w, lo, hi)
         v2 = new_solver()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         v2.load_ld(0, Rh)
         torch.cuda.synchronize()
         t_up = time.perf_counter() - t0
         xs2 = run(v2, None, iterations, None, write_outputs=False)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        h2d = (Rh.data.nbytes + Rh.indices.nbytes + (M + 1) * 8 + M * 8) / iterations + M
-        d2h = M * 8 + 256
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        h2d = sum_over_ranks([(Rh.data.nbytes + Rh.indices.nbytes + (Ml + 1) * 8 + Ml * 8) / iterations + Ml])[0]
+        d2h = M * 8 + 256 * world
+        diff = max_over_ranks(max(np.linalg.norm(x1 - x2) / max(np.linalg.norm(x1), 1e-300) for x1, x2 in zip(xs, xs2)))
         e2e = {"value": iterations / dt, "unit": "it/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "what": "VAMP.load_ld(scipy CSR fp32 in pinned host memory) + VAMP.infer(r host) for %d iterations from "
-                       "it=0: LD upload + layout conversion + every iteration's probe H2D and xhat D2H inside the "
-                       "timed region" % iterations,
-               "seconds": dt, "ld_upload_seconds": t_up, "max_rel_diff_vs_resident": float(
-                   max(np.linalg.norm(x1 - x2) / np.linalg.norm(x1) for x1, x2 in zip(xs, xs2)))}
+               "what": "VAMP.load_ld(scipy CSR fp32 rows of this rank in pinned host memory) + VAMP.infer(r host) for %d "
+                       "iterations from it=0: LD upload + layout conversion + every iteration's probe H2D and xhat D2H "
+                       "inside the timed region (wall clock between barriers, max over ranks)" % iterations,
+               "seconds": dt, "ld_upload_seconds": max_over_ranks(t_up), "max_rel_diff_vs_resident": diff}
         v2.close()
         del Rh, keep
 
     cpu = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:
         res = cpu_reference_run(M, w, a.cpu_sample_M, 2, a.seed, threads=ncores)
         cpu = {"value": res["value"], "unit": "it/s", "cores": ncores, "kind": "port",
                "sample": "oracle port of src/sgvamp.py, 2 VAMP iterations from it=0 on an M=%d w=%d banded sample "
                          "(%.1f s), scaled by M_sample/M" % (res["sample_M"], w, res["seconds"])}
     sampler.close()
-    align = aligns[-1]
+    traffic = None
+    try:   # dram bytes per launch of the dominant kernel from the committed ncu --set full capture (1 GPU, M=1M, w=500)
+        if world == 1 and M == 1_000_000 and w == 500:
+            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))["spmm_bytes_per_pass"]
+    except Exception:
+        pass
 
     line = {
         "metric": "VAMP iterations/s", "value": value, "unit": "it/s", "n_gpus": world, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload, "M": M, "half_bandwidth": w, "layout": info["layout"],
-                   "nnz_stored": info["nnz_stored"], "l2_policy": "inputs (%.1f GB band) larger than L2" % (info["nnz_stored"] * 4 / 1e9),
+                   "partition": "%d contiguous row shards, halo of %d vector entries read from the neighbours' HBM over NVLink, "
+                                "scalar reductions exchanged in-kernel through peer memory" % (world, w) if world > 1 else "single GPU",
+                   "nnz_stored_per_gpu": info["nnz_stored"],
+                   "l2_policy": "inputs (%.2f GB band per GPU) larger than L2" % (info["nnz_stored"] * 4 / 1e9),
                    "timed_iterations": "VAMP iterations %d..%d of one trajectory" % (a.warmup, iterations - 1),
                    "cg_iters_timed": [list(hist["cg_iters"][i][0]) for i in range(a.warmup, iterations)],
                    "spmm_passes_timed": passes, "its_per_s_from_it0": iterations / (ms_from0 / 1e3),
-                   "alignment_with_truth": align, "gen_seconds": t_gen},
+                   "alignment_with_truth": aligns[-1], "gen_seconds": t_gen},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_spmm_dia (2-RHS fused shifted SpMM + CG dots)",
-                     "bytes_per_launch": bytes_pass, "avg_launch_ms": avg_ms, "launches_timed": spmm_launches,
-                     "isolated_launch_ms": iso_ms, "isolated_gbs": bytes_pass / (iso_ms * 1e-3) / 1e9,
-                     "peak_source": peak_src, "spmm_share_of_step": spmm_ms / ms_total},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches["b"] - launches["a"], "clocks": clocks,
+                     "traffic": traffic, "kernel": "k_spmm_dsym (2-RHS symmetric half-band SpMM, fused CG direction update) + k_dsym_finish (q, p.q)",
+                     "per": "GPU (slowest rank)", "bytes_per_launch": bytes_pass, "avg_launch_ms": avg_ms_max,
+                     "launches_timed": spmm_launches, "isolated_launch_ms": iso_ms,
+                     "isolated_gbs": (bytes_pass / (iso_ms * 1e-3) / 1e9) if iso_ms else None,
+                     "peak_source": peak_src, "spmm_share_of_step": spmm_share},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(sum_over_ranks([launches["b"] - launches["a"]])[0]),
+        "clocks": clocks,
     }
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
     v.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -32,7 +32,8 @@ typedef struct sgv_ctx* sgv_handle;
 #define SGV_MAX_L 8   /* mixture components   */
 
 /* LD storage layouts in HBM */
-enum { SGV_LAYOUT_AUTO = 0, SGV_LAYOUT_DENSE = 1, SGV_LAYOUT_DIA = 2, SGV_LAYOUT_BLOCKDIAG = 3, SGV_LAYOUT_CSR = 4 };
+enum { SGV_LAYOUT_AUTO = 0, SGV_LAYOUT_DENSE = 1, SGV_LAYOUT_DIA = 2, SGV_LAYOUT_BLOCKDIAG = 3, SGV_LAYOUT_CSR = 4,
+       SGV_LAYOUT_DSYM = 5 /* symmetric half band: diagonals 0..w of the upper triangle only */ };
 /* element types of host LD values */
 enum { SGV_F32 = 0, SGV_F64 = 1 };
 /* vectors readable / writable through sgv_get_vec / sgv_set_vec (per cohort unless noted) */
@@ -78,6 +79,14 @@ int sgv_ld_upload_csr(sgv_handle h, int cohort, const int64_t* indptr, const int
  * dia: band[d*ldb + i] = Rused[i][i+d-w], d in [0,2w]; ldb multiple of 4 elements, base 16B aligned.
  * dense: row-major M x M, ld multiple of 4, base 16B aligned. */
 int sgv_ld_adopt_dia(sgv_handle h, int cohort, const float* band_dev, int64_t w, int64_t ldb);
+/* dsym: symmetric half band, U[d*ldb + j] = Rused[i][i+d] for d in [1,w] and HALF of Rused[i][i] for d = 0
+ * (the kernel applies every stored value twice: to row i and to row i+d), j = i + ext, stored with
+ * roundup(w+1,4) diagonals (the padding diagonals zero), zero where i+d is outside the matrix; ldb a
+ * multiple of 32 >= rows + ext.  `ext` (from sgv_dsym_extension: 0 on a single GPU / rank 0) is the
+ * number of rows BEFORE this rank's first row that the buffer also holds (their couplings to this
+ * rank's rows; anything else in them zero). */
+int sgv_ld_adopt_dsym(sgv_handle h, int cohort, const float* U_dev, int64_t w, int64_t ldb, int64_t ext);
+int sgv_dsym_extension(sgv_handle h, int64_t w, int64_t* ext);
 int sgv_ld_adopt_dense(sgv_handle h, int cohort, const float* R_dev, int64_t ld);
 /* layout actually chosen + stored bytes + algorithmic bytes of one SpMM pass at nrhs */
 int sgv_ld_info(sgv_handle h, int cohort, int* layout, int64_t* nnz_stored, int64_t* bandwidth,

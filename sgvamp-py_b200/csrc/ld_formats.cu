@@ -90,6 +90,42 @@ __global__ void k_csr_to_dia(int64_t M, const int64_t* __restrict__ indptr, cons
     }
 }
 
+// symmetric half band: own rows give the upper diagonals, the couplings of own rows to the E extension
+// rows before them (local column < 0) fill those rows' upper diagonals by symmetry
+template <typename T>
+__global__ void k_csr_to_dsym(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                              const T* __restrict__ data, float* __restrict__ U, int64_t ldb, int64_t E, double s,
+                              int col_base) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
+        const int64_t cl = (int64_t)indices[k] - col_base;
+        if (cl > row) U[(cl - row) * ldb + row + E] = reg_value(data[k], false, s);
+        else if (cl == row) U[row + E] = 0.5f * reg_value(data[k], true, s);   // the diagonal is stored halved
+        else if (cl < 0 && cl + E >= 0) U[(row - cl) * ldb + cl + E] = reg_value(data[k], false, s);
+    }
+}
+
+// entries below the diagonal inside the own rows must mirror the stored upper ones (to fp32 rounding)
+template <typename T>
+__global__ void k_dsym_check(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                             const T* __restrict__ data, const float* __restrict__ U, int64_t ldb, int64_t E, double s,
+                             int col_base, unsigned long long* __restrict__ mismatches) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    unsigned bad = 0;
+    for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
+        const int64_t cl = (int64_t)indices[k] - col_base;
+        if (cl >= 0 && cl < row) {
+            const float lo = reg_value(data[k], false, s), up = U[(row - cl) * ldb + cl + E];
+            if (fabsf(lo - up) > 4e-7f * fmaxf(fabsf(lo), fabsf(up))) ++bad;
+        }
+    }
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
 template <typename T>
 __global__ void k_csr_to_panels(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                                 const T* __restrict__ data, float* __restrict__ panels,
@@ -275,13 +311,65 @@ extern "C" int sgv_ld_adopt_dia(sgv_handle c, int cohort, const float* band_dev,
     return 0;
 }
 
+extern "C" int sgv_dsym_extension(sgv_handle c, int64_t w, int64_t* ext) {
+    SGV_CHECK(c != nullptr && ext != nullptr, "null argument");
+    *ext = sgv_dsym_ext(c, w);
+    return 0;
+}
+
+extern "C" int sgv_ld_adopt_dsym(sgv_handle c, int cohort, const float* U_dev, int64_t w, int64_t ldb, int64_t ext) {
+    SGV_TRY(check_cohort(c, cohort));
+    SGV_CHECK(U_dev != nullptr && ((uintptr_t)U_dev & 15) == 0, "device pointer must be 16-byte aligned");
+    SGV_CHECK(w >= 0 && sgv_dsym_feasible(w), "half-bandwidth %lld not supported by the DSYM kernel", (long long)w);
+    SGV_CHECK(ext == sgv_dsym_ext(c, w), "extension rows %lld, expected %lld (sgv_dsym_extension)", (long long)ext,
+              (long long)sgv_dsym_ext(c, w));
+    SGV_CHECK(ldb >= c->Ml + ext && ldb % 32 == 0, "ldb must be a multiple of 32 and >= local rows + extension");
+    LdMatrix& ld = c->coh[cohort].ld;
+    sgv_ld_free(ld);
+    ld.band = U_dev;
+    ld.owned = false;
+    ld.layout = SGV_LAYOUT_DSYM;
+    ld.w = w;
+    ld.ldb = ldb;
+    ld.ext = ext;
+    ld.nnz_stored = (w + 1) * c->Ml;
+    return sgv_dsym_ensure_scratch(c, ld);
+}
+
 template <typename T>
 static int convert_csr(sgv_ctx* c, LdMatrix& ld, int layout, const int64_t* d_indptr, const int32_t* d_indices,
                        const T* d_data, int64_t nnz, double s, int64_t w, const std::vector<int64_t>& starts) {
     const int64_t M = c->Ml;
     const int col_base = c->halo ? (int)c->row_lo : 0;
     const unsigned wgrid = (unsigned)((M * 32 + 255) / 256);
-    if (layout == SGV_LAYOUT_DIA) {
+    if (layout == SGV_LAYOUT_DSYM) {
+        const int64_t E = sgv_dsym_ext(c, w), Dp = round_up(w + 1, 4);
+        const int64_t ldb = round_up(M + E, 32);
+        float* U = nullptr;
+        SGV_CUDA(cudaMalloc(&U, (size_t)Dp * ldb * sizeof(float)));
+        ld.band = U;
+        ld.owned = true;
+        ld.w = w;
+        ld.ldb = ldb;
+        ld.ext = E;
+        ld.nnz_stored = (w + 1) * M;
+        SGV_CUDA(cudaMemsetAsync(U, 0, (size_t)Dp * ldb * sizeof(float), c->stream));
+        k_fill_f32<<<592, 256, 0, c->stream>>>(U + E, M, 0.5f * (float)s);   // absent diagonal entry (stored halved)
+        k_csr_to_dsym<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, U, ldb, E, s, col_base);
+        unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(c->counter + 8);   // spare words of the ticket block
+        SGV_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
+        k_dsym_check<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, U, ldb, E, s, col_base, d_bad);
+        c->launches += 3;
+        unsigned long long bad = 0;
+        SGV_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+        if (bad != 0) {   // not symmetric: the caller falls back to the full band
+            sgv_ld_free(ld);
+            return 1;
+        }
+        ld.layout = layout;
+        SGV_TRY(sgv_dsym_ensure_scratch(c, ld));
+    } else if (layout == SGV_LAYOUT_DIA) {
         const int64_t ldb = round_up(M, 32);
         float* band = nullptr;
         SGV_CUDA(cudaMalloc(&band, (size_t)(2 * w + 1) * ldb * sizeof(float)));
@@ -415,9 +503,15 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
 
     if (c->bandwidth_hint > w) w = c->bandwidth_hint;
     int layout = layout_hint;
+    const bool dsym_ok = sgv_dsym_feasible(w) && dia_cells * 2.0 < 0.8 * (double)free_b;
+    bool dsym_fallback = false;   // DSYM chosen automatically: fall back to the full band if R is not symmetric
     if (c->world > 1 && c->halo) {
-        SGV_CHECK(layout == SGV_LAYOUT_AUTO || layout == SGV_LAYOUT_DIA, "a row partition with halos needs the DIA layout");
-        layout = SGV_LAYOUT_DIA;
+        SGV_CHECK(layout == SGV_LAYOUT_AUTO || layout == SGV_LAYOUT_DIA || layout == SGV_LAYOUT_DSYM,
+                  "a row partition with halos needs a band layout (dia / dsym)");
+        if (layout == SGV_LAYOUT_AUTO) {
+            layout = dsym_ok ? SGV_LAYOUT_DSYM : SGV_LAYOUT_DIA;
+            dsym_fallback = dsym_ok;
+        }
     }
     if (layout == SGV_LAYOUT_AUTO) {
         layout = SGV_LAYOUT_CSR;
@@ -427,15 +521,28 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
         else if (blk_good) layout = SGV_LAYOUT_BLOCKDIAG;
         else if (dia_good) layout = SGV_LAYOUT_DIA;
         if (layout == SGV_LAYOUT_BLOCKDIAG && nb == 1) layout = SGV_LAYOUT_DENSE;
+        if (layout == SGV_LAYOUT_DIA && dsym_ok) {
+            layout = SGV_LAYOUT_DSYM;
+            dsym_fallback = true;
+        }
     }
     int rc = 0;
+    if (layout == SGV_LAYOUT_DSYM && !dsym_ok) { sgv_set_error("DSYM layout infeasible for half-bandwidth %lld", (long long)w); rc = -1; }
     if (layout == SGV_LAYOUT_DIA && !dia_ok) { sgv_set_error("DIA layout infeasible for half-bandwidth %lld", (long long)w); rc = -1; }
     if ((layout == SGV_LAYOUT_DENSE || layout == SGV_LAYOUT_BLOCKDIAG) && !blk_fits) { sgv_set_error("dense blocks do not fit in device memory"); rc = -1; }
     if (layout == SGV_LAYOUT_CSR && s != 0.0 && !all_diag) { sgv_set_error("CSR layout with s != 0 needs every diagonal entry stored"); rc = -3; }
     if (layout == SGV_LAYOUT_DENSE) starts = {0, M};
-    if (rc == 0) {
+    for (int attempt = 0; rc == 0 && attempt < 2; ++attempt) {
         if (dtype == SGV_F64) rc = convert_csr<double>(c, ld, layout, d_indptr, d_indices, (const double*)d_data, nnz, s, w, starts);
         else rc = convert_csr<float>(c, ld, layout, d_indptr, d_indices, (const float*)d_data, nnz, s, w, starts);
+        if (rc != 1) break;                       // rc == 1: the DSYM conversion found R not symmetric
+        if (dsym_fallback && dia_ok) {
+            layout = SGV_LAYOUT_DIA;
+            rc = 0;
+        } else {
+            sgv_set_error("LD matrix is not symmetric: the DSYM layout cannot hold it");
+            rc = -1;
+        }
     }
     cudaFree(d_data);
     cudaFree(d_lo);

@@ -189,3 +189,40 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], const RedCtx& rc, d
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// epilogues
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epi_row(const SpmmArgs& a, int64_t i, double2 acc, double2 vi, double (&dots)[2]) {
+    double2 o;
+    o.x = a.gamw * acc.x + a.gam2 * vi.x;
+    o.y = a.gamw * acc.y + a.gam2 * vi.y;
+    if (EPI == EPI_Q) {
+        a.out[i] = o;
+        dots[0] += vi.x * o.x;
+        dots[1] += vi.y * o.y;
+    } else if (EPI == EPI_RESID) {
+        double2 b = a.bb[i];
+        double2 r = make_double2(b.x - o.x, b.y - o.y);
+        a.out[i] = r;
+        dots[0] += r.x * r.x;
+        dots[1] += r.y * r.y;
+    } else if (EPI == EPI_STATS) {
+        double2 b = a.bb[i];
+        dots[0] += vi.x * o.x;   // xhat2^T R xhat2
+        dots[1] += b.y * o.y;    // u^T R Sigma2_u
+    } else {
+        a.out[i] = o;
+    }
+}
+
+
+// length of one of the 4 (index mod 4) planes of a shared-memory vector window of W entries; odd
+// multiple-of-8 padding keeps the planes on different banks
+__host__ __device__ inline int dia_plane_len(int W) {
+    int pl = (W + 3) / 4 + 1;
+    while ((pl & 7) != 1) ++pl;
+    return pl;
+}
+

@@ -92,8 +92,9 @@ struct LdMatrix {
     bool     owned = false;
     int64_t  nnz_stored = 0;   // fp32 values read by one pass
     // DIA
-    const float* band = nullptr;
+    const float* band = nullptr;   // DIA: 2w+1 diagonals; DSYM: roundup(w+1,4) upper diagonals
     int64_t  w = 0, ldb = 0;
+    int64_t  ext = 0;              // DSYM: extension rows stored before the first own row
     // dense panels (DENSE: one block; BLOCKDIAG: one per LD block)
     const float* panels = nullptr;
     PanelItem*   items = nullptr;
@@ -153,6 +154,9 @@ struct sgv_ctx {
     double2 *xx = nullptr, *rr = nullptr, *pp[2] = {nullptr, nullptr};   // inside the arena
     PeerView     peer[SGV_MAX_RANKS];
     unsigned long long seq = 0;      // reductions issued so far (identical on all ranks)
+    double2*     ds_ypart = nullptr; // DSYM kernel: per-row partial sums and per-tile tails
+    double2*     ds_tails = nullptr;
+    int64_t      ds_ypart_cap = 0, ds_tails_cap = 0;
     double2*     ypart = nullptr;    // cross-CTA partial outputs of the panel kernel
     int64_t      ypart_cap = 0;      // in double2 elements
     PriorParams  prior{};
@@ -217,6 +221,13 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, doub
 size_t sgv_dia_smem_bytes(int64_t w, int rw, int s);
 int    sgv_preload_spmm();   // load all kernels of the TU on the current device (see spmm.cu)
 int    sgv_preload_vamp();
+// spmm_dsym.cu
+int    sgv_preload_dsym();
+size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s);
+bool   sgv_dsym_feasible(int64_t w);
+int    sgv_dsym_ensure_scratch(sgv_ctx* c, const LdMatrix& ld);
+int    sgv_launch_dsym(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a);
+static inline int64_t sgv_dsym_ext(const sgv_ctx* c, int64_t w) { return (c->halo && c->rank > 0) ? round_up(w, 256) : 0; }
 bool   sgv_dia_feasible(int64_t w);
 // ld_formats.cu
 void sgv_ld_free(LdMatrix& ld);

@@ -13,33 +13,6 @@
 #include "sgv_device.cuh"
 
 // ---------------------------------------------------------------------------------------------
-// epilogues
-// ---------------------------------------------------------------------------------------------
-template <int EPI>
-__device__ __forceinline__ void epi_row(const SpmmArgs& a, int64_t i, double2 acc, double2 vi, double (&dots)[2]) {
-    double2 o;
-    o.x = a.gamw * acc.x + a.gam2 * vi.x;
-    o.y = a.gamw * acc.y + a.gam2 * vi.y;
-    if (EPI == EPI_Q) {
-        a.out[i] = o;
-        dots[0] += vi.x * o.x;
-        dots[1] += vi.y * o.y;
-    } else if (EPI == EPI_RESID) {
-        double2 b = a.bb[i];
-        double2 r = make_double2(b.x - o.x, b.y - o.y);
-        a.out[i] = r;
-        dots[0] += r.x * r.x;
-        dots[1] += r.y * r.y;
-    } else if (EPI == EPI_STATS) {
-        double2 b = a.bb[i];
-        dots[0] += vi.x * o.x;   // xhat2^T R xhat2
-        dots[1] += b.y * o.y;    // u^T R Sigma2_u
-    } else {
-        a.out[i] = o;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // DIA (banded) kernel
 //   CTA = RW row-warps x S diagonal-segments; a thread owns 4 consecutive rows (one float4 per
 //   diagonal) and a contiguous range of diagonals; the x window [r0-w, r0+TR+w) sits in shared
@@ -47,12 +20,6 @@ __device__ __forceinline__ void epi_row(const SpmmArgs& a, int64_t i, double2 ac
 //   is bank-conflict free; each thread slides a 4-entry register window along the diagonals, so a
 //   step of 4 rows x 1 diagonal x 2 RHS costs 1 LDG.128 + 1 LDS.128 + 4 cvt + 8 DFMA.
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ inline int dia_plane_len(int W) {
-    int pl = (W + 3) / 4 + 1;
-    while ((pl & 7) != 1) ++pl;
-    return pl;
-}
-
 size_t sgv_dia_smem_bytes(int64_t w, int rw, int s) {
     int TR = 128 * rw;
     int W = TR + 2 * (int)w;
@@ -417,6 +384,7 @@ static int launch_epi(sgv_ctx* c, Cohort& co, SpmmArgs& a) {
             return launch_dia<DIA_BIG_RW, DIA_BIG_S, EPI, DIA_PF, DIA_MINB>(c, ld, a);
         return launch_dia<1, 8, EPI, DIA_PF, DIA_MINB>(c, ld, a);
     }
+    if (ld.layout == SGV_LAYOUT_DSYM) return sgv_launch_dsym(c, ld, EPI, a);
     if (ld.layout == SGV_LAYOUT_DENSE || ld.layout == SGV_LAYOUT_BLOCKDIAG) {
         k_spmm_panel<4, 2><<<ld.n_items, 256, 0, c->stream>>>(a, ld.panels, ld.items, c->ypart);
         c->launches++;
@@ -483,11 +451,12 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, doub
     a.v = vec == VEC_XX ? c->xx : c->pp[vec - VEC_PP0];
     a.fused_p = fused_p;
     if (fused_p) {
-        SGV_CHECK(co.ld.layout == SGV_LAYOUT_DIA && vec != VEC_XX, "fused direction update needs the DIA layout");
+        SGV_CHECK((co.ld.layout == SGV_LAYOUT_DIA || co.ld.layout == SGV_LAYOUT_DSYM) && vec != VEC_XX,
+                  "fused direction update needs a band layout");
         a.r = c->rr;
         a.p_new = c->pp[1 - (vec - VEC_PP0)];
     }
-    if (c->world > 1 && c->halo && co.ld.layout == SGV_LAYOUT_DIA) {
+    if (c->world > 1 && c->halo && (co.ld.layout == SGV_LAYOUT_DIA || co.ld.layout == SGV_LAYOUT_DSYM)) {
         if (c->rank > 0) {
             const PeerView& pv = c->peer[c->rank - 1];
             SGV_CHECK(pv.base != nullptr && pv.Ml >= co.ld.w, "left neighbour not attached or shorter than the half-bandwidth");

@@ -1,0 +1,375 @@
+// Symmetric half-band SpMM ("DSYM" layout): out = gamw * (R v) + gam2 * v for a pair of fp64
+// vectors, R symmetric banded and stored ONCE: only the diagonals d = 0..w of the upper triangle,
+//     U[d*ldb + j] = R[i][i+d],   j = i + E   (E: leading extension rows, see below),
+// padded with zero diagonals to a multiple of 4; diagonal 0 holds HALF of R[i][i] (exact in fp32), because
+// the kernel uses every stored value twice - forward and transposed - and for d = 0 both uses hit row i.  One pass reads 4*(w+1) bytes per row instead of
+// the 4*(2w+1) of the full band - the matrix stream is the whole cost of a CG iteration (HBM bound),
+// so this halves it.
+//
+// Every loaded value is used twice, from registers:
+//   forward     y[i]   += U[d][i] * x[i+d]      x from a sliding register window over the shared-
+//                                                memory x window (as in the full-band kernel)
+//   transposed  y[i+d] += U[d][i] * x[i]        x[i] fixed in registers; the TARGET row moves with d.
+// The transposed sums run as a systolic pipeline over the lanes of a warp.  A thread owns rows
+// 4g..4g+3 and, for a group of 4 diagonals d..d+3, the 7 targets 4g+d..4g+d+6 in registers T0..T6.
+// After the group T0..T3 are final for this thread; they are exactly the targets that the thread
+// one lane below (rows 4(g-1)..) works on in ITS next group (4(g-1)+(d+4)+{0..3}), so they are
+// handed down with one shuffle and seed that thread's accumulators; T4..T6 stay in the thread.
+// Lane 0 emits 4 finished sums per group into a per-warp staging range, and after the last group
+// every lane holds 4 finished sums for disjoint targets.  No atomics, no shared-memory
+// read-modify-write in the loop, fixed summation order.
+//
+// A CTA (RW row-warps x S diagonal segments) then adds, in fixed order, the forward sums of its
+// S segments and the staging ranges of its warps: rows of its own tile go to ypart[], the
+// contributions to the Dp rows after the tile go to tails[cta][]; k_dsym_finish adds the (at most
+// ceil(Dp/TR)) tails that reach a row, applies the fused epilogue (q + p.q, residual + r.r,
+// gamw statistics) and the grid / cross-rank reduction.
+//
+// Row partition over GPUs: a rank also stores the E = roundup(w,256) rows BEFORE its first own row
+// (entries that couple them to its own rows; the rest zero) and computes their transposed
+// contributions itself, so no partial sums cross ranks - only vector halos are read from the
+// neighbours' memory when the x window is staged (left halo for the extension rows, right halo for
+// the forward part).  Results for the extension rows themselves are discarded.
+#include <cstring>
+#include "sgv_device.cuh"
+
+#define DS_FWD(C, XA, XB, XC, XD)                                                             \
+    do {                                                                                      \
+        const double v0 = (double)(C).x, v1 = (double)(C).y, v2 = (double)(C).z, v3 = (double)(C).w; \
+        acc0.x = fma(v0, (XA).x, acc0.x); acc0.y = fma(v0, (XA).y, acc0.y);                   \
+        acc1.x = fma(v1, (XB).x, acc1.x); acc1.y = fma(v1, (XB).y, acc1.y);                   \
+        acc2.x = fma(v2, (XC).x, acc2.x); acc2.y = fma(v2, (XC).y, acc2.y);                   \
+        acc3.x = fma(v3, (XD).x, acc3.x); acc3.y = fma(v3, (XD).y, acc3.y);                   \
+    } while (0)
+
+// transposed use of the 4 values of one diagonal: element e of diagonal d+k goes to target e+k
+#define DS_TRN(C, TA, TB, TC, TD)                                                             \
+    do {                                                                                      \
+        const double v0 = (double)(C).x, v1 = (double)(C).y, v2 = (double)(C).z, v3 = (double)(C).w; \
+        TA.x = fma(v0, O0.x, TA.x); TA.y = fma(v0, O0.y, TA.y);                               \
+        TB.x = fma(v1, O1.x, TB.x); TB.y = fma(v1, O1.y, TB.y);                               \
+        TC.x = fma(v2, O2.x, TC.x); TC.y = fma(v2, O2.y, TC.y);                               \
+        TD.x = fma(v3, O3.x, TD.x); TD.y = fma(v3, O3.y, TD.y);                               \
+    } while (0)
+
+__device__ __forceinline__ double2 shfl_down1(double2 v, int lane) {
+    double2 r;
+    r.x = __shfl_down_sync(0xffffffffu, v.x, 1);
+    r.y = __shfl_down_sync(0xffffffffu, v.y, 1);
+    if (lane == 31) r = make_double2(0.0, 0.0);
+    return r;
+}
+
+static inline int ds_per(int Dp, int S) { return (((Dp + S - 1) / S) + 3) & ~3; }
+
+size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s) {
+    const int Dp = (int)round_up(w + 1, 4);
+    const int TR = 128 * rw;
+    size_t b = (size_t)4 * dia_plane_len(TR + Dp) * sizeof(double2);     // x window
+    b += (size_t)rw * s * (ds_per(Dp, s) + 128) * sizeof(double2);        // per-warp staging of the transposed sums
+    b += (size_t)s * TR * sizeof(double2);                                // forward sums per segment
+    return b;
+}
+bool sgv_dsym_feasible(int64_t w) { return sgv_dsym_smem_bytes(w, 1, 8) <= 200 * 1024; }
+
+template <int RW, int S, int PF, int MINB>
+__global__ void __launch_bounds__(32 * RW * S, MINB)
+k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_t E, double2* __restrict__ ypart,
+            double2* __restrict__ tails) {
+    if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
+    constexpr int TR = 128 * RW;
+    constexpr int NT = 32 * RW * S;
+    constexpr int NW = RW * S;
+    extern __shared__ double2 smem2[];
+    const int W = TR + Dp;
+    const int PL = dia_plane_len(W);
+    const int per = (((Dp + S - 1) / S) + 3) & ~3;
+    const int SL = per + 128;
+    double2* xw = smem2;
+    double2* stag = xw + 4 * PL;
+    double2* fwd = stag + NW * SL;
+
+    const int64_t r0s = (int64_t)blockIdx.x * TR;   // storage index of the tile's first row
+    const int64_t r0 = r0s - E;                     // the same in local coordinates (0 = first own row)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int rw = wid % RW, s = wid / RW;
+    const int g = rw * 32 + lane;
+    const int64_t row4s = r0s + 4 * g;
+    const bool active = row4s < ldb;
+
+    const int d0 = s * per;
+    const int d1 = min(Dp, d0 + per);
+    const int ngroups = d0 < d1 ? ((d1 - d0) >> 2) : 0;   // warp-uniform; Dp and per are multiples of 4
+
+    // ring of PF groups (4 diagonals each) in flight, issued before the x window is staged
+    const float* bp = U + (int64_t)d0 * ldb + row4s;
+    float4 q[PF][4];
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && j < ngroups) {
+            const float* lp = bp + (int64_t)(4 * j) * ldb;
+            q[j][0] = ldg_stream_f4(lp);
+            q[j][1] = ldg_stream_f4(lp + ldb);
+            q[j][2] = ldg_stream_f4(lp + 2 * ldb);
+            q[j][3] = ldg_stream_f4(lp + 3 * ldb);
+        }
+    }
+
+    // stage the x window [r0, r0+TR+Dp) (local coordinates).  Entries left of 0 come from the left
+    // neighbour (extension rows), entries right of M from the right neighbour, zero at the matrix
+    // edges.  Fused mode: the window holds the new CG direction p = r + beta*p_old computed on the fly
+    // (scipy: p *= beta; p += r), and the owned part of the tile is written to p_new.
+    double beta0 = 0.0, beta1 = 0.0;
+    bool first = true, fz0 = false, fz1 = false;
+    if (a.fused_p) {
+        const CgState* st = a.rc.st;
+        first = st->step == 0;
+        fz0 = st->done[0] != 0;
+        fz1 = st->done[1] != 0;
+        if (!first) {
+            beta0 = st->rho[0] / st->rho_prev[0];
+            beta1 = st->rho[1] / st->rho_prev[1];
+        }
+    }
+    for (int j = threadIdx.x; j < 4 * PL; j += NT) {
+        const int64_t col = r0 + j;
+        double2 val = make_double2(0.0, 0.0);
+        if (j < W) {
+            const double2 *src = nullptr, *rsrc = nullptr;
+            int64_t idx = col;
+            if (col >= 0 && col < a.M) {
+                src = a.v;
+                rsrc = a.r;
+            } else if (col < 0 && a.v_left != nullptr && a.n_left + col >= 0) {
+                src = a.v_left;
+                rsrc = a.r_left;
+                idx = a.n_left + col;
+            } else if (col >= a.M && a.v_right != nullptr) {
+                src = a.v_right;
+                rsrc = a.r_right;
+                idx = col - a.M;
+            }
+            if (src != nullptr) {
+                if (!a.fused_p) {
+                    val = ld_vec2(src + idx);
+                } else {
+                    const double2 rv = ld_vec2(rsrc + idx);
+                    double2 po = make_double2(0.0, 0.0);
+                    if (!first || fz0 || fz1) po = ld_vec2(src + idx);
+                    val.x = fz0 ? po.x : (first ? rv.x : po.x * beta0 + rv.x);
+                    val.y = fz1 ? po.y : (first ? rv.y : po.y * beta1 + rv.y);
+                    if (j < TR && col >= 0 && col < a.M) a.p_new[col] = val;
+                }
+            }
+        }
+        xw[(j & 3) * PL + (j >> 2)] = val;
+    }
+    __syncthreads();
+
+    double2 acc0 = make_double2(0, 0), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+    if (ngroups > 0) {
+        double2 T0 = acc0, T1 = acc0, T2 = acc0, T3 = acc0, T4 = acc0, T5 = acc0, T6 = acc0;
+        const double2 O0 = xw[g], O1 = xw[PL + g], O2 = xw[2 * PL + g], O3 = xw[3 * PL + g];   // x[row4 .. row4+3]
+        int xi = g + (d0 >> 2);
+        double2 X0 = xw[xi], X1 = xw[PL + xi], X2 = xw[2 * PL + xi], X3 = xw[3 * PL + xi];
+        double2* st = stag + wid * SL;
+        for (int m = 0; m < ngroups; m += PF) {
+#pragma unroll
+            for (int j = 0; j < PF; ++j) {
+                if (m + j < ngroups) {
+                    const double2 N0 = xw[xi + 1], N1 = xw[PL + xi + 1], N2 = xw[2 * PL + xi + 1], N3 = xw[3 * PL + xi + 1];
+                    DS_FWD(q[j][0], X0, X1, X2, X3);
+                    DS_TRN(q[j][0], T0, T1, T2, T3);
+                    DS_FWD(q[j][1], X1, X2, X3, N0);
+                    DS_TRN(q[j][1], T1, T2, T3, T4);
+                    DS_FWD(q[j][2], X2, X3, N0, N1);
+                    DS_TRN(q[j][2], T2, T3, T4, T5);
+                    DS_FWD(q[j][3], X3, N0, N1, N2);
+                    DS_TRN(q[j][3], T3, T4, T5, T6);
+                    X0 = N0; X1 = N1; X2 = N2; X3 = N3;
+                    ++xi;
+                    if (active && m + j + PF < ngroups) {
+                        const float* lp = bp + (int64_t)(4 * (m + j + PF)) * ldb;
+                        q[j][0] = ldg_stream_f4(lp);
+                        q[j][1] = ldg_stream_f4(lp + ldb);
+                        q[j][2] = ldg_stream_f4(lp + 2 * ldb);
+                        q[j][3] = ldg_stream_f4(lp + 3 * ldb);
+                    }
+                    // hand the 4 finished sums down one lane; lane 0's are final for the warp
+                    if (lane == 0) {
+                        double2* e = st + 4 * (m + j);
+                        e[0] = T0; e[1] = T1; e[2] = T2; e[3] = T3;
+                    }
+                    const double2 I0 = shfl_down1(T0, lane), I1 = shfl_down1(T1, lane), I2 = shfl_down1(T2, lane),
+                                  I3 = shfl_down1(T3, lane);
+                    T0 = make_double2(T4.x + I0.x, T4.y + I0.y);
+                    T1 = make_double2(T5.x + I1.x, T5.y + I1.y);
+                    T2 = make_double2(T6.x + I2.x, T6.y + I2.y);
+                    T3 = I3;
+                    T4 = T5 = T6 = make_double2(0.0, 0.0);
+                }
+            }
+        }
+        // drain: every lane now holds finished sums for the disjoint targets (d1-d0) + 4*lane + {0..3}
+        double2* e = st + (d1 - d0) + 4 * lane;
+        e[0] = T0; e[1] = T1; e[2] = T2; e[3] = T3;
+    }
+    {
+        double2* f = fwd + s * TR + 4 * g;
+        f[0] = acc0; f[1] = acc1; f[2] = acc2; f[3] = acc3;
+    }
+    __syncthreads();
+
+    // fixed-order combination: forward sums of the S segments + the staging ranges that cover the target
+    for (int t = threadIdx.x; t < TR + Dp; t += NT) {
+        double2 sum = make_double2(0.0, 0.0);
+        if (t < TR) {
+#pragma unroll
+            for (int s2 = 0; s2 < S; ++s2) {
+                const double2 v = fwd[s2 * TR + t];
+                sum.x += v.x;
+                sum.y += v.y;
+            }
+        }
+#pragma unroll
+        for (int s2 = 0; s2 < S; ++s2) {
+            const int e0 = s2 * per, e1 = min(Dp, e0 + per);
+            if (e0 < e1) {
+#pragma unroll
+                for (int rw2 = 0; rw2 < RW; ++rw2) {
+                    const int rel = t - 128 * rw2 - e0;
+                    if (rel >= 0 && rel < (e1 - e0) + 128) {
+                        const double2 v = stag[(s2 * RW + rw2) * SL + rel];
+                        sum.x += v.x;
+                        sum.y += v.y;
+                    }
+                }
+            }
+        }
+        if (t < TR) {
+            if (r0s + t < ldb) ypart[r0s + t] = sum;
+        } else {
+            tails[(int64_t)blockIdx.x * Dp + (t - TR)] = sum;
+        }
+    }
+}
+
+// y[i] = ypart[i] + the tails of the preceding tiles that reach row i; fused epilogue + reduction.
+template <int EPI>
+__global__ void __launch_bounds__(256)
+k_dsym_finish(SpmmArgs a, const double2* __restrict__ ypart, const double2* __restrict__ tails, int Dp, int TR, int64_t E,
+              const double2* __restrict__ vin) {
+    if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
+    __shared__ double red[2 * 32];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double dots[2] = {0.0, 0.0};
+    if (i < a.M) {
+        const int64_t J = i + E;
+        const int64_t b = J / TR;
+        double2 y = ypart[J];
+        for (int64_t bb = b - 1; bb >= 0; --bb) {
+            const int64_t off = J - (bb + 1) * TR;
+            if (off >= Dp) break;
+            const double2 t = tails[bb * Dp + off];
+            y.x += t.x;
+            y.y += t.y;
+        }
+        epi_row<EPI>(a, i, y, vin[i], dots);
+    }
+    if (EPI != EPI_PLAIN) grid_reduce<2>(dots, a.rc, red);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+#define DS_BIG_RW 2
+#define DS_BIG_S 4
+#define DS_PF 2
+#define DS_MINB 2
+#define DS_SMEM_LIMIT (200 * 1024)
+
+static bool ds_use_big(const sgv_ctx* c, const LdMatrix& ld) {
+    return ld.ldb >= (int64_t)c->sm_count * 2 * 256 && sgv_dsym_smem_bytes(ld.w, DS_BIG_RW, DS_BIG_S) <= 100 * 1024;
+}
+
+int sgv_dsym_tile_rows(const sgv_ctx* c, const LdMatrix& ld) { return ds_use_big(c, ld) ? 128 * DS_BIG_RW : 128; }
+
+int sgv_preload_dsym() {
+    SGV_CUDA(cudaFuncSetAttribute(k_spmm_dsym<DS_BIG_RW, DS_BIG_S, DS_PF, DS_MINB>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM_LIMIT));
+    SGV_CUDA(cudaFuncSetAttribute(k_spmm_dsym<1, 8, DS_PF, DS_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  DS_SMEM_LIMIT));
+    cudaFuncAttributes fa;
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_dsym_finish<EPI_Q>));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_dsym_finish<EPI_RESID>));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_dsym_finish<EPI_STATS>));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_dsym_finish<EPI_PLAIN>));
+    return 0;
+}
+
+// scratch for the partial sums (per handle, sized for the largest DSYM matrix uploaded so far);
+// called at upload / adopt time only, never inside the solver loop
+int sgv_dsym_ensure_scratch(sgv_ctx* c, const LdMatrix& ld) {
+    const int64_t Dp = round_up(ld.w + 1, 4);
+    const int64_t tiles = (ld.ldb + 127) / 128;   // upper bound for either tile shape
+    const int64_t need_y = ld.ldb, need_t = tiles * Dp;
+    if (c->ds_ypart_cap < need_y) {
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->ds_ypart) cudaFree(c->ds_ypart);
+        c->ds_ypart = nullptr;
+        c->ds_ypart_cap = 0;
+        SGV_CUDA(cudaMalloc(&c->ds_ypart, need_y * sizeof(double2)));
+        c->ds_ypart_cap = need_y;
+    }
+    if (c->ds_tails_cap < need_t) {
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->ds_tails) cudaFree(c->ds_tails);
+        c->ds_tails = nullptr;
+        c->ds_tails_cap = 0;
+        SGV_CUDA(cudaMalloc(&c->ds_tails, need_t * sizeof(double2)));
+        c->ds_tails_cap = need_t;
+    }
+    return 0;
+}
+
+template <int RW, int S>
+static int launch_main(sgv_ctx* c, const LdMatrix& ld, const SpmmArgs& a) {
+    constexpr int TR = 128 * RW;
+    const size_t smem = sgv_dsym_smem_bytes(ld.w, RW, S);
+    SGV_CHECK(smem <= DS_SMEM_LIMIT, "half-bandwidth %lld too large for the DSYM kernel", (long long)ld.w);
+    const unsigned grid = (unsigned)((ld.ldb + TR - 1) / TR);
+    const int Dp = (int)round_up(ld.w + 1, 4);
+    k_spmm_dsym<RW, S, DS_PF, DS_MINB><<<grid, 32 * RW * S, smem, c->stream>>>(a, ld.band, Dp, ld.ldb, ld.ext, c->ds_ypart,
+                                                                               c->ds_tails);
+    c->launches++;
+    return 0;
+}
+
+template <int EPI>
+static int launch_finish(sgv_ctx* c, const LdMatrix& ld, SpmmArgs& a, int TR, const double2* vin) {
+    const unsigned grid = (unsigned)((c->Ml + 255) / 256);
+    SGV_TRY(sgv_ensure_partials(c, grid));
+    a.rc.partials = c->partials;
+    const int Dp = (int)round_up(ld.w + 1, 4);
+    k_dsym_finish<EPI><<<grid, 256, 0, c->stream>>>(a, c->ds_ypart, c->ds_tails, Dp, TR, ld.ext, vin);
+    c->launches++;
+    return 0;
+}
+
+// a: fully prepared SpmmArgs (vectors, halos, fused mode, epilogue operands, reduction context)
+int sgv_launch_dsym(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a) {
+    SGV_CHECK(c->ds_ypart != nullptr && c->ds_tails != nullptr, "DSYM scratch not allocated");
+    const bool big = ds_use_big(c, ld);
+    const int TR = big ? 128 * DS_BIG_RW : 128;
+    if (big) SGV_TRY((launch_main<DS_BIG_RW, DS_BIG_S>(c, ld, a)));
+    else SGV_TRY((launch_main<1, 8>(c, ld, a)));
+    const double2* vin = a.fused_p ? a.p_new : a.v;
+    switch (epi) {
+        case EPI_Q: return launch_finish<EPI_Q>(c, ld, a, TR, vin);
+        case EPI_RESID: return launch_finish<EPI_RESID>(c, ld, a, TR, vin);
+        case EPI_STATS: return launch_finish<EPI_STATS>(c, ld, a, TR, vin);
+        default: return launch_finish<EPI_PLAIN>(c, ld, a, TR, vin);
+    }
+}

@@ -472,7 +472,7 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
     Cohort& co = c->coh[cohort];
     SGV_CHECK(co.ld.layout != 0, "cohort %d has no LD matrix", cohort);
     const int64_t M = c->Ml;
-    const bool fused = co.ld.layout == SGV_LAYOUT_DIA;   // direction update fused into the SpMM staging
+    const bool fused = co.ld.layout == SGV_LAYOUT_DIA || co.ld.layout == SGV_LAYOUT_DSYM;   // direction update fused into the SpMM staging
     const unsigned vgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 8);
     SGV_TRY(sgv_ensure_partials(c, vgrid + 1));
     SGV_CUDA(cudaMemcpyAsync(co.probe, probe, M, cudaMemcpyHostToDevice, c->stream));

@@ -13,8 +13,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsgvamp_b200.so")
 
-LAYOUT_AUTO, LAYOUT_DENSE, LAYOUT_DIA, LAYOUT_BLOCKDIAG, LAYOUT_CSR = 0, 1, 2, 3, 4
-LAYOUT_NAMES = {0: "auto", 1: "dense", 2: "dia", 3: "blockdiag", 4: "csr"}
+LAYOUT_AUTO, LAYOUT_DENSE, LAYOUT_DIA, LAYOUT_BLOCKDIAG, LAYOUT_CSR, LAYOUT_DSYM = 0, 1, 2, 3, 4, 5
+LAYOUT_NAMES = {0: "auto", 1: "dense", 2: "dia", 3: "blockdiag", 4: "csr", 5: "dsym"}
 F32, F64 = 0, 1
 VEC_XHAT1, VEC_R1, VEC_XHAT2, VEC_SIGMA2U, VEC_R2, VEC_XTY = 0, 1, 2, 3, 4, 5
 
@@ -27,6 +27,7 @@ SYMBOLS = [
     "sgv_lagrangian", "sgv_lmmse", "sgv_update_r1", "sgv_metrics", "sgv_spmm", "sgv_spmm_bench",
     "sgv_launch_count", "sgv_profile", "sgv_profile_read", "sgv_configure_part", "sgv_ipc_export", "sgv_ipc_import",
     "sgv_peer_attach_local", "sgv_partition_info", "sgv_ld_set_bandwidth_hint", "sgv_spmm_stage", "sgv_spmm_run",
+    "sgv_ld_adopt_dsym", "sgv_dsym_extension",
 ]
 
 
@@ -157,6 +158,15 @@ class Handle:
 
     def adopt_dia(self, cohort, band_ptr, w, ldb):
         self._ck(self.lib.sgv_ld_adopt_dia(self.h, C.c_int(cohort), C.c_void_p(band_ptr), C.c_int64(w), C.c_int64(ldb)))
+
+    def adopt_dsym(self, cohort, U_ptr, w, ldb, ext):
+        self._ck(self.lib.sgv_ld_adopt_dsym(self.h, C.c_int(cohort), C.c_void_p(U_ptr), C.c_int64(w), C.c_int64(ldb),
+                                            C.c_int64(ext)))
+
+    def dsym_extension(self, w):
+        e = C.c_int64()
+        self._ck(self.lib.sgv_dsym_extension(self.h, C.c_int64(w), C.byref(e)))
+        return e.value
 
     def adopt_dense(self, cohort, ptr, ld):
         self._ck(self.lib.sgv_ld_adopt_dense(self.h, C.c_int(cohort), C.c_void_p(ptr), C.c_int64(ld)))

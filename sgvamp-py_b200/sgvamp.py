@@ -38,6 +38,13 @@ class DeviceDIA:
         self.ptr, self.w, self.ldb, self.keepalive = int(ptr), int(w), int(ldb), keepalive
 
 
+class DeviceDSYM:
+    """Symmetric LD already resident in HBM as a half band (upper diagonals 0..w; see sgv_ld_adopt_dsym)."""
+
+    def __init__(self, ptr, w, ldb, ext=0, keepalive=None):
+        self.ptr, self.w, self.ldb, self.ext, self.keepalive = int(ptr), int(w), int(ldb), int(ext), keepalive
+
+
 class DeviceDense:
     """Dense fp32 row-major LD already resident in HBM (see sgv_ld_adopt_dense)."""
 
@@ -196,10 +203,14 @@ class VAMP:
         (src/main.py:265).  R: scipy sparse, ndarray / np.matrix, DeviceDIA or DeviceDense."""
         h = self.handle
         lay = {"auto": nat.LAYOUT_AUTO, "dense": nat.LAYOUT_DENSE, "dia": nat.LAYOUT_DIA,
-               "blockdiag": nat.LAYOUT_BLOCKDIAG, "csr": nat.LAYOUT_CSR}[layout]
+               "blockdiag": nat.LAYOUT_BLOCKDIAG, "csr": nat.LAYOUT_CSR, "dsym": nat.LAYOUT_DSYM}[layout]
         if isinstance(R, DeviceDIA):
             assert s == 0.0, "device-resident LD must already be regularised"
             h.adopt_dia(cohort, R.ptr, R.w, R.ldb)
+            self._keep.append(R)
+        elif isinstance(R, DeviceDSYM):
+            assert s == 0.0, "device-resident LD must already be regularised"
+            h.adopt_dsym(cohort, R.ptr, R.w, R.ldb, R.ext)
             self._keep.append(R)
         elif isinstance(R, DeviceDense):
             assert s == 0.0, "device-resident LD must already be regularised"
@@ -214,13 +225,16 @@ class VAMP:
             if not R.has_canonical_format:
                 R = R.copy()
                 R.sum_duplicates()
-            indptr, indices = R.indptr.astype(np.int64), R.indices.astype(np.int32)
+            indptr, indices = R.indptr, R.indices
             if self.halo:                              # banded: neighbours supply w halo entries of the input vector
-                wmax = max(self.shard.allgather(shd.local_bandwidth(indptr, indices, self.lo)))
+                wmax = max(self.shard.allgather(shd.local_bandwidth(indptr, indices, self.lo,
+                                                                    sorted_indices=bool(R.has_sorted_indices))))
                 if min(hi_ - lo_ for lo_, hi_ in self.bounds) < wmax:
                     raise Exception("row shards are shorter than the LD half-bandwidth %d" % wmax)
                 h.set_bandwidth_hint(wmax)
-                h._ck(h.upload_csr(cohort, indptr, indices, R.data, s=s, layout=nat.LAYOUT_DIA))
+                if lay not in (nat.LAYOUT_AUTO, nat.LAYOUT_DIA, nat.LAYOUT_DSYM):
+                    raise Exception("a row partition with halos needs a band layout (auto / dia / dsym)")
+                h._ck(h.upload_csr(cohort, indptr, indices, R.data, s=s, layout=lay))
             else:                                      # block-diagonal sharded by block: no coupling across shards
                 Rl = R[:, self.lo:self.hi].tocsr()
                 if Rl.nnz != R.nnz:

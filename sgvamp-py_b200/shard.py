@@ -76,12 +76,21 @@ def slice_rows_csr(R, lo, hi):
     return sub.indptr.astype(np.int64), sub.indices.astype(np.int32), sub.data
 
 
-def local_bandwidth(indptr, indices, lo):
-    """max |col - row| over the local rows (global column indices)."""
+def local_bandwidth(indptr, indices, lo, sorted_indices=False):
+    """max |col - row| over the local rows (global column indices).  With sorted column indices only
+    the first and last entry of every row are looked at (O(rows), not O(nnz))."""
     if len(indices) == 0:
         return 0
-    rows = np.repeat(np.arange(len(indptr) - 1, dtype=np.int64) + lo, np.diff(indptr))
-    return int(np.abs(indices.astype(np.int64) - rows).max())
+    indptr = np.asarray(indptr, dtype=np.int64)
+    n = len(indptr) - 1
+    if sorted_indices:
+        nz = np.flatnonzero(np.diff(indptr) > 0)
+        rows = nz + lo
+        first = np.asarray(indices)[indptr[nz]].astype(np.int64)
+        last = np.asarray(indices)[indptr[nz + 1] - 1].astype(np.int64)
+        return int(max((rows - first).max(), (last - rows).max(), 0))
+    rows = np.repeat(np.arange(n, dtype=np.int64) + lo, np.diff(indptr))
+    return int(np.abs(np.asarray(indices).astype(np.int64) - rows).max())
 
 
 def gather_rows(shard, local, bounds):

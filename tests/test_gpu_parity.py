@@ -51,14 +51,14 @@ def _rand_sym_band(M, w, seed, fill=1.0):
 # SpMM, every layout
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,w", [(1, 0), (7, 3), (129, 5), (1000, 40), (5000, 257), (40000, 33)])
-@pytest.mark.parametrize("layout", ["dia", "csr"])
+@pytest.mark.parametrize("layout", ["dia", "dsym", "csr"])
 def test_spmm_banded(nat, M, w, layout):
     w = min(w, M - 1)
     R = _rand_sym_band(M, w, seed=M + w)
     h = nat.Handle()
     h.configure(M, 1)
     h._ck(h.upload_csr(0, R.indptr, R.indices, R.data, s=0.0,
-                       layout=nat.LAYOUT_DIA if layout == "dia" else nat.LAYOUT_CSR))
+                       layout={"dia": nat.LAYOUT_DIA, "dsym": nat.LAYOUT_DSYM, "csr": nat.LAYOUT_CSR}[layout]))
     info = h.ld_info(0)
     assert info["layout"] == layout
     rng = np.random.default_rng(1)
@@ -110,7 +110,17 @@ def test_spmm_blockdiag_and_auto_detection(nat):
     Rb = _rand_sym_band(3000, 20, 5)
     h.configure(3000, 1)
     h._ck(h.upload_csr(0, Rb.indptr, Rb.indices, Rb.data))
-    assert h.ld_info(0)["layout"] == "dia" and h.ld_info(0)["bandwidth"] == 20
+    assert h.ld_info(0)["layout"] == "dsym" and h.ld_info(0)["bandwidth"] == 20
+    # a banded matrix that is not symmetric cannot use the half band: full band instead, explicit dsym refuses
+    Ra = Rb.copy().tolil()
+    Ra[10, 12] = 0.25 if Ra[12, 10] != 0.25 else 0.75      # fp32-representable, differs from its mirror
+    Ra = Ra.tocsr()
+    Ra.sort_indices()
+    h._ck(h.upload_csr(0, Ra.indptr, Ra.indices, Ra.data))
+    assert h.ld_info(0)["layout"] == "dia"
+    Xa = rng.standard_normal((3000, 2))
+    assert rel_l2(h.spmm(0, Xa), Ra @ Xa) < 1e-13
+    assert h.upload_csr(0, Ra.indptr, Ra.indices, Ra.data, layout=nat.LAYOUT_DSYM) != 0
     Rs = _rand_sym_band(3000, 400, 6, fill=0.02)
     h._ck(h.upload_csr(0, Rs.indptr, Rs.indices, Rs.data))
     assert h.ld_info(0)["layout"] == "csr"
@@ -298,7 +308,7 @@ def test_trajectory_matches_reference(nat, name):
     with tempfile.TemporaryDirectory() as d:
         # the irregular-sparsity case is pinned to the CSR kernel (auto would pick DIA at this fill)
         xs, hist, info, fin = run_gpu(c, out_dir=d, layout="csr" if c["layout"] == "csr" else "auto")
-        expect_layout = {"dense": "dense", "banded": "dia", "blockdiag": "blockdiag", "csr": "csr"}[c["layout"]]
+        expect_layout = {"dense": "dense", "banded": "dsym", "blockdiag": "blockdiag", "csr": "csr"}[c["layout"]]
         assert info[0]["layout"] == expect_layout
         tol = 1e-4
         n_check = c["iterations"] if name not in UNSTABLE else 3    # chaotic regimes: first iterations only
@@ -328,7 +338,7 @@ def test_trajectory_matches_reference(nat, name):
             assert rel_err(m[:n_check, 1:], c["metrics"][:n_check, 1:]) <= tol
 
 
-@pytest.mark.parametrize("layout", ["csr", "dense"])
+@pytest.mark.parametrize("layout", ["csr", "dense", "dia"])
 def test_banded_case_other_layouts(nat, layout):
     c = load_case("banded_L2_em_s01")
     xs, hist, info, fin = run_gpu(c, layout=layout)
@@ -417,4 +427,18 @@ def test_spmm_properties_large(nat):
         i = 1000 + t
         assert abs(Rx[i] - bh[:, t] @ x[i - w: i + w + 1]) < 1e-9 * np.abs(Rx[i]) + 1e-9
     assert np.array_equal(h.spmm(0, x), Rx)                                         # run-to-run determinism
+    # the symmetric half-band layout of the same matrix (upper diagonals, padded to a multiple of 4)
+    Dp = (w + 1 + 3) // 4 * 4
+    ldb = (M + 31) // 32 * 32
+    U = torch.zeros((Dp, ldb), device="cuda", dtype=torch.float32)
+    U[: w + 1, :M] = band[w:, :]
+    U[0] *= 0.5                                                                     # diagonal stored halved
+    h.adopt_dsym(0, U.data_ptr(), w, ldb, 0)
+    assert h.ld_info(0)["layout"] == "dsym"
+    Sx = h.spmm(0, x)
+    assert rel_l2(Sx, Rx) < 1e-13                                                   # same product, half the bytes
+    both2 = h.spmm(0, np.stack([x, y], axis=1))
+    assert np.array_equal(both2[:, 0], Sx)
+    assert np.array_equal(h.spmm(0, x), Sx)
+    assert h.ld_info(0)["bytes_per_pass"] < 0.52 * (4.0 * (2 * w + 1) * M + 32.0 * M)
     h.close()

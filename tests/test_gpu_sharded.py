@@ -66,8 +66,9 @@ def _band(M, w, seed):
     return R
 
 
+@pytest.mark.parametrize("layout", ["dia", "dsym"])
 @pytest.mark.parametrize("M,w,world", [(5000, 257, 2), (4000, 33, 3), (2048, 500, 4), (40000, 64, 8)])
-def test_sharded_spmm_banded(nat, M, w, world):
+def test_sharded_spmm_banded(nat, M, w, world, layout):
     import shard as shd
     R = _band(M, w, seed=M + w)
     X = np.random.default_rng(2).standard_normal((M, 2))
@@ -80,7 +81,8 @@ def test_sharded_spmm_banded(nat, M, w, world):
         shd.attach_peers(h, sh)
         ip, ix, data = shd.slice_rows_csr(R, lo, hi)
         h.set_bandwidth_hint(w)
-        h._ck(h.upload_csr(0, ip, ix, data, s=0.0, layout=nat.LAYOUT_DIA))
+        h._ck(h.upload_csr(0, ip, ix, data, s=0.0, layout=nat.LAYOUT_DIA if layout == "dia" else nat.LAYOUT_DSYM))
+        assert h.ld_info(0)["layout"] == layout
         h.spmm_stage(X[lo:hi])
         sh.barrier()                       # every rank's vector is in place before anyone reads halos
         Y = h.spmm_run(0, 2, alpha=1.3, beta=-0.7)
@@ -124,7 +126,7 @@ def test_sharded_banded_trajectory_matches_reference(nat, world):
         xs1, hist1, _, fin1 = run_gpu(c)
         for r in range(world):
             xs, hist, info, lam, om = res[r]
-            assert info["layout"] == "dia"
+            assert info["layout"] == "dsym"
             for it in range(c["iterations"]):
                 assert rel_l2(xs[it], c["xhat"][it]) <= 1e-4
                 assert rel_l2(xs[it], xs1[it]) <= 1e-10                       # vs the single-rank run
