@@ -65,6 +65,11 @@ int sgv_configure_part(sgv_handle h, int64_t M, int K, int rank, int world, int6
 int sgv_ipc_export(sgv_handle h, void* handle64);                                   /* 64-byte CUDA IPC handle of the arena */
 int sgv_ipc_import(sgv_handle h, int peer_rank, const void* handle64, int64_t peer_rows);
 int sgv_peer_attach_local(sgv_handle h, int peer_rank, sgv_handle other);           /* same-process variant */
+/* Ranks that share one GPU (tests on a box with fewer GPUs than ranks, same process only): complete
+ * every cross-rank reduction with a host barrier instead of an in-kernel wait, so that no kernel ever
+ * waits for another rank's kernel.  Must be set identically on all ranks. */
+int sgv_set_host_barrier(sgv_handle h, int enable);
+int sgv_device_id(sgv_handle h, char* pci_bus_id, int len);   /* PCI bus id of the handle's GPU */
 int sgv_ld_set_bandwidth_hint(sgv_handle h, int64_t w);   /* common half-bandwidth of the DIA layout across ranks */
 int sgv_partition_info(sgv_handle h, int64_t* M, int64_t* rows, int64_t* row_lo, int* rank, int* world);
 

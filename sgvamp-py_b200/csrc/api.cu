@@ -2,7 +2,9 @@
 // the C ABI (include/sgvamp_b200.h).
 #include <cstdarg>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
+#include <thread>
 #include "sgv_device.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -225,6 +227,21 @@ RedCtx sgv_red_begin(sgv_ctx* c, int kind, int nv, int off, int maxit, int x0_ze
 }
 
 int sgv_red_end(sgv_ctx* c, const RedCtx& rc) {
+    if (c->world > 1 && c->host_barrier) {
+        // shared-GPU mode: wait on the host until every rank's reducing kernel has finished
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+        const unsigned long long my = ++c->host_seq;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int q = 0; q < c->world; ++q) {
+            if (q == c->rank) continue;
+            SGV_CHECK(c->peer_ctx[q] != nullptr, "host-barrier mode needs locally attached peers");
+            while (c->peer_ctx[q]->host_seq.load(std::memory_order_acquire) < my) {
+                std::this_thread::sleep_for(std::chrono::microseconds(20));
+                SGV_CHECK(std::chrono::steady_clock::now() - t0 < std::chrono::seconds(60),
+                          "host barrier timed out waiting for rank %d (rank %d of %d)", q, c->rank, c->world);
+            }
+        }
+    }
     if (c->world > 1) {
         k_resolve<<<1, 32, 0, c->stream>>>(rc);
         c->launches++;
@@ -252,6 +269,9 @@ extern "C" int sgv_configure_part(sgv_handle c, int64_t M, int K, int rank, int 
     c->halo = halo;
     c->K = K;
     c->seq = 0;
+    c->host_seq.store(0);
+    c->host_barrier = false;
+    for (int q = 0; q < SGV_MAX_RANKS; ++q) c->peer_ctx[q] = nullptr;
     c->prior.K = K;
     for (int k = 0; k < K; ++k) c->prior.a[k] = 1.0 / K;
     const int64_t Ml = c->Ml;
@@ -342,6 +362,19 @@ extern "C" int sgv_peer_attach_local(sgv_handle c, int peer_rank, sgv_handle oth
     c->peer[peer_rank].base = other->arena;
     c->peer[peer_rank].Ml = other->Ml;
     c->peer[peer_rank].ipc = false;
+    c->peer_ctx[peer_rank] = other;
+    return 0;
+}
+
+extern "C" int sgv_set_host_barrier(sgv_handle c, int enable) {
+    SGV_CHECK(c != nullptr, "null handle");
+    c->host_barrier = enable != 0;
+    return 0;
+}
+
+extern "C" int sgv_device_id(sgv_handle c, char* pci_bus_id, int len) {
+    SGV_CHECK(c != nullptr && pci_bus_id != nullptr && len >= 16, "bad arguments");
+    SGV_CUDA(cudaDeviceGetPCIBusId(pci_bus_id, len, c->device));
     return 0;
 }
 

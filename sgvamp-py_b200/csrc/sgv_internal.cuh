@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 #include <vector>
 #include "../../include/sgvamp_b200.h"
@@ -153,6 +154,13 @@ struct sgv_ctx {
     double2 *bb = nullptr, *qq = nullptr;             // private
     double2 *xx = nullptr, *rr = nullptr, *pp[2] = {nullptr, nullptr};   // inside the arena
     PeerView     peer[SGV_MAX_RANKS];
+    // Ranks that share one GPU (tests on a box with fewer GPUs than ranks): kernels of different ranks
+    // are not guaranteed to run concurrently, so no kernel may wait for another rank's kernel.  In this
+    // mode every cross-rank reduction is completed by a HOST barrier between the reducing kernel and the
+    // resolve kernel (the partial sums are already in the inbox when it starts; it never spins).
+    bool         host_barrier = false;
+    sgv_ctx*     peer_ctx[SGV_MAX_RANKS] = {};
+    std::atomic<unsigned long long> host_seq{0};
     unsigned long long seq = 0;      // reductions issued so far (identical on all ranks)
     double2*     ds_ypart = nullptr; // DSYM kernel: per-row partial sums and per-tile tails
     double2*     ds_tails = nullptr;
@@ -223,7 +231,7 @@ int    sgv_preload_spmm();   // load all kernels of the TU on the current device
 int    sgv_preload_vamp();
 // spmm_dsym.cu
 int    sgv_preload_dsym();
-size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s);
+size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s, int nst);
 bool   sgv_dsym_feasible(int64_t w);
 int    sgv_dsym_ensure_scratch(sgv_ctx* c, const LdMatrix& ld);
 int    sgv_launch_dsym(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a);

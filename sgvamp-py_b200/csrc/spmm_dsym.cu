@@ -62,17 +62,49 @@ __device__ __forceinline__ double2 shfl_down1(double2 v, int lane) {
 
 static inline int ds_per(int Dp, int S) { return (((Dp + S - 1) / S) + 3) & ~3; }
 
-size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s) {
+
+// ---- per-warp TMA ring: the matrix stream goes global -> shared memory with bulk asynchronous copies
+// (cp.async.bulk, completion on an mbarrier), so the bytes in flight cost no registers.  One stage = one
+// group of 4 diagonals x the warp's 128 rows = 4 x 512 contiguous bytes.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+#define DS_STAGE_FLOATS 512   // 4 diagonals x 128 rows
+
+size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s, int nst) {
     const int Dp = (int)round_up(w + 1, 4);
     const int TR = 128 * rw;
-    size_t b = (size_t)4 * dia_plane_len(TR + Dp) * sizeof(double2);     // x window
-    b += (size_t)rw * s * (ds_per(Dp, s) + 128) * sizeof(double2);        // per-warp staging of the transposed sums
-    b += (size_t)s * TR * sizeof(double2);                                // forward sums per segment
+    size_t b = (size_t)4 * dia_plane_len(TR + Dp) * sizeof(double2);                   // x window
+    b += (size_t)rw * s * (ds_per(Dp, s) + 128) * sizeof(double2);                      // per-warp staging of the transposed sums
+    const size_t ring = (size_t)rw * s * nst * DS_STAGE_FLOATS * sizeof(float);         // per-warp TMA ring ...
+    const size_t fwd = (size_t)s * TR * sizeof(double2);                                // ... reused for the forward sums
+    b += ring > fwd ? ring : fwd;
+    b += (size_t)rw * s * nst * 8;                                                      // mbarriers
     return b;
 }
-bool sgv_dsym_feasible(int64_t w) { return sgv_dsym_smem_bytes(w, 1, 8) <= 200 * 1024; }
 
-template <int RW, int S, int PF, int MINB>
+template <int RW, int S, int NST, int MINB>
 __global__ void __launch_bounds__(32 * RW * S, MINB)
 k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_t E, double2* __restrict__ ypart,
             double2* __restrict__ tails) {
@@ -80,14 +112,18 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
     constexpr int TR = 128 * RW;
     constexpr int NT = 32 * RW * S;
     constexpr int NW = RW * S;
-    extern __shared__ double2 smem2[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int W = TR + Dp;
     const int PL = dia_plane_len(W);
     const int per = (((Dp + S - 1) / S) + 3) & ~3;
     const int SL = per + 128;
-    double2* xw = smem2;
+    constexpr size_t RING_B = (size_t)NW * NST * DS_STAGE_FLOATS * sizeof(float);
+    constexpr size_t FWD_B = (size_t)S * TR * sizeof(double2);
+    float* ring = reinterpret_cast<float*>(smem_raw);                                   // 128-byte aligned stages
+    double2* fwd = reinterpret_cast<double2*>(smem_raw);                                // aliases the ring (used after the loop)
+    double2* xw = reinterpret_cast<double2*>(smem_raw + (RING_B > FWD_B ? RING_B : FWD_B));
     double2* stag = xw + 4 * PL;
-    double2* fwd = stag + NW * SL;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(stag + NW * SL);
 
     const int64_t r0s = (int64_t)blockIdx.x * TR;   // storage index of the tile's first row
     const int64_t r0 = r0s - E;                     // the same in local coordinates (0 = first own row)
@@ -99,21 +135,31 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
 
     const int d0 = s * per;
     const int d1 = min(Dp, d0 + per);
-    const int ngroups = d0 < d1 ? ((d1 - d0) >> 2) : 0;   // warp-uniform; Dp and per are multiples of 4
+    const int64_t wrow = r0s + 128 * rw;            // first row of this warp
+    const unsigned row_bytes = wrow < ldb ? (unsigned)min((int64_t)512, (ldb - wrow) * 4) : 0u;
+    // warp-uniform; Dp and per are multiples of 4.  A warp entirely beyond the stored rows has no work.
+    const int ngroups = (d0 < d1 && row_bytes) ? ((d1 - d0) >> 2) : 0;
 
-    // ring of PF groups (4 diagonals each) in flight, issued before the x window is staged
-    const float* bp = U + (int64_t)d0 * ldb + row4s;
-    float4 q[PF][4];
+    // arm the ring: lane 0 initialises the warp's barriers, lanes 0..3 issue one diagonal each
+    float* wring = ring + (size_t)wid * NST * DS_STAGE_FLOATS;
+    const unsigned bar0 = smem_u32(bars + wid * NST);
+    const float* gsrc = U + (int64_t)(d0 + (lane & 3)) * ldb + wrow;                   // lane k<4: diagonal d0 + 4*gi + k
+    if (ngroups > 0) {
+        if (lane == 0) {
 #pragma unroll
-    for (int j = 0; j < PF; ++j) {
+            for (int t = 0; t < NST; ++t) mbar_init(bar0 + 8 * t, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) q[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active && j < ngroups) {
-            const float* lp = bp + (int64_t)(4 * j) * ldb;
-            q[j][0] = ldg_stream_f4(lp);
-            q[j][1] = ldg_stream_f4(lp + ldb);
-            q[j][2] = ldg_stream_f4(lp + 2 * ldb);
-            q[j][3] = ldg_stream_f4(lp + 3 * ldb);
+        for (int t = 0; t < NST; ++t) {
+            if (t < ngroups) {
+                if (lane == 0) mbar_expect_tx(bar0 + 8 * t, 4 * row_bytes);
+                __syncwarp();
+                if (lane < 4)
+                    bulk_g2s(smem_u32(wring + t * DS_STAGE_FLOATS + lane * 128), gsrc + (int64_t)(4 * t) * ldb, row_bytes,
+                             bar0 + 8 * t);
+            }
         }
     }
 
@@ -175,47 +221,56 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
         int xi = g + (d0 >> 2);
         double2 X0 = xw[xi], X1 = xw[PL + xi], X2 = xw[2 * PL + xi], X3 = xw[3 * PL + xi];
         double2* st = stag + wid * SL;
-        for (int m = 0; m < ngroups; m += PF) {
-#pragma unroll
-            for (int j = 0; j < PF; ++j) {
-                if (m + j < ngroups) {
-                    const double2 N0 = xw[xi + 1], N1 = xw[PL + xi + 1], N2 = xw[2 * PL + xi + 1], N3 = xw[3 * PL + xi + 1];
-                    DS_FWD(q[j][0], X0, X1, X2, X3);
-                    DS_TRN(q[j][0], T0, T1, T2, T3);
-                    DS_FWD(q[j][1], X1, X2, X3, N0);
-                    DS_TRN(q[j][1], T1, T2, T3, T4);
-                    DS_FWD(q[j][2], X2, X3, N0, N1);
-                    DS_TRN(q[j][2], T2, T3, T4, T5);
-                    DS_FWD(q[j][3], X3, N0, N1, N2);
-                    DS_TRN(q[j][3], T3, T4, T5, T6);
-                    X0 = N0; X1 = N1; X2 = N2; X3 = N3;
-                    ++xi;
-                    if (active && m + j + PF < ngroups) {
-                        const float* lp = bp + (int64_t)(4 * (m + j + PF)) * ldb;
-                        q[j][0] = ldg_stream_f4(lp);
-                        q[j][1] = ldg_stream_f4(lp + ldb);
-                        q[j][2] = ldg_stream_f4(lp + 2 * ldb);
-                        q[j][3] = ldg_stream_f4(lp + 3 * ldb);
-                    }
-                    // hand the 4 finished sums down one lane; lane 0's are final for the warp
-                    if (lane == 0) {
-                        double2* e = st + 4 * (m + j);
-                        e[0] = T0; e[1] = T1; e[2] = T2; e[3] = T3;
-                    }
-                    const double2 I0 = shfl_down1(T0, lane), I1 = shfl_down1(T1, lane), I2 = shfl_down1(T2, lane),
-                                  I3 = shfl_down1(T3, lane);
-                    T0 = make_double2(T4.x + I0.x, T4.y + I0.y);
-                    T1 = make_double2(T5.x + I1.x, T5.y + I1.y);
-                    T2 = make_double2(T6.x + I2.x, T6.y + I2.y);
-                    T3 = I3;
-                    T4 = T5 = T6 = make_double2(0.0, 0.0);
-                }
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        int stage = 0;
+        unsigned parity = 0;
+        for (int gi = 0; gi < ngroups; ++gi) {
+            // take this group's 4 x float4 out of the ring, then hand the stage straight back to the copy engine
+            mbar_wait(bar0 + 8 * stage, parity);
+            const float4* sp = reinterpret_cast<const float4*>(wring + stage * DS_STAGE_FLOATS) + lane;
+            float4 c0 = sp[0], c1 = sp[32], c2 = sp[64], c3 = sp[96];
+            if (!active) c0 = c1 = c2 = c3 = zero4;     // rows past the stored range were not copied
+            __syncwarp();
+            if (gi + NST < ngroups) {
+                if (lane == 0) mbar_expect_tx(bar0 + 8 * stage, 4 * row_bytes);
+                __syncwarp();
+                if (lane < 4)
+                    bulk_g2s(smem_u32(wring + stage * DS_STAGE_FLOATS + lane * 128), gsrc + (int64_t)(4 * (gi + NST)) * ldb,
+                             row_bytes, bar0 + 8 * stage);
             }
+            if (++stage == NST) {
+                stage = 0;
+                parity ^= 1u;
+            }
+            const double2 N0 = xw[xi + 1], N1 = xw[PL + xi + 1], N2 = xw[2 * PL + xi + 1], N3 = xw[3 * PL + xi + 1];
+            DS_FWD(c0, X0, X1, X2, X3);
+            DS_TRN(c0, T0, T1, T2, T3);
+            DS_FWD(c1, X1, X2, X3, N0);
+            DS_TRN(c1, T1, T2, T3, T4);
+            DS_FWD(c2, X2, X3, N0, N1);
+            DS_TRN(c2, T2, T3, T4, T5);
+            DS_FWD(c3, X3, N0, N1, N2);
+            DS_TRN(c3, T3, T4, T5, T6);
+            X0 = N0; X1 = N1; X2 = N2; X3 = N3;
+            ++xi;
+            // hand the 4 finished sums down one lane; lane 0's are final for the warp
+            if (lane == 0) {
+                double2* e = st + 4 * gi;
+                e[0] = T0; e[1] = T1; e[2] = T2; e[3] = T3;
+            }
+            const double2 I0 = shfl_down1(T0, lane), I1 = shfl_down1(T1, lane), I2 = shfl_down1(T2, lane),
+                          I3 = shfl_down1(T3, lane);
+            T0 = make_double2(T4.x + I0.x, T4.y + I0.y);
+            T1 = make_double2(T5.x + I1.x, T5.y + I1.y);
+            T2 = make_double2(T6.x + I2.x, T6.y + I2.y);
+            T3 = I3;
+            T4 = T5 = T6 = make_double2(0.0, 0.0);
         }
         // drain: every lane now holds finished sums for the disjoint targets (d1-d0) + 4*lane + {0..3}
         double2* e = st + (d1 - d0) + 4 * lane;
         e[0] = T0; e[1] = T1; e[2] = T2; e[3] = T3;
     }
+    __syncthreads();   // every warp is done with its ring: the forward sums reuse that memory
     {
         double2* f = fwd + s * TR + 4 * g;
         f[0] = acc0; f[1] = acc1; f[2] = acc2; f[3] = acc3;
@@ -240,7 +295,7 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
 #pragma unroll
                 for (int rw2 = 0; rw2 < RW; ++rw2) {
                     const int rel = t - 128 * rw2 - e0;
-                    if (rel >= 0 && rel < (e1 - e0) + 128) {
+                    if (rel >= 0 && rel < (e1 - e0) + 128 && r0s + 128 * rw2 < ldb) {
                         const double2 v = stag[(s2 * RW + rw2) * SL + rel];
                         sum.x += v.x;
                         sum.y += v.y;
@@ -286,20 +341,22 @@ k_dsym_finish(SpmmArgs a, const double2* __restrict__ ypart, const double2* __re
 // ---------------------------------------------------------------------------------------------
 #define DS_BIG_RW 2
 #define DS_BIG_S 4
-#define DS_PF 2
+#define DS_NST 4       // ring stages per warp (2 KB each): 16 warps x 8 KB = 128 KB of matrix bytes in flight per SM
 #define DS_MINB 2
-#define DS_SMEM_LIMIT (200 * 1024)
+#define DS_SMEM_LIMIT (220 * 1024)
+
+bool sgv_dsym_feasible(int64_t w) { return sgv_dsym_smem_bytes(w, 1, 8, DS_NST) <= DS_SMEM_LIMIT; }
 
 static bool ds_use_big(const sgv_ctx* c, const LdMatrix& ld) {
-    return ld.ldb >= (int64_t)c->sm_count * 2 * 256 && sgv_dsym_smem_bytes(ld.w, DS_BIG_RW, DS_BIG_S) <= 100 * 1024;
+    return ld.ldb >= (int64_t)c->sm_count * 2 * 256 && sgv_dsym_smem_bytes(ld.w, DS_BIG_RW, DS_BIG_S, DS_NST) <= 112 * 1024;
 }
 
 int sgv_dsym_tile_rows(const sgv_ctx* c, const LdMatrix& ld) { return ds_use_big(c, ld) ? 128 * DS_BIG_RW : 128; }
 
 int sgv_preload_dsym() {
-    SGV_CUDA(cudaFuncSetAttribute(k_spmm_dsym<DS_BIG_RW, DS_BIG_S, DS_PF, DS_MINB>,
+    SGV_CUDA(cudaFuncSetAttribute(k_spmm_dsym<DS_BIG_RW, DS_BIG_S, DS_NST, DS_MINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM_LIMIT));
-    SGV_CUDA(cudaFuncSetAttribute(k_spmm_dsym<1, 8, DS_PF, DS_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SGV_CUDA(cudaFuncSetAttribute(k_spmm_dsym<1, 8, DS_NST, DS_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   DS_SMEM_LIMIT));
     cudaFuncAttributes fa;
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_dsym_finish<EPI_Q>));
@@ -337,11 +394,11 @@ int sgv_dsym_ensure_scratch(sgv_ctx* c, const LdMatrix& ld) {
 template <int RW, int S>
 static int launch_main(sgv_ctx* c, const LdMatrix& ld, const SpmmArgs& a) {
     constexpr int TR = 128 * RW;
-    const size_t smem = sgv_dsym_smem_bytes(ld.w, RW, S);
+    const size_t smem = sgv_dsym_smem_bytes(ld.w, RW, S, DS_NST);
     SGV_CHECK(smem <= DS_SMEM_LIMIT, "half-bandwidth %lld too large for the DSYM kernel", (long long)ld.w);
     const unsigned grid = (unsigned)((ld.ldb + TR - 1) / TR);
     const int Dp = (int)round_up(ld.w + 1, 4);
-    k_spmm_dsym<RW, S, DS_PF, DS_MINB><<<grid, 32 * RW * S, smem, c->stream>>>(a, ld.band, Dp, ld.ldb, ld.ext, c->ds_ypart,
+    k_spmm_dsym<RW, S, DS_NST, DS_MINB><<<grid, 32 * RW * S, smem, c->stream>>>(a, ld.band, Dp, ld.ldb, ld.ext, c->ds_ypart,
                                                                                c->ds_tails);
     c->launches++;
     return 0;

@@ -27,7 +27,7 @@ SYMBOLS = [
     "sgv_lagrangian", "sgv_lmmse", "sgv_update_r1", "sgv_metrics", "sgv_spmm", "sgv_spmm_bench",
     "sgv_launch_count", "sgv_profile", "sgv_profile_read", "sgv_configure_part", "sgv_ipc_export", "sgv_ipc_import",
     "sgv_peer_attach_local", "sgv_partition_info", "sgv_ld_set_bandwidth_hint", "sgv_spmm_stage", "sgv_spmm_run",
-    "sgv_ld_adopt_dsym", "sgv_dsym_extension",
+    "sgv_ld_adopt_dsym", "sgv_dsym_extension", "sgv_set_host_barrier", "sgv_device_id",
 ]
 
 
@@ -125,6 +125,14 @@ class Handle:
 
     def peer_attach_local(self, peer_rank, other):
         self._ck(self.lib.sgv_peer_attach_local(self.h, C.c_int(peer_rank), other.h))
+
+    def set_host_barrier(self, enable):
+        self._ck(self.lib.sgv_set_host_barrier(self.h, C.c_int(int(enable))))
+
+    def device_id(self):
+        buf = C.create_string_buffer(32)
+        self._ck(self.lib.sgv_device_id(self.h, buf, C.c_int(32)))
+        return buf.value.decode()
 
     def set_bandwidth_hint(self, w):
         self._ck(self.lib.sgv_ld_set_bandwidth_hint(self.h, C.c_int64(int(w))))

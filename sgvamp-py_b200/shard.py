@@ -156,17 +156,29 @@ class ThreadShard:
 
 def attach_peers(handle, shard):
     """Give every rank a mapping of every other rank's symmetric arena (CUDA IPC between
-    processes, direct peer access between threads of one process)."""
+    processes, direct peer access between threads of one process).
+
+    Ranks normally own one GPU each and complete cross-rank reductions inside their kernels.  If
+    two ranks share a GPU (in-process test ranks on a box with fewer GPUs than ranks) their kernels
+    are not guaranteed to run concurrently, so all ranks switch to completing the reductions with
+    a host barrier (sgv_set_host_barrier); separate processes sharing a GPU are refused."""
     if shard.world == 1:
         return
-    if isinstance(shard, ThreadShard):
-        peers = shard.allgather((handle, handle.M))
-        for q, (h, _rows) in enumerate(peers):
-            if q != shard.rank:
-                handle.peer_attach_local(q, h)
+    local = isinstance(shard, ThreadShard)
+    if local:
+        peers = shard.allgather((handle, handle.M, handle.device_id()))
     else:
-        peers = shard.allgather((handle.ipc_export(), handle.M))
-        for q, (hb, rows) in enumerate(peers):
-            if q != shard.rank:
-                handle.ipc_import(q, hb, rows)
+        peers = shard.allgather((handle.ipc_export(), handle.M, handle.device_id()))
+    devs = [p[2] for p in peers]
+    shared = len(set(devs)) < len(devs)
+    if shared and not local:
+        raise Exception("ranks %s share a GPU: the multi-process row partition needs one GPU per rank" % devs)
+    for q, (hq, rows, _dev) in enumerate(peers):
+        if q != shard.rank:
+            if local:
+                handle.peer_attach_local(q, hq)
+            else:
+                handle.ipc_import(q, hq, rows)
+    if local:
+        handle.set_host_barrier(shared)
     shard.barrier()
