@@ -94,7 +94,7 @@ def build_problem(torch, M, w, seed, dev, lo=0, hi=None, ext=0, keep_full=True):
     r += float(np.sqrt(1.0 - H2)) * (float(np.sqrt(1.0 - S_REG)) * noise[ext:] + float(np.sqrt(S_REG)) * z)
     # half band: U[d, j] = Rused[i, i+d], i = glo + j; extension rows keep only their couplings to own rows
     Dp = (w + 1 + 3) // 4 * 4
-    ldb = (n + 31) // 32 * 32
+    ldb = (n + 127) // 128 * 128
     U = torch.zeros((Dp, ldb), device=dev, dtype=torch.float32)
     U[: w + 1, :n] = band[w:, :]
     U[0] *= 0.5                                     # DSYM convention: the diagonal is stored halved
@@ -104,6 +104,7 @@ def build_problem(torch, M, w, seed, dev, lo=0, hi=None, ext=0, keep_full=True):
         U[:, :ext] *= (jj + dd >= ext).to(torch.float32)
     full = band[:, ext:].contiguous() if keep_full else None
     del band
+    U = ldgen.dsym_tile(torch, U)                   # [ldb/128][Dp/4][4][128]: one contiguous stream per 128-row block
     torch.cuda.synchronize()
     return U, ldb, full, r.cpu().numpy(), x0_host, time.time() - t0
 

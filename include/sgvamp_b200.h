@@ -84,12 +84,14 @@ int sgv_ld_upload_csr(sgv_handle h, int cohort, const int64_t* indptr, const int
  * dia: band[d*ldb + i] = Rused[i][i+d-w], d in [0,2w]; ldb multiple of 4 elements, base 16B aligned.
  * dense: row-major M x M, ld multiple of 4, base 16B aligned. */
 int sgv_ld_adopt_dia(sgv_handle h, int cohort, const float* band_dev, int64_t w, int64_t ldb);
-/* dsym: symmetric half band, U[d*ldb + j] = Rused[i][i+d] for d in [1,w] and HALF of Rused[i][i] for d = 0
- * (the kernel applies every stored value twice: to row i and to row i+d), j = i + ext, stored with
- * roundup(w+1,4) diagonals (the padding diagonals zero), zero where i+d is outside the matrix; ldb a
- * multiple of 32 >= rows + ext.  `ext` (from sgv_dsym_extension: 0 on a single GPU / rank 0) is the
- * number of rows BEFORE this rank's first row that the buffer also holds (their couplings to this
- * rank's rows; anything else in them zero). */
+/* dsym: symmetric half band.  Holds Rused[i][i+d] for d in [1,w] and HALF of Rused[i][i] for d = 0 (the
+ * kernel applies every stored value twice: to row i and to row i+d) at storage row j = i + ext, with
+ * Dp = roundup(w+1,4) diagonals (padding diagonals zero), zero where i+d is outside the matrix, and
+ * ldb = a multiple of 128 >= rows + ext storage rows (padding rows zero).  Tiled so that each block of 128
+ * rows is one contiguous stream of 2 KB groups of 4 diagonals:
+ *     U[ ((j/128)*(Dp/4) + d/4)*512 + (d%4)*128 + j%128 ]
+ * `ext` (from sgv_dsym_extension: 0 on a single GPU / rank 0) is the number of rows BEFORE this rank's
+ * first row that the buffer also holds (their couplings to this rank's rows; anything else in them zero). */
 int sgv_ld_adopt_dsym(sgv_handle h, int cohort, const float* U_dev, int64_t w, int64_t ldb, int64_t ext);
 int sgv_dsym_extension(sgv_handle h, int64_t w, int64_t* ext);
 int sgv_ld_adopt_dense(sgv_handle h, int cohort, const float* R_dev, int64_t ld);

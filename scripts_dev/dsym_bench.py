@@ -7,12 +7,14 @@ import sgv_native as nat
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 w = int(sys.argv[2]) if len(sys.argv) > 2 else 500
 Dp = (w + 1 + 3) // 4 * 4
-ldb = (M + 31) // 32 * 32
+ldb = (M + 127) // 128 * 128
 U = torch.randn((Dp, ldb), device="cuda", dtype=torch.float32) * 0.01
 U[w + 1:] = 0
 for d in range(1, w + 1):
     U[d, M - d:] = 0
 U[:, M:] = 0
+import ldgen
+U = ldgen.dsym_tile(torch, U)
 h = nat.Handle()
 h.configure(M, 1)
 h.adopt_dsym(0, U.data_ptr(), w, ldb, 0)

@@ -92,25 +92,30 @@ __global__ void k_csr_to_dia(int64_t M, const int64_t* __restrict__ indptr, cons
 
 // symmetric half band: own rows give the upper diagonals, the couplings of own rows to the E extension
 // rows before them (local column < 0) fill those rows' upper diagonals by symmetry
+__global__ void k_dsym_fill_diag(float* U, int64_t M, int64_t E, int64_t ngr, float v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x)
+        U[sgv_dsym_index(i + E, 0, ngr)] = v;
+}
+
 template <typename T>
 __global__ void k_csr_to_dsym(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                              const T* __restrict__ data, float* __restrict__ U, int64_t ldb, int64_t E, double s,
+                              const T* __restrict__ data, float* __restrict__ U, int64_t ngr, int64_t E, double s,
                               int col_base) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
     for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
         const int64_t cl = (int64_t)indices[k] - col_base;
-        if (cl > row) U[(cl - row) * ldb + row + E] = reg_value(data[k], false, s);
-        else if (cl == row) U[row + E] = 0.5f * reg_value(data[k], true, s);   // the diagonal is stored halved
-        else if (cl < 0 && cl + E >= 0) U[(row - cl) * ldb + cl + E] = reg_value(data[k], false, s);
+        if (cl > row) U[sgv_dsym_index(row + E, cl - row, ngr)] = reg_value(data[k], false, s);
+        else if (cl == row) U[sgv_dsym_index(row + E, 0, ngr)] = 0.5f * reg_value(data[k], true, s);   // diagonal stored halved
+        else if (cl < 0 && cl + E >= 0) U[sgv_dsym_index(cl + E, row - cl, ngr)] = reg_value(data[k], false, s);
     }
 }
 
 // entries below the diagonal inside the own rows must mirror the stored upper ones (to fp32 rounding)
 template <typename T>
 __global__ void k_dsym_check(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                             const T* __restrict__ data, const float* __restrict__ U, int64_t ldb, int64_t E, double s,
+                             const T* __restrict__ data, const float* __restrict__ U, int64_t ngr, int64_t E, double s,
                              int col_base, unsigned long long* __restrict__ mismatches) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -119,7 +124,7 @@ __global__ void k_dsym_check(int64_t M, const int64_t* __restrict__ indptr, cons
     for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
         const int64_t cl = (int64_t)indices[k] - col_base;
         if (cl >= 0 && cl < row) {
-            const float lo = reg_value(data[k], false, s), up = U[(row - cl) * ldb + cl + E];
+            const float lo = reg_value(data[k], false, s), up = U[sgv_dsym_index(cl + E, row - cl, ngr)];
             if (fabsf(lo - up) > 4e-7f * fmaxf(fabsf(lo), fabsf(up))) ++bad;
         }
     }
@@ -323,7 +328,7 @@ extern "C" int sgv_ld_adopt_dsym(sgv_handle c, int cohort, const float* U_dev, i
     SGV_CHECK(w >= 0 && sgv_dsym_feasible(w), "half-bandwidth %lld not supported by the DSYM kernel", (long long)w);
     SGV_CHECK(ext == sgv_dsym_ext(c, w), "extension rows %lld, expected %lld (sgv_dsym_extension)", (long long)ext,
               (long long)sgv_dsym_ext(c, w));
-    SGV_CHECK(ldb >= c->Ml + ext && ldb % 32 == 0, "ldb must be a multiple of 32 and >= local rows + extension");
+    SGV_CHECK(ldb >= c->Ml + ext && ldb % 128 == 0, "ldb must be a multiple of 128 and >= local rows + extension");
     LdMatrix& ld = c->coh[cohort].ld;
     sgv_ld_free(ld);
     ld.band = U_dev;
@@ -344,7 +349,7 @@ static int convert_csr(sgv_ctx* c, LdMatrix& ld, int layout, const int64_t* d_in
     const unsigned wgrid = (unsigned)((M * 32 + 255) / 256);
     if (layout == SGV_LAYOUT_DSYM) {
         const int64_t E = sgv_dsym_ext(c, w), Dp = round_up(w + 1, 4);
-        const int64_t ldb = round_up(M + E, 32);
+        const int64_t ldb = round_up(M + E, 128), ngr = Dp / 4;
         float* U = nullptr;
         SGV_CUDA(cudaMalloc(&U, (size_t)Dp * ldb * sizeof(float)));
         ld.band = U;
@@ -354,11 +359,11 @@ static int convert_csr(sgv_ctx* c, LdMatrix& ld, int layout, const int64_t* d_in
         ld.ext = E;
         ld.nnz_stored = (w + 1) * M;
         SGV_CUDA(cudaMemsetAsync(U, 0, (size_t)Dp * ldb * sizeof(float), c->stream));
-        k_fill_f32<<<592, 256, 0, c->stream>>>(U + E, M, 0.5f * (float)s);   // absent diagonal entry (stored halved)
-        k_csr_to_dsym<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, U, ldb, E, s, col_base);
+        k_dsym_fill_diag<<<592, 256, 0, c->stream>>>(U, M, E, ngr, 0.5f * (float)s);   // absent diagonal entry (stored halved)
+        k_csr_to_dsym<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, U, ngr, E, s, col_base);
         unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(c->counter + 8);   // spare words of the ticket block
         SGV_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
-        k_dsym_check<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, U, ldb, E, s, col_base, d_bad);
+        k_dsym_check<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, U, ngr, E, s, col_base, d_bad);
         c->launches += 3;
         unsigned long long bad = 0;
         SGV_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));

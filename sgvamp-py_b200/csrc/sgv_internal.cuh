@@ -235,6 +235,10 @@ size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s, int nst);
 bool   sgv_dsym_feasible(int64_t w);
 int    sgv_dsym_ensure_scratch(sgv_ctx* c, const LdMatrix& ld);
 int    sgv_launch_dsym(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a);
+// element offset of diagonal d (0..Dp-1) at storage row j in the tiled DSYM layout (ngr = Dp/4)
+__host__ __device__ static inline int64_t sgv_dsym_index(int64_t j, int64_t d, int64_t ngr) {
+    return ((j >> 7) * ngr + (d >> 2)) * 512 + (d & 3) * 128 + (j & 127);
+}
 static inline int64_t sgv_dsym_ext(const sgv_ctx* c, int64_t w) { return (c->halo && c->rank > 0) ? round_up(w, 256) : 0; }
 bool   sgv_dia_feasible(int64_t w);
 // ld_formats.cu

@@ -1,8 +1,11 @@
 // Symmetric half-band SpMM ("DSYM" layout): out = gamw * (R v) + gam2 * v for a pair of fp64
 // vectors, R symmetric banded and stored ONCE: only the diagonals d = 0..w of the upper triangle,
-//     U[d*ldb + j] = R[i][i+d],   j = i + E   (E: leading extension rows, see below),
-// padded with zero diagonals to a multiple of 4; diagonal 0 holds HALF of R[i][i] (exact in fp32), because
-// the kernel uses every stored value twice - forward and transposed - and for d = 0 both uses hit row i.  One pass reads 4*(w+1) bytes per row instead of
+// R[i][i+d] at storage row j = i + E (E: leading extension rows, see below), padded with zero diagonals to
+// Dp = roundup(w+1,4) and zero rows to ldb = roundup(rows,128); diagonal 0 holds HALF of R[i][i] (exact in
+// fp32), because the kernel uses every stored value twice - forward and transposed - and for d = 0 both
+// uses hit row i.  The values are TILED so that what one warp consumes is one contiguous stream:
+//     U[ ((j/128)*(Dp/4) + d/4)*512 + (d%4)*128 + j%128 ]        (sgv_dsym_index)
+// i.e. per block of 128 rows, groups of 4 diagonals of 2 KB each, in diagonal order.  One pass reads 4*(w+1) bytes per row instead of
 // the 4*(2w+1) of the full band - the matrix stream is the whole cost of a CG iteration (HBM bound),
 // so this halves it.
 //
@@ -52,11 +55,10 @@
         TD.x = fma(v3, O3.x, TD.x); TD.y = fma(v3, O3.y, TD.y);                               \
     } while (0)
 
-__device__ __forceinline__ double2 shfl_down1(double2 v, int lane) {
+__device__ __forceinline__ double2 shfl_down1(double2 v) {   // lane 31 gets its own value back
     double2 r;
     r.x = __shfl_down_sync(0xffffffffu, v.x, 1);
     r.y = __shfl_down_sync(0xffffffffu, v.y, 1);
-    if (lane == 31) r = make_double2(0.0, 0.0);
     return r;
 }
 
@@ -130,38 +132,30 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int rw = wid % RW, s = wid / RW;
     const int g = rw * 32 + lane;
-    const int64_t row4s = r0s + 4 * g;
-    const bool active = row4s < ldb;
-
     const int d0 = s * per;
     const int d1 = min(Dp, d0 + per);
-    const int64_t wrow = r0s + 128 * rw;            // first row of this warp
-    const unsigned row_bytes = wrow < ldb ? (unsigned)min((int64_t)512, (ldb - wrow) * 4) : 0u;
-    // warp-uniform; Dp and per are multiples of 4.  A warp entirely beyond the stored rows has no work.
-    const int ngroups = (d0 < d1 && row_bytes) ? ((d1 - d0) >> 2) : 0;
+    const int64_t wrow = r0s + 128 * rw;            // first row of this warp (ldb is a multiple of 128)
+    // warp-uniform; Dp and per are multiples of 4.  A warp beyond the stored rows has no work.
+    const int ngroups = (d0 < d1 && wrow < ldb) ? ((d1 - d0) >> 2) : 0;
 
-    // arm the ring: lane 0 initialises the warp's barriers, lanes 0..3 issue one diagonal each
+    // arm the ring: lane 0 initialises the warp's barriers and issues one 2 KB bulk copy per stage
     float* wring = ring + (size_t)wid * NST * DS_STAGE_FLOATS;
     const unsigned bar0 = smem_u32(bars + wid * NST);
-    const float* gsrc = U + (int64_t)(d0 + (lane & 3)) * ldb + wrow;                   // lane k<4: diagonal d0 + 4*gi + k
-    if (ngroups > 0) {
-        if (lane == 0) {
+    const unsigned ring0 = smem_u32(wring);
+    const float* gsrc = U + ((wrow >> 7) * (int64_t)(Dp >> 2) + (d0 >> 2)) * DS_STAGE_FLOATS;   // group gi: + gi*512 floats
+    if (ngroups > 0 && lane == 0) {
 #pragma unroll
-            for (int t = 0; t < NST; ++t) mbar_init(bar0 + 8 * t, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncwarp();
+        for (int t = 0; t < NST; ++t) mbar_init(bar0 + 8 * t, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
         for (int t = 0; t < NST; ++t) {
             if (t < ngroups) {
-                if (lane == 0) mbar_expect_tx(bar0 + 8 * t, 4 * row_bytes);
-                __syncwarp();
-                if (lane < 4)
-                    bulk_g2s(smem_u32(wring + t * DS_STAGE_FLOATS + lane * 128), gsrc + (int64_t)(4 * t) * ldb, row_bytes,
-                             bar0 + 8 * t);
+                mbar_expect_tx(bar0 + 8 * t, DS_STAGE_FLOATS * 4);
+                bulk_g2s(ring0 + t * DS_STAGE_FLOATS * 4, gsrc + (int64_t)t * DS_STAGE_FLOATS, DS_STAGE_FLOATS * 4, bar0 + 8 * t);
             }
         }
     }
+    __syncwarp();   // the barriers are initialised before any lane waits on them
 
     // stage the x window [r0, r0+TR+Dp) (local coordinates).  Entries left of 0 come from the left
     // neighbour (extension rows), entries right of M from the right neighbour, zero at the matrix
@@ -221,50 +215,47 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
         int xi = g + (d0 >> 2);
         double2 X0 = xw[xi], X1 = xw[PL + xi], X2 = xw[2 * PL + xi], X3 = xw[3 * PL + xi];
         double2* st = stag + wid * SL;
-        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        int stage = 0;
-        unsigned parity = 0;
-        for (int gi = 0; gi < ngroups; ++gi) {
-            // take this group's 4 x float4 out of the ring, then hand the stage straight back to the copy engine
-            mbar_wait(bar0 + 8 * stage, parity);
-            const float4* sp = reinterpret_cast<const float4*>(wring + stage * DS_STAGE_FLOATS) + lane;
-            float4 c0 = sp[0], c1 = sp[32], c2 = sp[64], c3 = sp[96];
-            if (!active) c0 = c1 = c2 = c3 = zero4;     // rows past the stored range were not copied
-            __syncwarp();
-            if (gi + NST < ngroups) {
-                if (lane == 0) mbar_expect_tx(bar0 + 8 * stage, 4 * row_bytes);
-                __syncwarp();
-                if (lane < 4)
-                    bulk_g2s(smem_u32(wring + stage * DS_STAGE_FLOATS + lane * 128), gsrc + (int64_t)(4 * (gi + NST)) * ldb,
-                             row_bytes, bar0 + 8 * stage);
+        const double hm = lane == 31 ? 0.0 : 1.0;   // lane 31 has no lane above: its incoming sums are zero
+        for (int gb = 0; gb < ngroups; gb += NST) {
+            const unsigned parity = (unsigned)(gb / NST) & 1u;
+#pragma unroll
+            for (int stage = 0; stage < NST; ++stage) {
+                const int gi = gb + stage;
+                if (gi < ngroups) {
+                    // take this group's 4 x float4 out of the ring, then hand the stage straight back to the copy engine
+                    mbar_wait(bar0 + 8 * stage, parity);
+                    const float4* sp = reinterpret_cast<const float4*>(wring + stage * DS_STAGE_FLOATS) + lane;
+                    const float4 c0 = sp[0], c1 = sp[32], c2 = sp[64], c3 = sp[96];
+                    __syncwarp();
+                    if (lane == 0 && gi + NST < ngroups) {
+                        mbar_expect_tx(bar0 + 8 * stage, DS_STAGE_FLOATS * 4);
+                        bulk_g2s(ring0 + stage * DS_STAGE_FLOATS * 4, gsrc + (int64_t)(gi + NST) * DS_STAGE_FLOATS,
+                                 DS_STAGE_FLOATS * 4, bar0 + 8 * stage);
+                    }
+                    const double2 N0 = xw[xi + 1], N1 = xw[PL + xi + 1], N2 = xw[2 * PL + xi + 1], N3 = xw[3 * PL + xi + 1];
+                    DS_FWD(c0, X0, X1, X2, X3);
+                    DS_TRN(c0, T0, T1, T2, T3);
+                    DS_FWD(c1, X1, X2, X3, N0);
+                    DS_TRN(c1, T1, T2, T3, T4);
+                    DS_FWD(c2, X2, X3, N0, N1);
+                    DS_TRN(c2, T2, T3, T4, T5);
+                    DS_FWD(c3, X3, N0, N1, N2);
+                    DS_TRN(c3, T3, T4, T5, T6);
+                    X0 = N0; X1 = N1; X2 = N2; X3 = N3;
+                    ++xi;
+                    // hand the 4 finished sums down one lane; lane 0's are final for the warp
+                    if (lane == 0) {
+                        double2* e = st + 4 * gi;
+                        e[0] = T0; e[1] = T1; e[2] = T2; e[3] = T3;
+                    }
+                    const double2 I0 = shfl_down1(T0), I1 = shfl_down1(T1), I2 = shfl_down1(T2), I3 = shfl_down1(T3);
+                    T0 = make_double2(fma(I0.x, hm, T4.x), fma(I0.y, hm, T4.y));
+                    T1 = make_double2(fma(I1.x, hm, T5.x), fma(I1.y, hm, T5.y));
+                    T2 = make_double2(fma(I2.x, hm, T6.x), fma(I2.y, hm, T6.y));
+                    T3 = make_double2(I3.x * hm, I3.y * hm);
+                    T4 = T5 = T6 = make_double2(0.0, 0.0);
+                }
             }
-            if (++stage == NST) {
-                stage = 0;
-                parity ^= 1u;
-            }
-            const double2 N0 = xw[xi + 1], N1 = xw[PL + xi + 1], N2 = xw[2 * PL + xi + 1], N3 = xw[3 * PL + xi + 1];
-            DS_FWD(c0, X0, X1, X2, X3);
-            DS_TRN(c0, T0, T1, T2, T3);
-            DS_FWD(c1, X1, X2, X3, N0);
-            DS_TRN(c1, T1, T2, T3, T4);
-            DS_FWD(c2, X2, X3, N0, N1);
-            DS_TRN(c2, T2, T3, T4, T5);
-            DS_FWD(c3, X3, N0, N1, N2);
-            DS_TRN(c3, T3, T4, T5, T6);
-            X0 = N0; X1 = N1; X2 = N2; X3 = N3;
-            ++xi;
-            // hand the 4 finished sums down one lane; lane 0's are final for the warp
-            if (lane == 0) {
-                double2* e = st + 4 * gi;
-                e[0] = T0; e[1] = T1; e[2] = T2; e[3] = T3;
-            }
-            const double2 I0 = shfl_down1(T0, lane), I1 = shfl_down1(T1, lane), I2 = shfl_down1(T2, lane),
-                          I3 = shfl_down1(T3, lane);
-            T0 = make_double2(T4.x + I0.x, T4.y + I0.y);
-            T1 = make_double2(T5.x + I1.x, T5.y + I1.y);
-            T2 = make_double2(T6.x + I2.x, T6.y + I2.y);
-            T3 = I3;
-            T4 = T5 = T6 = make_double2(0.0, 0.0);
         }
         // drain: every lane now holds finished sums for the disjoint targets (d1-d0) + 4*lane + {0..3}
         double2* e = st + (d1 - d0) + 4 * lane;

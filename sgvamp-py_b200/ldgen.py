@@ -227,6 +227,14 @@ def banded_dia_device(torch, M, w, lo, hi, seed, dev, N_ld=4096, chunk=4096):
     return band, noise
 
 
+def dsym_tile(torch, U):
+    """(Dp, ldb) diagonal-major half band (Dp % 4 == 0, ldb % 128 == 0) -> the tiled DSYM layout of
+    sgv_ld_adopt_dsym: [ldb/128][Dp/4][4][128], contiguous."""
+    Dp, ldb = U.shape
+    assert Dp % 4 == 0 and ldb % 128 == 0
+    return U.view(Dp // 4, 4, ldb // 128, 128).permute(2, 0, 1, 3).contiguous()
+
+
 def causal_effects(M, N, lam, h2, seed):
     """Sparse true effects scaled by sqrt(N) (the x0 the solver estimates)."""
     rng = np.random.default_rng(seed + 99)

@@ -429,10 +429,12 @@ def test_spmm_properties_large(nat):
     assert np.array_equal(h.spmm(0, x), Rx)                                         # run-to-run determinism
     # the symmetric half-band layout of the same matrix (upper diagonals, padded to a multiple of 4)
     Dp = (w + 1 + 3) // 4 * 4
-    ldb = (M + 31) // 32 * 32
+    ldb = (M + 127) // 128 * 128
     U = torch.zeros((Dp, ldb), device="cuda", dtype=torch.float32)
     U[: w + 1, :M] = band[w:, :]
     U[0] *= 0.5                                                                     # diagonal stored halved
+    import ldgen
+    U = ldgen.dsym_tile(torch, U)                                                   # tiled layout of sgv_ld_adopt_dsym
     h.adopt_dsym(0, U.data_ptr(), w, ldb, 0)
     assert h.ld_info(0)["layout"] == "dsym"
     Sx = h.spmm(0, x)
