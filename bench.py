@@ -76,6 +76,8 @@ def build_problem(torch, M, w, seed, dev, lo=0, hi=None, ext=0, keep_full=True):
     assert glo >= 0
     n = hi - glo
     band, noise = ldgen.banded_dia_device(torch, M, w, glo, hi, seed, dev, N_ld=N_LD)   # (2w+1) x n
+    for d in range(1, w + 1):                       # exactly symmetric: the lower triangle mirrors the upper one
+        band[w - d, d:] = band[w + d, : n - d]      # (fp32 sample LD differs in the last bit between the triangles)
     band *= (1.0 - S_REG)                           # Rused = (1-s) R + s I  (src/main.py:265)
     band[w, :] += S_REG
     x0_host = ldgen.causal_effects(M, n_gwas(M), LAM_TRUE, H2, seed)
@@ -373,7 +375,15 @@ def main():
         v2 = new_solver()
         barrier()
         t0 = time.perf_counter()
-        v2.load_ld(0, Rh)
+        if os.environ.get("SGV_TIMING"):
+            import cProfile, pstats
+            pr = cProfile.Profile()
+            pr.enable()
+            v2.load_ld(0, Rh)
+            pr.disable()
+            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(12)
+        else:
+            v2.load_ld(0, Rh)
         torch.cuda.synchronize()
         t_up = time.perf_counter() - t0
         xs2 = run(v2, None, iterations, None, write_outputs=False)
@@ -386,7 +396,8 @@ def main():
                "what": "VAMP.load_ld(scipy CSR fp32 rows of this rank in pinned host memory) + VAMP.infer(r host) for %d "
                        "iterations from it=0: LD upload + layout conversion + every iteration's probe H2D and xhat D2H "
                        "inside the timed region (wall clock between barriers, max over ranks)" % iterations,
-               "seconds": dt, "ld_upload_seconds": max_over_ranks(t_up), "max_rel_diff_vs_resident": diff}
+               "seconds": dt, "ld_upload_seconds": max_over_ranks(t_up), "max_rel_diff_vs_resident": diff,
+               "layout": v2.handle.ld_info(0)["layout"]}
         v2.close()
         del Rh, keep
 

@@ -3,7 +3,10 @@
 // Layout detection (bandwidth, diagonal blocks, fill) runs on per-row column extents computed on
 // the device, so the host never walks the nnz arrays.
 #include <algorithm>
+#include <chrono>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include "sgv_device.cuh"
 
 void sgv_ld_free(LdMatrix& ld) {
@@ -116,7 +119,7 @@ __global__ void k_csr_to_dsym(int64_t M, const int64_t* __restrict__ indptr, con
 template <typename T>
 __global__ void k_dsym_check(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                              const T* __restrict__ data, const float* __restrict__ U, int64_t ngr, int64_t E, double s,
-                             int col_base, unsigned long long* __restrict__ mismatches) {
+                             int col_base, float abs_tol, unsigned long long* __restrict__ mismatches) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
@@ -124,8 +127,10 @@ __global__ void k_dsym_check(int64_t M, const int64_t* __restrict__ indptr, cons
     for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
         const int64_t cl = (int64_t)indices[k] - col_base;
         if (cl >= 0 && cl < row) {
+            // symmetric to fp32 rounding: relative to the entry, or (LD computed in fp32: the two triangles come
+            // from different summation orders) to the largest diagonal entry
             const float lo = reg_value(data[k], false, s), up = U[sgv_dsym_index(cl + E, row - cl, ngr)];
-            if (fabsf(lo - up) > 4e-7f * fmaxf(fabsf(lo), fabsf(up))) ++bad;
+            if (fabsf(lo - up) > fmaxf(4e-7f * fmaxf(fabsf(lo), fabsf(up)), abs_tol)) ++bad;
         }
     }
     if (bad) atomicAdd(mismatches, (unsigned long long)bad);
@@ -363,7 +368,12 @@ static int convert_csr(sgv_ctx* c, LdMatrix& ld, int layout, const int64_t* d_in
         k_csr_to_dsym<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, U, ngr, E, s, col_base);
         unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(c->counter + 8);   // spare words of the ticket block
         SGV_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
-        k_dsym_check<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, U, ngr, E, s, col_base, d_bad);
+        // absolute tolerance 2e-6 x the scale of the diagonal (1 for a correlation matrix; read from row 0)
+        float diag0 = 1.f;
+        SGV_CUDA(cudaMemcpyAsync(&diag0, U + sgv_dsym_index(E, 0, ngr), sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+        const float abs_tol = 2e-6f * fmaxf(2.f * fabsf(diag0), 1e-30f);
+        k_dsym_check<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, U, ngr, E, s, col_base, abs_tol, d_bad);
         c->launches += 3;
         unsigned long long bad = 0;
         SGV_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
@@ -440,9 +450,25 @@ static int convert_csr(sgv_ctx* c, LdMatrix& ld, int layout, const int64_t* d_in
     return 0;
 }
 
+// SGV_TIMING=1: print the phases of an upload (host clock after a stream synchronise) to stderr
+struct PhaseTimer {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t;
+    PhaseTimer(cudaStream_t s) : on(getenv("SGV_TIMING") != nullptr), st(s), t(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sgv upload] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
 extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr, const int32_t* indices,
                                  const void* data, int dtype, int64_t nnz, double s, int layout_hint) {
     SGV_TRY(check_cohort(c, cohort));
+    PhaseTimer pt(c->stream);
     SGV_CHECK(indptr && (nnz == 0 || (indices && data)), "null CSR arrays");
     SGV_CHECK(dtype == SGV_F32 || dtype == SGV_F64, "bad dtype %d", dtype);
     SGV_CHECK(c->M < INT_MAX, "M too large for int32 column indices");
@@ -462,11 +488,13 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
     SGV_CUDA(cudaMalloc(&d_indices, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
     SGV_CUDA(cudaMalloc(&d_data, std::max<int64_t>(nnz, 1) * esz));
     SGV_CUDA(cudaMalloc(&d_lo, 3 * M * sizeof(int)));
+    pt.lap("free old + cudaMalloc staging");
     d_hi = d_lo + M;
     d_dg = d_hi + M;
     SGV_CUDA(cudaMemcpyAsync(d_indptr, indptr, (M + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     SGV_CUDA(cudaMemcpyAsync(d_indices, indices, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     SGV_CUDA(cudaMemcpyAsync(d_data, data, nnz * esz, cudaMemcpyHostToDevice, c->stream));
+    pt.lap("H2D copies");
     const unsigned wgrid = (unsigned)((M * 32 + 255) / 256);
     k_row_extent<<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_lo, d_hi, d_dg, col_base);
     c->launches++;
@@ -475,6 +503,7 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
     SGV_CUDA(cudaStreamSynchronize(c->stream));
     const int *lo = ext.data(), *hi = lo + M, *dg = hi + M;
 
+    pt.lap("row extents");
     // ---- structure analysis on M-length arrays ----
     int64_t w = 0;
     bool all_diag = true;
@@ -537,6 +566,7 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
     if ((layout == SGV_LAYOUT_DENSE || layout == SGV_LAYOUT_BLOCKDIAG) && !blk_fits) { sgv_set_error("dense blocks do not fit in device memory"); rc = -1; }
     if (layout == SGV_LAYOUT_CSR && s != 0.0 && !all_diag) { sgv_set_error("CSR layout with s != 0 needs every diagonal entry stored"); rc = -3; }
     if (layout == SGV_LAYOUT_DENSE) starts = {0, M};
+    pt.lap("structure analysis (host)");
     for (int attempt = 0; rc == 0 && attempt < 2; ++attempt) {
         if (dtype == SGV_F64) rc = convert_csr<double>(c, ld, layout, d_indptr, d_indices, (const double*)d_data, nnz, s, w, starts);
         else rc = convert_csr<float>(c, ld, layout, d_indptr, d_indices, (const float*)d_data, nnz, s, w, starts);
@@ -549,6 +579,7 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
             rc = -1;
         }
     }
+    pt.lap("layout conversion");
     cudaFree(d_data);
     cudaFree(d_lo);
     if (rc == 0 && layout == SGV_LAYOUT_CSR) {
@@ -559,6 +590,7 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
         cudaFree(d_indices);
     }
     if (rc != 0) sgv_ld_free(ld);
+    pt.lap("free staging");
     return rc;
 }
 
