@@ -171,40 +171,10 @@ extern "C" int sgv_profile_read(sgv_handle c, double* total_ms, int64_t* launche
 // rank order (bit-identical on all ranks) and applies the state transition.  A bounded spin: on
 // time-out the error flag is raised and both CG columns are marked done so that nothing hangs.
 __global__ void k_resolve(RedCtx rc) {
-    if (rc.skip_if_done && rc.st->done[0] && rc.st->done[1]) return;   // nobody published: the producers exited early too
-    Inbox* me = rc.inbox[rc.rank];
-    const int slot = (int)(rc.seq % SGV_INBOX_SLOTS);
-    const int lane = threadIdx.x;
-    bool good = true;
-    if (lane < rc.world) {
-        const long long t0 = clock64();
-        while (ld_acquire_sys(&me->flag[slot][lane]) != rc.seq) {
-            if (clock64() - t0 > 40000000000LL) {   // ~20 s: bounded, so a lost rank cannot hang the GPU
-                good = false;
-                break;
-            }
-            __nanosleep(64);
-        }
-    }
-    const unsigned bad = __ballot_sync(0xffffffffu, !good);
-    if (lane == 0) {
-        if (bad) {
-            if (!rc.st->error) {
-                rc.st->error = (int)bad;
-                rc.st->err_seq = rc.seq;
-            }
-            rc.st->done[0] = rc.st->done[1] = 1;
-            return;
-        }
-        double t[SGV_MAX_PARTIAL_VALUES];
-        for (int k = 0; k < rc.ap.nv; ++k) t[k] = rc.ap.is_min ? SGV_INF : 0.0;
-        for (int q = 0; q < rc.world; ++q)
-            for (int k = 0; k < rc.ap.nv; ++k) {
-                const double x = __ldcg(&me->vals[slot][q][k]);
-                t[k] = rc.ap.is_min ? fmin(t[k], x) : t[k] + x;
-            }
-        apply_totals(rc.ap, rc.st, t);
-    }
+    // nobody published: the producers exited early too
+    if (rc.skip_if_done == SKIP_CG_DONE && rc.st->done[0] && rc.st->done[1]) return;
+    if (rc.skip_if_done == SKIP_EM_DONE && rc.st->em.done) return;
+    resolve_warp(rc, threadIdx.x);
 }
 
 RedCtx sgv_red_begin(sgv_ctx* c, int kind, int nv, int off, int maxit, int x0_zero, int is_min) {
@@ -216,6 +186,7 @@ RedCtx sgv_red_begin(sgv_ctx* c, int kind, int nv, int off, int maxit, int x0_ze
     rc.world = c->world;
     rc.rank = c->rank;
     rc.seq = ++c->seq;
+    rc.inline_resolve = c->world > 1 && !c->host_barrier;
     for (int q = 0; q < c->world; ++q) rc.inbox[q] = reinterpret_cast<Inbox*>(c->peer[q].base);
     rc.ap.kind = kind;
     rc.ap.nv = nv;
@@ -242,7 +213,7 @@ int sgv_red_end(sgv_ctx* c, const RedCtx& rc) {
             }
         }
     }
-    if (c->world > 1) {
+    if (c->world > 1 && !rc.inline_resolve) {
         k_resolve<<<1, 32, 0, c->stream>>>(rc);
         c->launches++;
         SGV_CUDA(cudaGetLastError());

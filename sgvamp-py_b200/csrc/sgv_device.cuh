@@ -118,6 +118,27 @@ __device__ __forceinline__ void apply_totals(const ApplyArgs& ap, CgState* s, co
                 }
             }
             break;
+        case AP_EM: {   // one EM pass done (src/sgvamp.py:134-136) + the convergence test of the driver loop (:254-256)
+            EmState& e = s->em;
+            if (e.done) break;
+            double wsum = 0.0;
+            for (int q = 0; q < e.K; ++q) wsum += e.a[q] * t[q];
+            const double lam_new = wsum / e.asum / e.Mtot;
+            double om_new[SGV_MAX_L], dn = 0.0, on = 0.0;
+            for (int l = 0; l < e.Lm1; ++l) {
+                om_new[l] = t[8 + l] / t[15];
+                dn += (om_new[l] - e.omegas[l]) * (om_new[l] - e.omegas[l]);
+                on += e.omegas[l] * e.omegas[l];
+            }
+            const double om_err = sqrt(dn) / sqrt(on);
+            const double lam_err = fabs(lam_new - e.lam) / lam_new;
+            e.lam = lam_new;
+            for (int l = 0; l < e.Lm1; ++l) e.omegas[l] = om_new[l];
+            e.steps += 1;
+            e.relerr = fmax(om_err, lam_err);
+            if ((om_err < e.tol && lam_err < e.tol) || e.steps >= e.maxit) e.done = 1;
+            break;
+        }
         case AP_CGUPDATE:   // x, r updated: rho_prev <- rho, rho <- r.r, count, loop-top test
             for (int c = 0; c < 2; ++c) {
                 if (s->done[c]) continue;
@@ -138,6 +159,46 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+
+// Wait (bounded) until every rank's partial sums of reduction rc.seq are in this rank's inbox, add the
+// rows in rank order (bit-identical on all ranks) and apply the state transition.  Called by one full
+// warp: lane q watches rank q's flag.  On time-out the error flag is raised and both CG columns are
+// marked done, so that nothing hangs.
+__device__ __forceinline__ void resolve_warp(const RedCtx& rc, int lane) {
+    Inbox* me = rc.inbox[rc.rank];
+    const int slot = (int)(rc.seq % SGV_INBOX_SLOTS);
+    bool good = true;
+    if (lane < rc.world) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(&me->flag[slot][lane]) != rc.seq) {
+            if (clock64() - t0 > 40000000000LL) {   // ~20 s
+                good = false;
+                break;
+            }
+            __nanosleep(32);
+        }
+    }
+    const unsigned bad = __ballot_sync(0xffffffffu, !good);
+    if (lane == 0) {
+        if (bad) {
+            if (!rc.st->error) {
+                rc.st->error = (int)bad;
+                rc.st->err_seq = rc.seq;
+            }
+            rc.st->done[0] = rc.st->done[1] = 1;
+            rc.st->em.done = 1;
+            return;
+        }
+        double t[SGV_MAX_PARTIAL_VALUES];
+        for (int k = 0; k < rc.ap.nv; ++k) t[k] = rc.ap.is_min ? SGV_INF : 0.0;
+        for (int q = 0; q < rc.world; ++q)
+            for (int k = 0; k < rc.ap.nv; ++k) {
+                const double x = __ldcg(&me->vals[slot][q][k]);
+                t[k] = rc.ap.is_min ? fmin(t[k], x) : t[k] + x;
+            }
+        apply_totals(rc.ap, rc.st, t);
+    }
 }
 
 // Grid-wide deterministic reduction: every block contributes NV values; the block that takes the
@@ -187,6 +248,12 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], const RedCtx& rc, d
             __threadfence_system();
             for (int q = 0; q < rc.world; ++q) st_release_sys(&rc.inbox[q]->flag[slot][rc.rank], rc.seq);
         }
+    }
+    // one GPU per rank: this block completes the cross-rank reduction itself (the kernel ends when every
+    // rank has published, which is also the ordering point for the halo reads of the next kernel)
+    if (rc.world > 1 && rc.inline_resolve && threadIdx.x < 32) {
+        __syncwarp();
+        resolve_warp(rc, threadIdx.x);
     }
 }
 

@@ -40,6 +40,14 @@ void sgv_set_error(const char* fmt, ...);
 // ---------------------------------------------------------------------------------------------
 // device-resident CG / reduction state (one per handle, reused by every cohort in turn)
 // ---------------------------------------------------------------------------------------------
+// device-resident state of the EM prior-learning loop (src/sgvamp.py:250-257): the finaliser of every
+// EM pass updates it and raises `done`, so the host can enqueue passes in batches without reading back
+struct EmState {
+    double lam, omegas[SGV_MAX_L];
+    double a[SGV_MAX_K], asum, Mtot, tol, relerr;
+    int    K, Lm1, steps, maxit, done;
+};
+
 struct CgState {
     double rho[2], rho_prev[2], pq[2], bnorm2[2];
     double stats[16];      // results of non-CG reductions (read back by the host)
@@ -48,6 +56,7 @@ struct CgState {
     int    maxit;
     int    error;          // != 0: a cross-rank wait timed out; bit q set = rank q's partial never arrived
     unsigned long long err_seq;   // sequence number of the reduction that timed out
+    EmState em;
 };
 
 // Cross-rank reduction mailbox.  Lives at the start of every rank's symmetric arena; rank r
@@ -60,7 +69,8 @@ struct Inbox {
 };
 
 // What to do with the totals of a grid-wide (and, for world > 1, cross-rank) reduction.
-enum { AP_STATS = 0, AP_PQ = 1, AP_RESID = 2, AP_SETUP = 3, AP_CGUPDATE = 4 };
+enum { AP_STATS = 0, AP_PQ = 1, AP_RESID = 2, AP_SETUP = 3, AP_CGUPDATE = 4, AP_EM = 5 };
+enum { SKIP_NEVER = 0, SKIP_CG_DONE = 1, SKIP_EM_DONE = 2 };
 struct ApplyArgs {
     int kind, nv, off;      // AP_STATS: stats[off + k] = total[k]
     int maxit, x0_zero;     // AP_SETUP
@@ -74,7 +84,8 @@ struct RedCtx {
     Inbox*             inbox[SGV_MAX_RANKS];   // every rank's inbox, mapped into this rank's address space
     unsigned long long seq;
     int                world, rank;
-    int                skip_if_done;   // the reducing kernel exits early once both CG columns are done: so does the resolve
+    int                inline_resolve; // world > 1, one GPU per rank: the finalising block itself waits for the other ranks
+    int                skip_if_done;   // SKIP_*: the reducing kernel exits early in this state, and so does the resolve
     ApplyArgs          ap;
 };
 

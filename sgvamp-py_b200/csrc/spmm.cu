@@ -480,7 +480,7 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, doub
     const int kind = epi == EPI_Q ? AP_PQ : epi == EPI_RESID ? AP_RESID : AP_STATS;
     if (epi != EPI_PLAIN) {
         a.rc = sgv_red_begin(c, kind, 2, 0);
-        a.rc.skip_if_done = check_done;
+        a.rc.skip_if_done = check_done ? SKIP_CG_DONE : SKIP_NEVER;
     }
     a.rc.st = c->cg;
     int rc;

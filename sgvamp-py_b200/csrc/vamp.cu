@@ -107,19 +107,28 @@ extern "C" int sgv_denoise(sgv_handle c, const double* gam1s, double rho, int da
 // ---------------------------------------------------------------------------------------------
 struct EmConsts {
     int    K, Lm1;
-    double lam, one_minus_lam;
-    double a[SGV_MAX_K], g[SGV_MAX_K], ginv[SGV_MAX_K], sqginv[SGV_MAX_K];
-    double lo[SGV_MAX_L];                      // lam * omega_l
-    double den[SGV_MAX_K][SGV_MAX_L];          // sigma_l + 1/gam_k
-    double sqden[SGV_MAX_K][SGV_MAX_L];        // sqrt(1/gam_k + sigma_l)
+    double a[SGV_MAX_K];
+    double mhg[SGV_MAX_K];                     // -gam_k / 2
+    double sqg[SGV_MAX_K];                     // sqrt(gam_k) = 1 / sqrt(1/gam_k)
+    double ce[SGV_MAX_K][SGV_MAX_L];           // -1 / (2 (sigma_l + 1/gam_k))
+    double isq[SGV_MAX_K][SGV_MAX_L];          // 1 / sqrt(1/gam_k + sigma_l)
 };
 
+// One EM pass (src/sgvamp.py:116-136).  lam / omegas come from the device-resident EmState (updated by the
+// previous pass's finaliser).  The reference's quotients with loop-invariant denominators are
+// multiplications by reciprocals formed once on the host, and pi and xi~ share one division:
+//   pi = 1/(1 + t/S) = S/(S+t),   a pi xi_l/S = a xi_l/(S+t)     (S = sum_l xi_l, t = the spike term)
 __global__ void __launch_bounds__(256)
 k_em(int64_t M, const double* __restrict__ r1_all, EmConsts k, RedCtx rc) {
+    const EmState& em = rc.st->em;
+    if (em.done) return;
     __shared__ double red[16 * 32];
     double acc[16];
 #pragma unroll
     for (int t = 0; t < 16; ++t) acc[t] = 0.0;
+    double lo[SGV_MAX_L];
+    for (int l = 0; l < k.Lm1; ++l) lo[l] = em.lam * em.omegas[l];      // lam * omega_l
+    const double one_minus_lam = 1.0 - em.lam;
     // acc[0..K-1] = sum_j pi_kj ; acc[8..8+Lm1-1] = sum a_k pi xi~_l ; acc[15] = sum a_k pi
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
         for (int q = 0; q < k.K; ++q) {
@@ -127,23 +136,25 @@ k_em(int64_t M, const double* __restrict__ r1_all, EmConsts k, RedCtx rc) {
             const double r2 = r * r;
             double e[SGV_MAX_L], emax = 0.0;
             for (int l = 0; l < k.Lm1; ++l) {
-                e[l] = -r2 / 2 / k.den[q][l];                                       // :127
+                e[l] = r2 * k.ce[q][l];                                             // :127
                 if (l == 0 || e[l] > emax) emax = e[l];
             }
             double xi[SGV_MAX_L], sum_xi = 0.0;
             for (int l = 0; l < k.Lm1; ++l) {
-                xi[l] = k.lo[l] * exp(e[l] - emax) / k.sqden[q][l];                 // :128
+                xi[l] = lo[l] * exp(e[l] - emax) * k.isq[q][l];                     // :128
                 sum_xi += xi[l];
             }
-            const double pi = 1.0 / (1.0 + k.one_minus_lam * exp(-r2 / 2 * k.g[q] - emax) / k.sqginv[q] / sum_xi);   // :131
-            const double api = k.a[q] * pi;
+            const double t = one_minus_lam * exp(r2 * k.mhg[q] - emax) * k.sqg[q];  // spike term of :131
+            const double inv = 1.0 / (sum_xi + t);
+            const double pi = sum_xi * inv;                                          // :131
+            const double ainv = k.a[q] * inv;
 #pragma unroll
-            for (int t = 0; t < SGV_MAX_K; ++t)
-                if (t == q) acc[t] += pi;
+            for (int tt = 0; tt < SGV_MAX_K; ++tt)
+                if (tt == q) acc[tt] += pi;
 #pragma unroll
             for (int l = 0; l < SGV_MAX_L - 1; ++l)
-                if (l < k.Lm1) acc[8 + l] += api * (xi[l] / sum_xi);                // :130,:136
-            acc[15] += api;
+                if (l < k.Lm1) acc[8 + l] += ainv * xi[l];                          // a pi xi~_l  :130,:136
+            acc[15] += k.a[q] * pi;
         }
     }
     grid_reduce<16>(acc, rc, red);
@@ -157,55 +168,60 @@ extern "C" int sgv_prior_em(sgv_handle c, const double* gam1s, int maxit, double
     const int Lm1 = p.L - 1;
     const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 4);
     SGV_TRY(sgv_ensure_partials(c, grid + 1));
-    int steps = 0;
-    double rel = 0.0;
-    double asum = 0.0;
-    for (int q = 0; q < p.K; ++q) asum += p.a[q];
-    for (int it = 0; it < maxit; ++it) {
-        EmConsts k;
-        k.K = p.K;
-        k.Lm1 = Lm1;
-        k.lam = p.lam;
-        k.one_minus_lam = 1.0 - p.lam;
-        for (int q = 0; q < p.K; ++q) {
-            k.a[q] = p.a[q];
-            k.g[q] = gam1s[q];
-            k.ginv[q] = 1.0 / gam1s[q];
-            k.sqginv[q] = std::sqrt(k.ginv[q]);
-            for (int l = 0; l < Lm1; ++l) {
-                k.den[q][l] = p.sigmas[l] + k.ginv[q];
-                k.sqden[q][l] = std::sqrt(k.ginv[q] + p.sigmas[l]);
-            }
-        }
-        for (int l = 0; l < Lm1; ++l) k.lo[l] = p.lam * p.omegas[l];
-        RedCtx rc = sgv_red_begin(c, AP_STATS, 16, 0);
-        k_em<<<grid, 256, 0, c->stream>>>(c->Ml, c->r1_all, k, rc);
-        c->launches++;
-        SGV_CUDA(cudaGetLastError());
-        SGV_TRY(sgv_red_end(c, rc));
-        SGV_TRY(fetch_state(c));
-        const double* t = c->cg_host->stats;
-        double wsum = 0.0;
-        for (int q = 0; q < p.K; ++q) wsum += p.a[q] * t[q];
-        const double lam_new = wsum / asum / (double)c->M;                          // :134
-        double om_new[SGV_MAX_L], dn = 0.0, on = 0.0;
+    EmConsts k;
+    k.K = p.K;
+    k.Lm1 = Lm1;
+    for (int q = 0; q < p.K; ++q) {
+        const double ginv = 1.0 / gam1s[q];
+        k.a[q] = p.a[q];
+        k.mhg[q] = -0.5 * gam1s[q];
+        k.sqg[q] = 1.0 / std::sqrt(ginv);
         for (int l = 0; l < Lm1; ++l) {
-            om_new[l] = t[8 + l] / t[15];                                            // :136
-            dn += (om_new[l] - p.omegas[l]) * (om_new[l] - p.omegas[l]);
-            on += p.omegas[l] * p.omegas[l];
+            k.ce[q][l] = -0.5 / (p.sigmas[l] + ginv);
+            k.isq[q][l] = 1.0 / std::sqrt(ginv + p.sigmas[l]);
         }
-        const double om_err = std::sqrt(dn) / std::sqrt(on);                        // :254
-        const double lam_err = std::fabs(lam_new - p.lam) / lam_new;                // :255
-        p.lam = lam_new;
-        for (int l = 0; l < Lm1; ++l) p.omegas[l] = om_new[l];
-        steps = it + 1;
-        rel = std::max(om_err, lam_err);
-        if (om_err < tol && lam_err < tol) break;                                   // :256
+    }
+    // loop state on the device: passes are enqueued in batches, every pass after convergence exits at once
+    EmState* he = &c->cg_host->em;
+    memset(he, 0, sizeof(EmState));
+    he->lam = p.lam;
+    he->asum = 0.0;
+    for (int l = 0; l < Lm1; ++l) he->omegas[l] = p.omegas[l];
+    for (int q = 0; q < p.K; ++q) {
+        he->a[q] = p.a[q];
+        he->asum += p.a[q];
+    }
+    he->Mtot = (double)c->M;
+    he->tol = tol;
+    he->K = p.K;
+    he->Lm1 = Lm1;
+    he->maxit = maxit;
+    he->done = maxit <= 0;
+    SGV_CUDA(cudaMemcpyAsync(&c->cg->em, he, sizeof(EmState), cudaMemcpyHostToDevice, c->stream));
+    int launched = 0, batch = 12;
+    while (launched < maxit) {
+        const int nb = std::min(batch, maxit - launched);
+        for (int b = 0; b < nb; ++b) {
+            RedCtx rc = sgv_red_begin(c, AP_EM, 16, 0);
+            rc.skip_if_done = SKIP_EM_DONE;
+            k_em<<<grid, 256, 0, c->stream>>>(c->Ml, c->r1_all, k, rc);
+            c->launches++;
+            SGV_TRY(sgv_red_end(c, rc));
+        }
+        SGV_CUDA(cudaGetLastError());
+        launched += nb;
+        SGV_TRY(fetch_state(c));
+        if (he->done) break;
+        batch = std::min(48, batch * 2);
+    }
+    if (maxit > 0) {
+        p.lam = he->lam;
+        for (int l = 0; l < Lm1; ++l) p.omegas[l] = he->omegas[l];
     }
     *lam_out = p.lam;
     for (int l = 0; l < Lm1; ++l) omegas_out[l] = p.omegas[l];
-    if (steps_out) *steps_out = steps;
-    if (relerr_out) *relerr_out = rel;
+    if (steps_out) *steps_out = he->steps;
+    if (relerr_out) *relerr_out = he->relerr;
     return 0;
 }
 
@@ -506,7 +522,7 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
                 SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, VEC_PP0, c->qq, in->gamw, in->gam2, 1, 0));
             }
             RedCtx rc = sgv_red_begin(c, AP_CGUPDATE, 2, 0);
-            rc.skip_if_done = 1;
+            rc.skip_if_done = SKIP_CG_DONE;
             k_cg_update<<<vgrid, 256, 0, c->stream>>>(M, c->xx, c->rr, pcur, c->qq, rc);
             c->launches++;
             SGV_TRY(sgv_red_end(c, rc));
