@@ -85,6 +85,7 @@ static void free_vectors(sgv_ctx* c) {
         cudaFree(co.xhat2);
         cudaFree(co.sig);
         cudaFree(co.probe);
+        cudaFree(co.rxs);
         co = Cohort();
     }
     detach_peers(c);
@@ -259,6 +260,8 @@ extern "C" int sgv_configure_part(sgv_handle c, int64_t M, int K, int rank, int 
         SGV_CUDA(cudaMalloc(&co.xhat2, vb));
         SGV_CUDA(cudaMalloc(&co.sig, vb));
         SGV_CUDA(cudaMalloc(&co.probe, Ml));
+        SGV_CUDA(cudaMalloc(&co.rxs, v2));
+        SGV_CUDA(cudaMemsetAsync(co.rxs, 0, v2, c->stream));
         double* z[] = {co.xty, co.r2, co.xhat2, co.sig};
         for (double* p : z) SGV_CUDA(cudaMemsetAsync(p, 0, vb, c->stream));
     }
@@ -396,6 +399,8 @@ extern "C" int sgv_reset_state(sgv_handle c) {
         SGV_CUDA(cudaMemsetAsync(co.xhat2, 0, vb, c->stream));
         SGV_CUDA(cudaMemsetAsync(co.sig, 0, vb, c->stream));
         SGV_CUDA(cudaMemsetAsync(co.r2, 0, vb, c->stream));
+        SGV_CUDA(cudaMemsetAsync(co.rxs, 0, (size_t)c->Ml * sizeof(double2), c->stream));
+        co.rxs_valid = true;
     }
     return 0;
 }
@@ -413,6 +418,7 @@ extern "C" int sgv_set_vec(sgv_handle c, int cohort, int which, const double* sr
     SGV_TRY(vec_ptr(c, cohort, which, &p));
     SGV_CUDA(cudaMemcpyAsync(p, src, c->Ml * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
+    if (which == SGV_VEC_XHAT2 || which == SGV_VEC_SIGMA2U) c->coh[cohort].rxs_valid = false;
     return 0;
 }
 

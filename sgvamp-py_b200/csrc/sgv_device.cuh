@@ -112,8 +112,8 @@ __device__ __forceinline__ void apply_totals(const ApplyArgs& ap, CgState* s, co
                 if (t[c] == 0.0) {          // scipy: `if bnrm2 == 0: return b, 0`
                     s->done[c] = 1;
                     s->zero_b[c] = 1;
-                } else if (ap.x0_zero) {    // r = b.copy(); loop-top test of iteration 0
-                    s->rho[c] = t[c];
+                } else {                    // r = b.copy() or b - A x0 (formed by the set-up kernel); loop-top test of iteration 0
+                    s->rho[c] = ap.x0_zero ? t[c] : t[2 + c];
                     cg_top_test(s, c);
                 }
             }

@@ -122,6 +122,8 @@ struct LdMatrix {
 struct Cohort {
     LdMatrix ld;
     double *xty = nullptr, *r1 = nullptr, *r2 = nullptr, *xhat2 = nullptr, *sig = nullptr;
+    double2* rxs = nullptr;   // (R xhat2, R Sigma2_u), recovered from the CG recursion: A x = b - r  (vamp.cu)
+    bool     rxs_valid = true;  // false after xhat2 / Sigma2_u were overwritten from outside (sgv_set_vec)
     int8_t* probe = nullptr;
 };
 

@@ -361,25 +361,36 @@ extern "C" int sgv_metrics(sgv_handle c, const double* x0, double* dots) {
 // ---------------------------------------------------------------------------------------------
 // r2 = (xhat1 - alpha1 r1)/(1-alpha1) (:310); b0 = mu2 = gamw r + gam2 r2 (:313); b1 = u (:326);
 // x0 = (xhat2_prev, Sigma2_u_prev) (:316,:332); |b|^2 per column; initialise the CG state.
+// Warm start: r = b - A x0 = b - gamw (R x0) - gam2 x0 needs no matrix pass, because R x0 was recovered
+// from the previous solve's own recursion (rxs, see k_lmmse_post).
 __global__ void __launch_bounds__(256)
 k_lmmse_setup(int64_t M, const double* __restrict__ xhat1, const double* __restrict__ r1,
               const double* __restrict__ xty, const int8_t* __restrict__ probe, const double* __restrict__ xhat2,
-              const double* __restrict__ sig, double* __restrict__ r2, double2* __restrict__ bb,
-              double2* __restrict__ xx, double2* __restrict__ rr, double alpha1, double gamw, double gam2,
-              int x0_zero, RedCtx rc) {
-    __shared__ double red[2 * 32];
-    double acc[2] = {0.0, 0.0};
+              const double* __restrict__ sig, const double2* __restrict__ rxs, double* __restrict__ r2,
+              double2* __restrict__ bb, double2* __restrict__ xx, double2* __restrict__ rr, double alpha1, double gamw,
+              double gam2, int x0_zero, RedCtx rc) {
+    __shared__ double red[4 * 32];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
         const double r2j = (xhat1[j] - alpha1 * r1[j]) / (1.0 - alpha1);
         r2[j] = r2j;
         const double2 b = make_double2(gamw * xty[j] + gam2 * r2j, (double)probe[j]);
         bb[j] = b;
-        xx[j] = make_double2(xhat2[j], sig[j]);
-        if (x0_zero) rr[j] = b;
+        const double2 x0 = make_double2(xhat2[j], sig[j]);
+        xx[j] = x0;
+        double2 r = b;
+        if (!x0_zero) {
+            const double2 rx = rxs[j];
+            r.x = b.x - (gamw * rx.x + gam2 * x0.x);
+            r.y = b.y - (gamw * rx.y + gam2 * x0.y);
+        }
+        rr[j] = r;
         acc[0] += b.x * b.x;
         acc[1] += b.y * b.y;
+        acc[2] += r.x * r.x;
+        acc[3] += r.y * r.y;
     }
-    grid_reduce<2>(acc, rc, red);
+    grid_reduce<4>(acc, rc, red);
 }
 
 // p = r (first step) or p = r + (rho/rho_prev) p      (layouts without the fused update)
@@ -425,27 +436,54 @@ k_cg_update(int64_t M, double2* __restrict__ xx, double2* __restrict__ rr, const
 }
 
 // xhat2 <- CG col 0 (damped with the previous xhat2 if lmmse_damp, :322-323); Sigma2_u_prev <- col 1
-// (:333); dots u.Sigma2_u (:338) and xhat2.r (:352).  xx col 0 is overwritten with the final xhat2 so
-// that the statistics SpMM can read (xhat2, Sigma2_u) as one vector pair.
+// (:333); dots u.Sigma2_u (:338), xhat2.r (:352).  The products R xhat2 and R Sigma2_u that the gamw
+// update (:352,:359) and the next warm start need are recovered from the CG recursion itself,
+//     A x = b - r   =>   R x = (b - r - gam2 x) / gamw        (r: the solve's final recursive residual),
+// so neither costs a pass over the matrix; xhat2^T R xhat2 and u^T R Sigma2_u are summed here.
 __global__ void __launch_bounds__(256)
-k_lmmse_post(int64_t M, double2* __restrict__ xx, const double2* __restrict__ bb, const double* __restrict__ xty,
-             double* __restrict__ xhat2, double* __restrict__ sig, double rho, int damp, RedCtx rc) {
-    __shared__ double red[2 * 32];
+k_lmmse_post(int64_t M, double2* __restrict__ xx, const double2* __restrict__ rr, const double2* __restrict__ bb,
+             const double* __restrict__ xty, double* __restrict__ xhat2, double* __restrict__ sig,
+             double2* __restrict__ rxs, double gamw, double gam2, double rho, int damp, RedCtx rc) {
+    __shared__ double red[4 * 32];
     const int z0 = rc.st->zero_b[0], z1 = rc.st->zero_b[1];
-    double acc[2] = {0.0, 0.0};
+    const double igw = 1.0 / gamw;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
         double2 x = xx[j];
-        const double2 b = bb[j];
+        const double2 b = bb[j], r = rr[j];
+        double2 rx;
+        rx.x = z0 ? 0.0 : (b.x - r.x - gam2 * x.x) * igw;      // scipy returns x = b (= 0) when |b| = 0
+        rx.y = z1 ? 0.0 : (b.y - r.y - gam2 * x.y) * igw;
         if (z0) x.x = b.x;
         if (z1) x.y = b.y;
-        if (damp) x.x = rho * x.x + (1.0 - rho) * xhat2[j];
+        if (damp) {
+            x.x = rho * x.x + (1.0 - rho) * xhat2[j];
+            rx.x = rho * rx.x + (1.0 - rho) * rxs[j].x;
+        }
         xhat2[j] = x.x;
         sig[j] = x.y;
         xx[j] = x;
-        acc[0] += b.y * x.y;
-        acc[1] += x.x * xty[j];
+        rxs[j] = rx;
+        acc[0] += b.y * x.y;       // u . Sigma2_u
+        acc[1] += x.x * xty[j];    // xhat2 . r
+        acc[2] += x.x * rx.x;      // xhat2^T R xhat2
+        acc[3] += b.y * rx.y;      // u^T R Sigma2_u
     }
-    grid_reduce<2>(acc, rc, red);
+    grid_reduce<4>(acc, rc, red);
+}
+
+// xx = (xhat2, Sigma2_u) as a vector pair (only when a warm start was injected from outside and R x0 has
+// to be formed by a real pass); the reduction doubles as the cross-rank ordering point for the halo reads
+__global__ void __launch_bounds__(256)
+k_pack_x0(int64_t M, const double* __restrict__ xhat2, const double* __restrict__ sig, double2* __restrict__ xx, RedCtx rc) {
+    __shared__ double red[32];
+    double acc[1] = {0.0};
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        const double2 x = make_double2(xhat2[j], sig[j]);
+        xx[j] = x;
+        acc[0] += x.x * x.x + x.y * x.y;
+    }
+    grid_reduce<1>(acc, rc, red);
 }
 
 __global__ void __launch_bounds__(256)
@@ -478,6 +516,7 @@ int sgv_preload_vamp() {
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_cg_update));
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_lmmse_post));
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_update_r1));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_pack_x0));
     return 0;
 }
 
@@ -492,17 +531,32 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
     const unsigned vgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 8);
     SGV_TRY(sgv_ensure_partials(c, vgrid + 1));
     SGV_CUDA(cudaMemcpyAsync(co.probe, probe, M, cudaMemcpyHostToDevice, c->stream));
-    {
-        RedCtx rc = sgv_red_begin(c, AP_SETUP, 2, 0, in->cg_maxit, in->x0_zero);
-        k_lmmse_setup<<<vgrid, 256, 0, c->stream>>>(M, c->xhat1, co.r1, co.xty, co.probe, co.xhat2, co.sig, co.r2, c->bb,
-                                                   c->xx, c->rr, in->alpha1, in->gamw, in->gam2, in->x0_zero, rc);
+    int passes = 0;
+    if (in->x0_zero && !co.rxs_valid) {    // the caller states x0 = 0: so is R x0
+        SGV_CUDA(cudaMemsetAsync(co.rxs, 0, (size_t)M * sizeof(double2), c->stream));
+        co.rxs_valid = true;
+    }
+    if (!in->x0_zero && !co.rxs_valid) {   // injected warm start: R x0 by a real pass
+        RedCtx rc = sgv_red_begin(c, AP_STATS, 1, 15);
+        k_pack_x0<<<vgrid, 256, 0, c->stream>>>(M, co.xhat2, co.sig, c->xx, rc);
         c->launches++;
         SGV_TRY(sgv_red_end(c, rc));
-    }
-    int passes = 0;
-    if (!in->x0_zero) {   // r = b - A x0  and the loop-top test of iteration 0
-        SGV_TRY(sgv_launch_spmm(c, co, EPI_RESID, VEC_XX, c->rr, in->gamw, in->gam2, 1, 0));
+        SGV_TRY(sgv_launch_spmm(c, co, EPI_PLAIN, VEC_XX, co.rxs, 1.0, 0.0, 0, 0));
+        if (c->world > 1) {                 // the pass must be complete on every rank before xx is rewritten
+            RedCtx rc2 = sgv_red_begin(c, AP_STATS, 1, 15);
+            k_pack_x0<<<vgrid, 256, 0, c->stream>>>(M, co.xhat2, co.sig, c->xx, rc2);
+            c->launches++;
+            SGV_TRY(sgv_red_end(c, rc2));
+        }
+        co.rxs_valid = true;
         passes++;
+    }
+    {   // b, x0, r = b - A x0 (no matrix pass: R x0 is kept from the previous solve), |b|^2, r.r, loop-top test of iteration 0
+        RedCtx rc = sgv_red_begin(c, AP_SETUP, 4, 0, in->cg_maxit, in->x0_zero);
+        k_lmmse_setup<<<vgrid, 256, 0, c->stream>>>(M, c->xhat1, co.r1, co.xty, co.probe, co.xhat2, co.sig, co.rxs, co.r2,
+                                                   c->bb, c->xx, c->rr, in->alpha1, in->gamw, in->gam2, in->x0_zero, rc);
+        c->launches++;
+        SGV_TRY(sgv_red_end(c, rc));
     }
     int launched = 0;
     int batch = 4;
@@ -540,21 +594,19 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
     out->cg_info[1] = hs->done[1] ? hs->info[1] : in->cg_maxit;
     passes += std::max(hs->iters[0], hs->iters[1]);
     {
-        RedCtx rc = sgv_red_begin(c, AP_STATS, 2, 2);
-        k_lmmse_post<<<vgrid, 256, 0, c->stream>>>(M, c->xx, c->bb, co.xty, co.xhat2, co.sig, in->rho, in->lmmse_damp, rc);
+        RedCtx rc = sgv_red_begin(c, AP_STATS, 4, 0);
+        k_lmmse_post<<<vgrid, 256, 0, c->stream>>>(M, c->xx, c->rr, c->bb, co.xty, co.xhat2, co.sig, co.rxs, in->gamw, in->gam2,
+                                                  in->rho, in->lmmse_damp, rc);
         c->launches++;
         SGV_TRY(sgv_red_end(c, rc));
     }
-    if (in->learn_gamw) {   // R xhat2 and R Sigma2_u in one pass (:352,:359)
-        SGV_TRY(sgv_launch_spmm(c, co, EPI_STATS, VEC_XX, nullptr, 1.0, 0.0, 0, 0));
-        passes++;
-    }
+    co.rxs_valid = true;
     SGV_CUDA(cudaGetLastError());
     SGV_TRY(fetch_state(c));
-    out->xhat2_R_xhat2 = in->learn_gamw ? hs->stats[0] : 0.0;
-    out->u_R_sigma2u = in->learn_gamw ? hs->stats[1] : 0.0;
-    out->u_sigma2u = hs->stats[2];
-    out->xhat2_r = hs->stats[3];
+    out->u_sigma2u = hs->stats[0];
+    out->xhat2_r = hs->stats[1];
+    out->xhat2_R_xhat2 = hs->stats[2];      // (:352,:359) - no extra matrix pass, see k_lmmse_post
+    out->u_R_sigma2u = hs->stats[3];
     out->spmm_passes = passes;
     return 0;
 }
