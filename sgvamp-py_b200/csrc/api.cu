@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include "sgv_device.cuh"
@@ -91,9 +92,8 @@ static void free_vectors(sgv_ctx* c) {
     detach_peers(c);
     cudaFree(c->arena);
     cudaFree(c->bb);
-    cudaFree(c->qq);
     c->arena = nullptr;
-    c->bb = c->qq = c->xx = c->rr = c->pp[0] = c->pp[1] = nullptr;
+    c->bb = c->qq = c->xx = c->rr = c->pp[0] = c->pp[1] = c->rr2[0] = c->rr2[1] = c->qq2[0] = c->qq2[1] = nullptr;
     cudaFree(c->r1_all);
     cudaFree(c->xhat1);
     cudaFree(c->truth);
@@ -270,16 +270,18 @@ extern "C" int sgv_configure_part(sgv_handle c, int64_t M, int K, int rank, int 
     SGV_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
     SGV_CUDA(cudaMemsetAsync(c->arena, 0, c->arena_bytes, c->stream));
     c->xx = reinterpret_cast<double2*>(c->arena + arena_off_xx(Ml));
-    c->rr = reinterpret_cast<double2*>(c->arena + arena_off_rr(Ml));
-    c->pp[0] = reinterpret_cast<double2*>(c->arena + arena_off_pp(Ml, 0));
-    c->pp[1] = reinterpret_cast<double2*>(c->arena + arena_off_pp(Ml, 1));
+    for (int i = 0; i < 2; ++i) {
+        c->rr2[i] = reinterpret_cast<double2*>(c->arena + arena_off_rr(Ml, i));
+        c->pp[i] = reinterpret_cast<double2*>(c->arena + arena_off_pp(Ml, i));
+        c->qq2[i] = reinterpret_cast<double2*>(c->arena + arena_off_qq(Ml, i));
+    }
+    c->rr = c->rr2[1];   // where the set-up kernel puts r_0 (CG step 0 reads buffer 1, writes buffer 0)
+    c->qq = c->qq2[0];
     c->peer[rank].base = c->arena;
     c->peer[rank].Ml = Ml;
     c->peer[rank].ipc = false;
     SGV_CUDA(cudaMalloc(&c->bb, v2));
-    SGV_CUDA(cudaMalloc(&c->qq, v2));
     SGV_CUDA(cudaMemsetAsync(c->bb, 0, v2, c->stream));
-    SGV_CUDA(cudaMemsetAsync(c->qq, 0, v2, c->stream));
     SGV_CUDA(cudaMemsetAsync(c->cg, 0, sizeof(CgState), c->stream));
     for (int i = 0; i < sgv_ctx::NSNAP; ++i) {   // allocated up front: cudaMalloc inside the loop would synchronise
         SGV_CUDA(cudaMalloc(&c->snap[i], vb));

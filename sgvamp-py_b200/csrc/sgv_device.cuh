@@ -100,6 +100,7 @@ __device__ __forceinline__ void apply_totals(const ApplyArgs& ap, CgState* s, co
         case AP_SETUP:   // |b|^2 known: initialise the CG state of both columns
             s->maxit = ap.maxit;
             s->step = 0;
+            s->alpha[0] = s->alpha[1] = 0.0;
             for (int c = 0; c < 2; ++c) {
                 s->bnorm2[c] = t[c];
                 s->rho[c] = 0.0;
@@ -139,6 +140,28 @@ __device__ __forceinline__ void apply_totals(const ApplyArgs& ap, CgState* s, co
             if ((om_err < e.tol && lam_err < e.tol) || e.steps >= e.maxit) e.done = 1;
             break;
         }
+        case AP_CGFUSED:   // t = [p.q, r.q, q.q, r.r] x 2 columns of the step just multiplied
+            // alpha = rho/(p.q); the update x += alpha p, r -= alpha q is applied when the next kernel stages
+            // its window (or by the post kernel), but its effect on rho is known now:
+            //     |r - alpha q|^2 = r.r - 2 alpha r.q + alpha^2 q.q
+            // with r.r the exactly summed norm of the residual this step used (no drift accumulates).
+            for (int c = 0; c < 2; ++c) {
+                if (s->done[c]) {
+                    s->alpha[c] = 0.0;
+                    continue;
+                }
+                const double rr = t[6 + c];
+                const double al = rr / t[c];
+                double rn = rr - 2.0 * al * t[2 + c] + al * al * t[4 + c];
+                if (rn < 0.0) rn = 0.0;
+                s->alpha[c] = al;
+                s->rho_prev[c] = rr;
+                s->rho[c] = rn;
+                s->iters[c] += 1;
+                cg_top_test(s, c);
+            }
+            s->step += 1;
+            break;
         case AP_CGUPDATE:   // x, r updated: rho_prev <- rho, rho <- r.r, count, loop-top test
             for (int c = 0; c < 2; ++c) {
                 if (s->done[c]) continue;

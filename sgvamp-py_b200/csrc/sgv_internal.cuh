@@ -52,6 +52,7 @@ struct CgState {
     double rho[2], rho_prev[2], pq[2], bnorm2[2];
     double stats[16];      // results of non-CG reductions (read back by the host)
     int    done[2], iters[2], info[2], zero_b[2];
+    double alpha[2];       // fused CG (DSYM): step length of the update x += alpha p, r -= alpha q still to be applied (0: none)
     int    step;           // CG updates performed (0 -> p = r)
     int    maxit;
     int    error;          // != 0: a cross-rank wait timed out; bit q set = rank q's partial never arrived
@@ -69,7 +70,7 @@ struct Inbox {
 };
 
 // What to do with the totals of a grid-wide (and, for world > 1, cross-rank) reduction.
-enum { AP_STATS = 0, AP_PQ = 1, AP_RESID = 2, AP_SETUP = 3, AP_CGUPDATE = 4, AP_EM = 5 };
+enum { AP_STATS = 0, AP_PQ = 1, AP_RESID = 2, AP_SETUP = 3, AP_CGUPDATE = 4, AP_EM = 5, AP_CGFUSED = 6 };
 enum { SKIP_NEVER = 0, SKIP_CG_DONE = 1, SKIP_EM_DONE = 2 };
 struct ApplyArgs {
     int kind, nv, off;      // AP_STATS: stats[off + k] = total[k]
@@ -164,8 +165,11 @@ struct sgv_ctx {
     // symmetric arena (CG work vectors shared by all cohorts + the inbox), peer-mapped for world > 1
     char*        arena = nullptr;
     size_t       arena_bytes = 0;
-    double2 *bb = nullptr, *qq = nullptr;             // private
-    double2 *xx = nullptr, *rr = nullptr, *pp[2] = {nullptr, nullptr};   // inside the arena
+    double2 *bb = nullptr;                            // private
+    // inside the arena; r, p, q are double-buffered for the fused CG step (a kernel reads buffer `prev`
+    // - also the neighbours' - and writes buffer `cur`).  rr / qq: the buffers the classic path uses.
+    double2 *xx = nullptr, *rr2[2] = {nullptr, nullptr}, *pp[2] = {nullptr, nullptr}, *qq2[2] = {nullptr, nullptr};
+    double2 *rr = nullptr, *qq = nullptr;
     PeerView     peer[SGV_MAX_RANKS];
     // Ranks that share one GPU (tests on a box with fewer GPUs than ranks): kernels of different ranks
     // are not guaranteed to run concurrently, so no kernel may wait for another rank's kernel.  In this
@@ -207,12 +211,13 @@ static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * 
 // arena layout for a rank with Ml local markers
 static inline size_t arena_vec_bytes(int64_t Ml) { return (size_t)round_up(Ml, 64) * sizeof(double2); }
 static inline size_t arena_off_xx(int64_t) { return (size_t)round_up((int64_t)sizeof(Inbox), 4096); }
-static inline size_t arena_off_rr(int64_t Ml) { return arena_off_xx(Ml) + arena_vec_bytes(Ml); }
-static inline size_t arena_off_pp(int64_t Ml, int i) { return arena_off_rr(Ml) + (size_t)(1 + i) * arena_vec_bytes(Ml); }
-static inline size_t arena_size(int64_t Ml) { return arena_off_pp(Ml, 2); }
+static inline size_t arena_off_rr(int64_t Ml, int i) { return arena_off_xx(Ml) + (size_t)(1 + i) * arena_vec_bytes(Ml); }
+static inline size_t arena_off_pp(int64_t Ml, int i) { return arena_off_xx(Ml) + (size_t)(3 + i) * arena_vec_bytes(Ml); }
+static inline size_t arena_off_qq(int64_t Ml, int i) { return arena_off_xx(Ml) + (size_t)(5 + i) * arena_vec_bytes(Ml); }
+static inline size_t arena_size(int64_t Ml) { return arena_off_qq(Ml, 2); }
 
 // epilogues of the SpMM kernels
-enum { EPI_Q = 0, EPI_RESID = 1, EPI_STATS = 2, EPI_PLAIN = 3 };
+enum { EPI_Q = 0, EPI_RESID = 1, EPI_STATS = 2, EPI_PLAIN = 3, EPI_CG = 4 /* fused single-reduction CG step (DSYM) */ };
 // which symmetric vector an SpMM reads (so that the halos can be fetched from the neighbours)
 enum { VEC_XX = 0, VEC_PP0 = 1, VEC_PP1 = 2 };
 
@@ -233,6 +238,10 @@ struct SpmmArgs {
     double         gamw, gam2;
     int64_t        M;      // local number of markers
     int            check_done;   // 1: exit immediately when both CG columns are done
+    // fused CG step (EPI_CG): r_new = r - alpha q (pending update), p_new = r_new + beta p, x += alpha p are formed
+    // while the window is staged; v = p_old, r = r_old, q = q_old (each with the neighbours' halos)
+    const double2 *q, *q_left, *q_right;
+    double2 *r_new, *x;
     RedCtx         rc;
 };
 
@@ -248,6 +257,7 @@ size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s, int nst);
 bool   sgv_dsym_feasible(int64_t w);
 int    sgv_dsym_ensure_scratch(sgv_ctx* c, const LdMatrix& ld);
 int    sgv_launch_dsym(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a);
+int    sgv_launch_dsym_cg(sgv_ctx* c, Cohort& co, int n, double gamw, double gam2);   // CG step n (reads buffers (n+1)&1, writes n&1)
 // element offset of diagonal d (0..Dp-1) at storage row j in the tiled DSYM layout (ngr = Dp/4)
 __host__ __device__ static inline int64_t sgv_dsym_index(int64_t j, int64_t d, int64_t ngr) {
     return ((j >> 7) * ngr + (d >> 2)) * 512 + (d & 3) * 128 + (j & 127);

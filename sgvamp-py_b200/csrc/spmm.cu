@@ -451,8 +451,7 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, doub
     a.v = vec == VEC_XX ? c->xx : c->pp[vec - VEC_PP0];
     a.fused_p = fused_p;
     if (fused_p) {
-        SGV_CHECK((co.ld.layout == SGV_LAYOUT_DIA || co.ld.layout == SGV_LAYOUT_DSYM) && vec != VEC_XX,
-                  "fused direction update needs a band layout");
+        SGV_CHECK(co.ld.layout == SGV_LAYOUT_DIA && vec != VEC_XX, "fused direction update needs the DIA layout");
         a.r = c->rr;
         a.p_new = c->pp[1 - (vec - VEC_PP0)];
     }
@@ -461,14 +460,14 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, doub
             const PeerView& pv = c->peer[c->rank - 1];
             SGV_CHECK(pv.base != nullptr && pv.Ml >= co.ld.w, "left neighbour not attached or shorter than the half-bandwidth");
             a.v_left = arena_vec(c, c->rank - 1, vec);
-            a.r_left = reinterpret_cast<double2*>(pv.base + arena_off_rr(pv.Ml));
+            a.r_left = reinterpret_cast<double2*>(pv.base + arena_off_rr(pv.Ml, 1));
             a.n_left = pv.Ml;
         }
         if (c->rank + 1 < c->world) {
             const PeerView& pv = c->peer[c->rank + 1];
             SGV_CHECK(pv.base != nullptr && pv.Ml >= co.ld.w, "right neighbour not attached or shorter than the half-bandwidth");
             a.v_right = arena_vec(c, c->rank + 1, vec);
-            a.r_right = reinterpret_cast<double2*>(pv.base + arena_off_rr(pv.Ml));
+            a.r_right = reinterpret_cast<double2*>(pv.base + arena_off_rr(pv.Ml, 1));
         }
     }
     a.out = out;

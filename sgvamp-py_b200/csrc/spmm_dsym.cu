@@ -25,8 +25,18 @@
 // A CTA (RW row-warps x S diagonal segments) then adds, in fixed order, the forward sums of its
 // S segments and the staging ranges of its warps: rows of its own tile go to ypart[], the
 // contributions to the Dp rows after the tile go to tails[cta][]; k_dsym_finish adds the (at most
-// ceil(Dp/TR)) tails that reach a row, applies the fused epilogue (q + p.q, residual + r.r,
-// gamw statistics) and the grid / cross-rank reduction.
+// ceil(Dp/TR)) tails that reach a row, applies the fused epilogue and the grid / cross-rank reduction.
+// (Consuming the tails inside the main kernel - tiles ordered by an atomic ticket, per-tile flags - was
+// measured: the latency-bound tail of every CTA cost 0.43 ms per pass against 0.335 + 0.025 ms.)
+//
+// CG mode is a whole conjugate-gradient step in these two kernels (scipy.sparse.linalg.cg semantics, 2 RHS):
+// while the x window is staged, the pending update r = r - alpha q is applied and the new direction
+// p = r + beta p formed on the fly (also for the halo entries, from the neighbours' r, q, p), the owned
+// rows of r, p and x += alpha p are written; the finish kernel writes q = A p and sums p.q, r.q, q.q, r.r, from
+// which the finaliser gets alpha and |r - alpha q|^2 = r.r - 2 alpha r.q + alpha^2 q.q for the stopping test
+// and beta - so a CG iteration costs one matrix pass, one small kernel and ONE reduction (no vector-update
+// kernel, no second reduction).  r, p, q are double-buffered
+// (step n reads buffers (n+1)&1, writes n&1), so no rank overwrites what a neighbour still reads.
 //
 // Row partition over GPUs: a rank also stores the E = roundup(w,256) rows BEFORE its first own row
 // (entries that couple them to its own rows; the rest zero) and computes their transposed
@@ -93,6 +103,9 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 }
 
 #define DS_STAGE_FLOATS 512   // 4 diagonals x 128 rows
+#ifndef DS_O_IN_REGS
+#define DS_O_IN_REGS 1
+#endif
 
 size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s, int nst) {
     const int Dp = (int)round_up(w + 1, 4);
@@ -106,11 +119,12 @@ size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s, int nst) {
     return b;
 }
 
-template <int RW, int S, int NST, int MINB>
+template <int RW, int S, int NST, int MINB, bool CG>
 __global__ void __launch_bounds__(32 * RW * S, MINB)
 k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_t E, double2* __restrict__ ypart,
             double2* __restrict__ tails) {
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
+    const int tile = blockIdx.x;
     constexpr int TR = 128 * RW;
     constexpr int NT = 32 * RW * S;
     constexpr int NW = RW * S;
@@ -127,7 +141,7 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
     double2* stag = xw + 4 * PL;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(stag + NW * SL);
 
-    const int64_t r0s = (int64_t)blockIdx.x * TR;   // storage index of the tile's first row
+    const int64_t r0s = (int64_t)tile * TR;         // storage index of the tile's first row
     const int64_t r0 = r0s - E;                     // the same in local coordinates (0 = first own row)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int rw = wid % RW, s = wid / RW;
@@ -158,17 +172,18 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
     __syncwarp();   // the barriers are initialised before any lane waits on them
 
     // stage the x window [r0, r0+TR+Dp) (local coordinates).  Entries left of 0 come from the left
-    // neighbour (extension rows), entries right of M from the right neighbour, zero at the matrix
-    // edges.  Fused mode: the window holds the new CG direction p = r + beta*p_old computed on the fly
-    // (scipy: p *= beta; p += r), and the owned part of the tile is written to p_new.
-    double beta0 = 0.0, beta1 = 0.0;
+    // neighbour (extension rows), entries right of M from the right neighbour, zero at the matrix edges.
+    // CG mode: the window holds the new CG direction, computed on the fly (see the header comment).
+    double al0 = 0.0, al1 = 0.0, beta0 = 0.0, beta1 = 0.0;
     bool first = true, fz0 = false, fz1 = false;
-    if (a.fused_p) {
+    if (CG) {
         const CgState* st = a.rc.st;
         first = st->step == 0;
         fz0 = st->done[0] != 0;
         fz1 = st->done[1] != 0;
         if (!first) {
+            al0 = st->alpha[0];
+            al1 = st->alpha[1];
             beta0 = st->rho[0] / st->rho_prev[0];
             beta1 = st->rho[1] / st->rho_prev[1];
         }
@@ -177,30 +192,48 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
         const int64_t col = r0 + j;
         double2 val = make_double2(0.0, 0.0);
         if (j < W) {
-            const double2 *src = nullptr, *rsrc = nullptr;
+            const double2 *src = nullptr, *rsrc = nullptr, *qsrc = nullptr;
             int64_t idx = col;
             if (col >= 0 && col < a.M) {
                 src = a.v;
                 rsrc = a.r;
+                qsrc = a.q;
             } else if (col < 0 && a.v_left != nullptr && a.n_left + col >= 0) {
                 src = a.v_left;
                 rsrc = a.r_left;
+                qsrc = a.q_left;
                 idx = a.n_left + col;
             } else if (col >= a.M && a.v_right != nullptr) {
                 src = a.v_right;
                 rsrc = a.r_right;
+                qsrc = a.q_right;
                 idx = col - a.M;
             }
             if (src != nullptr) {
-                if (!a.fused_p) {
+                if (!CG) {
                     val = ld_vec2(src + idx);
                 } else {
-                    const double2 rv = ld_vec2(rsrc + idx);
+                    double2 rv = ld_vec2(rsrc + idx);
                     double2 po = make_double2(0.0, 0.0);
-                    if (!first || fz0 || fz1) po = ld_vec2(src + idx);
+                    if (!first) {                       // nothing is pending before the first step (p, q not yet defined)
+                        po = ld_vec2(src + idx);
+                        const double2 qo = ld_vec2(qsrc + idx);
+                        if (al0 != 0.0) rv.x -= al0 * qo.x;     // scipy: r -= alpha*q
+                        if (al1 != 0.0) rv.y -= al1 * qo.y;
+                    }
+                    // scipy: p *= beta; p += r   (first step: p = r); a finished column keeps its p
                     val.x = fz0 ? po.x : (first ? rv.x : po.x * beta0 + rv.x);
                     val.y = fz1 ? po.y : (first ? rv.y : po.y * beta1 + rv.y);
-                    if (j < TR && col >= 0 && col < a.M) a.p_new[col] = val;
+                    if (j < TR && col >= 0 && col < a.M) {      // owned rows of this tile
+                        a.r_new[col] = rv;
+                        a.p_new[col] = val;
+                        if (al0 != 0.0 || al1 != 0.0) {
+                            double2 xv = a.x[col];
+                            if (al0 != 0.0) xv.x += al0 * po.x; // scipy: x += alpha*p
+                            if (al1 != 0.0) xv.y += al1 * po.y;
+                            a.x[col] = xv;
+                        }
+                    }
                 }
             }
         }
@@ -211,7 +244,9 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
     double2 acc0 = make_double2(0, 0), acc1 = acc0, acc2 = acc0, acc3 = acc0;
     if (ngroups > 0) {
         double2 T0 = acc0, T1 = acc0, T2 = acc0, T3 = acc0, T4 = acc0, T5 = acc0, T6 = acc0;
+#if DS_O_IN_REGS
         const double2 O0 = xw[g], O1 = xw[PL + g], O2 = xw[2 * PL + g], O3 = xw[3 * PL + g];   // x[row4 .. row4+3]
+#endif
         int xi = g + (d0 >> 2);
         double2 X0 = xw[xi], X1 = xw[PL + xi], X2 = xw[2 * PL + xi], X3 = xw[3 * PL + xi];
         double2* st = stag + wid * SL;
@@ -233,6 +268,10 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
                                  DS_STAGE_FLOATS * 4, bar0 + 8 * stage);
                     }
                     const double2 N0 = xw[xi + 1], N1 = xw[PL + xi + 1], N2 = xw[2 * PL + xi + 1], N3 = xw[3 * PL + xi + 1];
+#if !DS_O_IN_REGS
+                    // x[row4 .. row4+3] re-read per group: 4 conflict-free LDS.128 instead of 16 live registers
+                    const double2 O0 = xw[g], O1 = xw[PL + g], O2 = xw[2 * PL + g], O3 = xw[3 * PL + g];
+#endif
                     DS_FWD(c0, X0, X1, X2, X3);
                     DS_TRN(c0, T0, T1, T2, T3);
                     DS_FWD(c1, X1, X2, X3, N0);
@@ -269,6 +308,7 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
     __syncthreads();
 
     // fixed-order combination: forward sums of the S segments + the staging ranges that cover the target
+    double2* mytails = tails + (int64_t)tile * Dp;
     for (int t = threadIdx.x; t < TR + Dp; t += NT) {
         double2 sum = make_double2(0.0, 0.0);
         if (t < TR) {
@@ -297,20 +337,24 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
         if (t < TR) {
             if (r0s + t < ldb) ypart[r0s + t] = sum;
         } else {
-            tails[(int64_t)blockIdx.x * Dp + (t - TR)] = sum;
+            mytails[t - TR] = sum;
         }
     }
 }
 
 // y[i] = ypart[i] + the tails of the preceding tiles that reach row i; fused epilogue + reduction.
+// EPI_CG: q = A p and the four dot products of the fused CG step.
 template <int EPI>
 __global__ void __launch_bounds__(256)
 k_dsym_finish(SpmmArgs a, const double2* __restrict__ ypart, const double2* __restrict__ tails, int Dp, int TR, int64_t E,
               const double2* __restrict__ vin) {
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
-    __shared__ double red[2 * 32];
+    constexpr int NV = EPI == EPI_CG ? 8 : 2;
+    __shared__ double red[NV * 32];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double dots[2] = {0.0, 0.0};
+    double dots[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) dots[k] = 0.0;
     if (i < a.M) {
         const int64_t J = i + E;
         const int64_t b = J / TR;
@@ -322,9 +366,22 @@ k_dsym_finish(SpmmArgs a, const double2* __restrict__ ypart, const double2* __re
             y.x += t.x;
             y.y += t.y;
         }
-        epi_row<EPI>(a, i, y, vin[i], dots);
+        const double2 vi = vin[i];
+        if constexpr (EPI == EPI_CG) {
+            double2 o;
+            o.x = a.gamw * y.x + a.gam2 * vi.x;
+            o.y = a.gamw * y.y + a.gam2 * vi.y;
+            a.out[i] = o;                                    // q = A p
+            const double2 rv = a.r_new[i];
+            dots[0] += vi.x * o.x; dots[1] += vi.y * o.y;    // p.q
+            dots[2] += rv.x * o.x; dots[3] += rv.y * o.y;    // r.q
+            dots[4] += o.x * o.x;  dots[5] += o.y * o.y;     // q.q
+            dots[6] += rv.x * rv.x; dots[7] += rv.y * rv.y;  // r.r
+        } else {
+            epi_row<EPI>(a, i, y, vi, dots);
+        }
     }
-    if (EPI != EPI_PLAIN) grid_reduce<2>(dots, a.rc, red);
+    if constexpr (EPI != EPI_PLAIN) grid_reduce<NV>(dots, a.rc, red);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -342,35 +399,33 @@ static bool ds_use_big(const sgv_ctx* c, const LdMatrix& ld) {
     return ld.ldb >= (int64_t)c->sm_count * 2 * 256 && sgv_dsym_smem_bytes(ld.w, DS_BIG_RW, DS_BIG_S, DS_NST) <= 112 * 1024;
 }
 
-int sgv_dsym_tile_rows(const sgv_ctx* c, const LdMatrix& ld) { return ds_use_big(c, ld) ? 128 * DS_BIG_RW : 128; }
+template <bool CG>
+static int preload_main() {
+    SGV_CUDA(cudaFuncSetAttribute(k_spmm_dsym<DS_BIG_RW, DS_BIG_S, DS_NST, DS_MINB, CG>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM_LIMIT));
+    SGV_CUDA(cudaFuncSetAttribute(k_spmm_dsym<1, 8, DS_NST, DS_MINB, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  DS_SMEM_LIMIT));
+    return 0;
+}
 
 int sgv_preload_dsym() {
-    SGV_CUDA(cudaFuncSetAttribute(k_spmm_dsym<DS_BIG_RW, DS_BIG_S, DS_NST, DS_MINB>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM_LIMIT));
-    SGV_CUDA(cudaFuncSetAttribute(k_spmm_dsym<1, 8, DS_NST, DS_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  DS_SMEM_LIMIT));
+    SGV_TRY(preload_main<false>());
+    SGV_TRY(preload_main<true>());
     cudaFuncAttributes fa;
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_dsym_finish<EPI_Q>));
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_dsym_finish<EPI_RESID>));
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_dsym_finish<EPI_STATS>));
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_dsym_finish<EPI_PLAIN>));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_dsym_finish<EPI_CG>));
     return 0;
 }
 
-// scratch for the partial sums (per handle, sized for the largest DSYM matrix uploaded so far);
-// called at upload / adopt time only, never inside the solver loop
+// scratch (per handle, sized for the largest DSYM matrix uploaded so far); called at upload / adopt time
+// only, never inside the solver loop
 int sgv_dsym_ensure_scratch(sgv_ctx* c, const LdMatrix& ld) {
     const int64_t Dp = round_up(ld.w + 1, 4);
     const int64_t tiles = (ld.ldb + 127) / 128;   // upper bound for either tile shape
-    const int64_t need_y = ld.ldb, need_t = tiles * Dp;
-    if (c->ds_ypart_cap < need_y) {
-        SGV_CUDA(cudaStreamSynchronize(c->stream));
-        if (c->ds_ypart) cudaFree(c->ds_ypart);
-        c->ds_ypart = nullptr;
-        c->ds_ypart_cap = 0;
-        SGV_CUDA(cudaMalloc(&c->ds_ypart, need_y * sizeof(double2)));
-        c->ds_ypart_cap = need_y;
-    }
+    const int64_t need_t = tiles * Dp;
     if (c->ds_tails_cap < need_t) {
         SGV_CUDA(cudaStreamSynchronize(c->stream));
         if (c->ds_tails) cudaFree(c->ds_tails);
@@ -379,18 +434,26 @@ int sgv_dsym_ensure_scratch(sgv_ctx* c, const LdMatrix& ld) {
         SGV_CUDA(cudaMalloc(&c->ds_tails, need_t * sizeof(double2)));
         c->ds_tails_cap = need_t;
     }
+    if (c->ds_ypart_cap < ld.ldb) {
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->ds_ypart) cudaFree(c->ds_ypart);
+        c->ds_ypart = nullptr;
+        c->ds_ypart_cap = 0;
+        SGV_CUDA(cudaMalloc(&c->ds_ypart, ld.ldb * sizeof(double2)));
+        c->ds_ypart_cap = ld.ldb;
+    }
     return 0;
 }
 
-template <int RW, int S>
+template <int RW, int S, bool CG>
 static int launch_main(sgv_ctx* c, const LdMatrix& ld, const SpmmArgs& a) {
     constexpr int TR = 128 * RW;
     const size_t smem = sgv_dsym_smem_bytes(ld.w, RW, S, DS_NST);
     SGV_CHECK(smem <= DS_SMEM_LIMIT, "half-bandwidth %lld too large for the DSYM kernel", (long long)ld.w);
     const unsigned grid = (unsigned)((ld.ldb + TR - 1) / TR);
     const int Dp = (int)round_up(ld.w + 1, 4);
-    k_spmm_dsym<RW, S, DS_NST, DS_MINB><<<grid, 32 * RW * S, smem, c->stream>>>(a, ld.band, Dp, ld.ldb, ld.ext, c->ds_ypart,
-                                                                               c->ds_tails);
+    k_spmm_dsym<RW, S, DS_NST, DS_MINB, CG><<<grid, 32 * RW * S, smem, c->stream>>>(a, ld.band, Dp, ld.ldb, ld.ext, c->ds_ypart,
+                                                                                   c->ds_tails);
     c->launches++;
     return 0;
 }
@@ -406,18 +469,80 @@ static int launch_finish(sgv_ctx* c, const LdMatrix& ld, SpmmArgs& a, int TR, co
     return 0;
 }
 
-// a: fully prepared SpmmArgs (vectors, halos, fused mode, epilogue operands, reduction context)
+// a: fully prepared SpmmArgs (vectors, halos, epilogue operands, reduction context)
 int sgv_launch_dsym(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a) {
     SGV_CHECK(c->ds_ypart != nullptr && c->ds_tails != nullptr, "DSYM scratch not allocated");
     const bool big = ds_use_big(c, ld);
     const int TR = big ? 128 * DS_BIG_RW : 128;
-    if (big) SGV_TRY((launch_main<DS_BIG_RW, DS_BIG_S>(c, ld, a)));
-    else SGV_TRY((launch_main<1, 8>(c, ld, a)));
-    const double2* vin = a.fused_p ? a.p_new : a.v;
-    switch (epi) {
-        case EPI_Q: return launch_finish<EPI_Q>(c, ld, a, TR, vin);
-        case EPI_RESID: return launch_finish<EPI_RESID>(c, ld, a, TR, vin);
-        case EPI_STATS: return launch_finish<EPI_STATS>(c, ld, a, TR, vin);
-        default: return launch_finish<EPI_PLAIN>(c, ld, a, TR, vin);
+    if (epi == EPI_CG) {
+        if (big) SGV_TRY((launch_main<DS_BIG_RW, DS_BIG_S, true>(c, ld, a)));
+        else SGV_TRY((launch_main<1, 8, true>(c, ld, a)));
+        return launch_finish<EPI_CG>(c, ld, a, TR, a.p_new);
     }
+    if (big) SGV_TRY((launch_main<DS_BIG_RW, DS_BIG_S, false>(c, ld, a)));
+    else SGV_TRY((launch_main<1, 8, false>(c, ld, a)));
+    switch (epi) {
+        case EPI_Q: return launch_finish<EPI_Q>(c, ld, a, TR, a.v);
+        case EPI_RESID: return launch_finish<EPI_RESID>(c, ld, a, TR, a.v);
+        case EPI_STATS: return launch_finish<EPI_STATS>(c, ld, a, TR, a.v);
+        default: return launch_finish<EPI_PLAIN>(c, ld, a, TR, a.v);
+    }
+}
+
+// One fused CG step (EPI_CG): step n reads r, p, q from buffers (n+1)&1 - the neighbours' too - and writes n&1.
+int sgv_launch_dsym_cg(sgv_ctx* c, Cohort& co, int n, double gamw, double gam2) {
+    const LdMatrix& ld = co.ld;
+    SGV_CHECK(ld.layout == SGV_LAYOUT_DSYM, "fused CG step needs the DSYM layout");
+    const int prev = (n + 1) & 1, cur = n & 1;
+    SpmmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.v = c->pp[prev];
+    a.r = c->rr2[prev];
+    a.q = c->qq2[prev];
+    a.p_new = c->pp[cur];
+    a.r_new = c->rr2[cur];
+    a.out = c->qq2[cur];
+    a.x = c->xx;
+    if (c->world > 1 && c->halo) {
+        if (c->rank > 0) {
+            const PeerView& pv = c->peer[c->rank - 1];
+            SGV_CHECK(pv.base != nullptr && pv.Ml >= ld.w, "left neighbour not attached or shorter than the half-bandwidth");
+            a.v_left = reinterpret_cast<double2*>(pv.base + arena_off_pp(pv.Ml, prev));
+            a.r_left = reinterpret_cast<double2*>(pv.base + arena_off_rr(pv.Ml, prev));
+            a.q_left = reinterpret_cast<double2*>(pv.base + arena_off_qq(pv.Ml, prev));
+            a.n_left = pv.Ml;
+        }
+        if (c->rank + 1 < c->world) {
+            const PeerView& pv = c->peer[c->rank + 1];
+            SGV_CHECK(pv.base != nullptr && pv.Ml >= ld.w, "right neighbour not attached or shorter than the half-bandwidth");
+            a.v_right = reinterpret_cast<double2*>(pv.base + arena_off_pp(pv.Ml, prev));
+            a.r_right = reinterpret_cast<double2*>(pv.base + arena_off_rr(pv.Ml, prev));
+            a.q_right = reinterpret_cast<double2*>(pv.base + arena_off_qq(pv.Ml, prev));
+        }
+    }
+    a.bb = c->bb;
+    a.gamw = gamw;
+    a.gam2 = gam2;
+    a.M = c->Ml;
+    a.check_done = 1;
+    a.rc = sgv_red_begin(c, AP_CGFUSED, 8, 0);
+    a.rc.skip_if_done = SKIP_CG_DONE;
+    a.rc.st = c->cg;
+    if (c->prof) {
+        if (c->prof_n + 2 > c->prof_ev.size()) {
+            for (int i = 0; i < 256; ++i) {
+                cudaEvent_t e;
+                SGV_CUDA(cudaEventCreate(&e));
+                c->prof_ev.push_back(e);
+            }
+        }
+        SGV_CUDA(cudaEventRecord(c->prof_ev[c->prof_n], c->stream));
+    }
+    SGV_TRY(sgv_launch_dsym(c, ld, EPI_CG, a));
+    if (c->prof) {
+        SGV_CUDA(cudaEventRecord(c->prof_ev[c->prof_n + 1], c->stream));
+        c->prof_n += 2;
+    }
+    SGV_CUDA(cudaGetLastError());
+    return sgv_red_end(c, a.rc);
 }

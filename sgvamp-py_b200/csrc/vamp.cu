@@ -440,17 +440,35 @@ k_cg_update(int64_t M, double2* __restrict__ xx, double2* __restrict__ rr, const
 // update (:352,:359) and the next warm start need are recovered from the CG recursion itself,
 //     A x = b - r   =>   R x = (b - r - gam2 x) / gamw        (r: the solve's final recursive residual),
 // so neither costs a pass over the matrix; xhat2^T R xhat2 and u^T R Sigma2_u are summed here.
+// fusedcg: the solve ran as fused steps (spmm_dsym.cu); the last step's update x += alpha p, r -= alpha q is
+// still pending and is applied here (buffers (step-1)&1 hold the last r, p, q).
+struct CgBufs {
+    const double2 *rr[2], *pp[2], *qq[2];
+    int fusedcg;
+};
+
 __global__ void __launch_bounds__(256)
-k_lmmse_post(int64_t M, double2* __restrict__ xx, const double2* __restrict__ rr, const double2* __restrict__ bb,
+k_lmmse_post(int64_t M, double2* __restrict__ xx, CgBufs cb, const double2* __restrict__ bb,
              const double* __restrict__ xty, double* __restrict__ xhat2, double* __restrict__ sig,
              double2* __restrict__ rxs, double gamw, double gam2, double rho, int damp, RedCtx rc) {
     __shared__ double red[4 * 32];
     const int z0 = rc.st->zero_b[0], z1 = rc.st->zero_b[1];
     const double igw = 1.0 / gamw;
+    const int step = rc.st->step;
+    const bool pend = cb.fusedcg && step > 0;
+    const int cur = pend ? ((step - 1) & 1) : 1;        // r_0 from the set-up kernel lives in buffer 1
+    const double al0 = pend ? rc.st->alpha[0] : 0.0, al1 = pend ? rc.st->alpha[1] : 0.0;
+    const double2* __restrict__ rr = cb.rr[cur];
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
         double2 x = xx[j];
-        const double2 b = bb[j], r = rr[j];
+        const double2 b = bb[j];
+        double2 r = rr[j];
+        if (al0 != 0.0 || al1 != 0.0) {
+            const double2 p = cb.pp[cur][j], q = cb.qq[cur][j];
+            if (al0 != 0.0) { x.x += al0 * p.x; r.x -= al0 * q.x; }
+            if (al1 != 0.0) { x.y += al1 * p.y; r.y -= al1 * q.y; }
+        }
         double2 rx;
         rx.x = z0 ? 0.0 : (b.x - r.x - gam2 * x.x) * igw;      // scipy returns x = b (= 0) when |b| = 0
         rx.y = z1 ? 0.0 : (b.y - r.y - gam2 * x.y) * igw;
@@ -527,7 +545,8 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
     Cohort& co = c->coh[cohort];
     SGV_CHECK(co.ld.layout != 0, "cohort %d has no LD matrix", cohort);
     const int64_t M = c->Ml;
-    const bool fused = co.ld.layout == SGV_LAYOUT_DIA || co.ld.layout == SGV_LAYOUT_DSYM;   // direction update fused into the SpMM staging
+    const bool fused = co.ld.layout == SGV_LAYOUT_DIA;     // direction update fused into the SpMM staging
+    const bool fusedcg = co.ld.layout == SGV_LAYOUT_DSYM;  // whole CG step in one kernel   // direction update fused into the SpMM staging
     const unsigned vgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 8);
     SGV_TRY(sgv_ensure_partials(c, vgrid + 1));
     SGV_CUDA(cudaMemcpyAsync(co.probe, probe, M, cudaMemcpyHostToDevice, c->stream));
@@ -565,6 +584,10 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
         const int nb = std::min(batch, in->cg_maxit - launched);
         for (int b = 0; b < nb; ++b) {
             const int n = launched + b;             // == device step while the solve is active
+            if (fusedcg) {
+                SGV_TRY(sgv_launch_dsym_cg(c, co, n, in->gamw, in->gam2));
+                continue;
+            }
             double2* pcur;
             if (fused) {
                 pcur = c->pp[n & 1];
@@ -595,7 +618,14 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
     passes += std::max(hs->iters[0], hs->iters[1]);
     {
         RedCtx rc = sgv_red_begin(c, AP_STATS, 4, 0);
-        k_lmmse_post<<<vgrid, 256, 0, c->stream>>>(M, c->xx, c->rr, c->bb, co.xty, co.xhat2, co.sig, co.rxs, in->gamw, in->gam2,
+        CgBufs cb;
+        for (int i = 0; i < 2; ++i) {
+            cb.rr[i] = c->rr2[i];
+            cb.pp[i] = c->pp[i];
+            cb.qq[i] = c->qq2[i];
+        }
+        cb.fusedcg = fusedcg;
+        k_lmmse_post<<<vgrid, 256, 0, c->stream>>>(M, c->xx, cb, c->bb, co.xty, co.xhat2, co.sig, co.rxs, in->gamw, in->gam2,
                                                   in->rho, in->lmmse_damp, rc);
         c->launches++;
         SGV_TRY(sgv_red_end(c, rc));

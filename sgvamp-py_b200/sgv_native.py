@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsgvamp_b200.so")
+LIB_PATH = os.environ.get("SGV_LIB") or os.path.join(HERE, "libsgvamp_b200.so")   # SGV_LIB: A/B of builds (dev only)
 
 LAYOUT_AUTO, LAYOUT_DENSE, LAYOUT_DIA, LAYOUT_BLOCKDIAG, LAYOUT_CSR, LAYOUT_DSYM = 0, 1, 2, 3, 4, 5
 LAYOUT_NAMES = {0: "auto", 1: "dense", 2: "dia", 3: "blockdiag", 4: "csr", 5: "dsym"}
