@@ -124,6 +124,7 @@ struct Cohort {
     LdMatrix ld;
     double *xty = nullptr, *r1 = nullptr, *r2 = nullptr, *xhat2 = nullptr, *sig = nullptr;
     double2* rxs = nullptr;   // (R xhat2, R Sigma2_u), recovered from the CG recursion: A x = b - r  (vamp.cu)
+    int      last_cg_iters = 0; // iterations the previous solve needed: size of the first batch enqueued by the next one
     bool     rxs_valid = true;  // false after xhat2 / Sigma2_u were overwritten from outside (sgv_set_vec)
     int8_t* probe = nullptr;
 };
@@ -179,6 +180,7 @@ struct sgv_ctx {
     sgv_ctx*     peer_ctx[SGV_MAX_RANKS] = {};
     std::atomic<unsigned long long> host_seq{0};
     unsigned long long seq = 0;      // reductions issued so far (identical on all ranks)
+    int          last_em_steps = 0;  // EM passes the previous prior update needed (first batch of the next one)
     double2*     ds_ypart = nullptr; // DSYM kernel: per-row partial sums and per-tile tails
     double2*     ds_tails = nullptr;
     int64_t      ds_ypart_cap = 0, ds_tails_cap = 0;

@@ -198,7 +198,9 @@ extern "C" int sgv_prior_em(sgv_handle c, const double* gam1s, int maxit, double
     he->maxit = maxit;
     he->done = maxit <= 0;
     SGV_CUDA(cudaMemcpyAsync(&c->cg->em, he, sizeof(EmState), cudaMemcpyHostToDevice, c->stream));
-    int launched = 0, batch = 12;
+    // first batch: what the previous update needed plus a margin (the counts drift slowly from one VAMP
+    // iteration to the next); a pass enqueued after convergence exits at once
+    int launched = 0, batch = c->last_em_steps > 0 ? c->last_em_steps + 3 : 12;
     while (launched < maxit) {
         const int nb = std::min(batch, maxit - launched);
         for (int b = 0; b < nb; ++b) {
@@ -214,6 +216,7 @@ extern "C" int sgv_prior_em(sgv_handle c, const double* gam1s, int maxit, double
         if (he->done) break;
         batch = std::min(48, batch * 2);
     }
+    c->last_em_steps = he->steps;
     if (maxit > 0) {
         p.lam = he->lam;
         for (int l = 0; l < Lm1; ++l) p.omegas[l] = he->omegas[l];
@@ -578,7 +581,7 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
         SGV_TRY(sgv_red_end(c, rc));
     }
     int launched = 0;
-    int batch = 4;
+    int batch = co.last_cg_iters > 0 ? co.last_cg_iters + 2 : 4;   // see sgv_prior_em: counts drift slowly
     CgState* hs = c->cg_host;
     while (launched < in->cg_maxit) {
         const int nb = std::min(batch, in->cg_maxit - launched);
@@ -607,11 +610,12 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
         launched += nb;
         SGV_TRY(fetch_state(c));
         if (hs->done[0] && hs->done[1]) break;
-        batch = std::min(16, batch * 2);
+        batch = 8;
     }
     if (in->cg_maxit == 0 || launched == 0) SGV_TRY(fetch_state(c));
     out->cg_iters[0] = hs->iters[0];
     out->cg_iters[1] = hs->iters[1];
+    co.last_cg_iters = std::max(hs->iters[0], hs->iters[1]);
     // a column that ran out of iterations without ever passing the test reports maxiter (scipy)
     out->cg_info[0] = hs->done[0] ? hs->info[0] : in->cg_maxit;
     out->cg_info[1] = hs->done[1] ? hs->info[1] : in->cg_maxit;
