@@ -184,25 +184,49 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
+__device__ __forceinline__ void st_entry(InboxEntry* p, double v, unsigned long long seq) {
+    asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(seq) : "memory");
+}
+__device__ __forceinline__ bool ld_entry(const InboxEntry* p, unsigned long long seq, double& v) {
+    long long bits;
+    unsigned long long s;
+    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(s) : "l"(p) : "memory");
+    v = __longlong_as_double(bits);
+    return s == seq;
+}
+
 // Wait (bounded) until every rank's partial sums of reduction rc.seq are in this rank's inbox, add the
 // rows in rank order (bit-identical on all ranks) and apply the state transition.  Called by one full
-// warp: lane q watches rank q's flag.  On time-out the error flag is raised and both CG columns are
+// warp: lane q collects rank q's row.  On time-out the error flag is raised and the CG / EM loops are
 // marked done, so that nothing hangs.
 __device__ __forceinline__ void resolve_warp(const RedCtx& rc, int lane) {
     Inbox* me = rc.inbox[rc.rank];
     const int slot = (int)(rc.seq % SGV_INBOX_SLOTS);
+    const int nv = rc.ap.nv;
+    double mine[SGV_MAX_PARTIAL_VALUES];
     bool good = true;
     if (lane < rc.world) {
         const long long t0 = clock64();
-        while (ld_acquire_sys(&me->flag[slot][lane]) != rc.seq) {
-            if (clock64() - t0 > 40000000000LL) {   // ~20 s
-                good = false;
-                break;
+        for (int k = 0; k < nv && good; ++k) {
+            while (!ld_entry(&me->e[slot][lane][k], rc.seq, mine[k])) {
+                if (clock64() - t0 > 40000000000LL) {   // ~20 s
+                    good = false;
+                    break;
+                }
             }
-            __nanosleep(32);
         }
     }
     const unsigned bad = __ballot_sync(0xffffffffu, !good);
+    double t[SGV_MAX_PARTIAL_VALUES];
+    for (int k = 0; k < nv; ++k) {
+        double acc = rc.ap.is_min ? SGV_INF : 0.0;
+        const double v = lane < rc.world ? mine[k] : 0.0;
+        for (int q = 0; q < rc.world; ++q) {           // rank order
+            const double x = __shfl_sync(0xffffffffu, v, q);
+            acc = rc.ap.is_min ? fmin(acc, x) : acc + x;
+        }
+        t[k] = acc;
+    }
     if (lane == 0) {
         if (bad) {
             if (!rc.st->error) {
@@ -213,13 +237,6 @@ __device__ __forceinline__ void resolve_warp(const RedCtx& rc, int lane) {
             rc.st->em.done = 1;
             return;
         }
-        double t[SGV_MAX_PARTIAL_VALUES];
-        for (int k = 0; k < rc.ap.nv; ++k) t[k] = rc.ap.is_min ? SGV_INF : 0.0;
-        for (int q = 0; q < rc.world; ++q)
-            for (int k = 0; k < rc.ap.nv; ++k) {
-                const double x = __ldcg(&me->vals[slot][q][k]);
-                t[k] = rc.ap.is_min ? fmin(t[k], x) : t[k] + x;
-            }
         apply_totals(rc.ap, rc.st, t);
     }
 }
@@ -261,15 +278,16 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], const RedCtx& rc, d
         if (rc.world == 1) {
             apply_totals(rc.ap, rc.st, acc);
         } else {
+            // This rank's vector writes of the kernel (read by the neighbours as halos once they have seen
+            // these entries) are already ordered: every block fenced at GPU scope before taking its ticket,
+            // and peers read this memory through this GPU's L2.
             const int slot = (int)(rc.seq % SGV_INBOX_SLOTS);
-            __threadfence_system();   // everything this rank wrote in this kernel is visible before the flag
+            __threadfence();
             for (int q = 0; q < rc.world; ++q) {
-                Inbox* ib = rc.inbox[q];
+                InboxEntry* row = rc.inbox[q]->e[slot][rc.rank];
 #pragma unroll
-                for (int k = 0; k < NV; ++k) ib->vals[slot][rc.rank][k] = acc[k];
+                for (int k = 0; k < NV; ++k) st_entry(row + k, acc[k], rc.seq);
             }
-            __threadfence_system();
-            for (int q = 0; q < rc.world; ++q) st_release_sys(&rc.inbox[q]->flag[slot][rc.rank], rc.seq);
         }
     }
     // one GPU per rank: this block completes the cross-rank reduction itself (the kernel ends when every

@@ -60,13 +60,18 @@ struct CgState {
     EmState em;
 };
 
-// Cross-rank reduction mailbox.  Lives at the start of every rank's symmetric arena; rank r
-// writes its partial sums of reduction `seq` into slot seq % SLOTS, row r, of EVERY rank's inbox
-// (peer stores over NVLink), then the flag.  Consumers add the rows in rank order, so all ranks
-// obtain bit-identical totals.
+// Cross-rank reduction mailbox.  Lives at the start of every rank's symmetric arena; rank r writes its
+// partial sums of reduction `seq` into slot seq % SLOTS, row r, of EVERY rank's inbox with peer stores
+// over NVLink.  Every value travels with the sequence number in ONE 16-byte store (the "LL" scheme of
+// NCCL's low-latency protocol): a reader that sees the right sequence number in an entry has the value,
+// so neither side needs a system-scope fence and there is no separate flag round trip.  Consumers add
+// the rows in rank order, so all ranks obtain bit-identical totals.
+struct __align__(16) InboxEntry {
+    double             value;
+    unsigned long long seq;
+};
 struct Inbox {
-    double             vals[SGV_INBOX_SLOTS][SGV_MAX_RANKS][SGV_MAX_PARTIAL_VALUES];
-    unsigned long long flag[SGV_INBOX_SLOTS][SGV_MAX_RANKS];
+    InboxEntry e[SGV_INBOX_SLOTS][SGV_MAX_RANKS][SGV_MAX_PARTIAL_VALUES];
 };
 
 // What to do with the totals of a grid-wide (and, for world > 1, cross-rank) reduction.
