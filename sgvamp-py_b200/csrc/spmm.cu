@@ -8,6 +8,7 @@
 //   CSR        fp32 value + int32 column                                  8 B / stored value
 // All three are HBM-bound streaming kernels (0.5 - 1 flop/B): 128-bit coalesced loads of the
 // matrix, vector operands in shared memory / registers, fp64 FMA accumulation.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include "sgv_device.cuh"
@@ -301,9 +302,8 @@ template <int EPI>
 __global__ void __launch_bounds__(256) k_panel_finish(SpmmArgs a, const double2* __restrict__ ypart, int nslots) {
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     __shared__ double red[2 * 32];
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double dots[2] = {0.0, 0.0};
-    if (i < a.M) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.M; i += (int64_t)gridDim.x * blockDim.x) {
         double2 acc = ypart[i];
         for (int sl = 1; sl < nslots; ++sl) {
             const double2 t = ypart[(int64_t)sl * a.M + i];
@@ -388,7 +388,7 @@ static int launch_epi(sgv_ctx* c, Cohort& co, SpmmArgs& a) {
     if (ld.layout == SGV_LAYOUT_DENSE || ld.layout == SGV_LAYOUT_BLOCKDIAG) {
         k_spmm_panel<4, 2><<<ld.n_items, 256, 0, c->stream>>>(a, ld.panels, ld.items, c->ypart);
         c->launches++;
-        const unsigned grid = (unsigned)((c->Ml + 255) / 256);
+        const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 6);
         SGV_TRY(sgv_ensure_partials(c, grid));
         a.rc.partials = c->partials;
         k_panel_finish<EPI><<<grid, 256, 0, c->stream>>>(a, c->ypart, ld.s_cross);

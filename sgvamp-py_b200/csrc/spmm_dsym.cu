@@ -43,6 +43,7 @@
 // contributions itself, so no partial sums cross ranks - only vector halos are read from the
 // neighbours' memory when the x window is staged (left halo for the extension rows, right halo for
 // the forward part).  Results for the extension rows themselves are discarded.
+#include <algorithm>
 #include <cstring>
 #include "sgv_device.cuh"
 
@@ -351,11 +352,11 @@ k_dsym_finish(SpmmArgs a, const double2* __restrict__ ypart, const double2* __re
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     constexpr int NV = EPI == EPI_CG ? 8 : 2;
     __shared__ double red[NV * 32];
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double dots[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) dots[k] = 0.0;
-    if (i < a.M) {
+    // grid-stride: a few hundred blocks (one ticket atomic and one partial row each), not one per 256 rows
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.M; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t J = i + E;
         const int64_t b = J / TR;
         double2 y = ypart[J];
@@ -460,7 +461,7 @@ static int launch_main(sgv_ctx* c, const LdMatrix& ld, const SpmmArgs& a) {
 
 template <int EPI>
 static int launch_finish(sgv_ctx* c, const LdMatrix& ld, SpmmArgs& a, int TR, const double2* vin) {
-    const unsigned grid = (unsigned)((c->Ml + 255) / 256);
+    const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 6);
     SGV_TRY(sgv_ensure_partials(c, grid));
     a.rc.partials = c->partials;
     const int Dp = (int)round_up(ld.w + 1, 4);
