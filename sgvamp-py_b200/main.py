@@ -5,10 +5,9 @@ Same flags (both the code spellings of src/main.py:28-50 and the README spelling
 same output files.  One process drives all K cohorts on the GPU (the reference starts one MPI
 rank per cohort); ``Rused = (1-s) R + s I`` (src/main.py:265) is applied on the device at upload.
 
-Not built yet (SURVEY 8f "next"): the ``.bim`` reference-order merge with missing SNPs and the
-PLINK ``.ld`` triple loader with its MPI exchange (src/main.py:126-165, 203-257).  ``--bim-files``
-is accepted; if the files list identical SNP sets the run proceeds, otherwise it stops with a
-clear message.
+The `.bim` reference-order merge with missing SNPs and the PLINK `.ld` triple loader
+(src/main.py:126-165, 203-257) live in ``ingest.py``; the reference's MPI exchange of missing rows
+becomes an in-memory lookup because one process holds all cohorts.
 """
 import argparse
 import logging
@@ -21,6 +20,7 @@ import numpy as np
 import scipy.sparse
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ingest  # noqa: E402
 from sgvamp import VAMP  # noqa: E402
 
 
@@ -51,32 +51,10 @@ def build_parser():
     p.add_argument("-em_prior_maxit", "--em-prior-maxit", help="Max EM prior-learning iterations", default=100)
     p.add_argument("-bim_files", "--bim-files", help="Path to files containing list of snps", default=None)
     p.add_argument("--device", help="CUDA device index", default=0)
+    p.add_argument("--bim-source-quirk", help="1 (default): choose the cohort that supplies a missing SNP exactly as "
+                   "src/main.py:162 does (argmax position); 0: the candidate cohort with the largest N", default=1)
     p.add_argument("--layout", help="LD layout in HBM: auto|dense|dia|blockdiag|csr", default="auto")
     return p
-
-
-def load_r(path, M, N):
-    if path.endswith(".txt"):
-        return np.loadtxt(path).reshape(M)
-    if path.endswith(".npy"):
-        return np.load(path).reshape(M)
-    if path.endswith(".linear"):
-        import pandas as pd
-        df = pd.read_table(path, sep=r"\s+")
-        r = np.array(df["BETA"], dtype=np.float64).reshape(M)
-        r[np.isnan(r)] = 0
-        return r * np.sqrt(N)                                       # src/main.py:183-185
-    raise Exception("Unsupported r vector format!")
-
-
-def load_R(path):
-    if path.endswith(".npz"):
-        return scipy.sparse.load_npz(path)
-    if path.endswith(".npy"):
-        return np.load(path, mmap_mode="r")
-    if path.endswith(".ld"):
-        raise Exception("PLINK .ld input is not supported by the B200 driver yet; convert it with scripts/plink2np.py")
-    raise Exception("Unsupported R matrix format!")
 
 
 def main(argv=None):
@@ -97,21 +75,19 @@ def main(argv=None):
         raise Exception("Number of prior variances must be L!")
     if len(prior_probs) != L:
         raise Exception("Number of prior mixture probabilites must be L!")
-    if len(set(M_list)) != 1:
-        raise Exception("cohorts with different marker sets need the .bim merge, which is not built yet")
-    M = M_list[0]
-    if a.bim_files is not None:
-        import pandas as pd
-        sets = [list(pd.read_table(f, sep=r"\s+", header=None)[1]) for f in a.bim_files.split(",")]
-        if any(s_ != sets[0] for s_ in sets[1:]):
-            raise Exception("cohorts with different marker sets need the .bim merge, which is not built yet")
     Nt = sum(N_list)
     lmmse_damp, learn_gamw = bool(int(a.lmmse_damp)), bool(int(a.learn_gamw))
     s = float(a.s)
 
     ts = time.time()
-    rs = [load_r(r_list[k], M, N_list[k]) for k in range(K)]
-    Rs = [load_R(ld_list[k]) for k in range(K)]
+    bim_list = a.bim_files.split(",") if a.bim_files is not None else None
+    if bim_list is not None and len(bim_list) != K:
+        raise Exception("Specified number of cohorts is not equal to number of .bim files provided!")
+    M, Rs, rs, merged = ingest.load_all(ld_list, r_list, bim_list, N_list, M_list,
+                                        source_quirk=bool(int(a.bim_source_quirk)))
+    if merged is not None:
+        logging.info(f"Total number of markers in reference is {M} \n")
+        ingest.write_ref_bim(merged["ref_df"], os.path.join(a.out_dir, a.out_name + ".bim"))   # src/main.py:150
     logging.info(f"Loading R and r took {time.time() - ts:0.2f} seconds\n")
     x0 = None
     if a.true_signal_file is not None:

@@ -68,3 +68,30 @@ def test_cli_end_to_end_matches_reference():
                 assert os.path.getsize(os.path.join(d, nm % it)) == c["M"] * 8
         m = open(os.path.join(d, "run_metrics.csv"), "rb").read()
         assert m.startswith(b"it\talignment\tl2\r\n") and m.count(b"\r\n") == its + 1
+
+
+@pytest.mark.gpu
+def test_cli_two_cohorts_from_plink_ld_and_bim():
+    """K = 2 cohorts with different SNP sets from PLINK .ld / .assoc.linear / .bim files (the inputs of
+    tests/golden/ingest, whose ingestion is pinned to the reference in tests/test_ingest_cpu.py) through the
+    whole driver: merged .bim written, per-cohort CSVs and dumps of the merged length."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import main as cli
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ingest")
+    p = lambda n: os.path.join(g, n)
+    np.random.seed(5)
+    with tempfile.TemporaryDirectory() as d:
+        xs = cli.main(["--ld-files", p("c1.ld") + "," + p("c2.ld"), "--r-files", p("c1.assoc.linear") + "," + p("c2.assoc.linear"),
+                       "--bim-files", p("c1.bim") + "," + p("c2.bim"), "--true-signal-file", p("x0.npy"),
+                       "--out-dir", d, "--out-name", "k2", "--N", "400,900", "--M", "8,9", "--K", "2", "--iterations", "3",
+                       "--s", "0.3", "--prior-vars", "0,0.001", "--prior-probs", "0.7,0.3", "--gamw", "2"])
+        assert len(xs) == 3 and xs[0].shape == (10, 1) and np.all(np.isfinite(xs[2]))
+        assert open(os.path.join(d, "k2.bim")).read().count("\n") == 10
+        for k in (1, 2):
+            raw = open(os.path.join(d, "k2_cohort_%d.csv" % k), "rb").read()
+            assert raw.count(b"\r\n") == 4
+            for it in range(3):
+                assert os.path.getsize(os.path.join(d, "k2_r1_cohort_%d_it_%d.bin" % (k, it))) == 80
+        assert os.path.getsize(os.path.join(d, "k2_xhat_it_2.bin")) == 80
