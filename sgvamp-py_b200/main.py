@@ -100,18 +100,39 @@ def main(argv=None):
             raise Exception("Unsupported true signal format!")
         x0 = x0 * np.sqrt(N_list[0])                                # src/main.py:276 (rank 0 writes the metrics)
     avec = np.array(N_list) / sum(N_list)                           # src/main.py:287
-    solver = VAMP(N=N_list if K > 1 else N_list[0], Nt=Nt, M=M, K=K, rho=float(a.rho), gam1=float(a.gam1),
-                  gamw=float(a.gamw), a=avec, prior_vars=prior_vars, prior_probs=prior_probs, out_dir=a.out_dir,
-                  out_name=a.out_name, comm=None, device=int(a.device))
+    # Deployment shapes: (default) one process drives all K cohorts on one GPU; or the reference's own shape,
+    # one rank per cohort (src/main.py:16-18,85): `torchrun --nproc-per-node K main.py ...` puts cohort k on GPU k
+    # and the per-iteration exchange of r1 / gam1 (src/sgvamp.py:228-233) goes over NCCL.
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    comm, device = None, int(a.device)
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        import shard
+        if world != K:
+            raise Exception("one rank per cohort: WORLD_SIZE (%d) must equal K (%d)" % (world, K))
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+        if not dist.is_initialized():
+            torch.cuda.set_device(device)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+        comm = shard.TorchComm()
+        me = comm.Get_rank()
+        Rs, rs = [Rs[me]], [rs[me]]
+        if x0 is not None:
+            x0 = x0 / np.sqrt(N_list[0]) * np.sqrt(N_list[me])     # src/main.py:276 scales by the rank's own N
+    solver = VAMP(N=(N_list[comm.Get_rank()] if comm else (N_list if K > 1 else N_list[0])), Nt=Nt, M=M, K=K,
+                  rho=float(a.rho), gam1=float(a.gam1), gamw=float(a.gamw), a=avec, prior_vars=prior_vars,
+                  prior_probs=prior_probs, out_dir=a.out_dir, out_name=a.out_name, comm=comm, device=device)
     logging.info("...Running sgVAMP\n")
     ts = time.time()
-    xhat1 = solver.infer(Rs if K > 1 else Rs[0], rs if K > 1 else rs[0], int(a.iterations), x0=x0,
+    one = comm is not None or K == 1
+    xhat1 = solver.infer(Rs[0] if one else Rs, rs[0] if one else rs, int(a.iterations), x0=x0,
                          cg_maxit=int(a.cg_maxit), em_prior_maxit=int(a.em_prior_maxit), learn_gamw=learn_gamw,
                          lmmse_damp=lmmse_damp, prior_update=a.prior_update,
                          update_prior_from=int(a.update_prior_from), s=s, layout=a.layout)
     logging.info(f"sgVAMP inference running time: {(time.time() - ts):0.4f}s\n")
     # README names the dump {out}__xhat_it_{it}.bin, the code writes {out}_xhat_it_{it}.bin: provide both
-    for it in range(int(a.iterations)):
+    for it in range(int(a.iterations) if (comm is None or comm.Get_rank() == 0) else 0):
         src = os.path.join(a.out_dir, "%s_xhat_it_%d.bin" % (a.out_name, it))
         dst = os.path.join(a.out_dir, "%s__xhat_it_%d.bin" % (a.out_name, it))
         if os.path.exists(src) and not os.path.exists(dst):

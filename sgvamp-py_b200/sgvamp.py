@@ -155,7 +155,12 @@ class VAMP:
         self.device = device
         self.out_dir, self.out_name = out_dir, out_name
         if out_dir is not None and self.root:
-            self.setup_io(out_dir, out_name)
+            # the reference truncates every cohort's CSV from every rank (src/sgvamp.py:38-43), racing with ranks
+            # that already append; here rank 0 creates the files and the others wait for it
+            if not self.rank_mode or self.rank == 0:
+                self.setup_io(out_dir, out_name)
+            if self.rank_mode:
+                self.comm.bcast(0, root=0)
         self.handle = nat.Handle(device=device, stream=stream)
         if self.shard.world == 1:
             self.handle.configure(self.M, self.K)

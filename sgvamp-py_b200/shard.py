@@ -126,6 +126,45 @@ class TorchShard:
         self.dist.barrier(group=self.group)
 
 
+class TorchComm:
+    """The `comm` duck type of the reference solver (`Get_rank`, `Get_size`, `bcast(obj, root=)`;
+    src/sgvamp.py:202,230-233) over torch.distributed, for the reference's deployment shape
+    "one rank per cohort" on a multi-GPU box: `torchrun --nproc-per-node K main.py ...` (NCCL on GPUs,
+    gloo on CPU).  ndarrays travel as tensors (on the GPU with NCCL), anything else pickled."""
+
+    def __init__(self, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = device if device is not None else ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+
+    def Get_rank(self):
+        return self.rank
+
+    def Get_size(self):
+        return self.world
+
+    def bcast(self, obj, root=0):
+        # every rank knows whether a vector or a scalar travels (src/sgvamp.py:232 scalar gam1, :233 the r1 vector),
+        # but only the root has the value: the header (kind, shape) goes first
+        head = [None]
+        if self.rank == root:
+            head[0] = ("nd", obj.shape, str(obj.dtype)) if isinstance(obj, np.ndarray) else ("py",)
+        self.dist.broadcast_object_list(head, src=root, group=self.group)
+        if head[0][0] == "py":
+            box = [obj if self.rank == root else None]
+            self.dist.broadcast_object_list(box, src=root, group=self.group)
+            return box[0]
+        _, shape, dtype = head[0]
+        if self.rank == root:
+            t = self.torch.from_numpy(np.ascontiguousarray(obj)).to(self.device)
+        else:
+            t = self.torch.empty(shape, dtype=getattr(self.torch, dtype), device=self.device)
+        self.dist.broadcast(t, src=root, group=self.group)
+        return t.cpu().numpy()
+
+
 class ThreadShard:
     """In-process ranks (one host thread per GPU) for tests: barrier-based allgather."""
 

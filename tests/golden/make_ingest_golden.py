@@ -147,11 +147,11 @@ def main():
                          "--iterations", "1", "--s", "0.0"], 1)
     out["k1_R_0"], out["k1_r_0"], out["k1_M"] = cap[0]["R"], cap[0]["r"], cap[0]["M"]
     out["k1_bim"] = open(p("ref_k1.bim")).read()
-    np.savez_compressed(os.path.join(HERE, "ingest_reference.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "reference.npz"), **out)
     for n in os.listdir(OUT):
         if n.startswith("ref_k"):
             os.remove(p(n))
-    print("wrote", os.path.join(HERE, "ingest_reference.npz"), {k: getattr(v, "shape", None) for k, v in out.items()})
+    print("wrote", os.path.join(OUT, "reference.npz"), {k: getattr(v, "shape", None) for k, v in out.items()})
 
 
 if __name__ == "__main__":

@@ -1,5 +1,5 @@
 """Ingestion (sgvamp-py_b200/ingest.py) against what the UNMODIFIED reference driver hands to its solver
-(tests/golden/ingest_reference.npz, made by tests/golden/make_ingest_golden.py from src/main.py run with
+(tests/golden/ingest/reference.npz, made by tests/golden/make_ingest_golden.py from src/main.py run with
 one thread per MPI rank): merged marker order, reordered XTy (.assoc.linear with NaN and sqrt(N) scaling),
 PLINK .ld matrices after the exchange of missing SNPs, the regularised Rused, and the saved .bim."""
 import os
@@ -16,7 +16,7 @@ p = lambda n: os.path.join(D, n)
 
 @pytest.fixture(scope="module")
 def ref():
-    return np.load(os.path.join(GOLD, "ingest_reference.npz"), allow_pickle=False)
+    return np.load(os.path.join(D, "reference.npz"), allow_pickle=False)
 
 
 def test_k2_ld_bim_exchange_matches_reference(ref, tmp_path):

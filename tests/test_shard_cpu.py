@@ -108,3 +108,36 @@ def test_torch_shard_gloo_world2(tmp_path):
                        capture_output=True, text=True, timeout=240, env=env)
     assert p.returncode == 0, p.stdout + p.stderr
     assert p.stdout.count("ok") == 2
+
+
+def test_torch_comm_gloo_world3(tmp_path):
+    """TorchComm (the reference's `comm` duck type over torch.distributed) on gloo, 3 ranks = 3 cohorts:
+    the exchange pattern of src/sgvamp.py:230-233 (scalar gam1 and the r1 vector from every root)."""
+    script = tmp_path / "c.py"
+    script.write_text(textwrap.dedent("""
+        import os, sys
+        sys.path.insert(0, %r)
+        import numpy as np
+        import torch.distributed as dist
+        import shard as shd
+        dist.init_process_group("gloo")
+        comm = shd.TorchComm()
+        K, rank, M = comm.Get_size(), comm.Get_rank(), 11
+        assert K == 3
+        gam1, r1 = 0.5 + rank, np.arange(M, dtype=np.float64) * (rank + 1)
+        gam1s, r1s = np.zeros(K), np.zeros((K, M))
+        for i in range(K):
+            gam1s[i] = comm.bcast(gam1 if i == rank else None, root=i)
+            r1s[i] = comm.bcast(r1 if i == rank else None, root=i)
+        assert np.array_equal(gam1s, [0.5, 1.5, 2.5])
+        assert np.array_equal(r1s, np.arange(M)[None, :] * np.arange(1, K + 1)[:, None])
+        assert comm.bcast({"a": rank} if rank == 2 else None, root=2) == {"a": 2}
+        dist.destroy_process_group()
+        print("ok", rank)
+    """ % os.path.join(REPO, "sgvamp-py_b200")))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "3",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.count("ok") == 3
