@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cpu-sample-M", type=int, default=60_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-format", default="dia", choices=["dia", "csr"],
+                    help="host container of the LD matrix in the end-to-end leg (scipy DIA arrays or CSR)")
     ap.add_argument("--seed", type=int, default=5)
     return ap.parse_args()
 
@@ -67,7 +69,7 @@ def make_probes(iterations, M, seed):
 def build_problem(torch, M, w, seed, dev, lo=0, hi=None, ext=0, keep_full=True):
     """Rows [lo, hi) of the workload.  Returns the symmetric half band of Rused in the DSYM layout
     (fp32, device; with `ext` leading extension rows for ranks > 0, sgv_ld_adopt_dsym), the full band
-    of the own rows (for the host-CSR leg; None unless keep_full), r (host), x0 (host, global)."""
+    of the rows [lo-ext, hi) (for the host-side end-to-end leg; None unless keep_full), r (host), x0 (host, global)."""
     import ldgen
     t0 = time.time()
     hi = M if hi is None else hi
@@ -104,7 +106,7 @@ def build_problem(torch, M, w, seed, dev, lo=0, hi=None, ext=0, keep_full=True):
         jj = torch.arange(ext, device=dev)[None, :]
         dd = torch.arange(Dp, device=dev)[:, None]
         U[:, :ext] *= (jj + dd >= ext).to(torch.float32)
-    full = band[:, ext:].contiguous() if keep_full else None
+    full = band if keep_full else None              # full band of the rows [glo, hi) (host-side legs)
     del band
     U = ldgen.dsym_tile(torch, U)                   # [ldb/128][Dp/4][4][128]: one contiguous stream per 128-row block
     torch.cuda.synchronize()
@@ -144,6 +146,24 @@ def band_to_host_csr(torch, band, M, w, lo=0, hi=None, pinned=True):
                                 shape=(Ml, M))
     R.has_canonical_format = True
     return R, (data, idx)
+
+
+def band_to_host_dia(torch, band, M, w, glo, hi, pinned=True):
+    """The rows [glo, hi) of the banded matrix as a column window of scipy's DIA format in (pinned) host
+    memory: data[k, j - col0] = R[j - off_k, j], off_k = k - w  (band[k, t] = R[glo + t, glo + t + off_k])."""
+    n = hi - glo
+    col0 = max(0, glo - w)
+    ldd = min(M, hi + w) - col0
+    data = torch.zeros((2 * w + 1, ldd), device=band.device, dtype=torch.float32)
+    for k in range(2 * w + 1):
+        sh = glo + (k - w) - col0                       # column of row glo inside the window
+        t0, t1 = max(0, -sh), min(n, ldd - sh)
+        if t1 > t0:
+            data[k, t0 + sh: t1 + sh] = band[k, t0:t1]
+    host = torch.empty((2 * w + 1, ldd), dtype=torch.float32, pin_memory=pinned)
+    host.copy_(data)
+    torch.cuda.synchronize()
+    return host, np.arange(-w, w + 1, dtype=np.int64), col0
 
 
 class ClockSampler:
@@ -370,36 +390,40 @@ def main():
             sys.stderr.write("  %2d %.4g %.4g %.4g %.4g %.4g %.4g | %s em=%d | %.4f\n" % (
                 rw[0], rw[1], rw[2], rw[3], rw[4], rw[5], rw[6], hist["cg_iters"][i][0], hist["em_steps"][i], aligns[i]))
 
-    # ---- end-to-end leg: host CSR in pinned memory -> VAMP.infer -> host xhat ----
+    # ---- end-to-end leg: host LD (scipy DIA arrays in pinned memory) -> VAMP.load_ld -> VAMP.infer -> host xhat ----
     e2e = None
     if not a.no_e2e:
-        Rh, keep = band_to_host_csr(torch, band, M, w, lo, hi)
+        import scipy.sparse
+        del U, dia
+        glo = lo - ext
+        if a.e2e_format == "csr":
+            Rh, keep = band_to_host_csr(torch, band[:, ext:], M, w, lo, hi)
+            h2d_ld = Rh.data.nbytes + Rh.indices.nbytes + (Ml + 1) * 8
+        else:
+            host, offsets, col0 = band_to_host_dia(torch, band, M, w, glo, hi)
+            keep = host
+            Rh = (scipy.sparse.dia_matrix((host.numpy(), offsets), shape=(M, M)) if world == 1
+                  else sgvamp.DiaWindow(host.numpy(), offsets, col0, M))
+            h2d_ld = (2 * w + 1) * (hi - glo) * 4            # upper diagonals + the lower ones for the symmetry check
         v2 = new_solver()
         barrier()
         t0 = time.perf_counter()
-        if os.environ.get("SGV_TIMING"):
-            import cProfile, pstats
-            pr = cProfile.Profile()
-            pr.enable()
-            v2.load_ld(0, Rh)
-            pr.disable()
-            pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(12)
-        else:
-            v2.load_ld(0, Rh)
+        v2.load_ld(0, Rh)
         torch.cuda.synchronize()
         t_up = time.perf_counter() - t0
         xs2 = run(v2, None, iterations, None, write_outputs=False)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
-        h2d = sum_over_ranks([(Rh.data.nbytes + Rh.indices.nbytes + (Ml + 1) * 8 + Ml * 8) / iterations + Ml])[0]
+        h2d = sum_over_ranks([(h2d_ld + Ml * 8) / iterations + Ml])[0]
         d2h = M * 8 + 256 * world
         diff = max_over_ranks(max(np.linalg.norm(x1 - x2) / max(np.linalg.norm(x1), 1e-300) for x1, x2 in zip(xs, xs2)))
         e2e = {"value": iterations / dt, "unit": "it/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "what": "VAMP.load_ld(scipy CSR fp32 rows of this rank in pinned host memory) + VAMP.infer(r host) for %d "
-                       "iterations from it=0: LD upload + layout conversion + every iteration's probe H2D and xhat D2H "
-                       "inside the timed region (wall clock between barriers, max over ranks)" % iterations,
+               "what": "VAMP.load_ld(host LD of this rank's rows as scipy %s arrays, fp32, pinned) + VAMP.infer(r host) for %d "
+                       "iterations from it=0: LD upload (symmetry verified on the device) + layout conversion + every "
+                       "iteration's probe H2D and xhat D2H inside the timed region (wall clock between barriers, max over "
+                       "ranks)" % (a.e2e_format.upper(), iterations),
                "seconds": dt, "ld_upload_seconds": max_over_ranks(t_up), "max_rel_diff_vs_resident": diff,
-               "layout": v2.handle.ld_info(0)["layout"]}
+               "layout": v2.handle.ld_info(0)["layout"], "host_format": a.e2e_format}
         v2.close()
         del Rh, keep
 

@@ -79,6 +79,14 @@ int sgv_partition_info(sgv_handle h, int64_t* M, int64_t* rows, int64_t* row_lo,
 int sgv_ld_upload_dense(sgv_handle h, int cohort, const void* R, int dtype, int64_t ld, double s);
 int sgv_ld_upload_csr(sgv_handle h, int cohort, const int64_t* indptr, const int32_t* indices,
                       const void* data, int dtype, int64_t nnz, double s, int layout_hint);
+/* LD in scipy's DIA format (the natural container of banded LD; `scipy.sparse.load_npz` returns it when the
+ * matrix was saved so, src/main.py:199-200): data[k*ldd + (j - col0)] = R[j - offsets[k]][j], the entry of diagonal
+ * offsets[k] in COLUMN j, for the column window j in [col0, col0+ldd) (col0 = 0, ldd >= M: the whole matrix; a
+ * rank of a row partition may pass just the window its rows touch).  No index arrays travel, and for the
+ * symmetric half-band layout only the diagonals >= 0 are copied; unless assume_symmetric, the diagonals < 0
+ * are streamed through the device once and compared with their mirrors (mismatch: full band / error). */
+int sgv_ld_upload_dia(sgv_handle h, int cohort, const void* data, int dtype, int64_t ldd, int64_t col0,
+                      const int64_t* offsets, int ndiag, double s, int layout_hint, int assume_symmetric);
 /* Adopt LD already resident in HBM (benchmarks: inputs generated on the device).  The library
  * does not take ownership; the buffers must outlive the handle's use of them.
  * dia: band[d*ldb + i] = Rused[i][i+d-w], d in [0,2w]; ldb multiple of 4 elements, base 16B aligned.

@@ -594,6 +594,238 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// LD given in scipy's DIA format (what banded LD is naturally stored as): no index arrays to ship,
+// and for the symmetric half-band layout only the upper diagonals are needed on the device.
+// ---------------------------------------------------------------------------------------------
+// stage[kk*n + t] = value of diagonal `off` at global row g0 + t  (= R[g0+t][g0+t+off]), kk-th diagonal of the chunk
+template <typename T>
+__global__ void k_dia_to_dsym(const T* __restrict__ stage, int64_t n, const int* __restrict__ offs, int nk, float* __restrict__ U,
+                              int64_t ngr, int64_t g0, int64_t row_lo, int64_t M, double s) {
+    const int kk = blockIdx.y;
+    if (kk >= nk) return;
+    const int off = offs[kk];
+    const T* src = stage + (int64_t)kk * n;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = g0 + t;                       // global row; storage row = t (the buffer starts at g0 = row_lo - E)
+        float v = 0.f;
+        if (g >= 0 && g + off < M && g + off >= row_lo)  // extension rows keep only their couplings to own rows
+            v = off == 0 ? 0.5f * reg_value(src[t], true, s) : reg_value(src[t], false, s);
+        U[sgv_dsym_index(t, off, ngr)] = v;
+    }
+}
+
+// lower diagonals against the stored upper ones: R[g][g-off] (lower, off > 0) must equal R[g-off][g]
+template <typename T>
+__global__ void k_dia_check_lower(const T* __restrict__ stage, int64_t n, const int* __restrict__ offs, int nk,
+                                  const float* __restrict__ U, int64_t ngr, int64_t g0, int64_t row_lo, int64_t M, double s,
+                                  float abs_tol, unsigned long long* __restrict__ mismatches) {
+    const int kk = blockIdx.y;
+    if (kk >= nk) return;
+    const int off = offs[kk];                           // > 0: the diagonal -off
+    const T* src = stage + (int64_t)kk * n;
+    unsigned bad = 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = g0 + t;                       // row of the lower entry; its mirror is row g - off
+        if (g >= row_lo && g < M && g - off >= g0 && g - off >= 0) {
+            const float lo = reg_value(src[t], false, s), up = U[sgv_dsym_index(t - off, off, ngr)];
+            if (fabsf(lo - up) > fmaxf(4e-7f * fmaxf(fabsf(lo), fabsf(up)), abs_tol)) ++bad;
+        }
+    }
+    if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
+template <typename T>
+__global__ void k_dia_to_band(const T* __restrict__ stage, int64_t n, const int* __restrict__ offs, int nk, float* __restrict__ band,
+                              int64_t w, int64_t ldb, int64_t g0, int64_t M, double s) {
+    const int kk = blockIdx.y;
+    if (kk >= nk) return;
+    const int off = offs[kk];
+    const T* src = stage + (int64_t)kk * n;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = g0 + t;
+        float v = 0.f;
+        if (g + off >= 0 && g + off < M) v = reg_value(src[t], off == 0, s);
+        band[(int64_t)(off + w) * ldb + t] = v;
+    }
+}
+
+// Copies, for the diagonals listed in ks, the entries of global rows [g0, g0+n) into the staging buffer (chunks of
+// diagonals; host -> device on the copy stream, double-buffered against the conversion kernel on the compute stream)
+// and calls `convert(stage_ptr, dev_offsets, nk)` for every chunk.
+template <typename F>
+static int stream_diagonals(sgv_ctx* c, const void* data, size_t esz, int64_t ldd, int64_t col0, const int64_t* offsets,
+                            const std::vector<int>& ks, bool negate, int64_t g0, int64_t n, int64_t M, F convert) {
+    const int CH = 16;
+    const size_t chunk_bytes = (size_t)CH * n * esz;
+    SGV_TRY(sgv_ensure_stage(c, 2 * (int64_t)chunk_bytes + 2 * CH * (int64_t)sizeof(int)));
+    char* base = static_cast<char*>(c->stage);
+    int* d_offs = reinterpret_cast<int*>(base + 2 * chunk_bytes);
+    cudaEvent_t h2d[2], done[2];
+    for (int i = 0; i < 2; ++i) {
+        SGV_CUDA(cudaEventCreateWithFlags(&h2d[i], cudaEventDisableTiming));
+        SGV_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    }
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    int rc = 0;
+    std::vector<int> hoffs(2 * CH);
+    for (size_t c0 = 0, ci = 0; c0 < ks.size() && rc == 0; c0 += CH, ++ci) {
+        const int b = (int)(ci & 1), nk = (int)std::min<size_t>(CH, ks.size() - c0);
+        char* st = base + (size_t)b * chunk_bytes;
+        if (ci >= 2) SGV_CUDA(cudaStreamWaitEvent(c->copy_stream, done[b], 0));
+        SGV_CUDA(cudaMemsetAsync(st, 0, chunk_bytes, c->copy_stream));
+        for (int kk = 0; kk < nk; ++kk) {
+            const int k = ks[c0 + kk];
+            const int64_t off = offsets[k];
+            hoffs[b * CH + kk] = (int)(negate ? -off : off);
+            // scipy DIA: the entry of diagonal `off` in row g sits at column j = g + off of data row k
+            int64_t j_lo = g0 + off, j_hi = g0 + n + off;                    // wanted columns [j_lo, j_hi)
+            const int64_t a_lo = std::max<int64_t>(std::max<int64_t>(j_lo, col0), 0);
+            const int64_t a_hi = std::min<int64_t>(std::min<int64_t>(j_hi, col0 + ldd), M);
+            if (a_hi > a_lo)
+                SGV_CUDA(cudaMemcpyAsync(st + ((size_t)kk * n + (size_t)(a_lo - j_lo)) * esz,
+                                         static_cast<const char*>(data) + ((size_t)k * ldd + (size_t)(a_lo - col0)) * esz,
+                                         (size_t)(a_hi - a_lo) * esz, cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        SGV_CUDA(cudaMemcpyAsync(d_offs + b * CH, hoffs.data() + b * CH, nk * sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
+        SGV_CUDA(cudaEventRecord(h2d[b], c->copy_stream));
+        SGV_CUDA(cudaStreamWaitEvent(c->stream, h2d[b], 0));
+        rc = convert(st, d_offs + b * CH, nk);
+        c->launches++;
+        SGV_CUDA(cudaEventRecord(done[b], c->stream));
+    }
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(h2d[i]);
+        cudaEventDestroy(done[i]);
+    }
+    SGV_CUDA(cudaGetLastError());
+    return rc;
+}
+
+template <typename T>
+static int upload_dia_t(sgv_ctx* c, LdMatrix& ld, const T* data, int64_t ldd, int64_t col0, const int64_t* offsets, int ndiag,
+                        double s, int layout, int assume_symmetric, int64_t w) {
+    const int64_t M = c->M, Ml = c->Ml;
+    std::vector<int> up, lowr, all;
+    for (int k = 0; k < ndiag; ++k) {
+        all.push_back(k);
+        if (offsets[k] >= 0) up.push_back(k);
+        else lowr.push_back(k);
+    }
+    const dim3 blk(256);
+    if (layout == SGV_LAYOUT_DSYM) {
+        const int64_t E = sgv_dsym_ext(c, w), Dp = round_up(w + 1, 4), ngr = Dp / 4;
+        const int64_t n = round_up(Ml + E, 128), g0 = c->row_lo - E;
+        float* U = nullptr;
+        SGV_CUDA(cudaMalloc(&U, (size_t)Dp * n * sizeof(float)));
+        ld.band = U;
+        ld.owned = true;
+        ld.w = w;
+        ld.ldb = n;
+        ld.ext = E;
+        ld.nnz_stored = (w + 1) * Ml;
+        SGV_CUDA(cudaMemsetAsync(U, 0, (size_t)Dp * n * sizeof(float), c->stream));
+        const int64_t row_lo = c->row_lo;
+        // rows of the buffer beyond the local range (padding to 128) convert to zeros: g + off < M fails or data is zero
+        k_dsym_fill_diag<<<592, 256, 0, c->stream>>>(U, Ml, E, ngr, 0.5f * (float)s);
+        const int64_t n_rows = std::min<int64_t>(n, Ml + E);
+        auto conv = [&](char* st, int* d_offs, int nk) -> int {
+            const dim3 grid((unsigned)std::min<int64_t>((n_rows + 255) / 256, 2048), (unsigned)nk);
+            k_dia_to_dsym<T><<<grid, blk, 0, c->stream>>>((const T*)st, n_rows, d_offs, nk, U, ngr, g0, row_lo, M, s);
+            return 0;
+        };
+        SGV_TRY(stream_diagonals(c, data, sizeof(T), ldd, col0, offsets, up, false, g0, n_rows, M, conv));
+        if (!assume_symmetric && !lowr.empty()) {
+            unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(c->counter + 8);
+            SGV_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
+            float diag0 = 1.f;
+            SGV_CUDA(cudaMemcpyAsync(&diag0, U + sgv_dsym_index(E, 0, ngr), sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            SGV_CUDA(cudaStreamSynchronize(c->stream));
+            const float abs_tol = 2e-6f * fmaxf(2.f * fabsf(diag0), 1e-30f);
+            auto chk = [&](char* st, int* d_offs, int nk) -> int {
+                const dim3 grid((unsigned)std::min<int64_t>((n_rows + 255) / 256, 2048), (unsigned)nk);
+                k_dia_check_lower<T><<<grid, blk, 0, c->stream>>>((const T*)st, n_rows, d_offs, nk, U, ngr, g0, row_lo, M, s, abs_tol,
+                                                                  d_bad);
+                return 0;
+            };
+            SGV_TRY(stream_diagonals(c, data, sizeof(T), ldd, col0, offsets, lowr, true, g0, n_rows, M, chk));
+            unsigned long long bad = 0;
+            SGV_CUDA(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
+            if (bad != 0) {
+                sgv_ld_free(ld);
+                return 1;   // not symmetric: the caller falls back to the full band
+            }
+        }
+        ld.layout = SGV_LAYOUT_DSYM;
+        return sgv_dsym_ensure_scratch(c, ld);
+    }
+    // full band
+    const int64_t ldb = round_up(Ml, 32), g0 = c->row_lo;
+    float* band = nullptr;
+    SGV_CUDA(cudaMalloc(&band, (size_t)(2 * w + 1) * ldb * sizeof(float)));
+    ld.band = band;
+    ld.owned = true;
+    ld.w = w;
+    ld.ldb = ldb;
+    ld.nnz_stored = (2 * w + 1) * Ml;
+    SGV_CUDA(cudaMemsetAsync(band, 0, (size_t)(2 * w + 1) * ldb * sizeof(float), c->stream));
+    k_fill_f32<<<592, 256, 0, c->stream>>>(band + w * ldb, Ml, (float)s);
+    auto conv = [&](char* st, int* d_offs, int nk) -> int {
+        const dim3 grid((unsigned)std::min<int64_t>((Ml + 255) / 256, 2048), (unsigned)nk);
+        k_dia_to_band<T><<<grid, blk, 0, c->stream>>>((const T*)st, Ml, d_offs, nk, band, w, ldb, g0, M, s);
+        return 0;
+    };
+    SGV_TRY(stream_diagonals(c, data, sizeof(T), ldd, col0, offsets, all, false, g0, Ml, M, conv));
+    ld.layout = SGV_LAYOUT_DIA;
+    return 0;
+}
+
+extern "C" int sgv_ld_upload_dia(sgv_handle c, int cohort, const void* data, int dtype, int64_t ldd, int64_t col0,
+                                 const int64_t* offsets, int ndiag, double s, int layout_hint, int assume_symmetric) {
+    SGV_TRY(check_cohort(c, cohort));
+    SGV_CHECK(data != nullptr && offsets != nullptr && ndiag > 0, "null / empty DIA arrays");
+    SGV_CHECK(dtype == SGV_F32 || dtype == SGV_F64, "bad dtype %d", dtype);
+    SGV_CHECK(layout_hint == SGV_LAYOUT_AUTO || layout_hint == SGV_LAYOUT_DIA || layout_hint == SGV_LAYOUT_DSYM,
+              "DIA input maps to the band layouts (auto / dia / dsym)");
+    SGV_CHECK(c->world == 1 || c->halo, "DIA input needs a halo partition when sharded");
+    PhaseTimer pt(c->stream);
+    int64_t w = 0;
+    for (int k = 0; k < ndiag; ++k) {
+        SGV_CHECK(offsets[k] > -c->M && offsets[k] < c->M, "diagonal offset %lld outside the matrix", (long long)offsets[k]);
+        w = std::max<int64_t>(w, offsets[k] < 0 ? -offsets[k] : offsets[k]);
+        for (int q = 0; q < k; ++q) SGV_CHECK(offsets[q] != offsets[k], "duplicate diagonal offset %lld", (long long)offsets[k]);
+    }
+    if (c->bandwidth_hint > w) w = c->bandwidth_hint;
+    LdMatrix& ld = c->coh[cohort].ld;
+    sgv_ld_free(ld);
+    int layout = layout_hint;
+    bool fallback = false;
+    if (layout == SGV_LAYOUT_AUTO) {
+        layout = sgv_dsym_feasible(w) ? SGV_LAYOUT_DSYM : SGV_LAYOUT_DIA;
+        fallback = layout == SGV_LAYOUT_DSYM;
+    }
+    SGV_CHECK(layout != SGV_LAYOUT_DSYM || sgv_dsym_feasible(w), "DSYM layout infeasible for half-bandwidth %lld", (long long)w);
+    SGV_CHECK(layout != SGV_LAYOUT_DIA || sgv_dia_feasible(w), "DIA layout infeasible for half-bandwidth %lld", (long long)w);
+    int rc = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        rc = dtype == SGV_F64 ? upload_dia_t<double>(c, ld, (const double*)data, ldd, col0, offsets, ndiag, s, layout, assume_symmetric, w)
+                              : upload_dia_t<float>(c, ld, (const float*)data, ldd, col0, offsets, ndiag, s, layout, assume_symmetric, w);
+        if (rc != 1) break;
+        if (fallback && sgv_dia_feasible(w)) {
+            layout = SGV_LAYOUT_DIA;
+        } else {
+            sgv_set_error("LD matrix is not symmetric: the DSYM layout cannot hold it");
+            rc = -1;
+            break;
+        }
+    }
+    if (rc != 0) sgv_ld_free(ld);
+    pt.lap("DIA upload + conversion");
+    return rc;
+}
+
 extern "C" int sgv_ld_set_bandwidth_hint(sgv_handle c, int64_t w) {
     SGV_CHECK(c != nullptr, "null handle");
     c->bandwidth_hint = w;

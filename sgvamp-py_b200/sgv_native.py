@@ -27,7 +27,7 @@ SYMBOLS = [
     "sgv_lagrangian", "sgv_lmmse", "sgv_update_r1", "sgv_metrics", "sgv_spmm", "sgv_spmm_bench",
     "sgv_launch_count", "sgv_profile", "sgv_profile_read", "sgv_configure_part", "sgv_ipc_export", "sgv_ipc_import",
     "sgv_peer_attach_local", "sgv_partition_info", "sgv_ld_set_bandwidth_hint", "sgv_spmm_stage", "sgv_spmm_run",
-    "sgv_ld_adopt_dsym", "sgv_dsym_extension", "sgv_set_host_barrier", "sgv_device_id",
+    "sgv_ld_adopt_dsym", "sgv_dsym_extension", "sgv_set_host_barrier", "sgv_device_id", "sgv_ld_upload_dia",
 ]
 
 
@@ -163,6 +163,18 @@ class Handle:
                                         C.c_int(F64 if data.dtype == np.float64 else F32),
                                         C.c_int64(data.shape[0]), C.c_double(s), C.c_int(layout))
         return rc
+
+    def upload_dia(self, cohort, data, offsets, s=0.0, layout=LAYOUT_AUTO, assume_symmetric=False, col0=0):
+        """scipy DIA arrays: data[k, j - col0] = R[j - offsets[k], j] (see sgv_ld_upload_dia)."""
+        data = np.ascontiguousarray(data)
+        if data.dtype not in (np.float32, np.float64):
+            data = data.astype(np.float64)
+        offs = np.ascontiguousarray(offsets, dtype=np.int64)
+        assert data.ndim == 2 and data.shape[0] == offs.shape[0]
+        return self.lib.sgv_ld_upload_dia(self.h, C.c_int(cohort), data.ctypes.data_as(C.c_void_p),
+                                          C.c_int(F64 if data.dtype == np.float64 else F32), C.c_int64(data.shape[1]),
+                                          C.c_int64(col0), offs.ctypes.data_as(C.POINTER(C.c_int64)), C.c_int(len(offs)),
+                                          C.c_double(s), C.c_int(layout), C.c_int(int(bool(assume_symmetric))))
 
     def adopt_dia(self, cohort, band_ptr, w, ldb):
         self._ck(self.lib.sgv_ld_adopt_dia(self.h, C.c_int(cohort), C.c_void_p(band_ptr), C.c_int64(w), C.c_int64(ldb)))

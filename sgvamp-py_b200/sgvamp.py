@@ -45,6 +45,14 @@ class DeviceDSYM:
         self.ptr, self.w, self.ldb, self.ext, self.keepalive = int(ptr), int(w), int(ldb), int(ext), keepalive
 
 
+class DiaWindow:
+    """Column window of a matrix in scipy's DIA format: data[k, j - col0] = R[j - offsets[k], j] for the
+    columns j in [col0, col0 + data.shape[1]) of an M x M matrix (what one rank of a row partition needs)."""
+
+    def __init__(self, data, offsets, col0, M):
+        self.data, self.offsets, self.col0, self.M = data, np.asarray(offsets), int(col0), int(M)
+
+
 class DeviceDense:
     """Dense fp32 row-major LD already resident in HBM (see sgv_ld_adopt_dense)."""
 
@@ -203,7 +211,7 @@ class VAMP:
     # ------------------------------------------------------------------------------------------
     # LD / XTy ingestion
     # ------------------------------------------------------------------------------------------
-    def load_ld(self, cohort, R, s=0.0, layout="auto"):
+    def load_ld(self, cohort, R, s=0.0, layout="auto", assume_symmetric=False):
         """Upload one cohort's LD matrix; Rused = (1-s) R + s I is applied on the device
         (src/main.py:265).  R: scipy sparse, ndarray / np.matrix, DeviceDIA or DeviceDense."""
         h = self.handle
@@ -221,6 +229,25 @@ class VAMP:
             assert s == 0.0, "device-resident LD must already be regularised"
             h.adopt_dense(cohort, R.ptr, R.ld)
             self._keep.append(R)
+        elif isinstance(R, DiaWindow) or (scipy.sparse.issparse(R) and R.format == "dia"):
+            # banded LD in DIA form: diagonals travel as they are (no index arrays; half of them for symmetric LD)
+            if isinstance(R, DiaWindow):
+                data, offsets, col0, Mr = R.data, R.offsets, R.col0, R.M
+            else:
+                data, offsets, col0, Mr = R.data, R.offsets, 0, R.shape[0]
+                if R.shape != (self.M, self.M):
+                    raise Exception("LD matrix shape %s does not match M=%d" % (R.shape, self.M))
+            if Mr != self.M:
+                raise Exception("LD matrix size %d does not match M=%d" % (Mr, self.M))
+            if lay not in (nat.LAYOUT_AUTO, nat.LAYOUT_DIA, nat.LAYOUT_DSYM):
+                raise Exception("LD in DIA format maps to the band layouts (auto / dia / dsym)")
+            if self.shard.world > 1:
+                wmax = int(np.max(np.abs(offsets))) if len(offsets) else 0
+                if not self.halo:
+                    raise Exception("banded LD in DIA format needs halo=True when sharded")
+                if min(hi_ - lo_ for lo_, hi_ in self.bounds) < wmax:
+                    raise Exception("row shards are shorter than the LD half-bandwidth %d" % wmax)
+            h._ck(h.upload_dia(cohort, data, offsets, s=s, layout=lay, assume_symmetric=assume_symmetric, col0=col0))
         elif scipy.sparse.issparse(R) and self.shard.world > 1:
             R = R.tocsr()
             if R.shape == (self.M, self.M):

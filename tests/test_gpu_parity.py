@@ -133,6 +133,52 @@ def test_spmm_blockdiag_and_auto_detection(nat):
     h.close()
 
 
+@pytest.mark.parametrize("layout", ["auto", "dia", "dsym"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_upload_scipy_dia_format(nat, layout, dtype):
+    """LD handed over in scipy's DIA format (no index arrays; only the upper diagonals travel for the symmetric
+    half band, the lower ones are verified on the device): same products as the CSR route, Rused applied."""
+    M, w, s = 3000, 37, 0.1
+    R = _rand_sym_band(M, w, seed=8)
+    Rd = R.todia()
+    Rd.data = Rd.data.astype(dtype)
+    lay = {"auto": nat.LAYOUT_AUTO, "dia": nat.LAYOUT_DIA, "dsym": nat.LAYOUT_DSYM}[layout]
+    h = nat.Handle()
+    h.configure(M, 1)
+    X = np.random.default_rng(1).standard_normal((M, 2))
+    h._ck(h.upload_dia(0, Rd.data, Rd.offsets, s=0.0, layout=lay))
+    info = h.ld_info(0)
+    assert info["layout"] == ("dia" if layout == "dia" else "dsym") and info["bandwidth"] == w
+    assert rel_l2(h.spmm(0, X), R @ X) < 1e-13                         # values are fp32-representable: exact storage
+    h._ck(h.upload_dia(0, Rd.data, Rd.offsets, s=s, layout=lay))       # Rused rounds once to fp32
+    ref = (1 - s) * (R @ X) + s * X
+    assert rel_l2(h.spmm(0, X), ref) < 1e-6
+    # a column window of the DIA arrays (what one rank of a row partition passes) gives the same matrix
+    h._ck(h.upload_dia(0, np.ascontiguousarray(Rd.data[:, 5:M - 3]), Rd.offsets, s=0.0, layout=lay, col0=5))
+    got = h.spmm(0, X)
+    Rw = R.tolil()
+    Rw[:, :5] = 0                                                       # columns outside the window read as zero ...
+    Rw[:, M - 3:] = 0
+    Rw = Rw.tocsr()
+    if layout == "dia":
+        assert rel_l2(got, Rw @ X) < 1e-13
+    # not symmetric: auto falls back to the full band, explicit dsym refuses, assume_symmetric uses the upper half
+    Ra = R.tolil()
+    Ra[100, 103] = 0.25 if Ra[103, 100] != 0.25 else 0.75
+    Ra = Ra.tocsr().todia()
+    if layout == "auto":
+        h._ck(h.upload_dia(0, Ra.data, Ra.offsets, s=0.0, layout=lay))
+        assert h.ld_info(0)["layout"] == "dia"
+        assert rel_l2(h.spmm(0, X), Ra @ X) < 1e-13
+    if layout == "dsym":
+        assert h.upload_dia(0, Ra.data, Ra.offsets, s=0.0, layout=lay) != 0
+        h._ck(h.upload_dia(0, Ra.data, Ra.offsets, s=0.0, layout=lay, assume_symmetric=True))
+        Rsym = scipy.sparse.triu(Ra.tocsr(), 0)
+        Rsym = (Rsym + scipy.sparse.triu(Ra.tocsr(), 1).T).tocsr()
+        assert rel_l2(h.spmm(0, X), Rsym @ X) < 1e-13
+    h.close()
+
+
 def test_regularisation_at_upload(nat):
     """Rused = (1-s) R + s I (src/main.py:265) on every layout, including absent diagonal entries."""
     rng = np.random.default_rng(9)
