@@ -41,6 +41,7 @@ extern "C" int sgv_create(int device, void* stream, sgv_handle* out) {
     sgv_ctx* c = new sgv_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    c->coop_ok = prop.cooperativeLaunch != 0 && getenv("SGV_NO_COOP") == nullptr;
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {

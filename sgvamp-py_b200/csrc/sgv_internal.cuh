@@ -185,6 +185,8 @@ struct sgv_ctx {
     sgv_ctx*     peer_ctx[SGV_MAX_RANKS] = {};
     std::atomic<unsigned long long> host_seq{0};
     unsigned long long seq = 0;      // reductions issued so far (identical on all ranks)
+    bool         coop_ok = false;      // device supports cooperative launches (persistent EM loop kernel)
+    int          em_loop_blocks_per_sm = 0;
     int          last_em_steps = 0;  // EM passes the previous prior update needed (first batch of the next one)
     double2*     ds_ypart = nullptr; // DSYM kernel: per-row partial sums and per-tile tails
     double2*     ds_tails = nullptr;
