@@ -488,3 +488,46 @@ def test_spmm_properties_large(nat):
     assert np.array_equal(h.spmm(0, x), Sx)
     assert h.ld_info(0)["bytes_per_pass"] < 0.52 * (4.0 * (2 * w + 1) * M + 32.0 * M)
     h.close()
+
+
+def test_full_size_trajectory_properties(nat):
+    """BASELINE.json's full size (M = 1M banded, w = 500) is out of the oracle's reach, so the trajectory is
+    checked through size-independent properties: the symmetric half-band kernels (fused CG) and the full-band
+    kernels (classic CG loop) - two independent implementations - must agree on every iteration to rounding,
+    with identical CG iteration counts; a rerun is bit-identical; the estimate aligns with the planted signal."""
+    import torch
+    import bench
+    import sgvamp
+    M, w, its = 1_000_000, 500, 3
+    dev = torch.device("cuda", 0)
+    U, ldb, band, r, x0, _ = bench.build_problem(torch, M, w, 5, dev)
+    p = bench.vamp_params(M)
+    probes = bench.make_probes(its, M, 5)
+
+    def run(R):
+        v = sgvamp.VAMP(N=bench.n_gwas(M), Nt=bench.n_gwas(M), M=M, K=1, rho=p["rho"], gamw=p["gamw"], gam1=p["gam1"],
+                        a=np.array([1.0]), prior_vars=p["prior_vars"], prior_probs=p["prior_probs"], out_dir=None,
+                        out_name="t")
+        xs = v.infer(R, r, its, cg_maxit=p["cg_maxit"], em_prior_maxit=p["em_prior_maxit"], learn_gamw=True,
+                     lmmse_damp=False, prior_update="em", update_prior_from=1, probes=probes)
+        out = (xs, [v.history["rows"][i][0] for i in range(its)], [v.history["cg_iters"][i][0] for i in range(its)],
+               v.handle.ld_info(0)["layout"])
+        v.close()
+        return out
+
+    xs_a, rows_a, cg_a, lay_a = run(sgvamp.DeviceDSYM(U.data_ptr(), w, ldb, 0, keepalive=U))
+    xs_b, rows_b, cg_b, lay_b = run(sgvamp.DeviceDSYM(U.data_ptr(), w, ldb, 0, keepalive=U))
+    ldf = (M + 31) // 32 * 32
+    full = torch.zeros((2 * w + 1, ldf), device=dev, dtype=torch.float32)
+    full[:, :M] = band
+    del band
+    xs_c, rows_c, cg_c, lay_c = run(sgvamp.DeviceDIA(full.data_ptr(), w, ldf, keepalive=full))
+    assert (lay_a, lay_c) == ("dsym", "dia")
+    for it in range(its):
+        assert np.array_equal(xs_a[it], xs_b[it]) and rows_a[it] == rows_b[it]            # bit-reproducible
+        assert rel_l2(xs_a[it], xs_c[it]) <= 1e-9                                           # two kernel families agree
+        assert rel_err(rows_a[it][1:6], rows_c[it][1:6]) <= 1e-9
+        assert tuple(cg_a[it]) == tuple(cg_c[it])
+        assert np.all(np.isfinite(xs_a[it]))
+    al = float(np.dot(xs_a[-1].ravel(), x0) / (np.linalg.norm(xs_a[-1]) * np.linalg.norm(x0)))
+    assert al > 0.5
