@@ -65,6 +65,7 @@ extern "C" int sgv_create(int device, void* stream, sgv_handle* out) {
         SGV_CUDA(cudaFuncGetAttributes(&fa, k_scale_copy));
         SGV_TRY(sgv_preload_spmm());
         SGV_TRY(sgv_preload_dsym());
+        SGV_TRY(sgv_preload_psym());
         SGV_TRY(sgv_preload_vamp());
     }
     *out = c;
@@ -117,6 +118,7 @@ extern "C" int sgv_destroy(sgv_handle c) {
     cudaStreamSynchronize(c->copy_stream);
     free_vectors(c);
     cudaFree(c->ypart);
+    cudaFree(c->ypartT);
     cudaFree(c->ds_ypart);
     cudaFree(c->ds_tails);
     cudaFree(c->partials);

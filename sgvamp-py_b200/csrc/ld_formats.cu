@@ -15,6 +15,8 @@ void sgv_ld_free(LdMatrix& ld) {
         if (ld.panels) cudaFree(const_cast<float*>(ld.panels));
     }
     if (ld.items) cudaFree(ld.items);
+    if (ld.sym_items) cudaFree(ld.sym_items);
+    if (ld.rowmeta) cudaFree(ld.rowmeta);
     if (ld.indptr) cudaFree(ld.indptr);
     if (ld.indices) cudaFree(ld.indices);
     if (ld.vals) cudaFree(ld.vals);
@@ -243,7 +245,7 @@ int sgv_build_panel_items(sgv_ctx* c, LdMatrix& ld, const std::vector<int64_t>& 
         SGV_CUDA(cudaMalloc(&c->ypart, need * sizeof(double2)));
         c->ypart_cap = need;
     }
-    return 0;
+    return sgv_build_psym_items(c, ld, starts, offs, lds);   // + the upper-triangle items (default kernel)
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -117,6 +117,9 @@ struct LdMatrix {
     const float* panels = nullptr;
     PanelItem*   items = nullptr;
     int      n_items = 0, s_cross = 1, panel_rw = 4;
+    struct SymItem* sym_items = nullptr;   // upper-triangle work items of the symmetric panel kernel (spmm_psym.cu)
+    int*     rowmeta = nullptr;            // per row: strip, strips of its block, forward slots of its strip
+    int      n_sym_items = 0;
     int64_t  nblocks = 0;
     // CSR
     int64_t* indptr = nullptr;
@@ -193,6 +196,8 @@ struct sgv_ctx {
     int64_t      ds_ypart_cap = 0, ds_tails_cap = 0;
     double2*     ypart = nullptr;    // cross-CTA partial outputs of the panel kernel
     int64_t      ypart_cap = 0;      // in double2 elements
+    double2*     ypartT = nullptr;   // transposed partial outputs of the symmetric panel kernel, per strip
+    int64_t      ypartT_cap = 0;
     PriorParams  prior{};
     // reductions
     double*      partials = nullptr;   // per-block partial sums
@@ -260,6 +265,11 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, doub
 size_t sgv_dia_smem_bytes(int64_t w, int rw, int s);
 int    sgv_preload_spmm();   // load all kernels of the TU on the current device (see spmm.cu)
 int    sgv_preload_vamp();
+// spmm_psym.cu
+int    sgv_preload_psym();
+int    sgv_build_psym_items(sgv_ctx* c, LdMatrix& ld, const std::vector<int64_t>& starts, const std::vector<int64_t>& offs,
+                            const std::vector<int>& lds);
+int    sgv_launch_psym(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a);
 // spmm_dsym.cu
 int    sgv_preload_dsym();
 size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s, int nst);

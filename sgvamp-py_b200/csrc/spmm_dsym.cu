@@ -44,6 +44,7 @@
 // neighbours' memory when the x window is staged (left halo for the extension rows, right halo for
 // the forward part).  Results for the extension rows themselves are discarded.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include "sgv_device.cuh"
 
@@ -397,7 +398,8 @@ k_dsym_finish(SpmmArgs a, const double2* __restrict__ ypart, const double2* __re
 bool sgv_dsym_feasible(int64_t w) { return sgv_dsym_smem_bytes(w, 1, 8, DS_NST) <= DS_SMEM_LIMIT; }
 
 static bool ds_use_big(const sgv_ctx* c, const LdMatrix& ld) {
-    return ld.ldb >= (int64_t)c->sm_count * 2 * 256 && sgv_dsym_smem_bytes(ld.w, DS_BIG_RW, DS_BIG_S, DS_NST) <= 112 * 1024;
+    static const long long waves = getenv("SGV_DS_BIG_WAVES") ? atoll(getenv("SGV_DS_BIG_WAVES")) : 1;   // tuning knob
+    return ld.ldb >= (int64_t)c->sm_count * 2 * 256 * waves && sgv_dsym_smem_bytes(ld.w, DS_BIG_RW, DS_BIG_S, DS_NST) <= 112 * 1024;
 }
 
 template <bool CG>

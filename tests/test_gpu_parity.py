@@ -177,6 +177,35 @@ def test_upload_scipy_dia_format(nat, layout, dtype):
     h.close()
 
 
+def test_symmetric_panel_kernel_opt_in(nat, monkeypatch):
+    """SGV_PANEL_SYM=1 routes dense / block-diagonal LD through the upper-triangle kernel (spmm_psym.cu):
+    same products as the default full-panel kernel, to rounding."""
+    rng = np.random.default_rng(4)
+    for sizes in ([1], [5], [515], [2049], [37, 512, 513, 260, 4, 1030, 1]):
+        blocks = []
+        for b in sizes:
+            B = rng.standard_normal((b, b))
+            blocks.append((B + B.T).astype(np.float32).astype(np.float64))
+        R = scipy.sparse.block_diag([scipy.sparse.csr_matrix(b) for b in blocks], format="csr")
+        R.sort_indices()
+        M = R.shape[0]
+        h = nat.Handle()
+        h.configure(M, 1)
+        if len(sizes) == 1:
+            h.upload_dense(0, blocks[0], s=0.0)
+        else:
+            h._ck(h.upload_csr(0, R.indptr, R.indices, R.data, layout=nat.LAYOUT_BLOCKDIAG))
+        X = rng.standard_normal((M, 2))
+        monkeypatch.delenv("SGV_PANEL_SYM", raising=False)
+        full = h.spmm(0, X, alpha=1.1, beta=0.3)
+        monkeypatch.setenv("SGV_PANEL_SYM", "1")
+        sym = h.spmm(0, X, alpha=1.1, beta=0.3)
+        monkeypatch.delenv("SGV_PANEL_SYM", raising=False)
+        ref = 1.1 * (R @ X) + 0.3 * X
+        assert rel_l2(full, ref) < 1e-13 and rel_l2(sym, ref) < 1e-13, sizes
+        h.close()
+
+
 def test_regularisation_at_upload(nat):
     """Rused = (1-s) R + s I (src/main.py:265) on every layout, including absent diagonal entries."""
     rng = np.random.default_rng(9)
