@@ -185,14 +185,18 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 __device__ __forceinline__ void st_entry(InboxEntry* p, double v, unsigned long long seq) {
-    asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(seq) : "memory");
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned f = (unsigned)seq;
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)bits), "r"(f),
+                 "r"((unsigned)(bits >> 32)), "r"(f)
+                 : "memory");
 }
 __device__ __forceinline__ bool ld_entry(const InboxEntry* p, unsigned long long seq, double& v) {
-    long long bits;
-    unsigned long long s;
-    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(bits), "=l"(s) : "l"(p) : "memory");
-    v = __longlong_as_double(bits);
-    return s == seq;
+    unsigned lo, f1, hi, f2;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p) : "memory");
+    v = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+    const unsigned f = (unsigned)seq;
+    return f1 == f && f2 == f;
 }
 
 // Wait (bounded) until every rank's partial sums of reduction rc.seq are in this rank's inbox, add the

@@ -62,13 +62,13 @@ struct CgState {
 
 // Cross-rank reduction mailbox.  Lives at the start of every rank's symmetric arena; rank r writes its
 // partial sums of reduction `seq` into slot seq % SLOTS, row r, of EVERY rank's inbox with peer stores
-// over NVLink.  Every value travels with the sequence number in ONE 16-byte store (the "LL" scheme of
-// NCCL's low-latency protocol): a reader that sees the right sequence number in an entry has the value,
-// so neither side needs a system-scope fence and there is no separate flag round trip.  Consumers add
-// the rows in rank order, so all ranks obtain bit-identical totals.
+// over NVLink.  Every value travels with the sequence number in ONE 16-byte store, laid out as in NCCL's
+// low-latency (LL) protocol: each 8-byte half carries 32 bits of the double and its own 32-bit copy of the
+// sequence number, so the scheme only relies on 8-byte store atomicity.  A reader that sees the right
+// sequence number in both halves has the value: neither side needs a system-scope fence and there is no
+// separate flag round trip.  Consumers add the rows in rank order, so all ranks obtain bit-identical totals.
 struct __align__(16) InboxEntry {
-    double             value;
-    unsigned long long seq;
+    unsigned lo, flag_lo, hi, flag_hi;
 };
 struct Inbox {
     InboxEntry e[SGV_INBOX_SLOTS][SGV_MAX_RANKS][SGV_MAX_PARTIAL_VALUES];
