@@ -385,13 +385,13 @@ static int launch_epi(sgv_ctx* c, Cohort& co, SpmmArgs& a) {
         return launch_dia<1, 8, EPI, DIA_PF, DIA_MINB>(c, ld, a);
     }
     if (ld.layout == SGV_LAYOUT_DSYM) return sgv_launch_dsym(c, ld, EPI, a);
-    // SGV_PANEL_SYM=1: the upper-triangle kernel of spmm_psym.cu (half the bytes, twice the arithmetic per byte).
-    // Measured on B200: dense M=50k 1.42 ms vs 1.53 ms, block-diagonal M=300k 0.59 ms vs 0.52 ms - its plain
-    // register prefetch does not keep enough bytes in flight, so the full-panel kernel (at the HBM roofline) stays
-    // the default until it gets the TMA ring of the half-band kernel.
+    // Default for dense / block-diagonal LD: the upper-triangle kernel of spmm_psym.cu (half the bytes read).
+    // Measured on B200 (2-RHS pass): dense M=50k 1.10 ms vs 1.53 ms for the full-panel kernel below (which runs at
+    // the HBM roofline of the FULL matrix), M=10k 0.070 vs 0.086 ms, block-diagonal M=300k 0.45 vs 0.52 ms.
+    // SGV_PANEL_FULL=1 selects the full-panel kernel.
     if ((ld.layout == SGV_LAYOUT_DENSE || ld.layout == SGV_LAYOUT_BLOCKDIAG) && ld.sym_items != nullptr) {
-        const char* e = getenv("SGV_PANEL_SYM");
-        if (e != nullptr && e[0] == '1') return sgv_launch_psym(c, ld, EPI, a);
+        const char* e = getenv("SGV_PANEL_FULL");
+        if (e == nullptr || e[0] != '1') return sgv_launch_psym(c, ld, EPI, a);
     }
     if (ld.layout == SGV_LAYOUT_DENSE || ld.layout == SGV_LAYOUT_BLOCKDIAG) {
         k_spmm_panel<4, 2><<<ld.n_items, 256, 0, c->stream>>>(a, ld.panels, ld.items, c->ypart);

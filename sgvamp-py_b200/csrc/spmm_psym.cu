@@ -95,16 +95,26 @@ k_spmm_psym(SpmmArgs a, const float* __restrict__ panels, const SymItem* __restr
         const int per = (((cnt + PS_S - 1) / PS_S) + 3) & ~3;
         const int lo = min(cnt, s * per), hi = min(cnt, lo + per);
         const float* p = base + (int64_t)(jb + lo) * it.ld;
+        // software pipeline: the 4 rows of the next group are in flight while the current group is multiplied
+        float4 n0 = zero4, n1 = zero4, n2 = zero4, n3 = zero4;
+        if (active && lo < hi) {
+            const int nr = min(4, hi - lo);
+            n0 = ldg_stream_f4(p);
+            if (nr > 1) n1 = ldg_stream_f4(p + it.ld);
+            if (nr > 2) n2 = ldg_stream_f4(p + 2 * (int64_t)it.ld);
+            if (nr > 3) n3 = ldg_stream_f4(p + 3 * (int64_t)it.ld);
+        }
         for (int jj = lo; jj < hi; jj += 4) {
-            const int nr = min(4, hi - jj);                  // warp-uniform
-            float4 c0 = zero4, c1 = zero4, c2 = zero4, c3 = zero4;
-            if (active) {
-                c0 = ldg_stream_f4(p);
-                if (nr > 1) c1 = ldg_stream_f4(p + it.ld);
-                if (nr > 2) c2 = ldg_stream_f4(p + 2 * (int64_t)it.ld);
-                if (nr > 3) c3 = ldg_stream_f4(p + 3 * (int64_t)it.ld);
-            }
+            float4 c0 = n0, c1 = n1, c2 = n2, c3 = n3;
             p += 4 * (int64_t)it.ld;
+            n0 = n1 = n2 = n3 = zero4;
+            if (active && jj + 4 < hi) {
+                const int nr = min(4, hi - (jj + 4));        // warp-uniform
+                n0 = ldg_stream_f4(p);
+                if (nr > 1) n1 = ldg_stream_f4(p + it.ld);
+                if (nr > 2) n2 = ldg_stream_f4(p + 2 * (int64_t)it.ld);
+                if (nr > 3) n3 = ldg_stream_f4(p + 3 * (int64_t)it.ld);
+            }
             const int jg = it.j0 + jb + jj;                  // global row of c0
             float4 t0 = c0, t1 = c1, t2 = c2, t3 = c3;
             if (it.diag && jg + 3 >= it.i0) {                // inside the strip's diagonal tile (warp-uniform)

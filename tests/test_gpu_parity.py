@@ -177,9 +177,9 @@ def test_upload_scipy_dia_format(nat, layout, dtype):
     h.close()
 
 
-def test_symmetric_panel_kernel_opt_in(nat, monkeypatch):
-    """SGV_PANEL_SYM=1 routes dense / block-diagonal LD through the upper-triangle kernel (spmm_psym.cu):
-    same products as the default full-panel kernel, to rounding."""
+def test_symmetric_and_full_panel_kernels_agree(nat, monkeypatch):
+    """Dense / block-diagonal LD goes through the upper-triangle kernel (spmm_psym.cu) by default and through
+    the full-panel kernel with SGV_PANEL_FULL=1: same products, to rounding."""
     rng = np.random.default_rng(4)
     for sizes in ([1], [5], [515], [2049], [37, 512, 513, 260, 4, 1030, 1]):
         blocks = []
@@ -196,11 +196,11 @@ def test_symmetric_panel_kernel_opt_in(nat, monkeypatch):
         else:
             h._ck(h.upload_csr(0, R.indptr, R.indices, R.data, layout=nat.LAYOUT_BLOCKDIAG))
         X = rng.standard_normal((M, 2))
-        monkeypatch.delenv("SGV_PANEL_SYM", raising=False)
-        full = h.spmm(0, X, alpha=1.1, beta=0.3)
-        monkeypatch.setenv("SGV_PANEL_SYM", "1")
+        monkeypatch.delenv("SGV_PANEL_FULL", raising=False)
         sym = h.spmm(0, X, alpha=1.1, beta=0.3)
-        monkeypatch.delenv("SGV_PANEL_SYM", raising=False)
+        monkeypatch.setenv("SGV_PANEL_FULL", "1")
+        full = h.spmm(0, X, alpha=1.1, beta=0.3)
+        monkeypatch.delenv("SGV_PANEL_FULL", raising=False)
         ref = 1.1 * (R @ X) + 0.3 * X
         assert rel_l2(full, ref) < 1e-13 and rel_l2(sym, ref) < 1e-13, sizes
         h.close()
