@@ -326,9 +326,9 @@ k_spmm_csr(SpmmArgs a, const int64_t* __restrict__ indptr, const int32_t* __rest
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     __shared__ double red[2 * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int64_t row = (int64_t)blockIdx.x * 8 + wid;
     double dots[2] = {0.0, 0.0};
-    if (row < a.M) {
+    // grid-stride over rows: a bounded number of blocks (one ticket atomic and one partial row each)
+    for (int64_t row = (int64_t)blockIdx.x * 8 + wid; row < a.M; row += (int64_t)gridDim.x * 8) {
         const int64_t beg = indptr[row], end = indptr[row + 1];
         double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
         int64_t k = beg + lane;
@@ -404,7 +404,7 @@ static int launch_epi(sgv_ctx* c, Cohort& co, SpmmArgs& a) {
         return 0;
     }
     if (ld.layout == SGV_LAYOUT_CSR) {
-        const unsigned grid = (unsigned)((c->Ml + 7) / 8);
+        const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 7) / 8, (int64_t)c->sm_count * 32);
         SGV_TRY(sgv_ensure_partials(c, grid));
         a.rc.partials = c->partials;
         k_spmm_csr<EPI><<<grid, 256, 0, c->stream>>>(a, ld.indptr, ld.indices, ld.vals);
