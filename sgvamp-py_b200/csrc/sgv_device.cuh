@@ -259,6 +259,22 @@ __device__ __forceinline__ void resolve_warp(const RedCtx& rc, int lane) {
     }
 }
 
+// Write this rank's NV partial sums of reduction `seq` into every rank's inbox; called by a full warp, lane e
+// handles entry e = (peer, value) so that the peer stores are issued in parallel.
+template <int NV>
+__device__ __forceinline__ void publish_warp(const double (&acc)[NV], const RedCtx& rc, unsigned long long seq, int lane) {
+    const int slot = (int)(seq % SGV_INBOX_SLOTS);
+    __threadfence();
+    for (int e = lane; e < rc.world * NV; e += 32) {
+        const int q = e / NV, k = e % NV;
+        double val = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < NV; ++kk)
+            if (kk == k) val = acc[kk];
+        st_entry(&rc.inbox[q]->e[slot][rc.rank][k], val, seq);
+    }
+}
+
 // Grid-wide deterministic reduction: every block contributes NV values; the block that takes the
 // last ticket combines the per-block partials in index order.  world == 1: it applies the state
 // transition directly.  world > 1: it publishes this rank's totals into every rank's inbox (peer
@@ -290,29 +306,23 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], const RedCtx& rc, d
             acc[k] = MIN ? fmin(acc[k], x) : acc[k] + x;
         }
     }
-    block_reduce<NV, MIN>(acc, red);
+    block_reduce<NV, MIN>(acc, red);          // totals valid in every lane of warp 0
     if (threadIdx.x == 0) {
         *rc.counter = 0u;
-        if (rc.world == 1) {
-            apply_totals(rc.ap, rc.st, acc);
-        } else {
-            // This rank's vector writes of the kernel (read by the neighbours as halos once they have seen
-            // these entries) are already ordered: every block fenced at GPU scope before taking its ticket,
-            // and peers read this memory through this GPU's L2.
-            const int slot = (int)(rc.seq % SGV_INBOX_SLOTS);
-            __threadfence();
-            for (int q = 0; q < rc.world; ++q) {
-                InboxEntry* row = rc.inbox[q]->e[slot][rc.rank];
-#pragma unroll
-                for (int k = 0; k < NV; ++k) st_entry(row + k, acc[k], rc.seq);
-            }
-        }
+        if (rc.world == 1) apply_totals(rc.ap, rc.st, acc);
     }
-    // one GPU per rank: this block completes the cross-rank reduction itself (the kernel ends when every
-    // rank has published, which is also the ordering point for the halo reads of the next kernel)
-    if (rc.world > 1 && rc.inline_resolve && threadIdx.x < 32) {
-        __syncwarp();
-        resolve_warp(rc, threadIdx.x);
+    if (rc.world > 1 && threadIdx.x < 32) {
+        // This rank's vector writes of the kernel (read by the neighbours as halos once they have seen these
+        // entries) are already ordered: every block fenced at GPU scope before taking its ticket, and peers read
+        // this memory through this GPU's L2.  The world x NV entries are written by the 32 lanes in parallel: a
+        // single thread issuing them one after the other costs ~0.25 us per peer store (16 us at 8 ranks x 8 sums).
+        publish_warp<NV>(acc, rc, rc.seq, threadIdx.x);
+        // one GPU per rank: this block completes the cross-rank reduction itself (the kernel ends when every
+        // rank has published, which is also the ordering point for the halo reads of the next kernel)
+        if (rc.inline_resolve) {
+            __syncwarp();
+            resolve_warp(rc, threadIdx.x);
+        }
     }
 }
 

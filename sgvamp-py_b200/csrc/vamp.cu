@@ -240,19 +240,9 @@ k_em_loop(int64_t M, const double* __restrict__ r1_all, EmConsts k, RedCtx rc, u
             block_reduce<16>(tot, red);
             RedCtx rp = rc;
             rp.seq = rc.seq + (unsigned long long)pass;
-            if (threadIdx.x == 0) {
-                if (rc.world == 1) {
-                    apply_totals(rp.ap, rp.st, tot);
-                } else {
-                    const int slot = (int)(rp.seq % SGV_INBOX_SLOTS);
-                    for (int q = 0; q < rp.world; ++q) {
-                        InboxEntry* row = rp.inbox[q]->e[slot][rp.rank];
-#pragma unroll
-                        for (int t = 0; t < 16; ++t) st_entry(row + t, tot[t], rp.seq);
-                    }
-                }
-            }
-            if (rc.world > 1 && threadIdx.x < 32) {
+            if (threadIdx.x == 0 && rc.world == 1) apply_totals(rp.ap, rp.st, tot);
+            if (rc.world > 1 && threadIdx.x < 32) {     // totals are valid in every lane of warp 0
+                publish_warp<16>(tot, rp, rp.seq, threadIdx.x);
                 __syncwarp();
                 resolve_warp(rp, threadIdx.x);
             }
