@@ -162,7 +162,8 @@ def band_to_host_dia(torch, band, M, w, glo, hi, pinned=True):
             data[k, t0 + sh: t1 + sh] = band[k, t0:t1]
     host = torch.empty((2 * w + 1, ldd), dtype=torch.float32, pin_memory=pinned)
     host.copy_(data)
-    torch.cuda.synchronize()
+    if band.is_cuda:
+        torch.cuda.synchronize()
     return host, np.arange(-w, w + 1, dtype=np.int64), col0
 
 
