@@ -53,7 +53,10 @@ def build_parser():
     p.add_argument("--device", help="CUDA device index", default=0)
     p.add_argument("--bim-source-quirk", help="1 (default): choose the cohort that supplies a missing SNP exactly as "
                    "src/main.py:162 does (argmax position); 0: the candidate cohort with the largest N", default=1)
-    p.add_argument("--layout", help="LD layout in HBM: auto|dense|dia|blockdiag|csr", default="auto")
+    p.add_argument("--layout", help="LD layout in HBM: auto|dense|dia|dsym|blockdiag|csr", default="auto")
+    p.add_argument("--row-partition", help="under torchrun with N ranks: 1 = split the marker rows of every cohort over the "
+                   "N GPUs (banded LD; halos and reductions exchanged inside the kernels) instead of one rank per cohort; "
+                   "default: 1 when K == 1", default=None)
     return p
 
 
@@ -87,7 +90,8 @@ def main(argv=None):
                                         source_quirk=bool(int(a.bim_source_quirk)))
     if merged is not None:
         logging.info(f"Total number of markers in reference is {M} \n")
-        ingest.write_ref_bim(merged["ref_df"], os.path.join(a.out_dir, a.out_name + ".bim"))   # src/main.py:150
+        if int(os.environ.get("RANK", "0")) == 0:                                               # rank 0 saves it, src/main.py:148-150
+            ingest.write_ref_bim(merged["ref_df"], os.path.join(a.out_dir, a.out_name + ".bim"))
     logging.info(f"Loading R and r took {time.time() - ts:0.2f} seconds\n")
     x0 = None
     if a.true_signal_file is not None:
@@ -105,7 +109,20 @@ def main(argv=None):
     # and the per-iteration exchange of r1 / gam1 (src/sgvamp.py:228-233) goes over NCCL.
     world = int(os.environ.get("WORLD_SIZE", "1"))
     comm, device = None, int(a.device)
-    if world > 1:
+    row_part = world > 1 and (bool(int(a.row_partition)) if a.row_partition is not None else K == 1)
+    shard_obj = None
+    if row_part:
+        # one cohort (or all of them) row-partitioned over the N GPUs of the box: every rank reads the inputs and
+        # keeps its own rows; rank 0 writes the outputs
+        import torch
+        import torch.distributed as dist
+        import shard
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+        if not dist.is_initialized():
+            torch.cuda.set_device(device)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", device))
+        shard_obj = shard.TorchShard()
+    elif world > 1:
         import torch
         import torch.distributed as dist
         import shard
@@ -122,7 +139,8 @@ def main(argv=None):
             x0 = x0 / np.sqrt(N_list[0]) * np.sqrt(N_list[me])     # src/main.py:276 scales by the rank's own N
     solver = VAMP(N=(N_list[comm.Get_rank()] if comm else (N_list if K > 1 else N_list[0])), Nt=Nt, M=M, K=K,
                   rho=float(a.rho), gam1=float(a.gam1), gamw=float(a.gamw), a=avec, prior_vars=prior_vars,
-                  prior_probs=prior_probs, out_dir=a.out_dir, out_name=a.out_name, comm=comm, device=device)
+                  prior_probs=prior_probs, out_dir=a.out_dir, out_name=a.out_name, comm=comm, device=device,
+                  shard=shard_obj, halo=True)
     logging.info("...Running sgVAMP\n")
     ts = time.time()
     one = comm is not None or K == 1
@@ -132,7 +150,8 @@ def main(argv=None):
                          update_prior_from=int(a.update_prior_from), s=s, layout=a.layout)
     logging.info(f"sgVAMP inference running time: {(time.time() - ts):0.4f}s\n")
     # README names the dump {out}__xhat_it_{it}.bin, the code writes {out}_xhat_it_{it}.bin: provide both
-    for it in range(int(a.iterations) if (comm is None or comm.Get_rank() == 0) else 0):
+    is_root = (comm is None or comm.Get_rank() == 0) and (shard_obj is None or shard_obj.rank == 0)
+    for it in range(int(a.iterations) if is_root else 0):
         src = os.path.join(a.out_dir, "%s_xhat_it_%d.bin" % (a.out_name, it))
         dst = os.path.join(a.out_dir, "%s__xhat_it_%d.bin" % (a.out_name, it))
         if os.path.exists(src) and not os.path.exists(dst):
@@ -143,6 +162,11 @@ def main(argv=None):
         logging.info(f"Alignment(x1hat, x0) over iterations: \n {al}\n")
         logging.info(f"L2 error(x1hat, x0) over iterations: \n {l2}\n")
     solver.close()
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
     return xhat1
 
 
