@@ -35,7 +35,14 @@ def merge_bims(bim_paths, N_list, source_quirk=True):
     for k in range(K):
         df = read_bim(bim_paths[k])
         lists.append(list(df["Variant"]))
-        ref_df = df if k == 0 else pd.merge(ref_df, df, on=["Variant"], how="outer", suffixes=("", "_y"))   # :138
+        if k == 0:
+            ref_df = df
+        else:
+            ref_df = pd.merge(ref_df, df, on=["Variant"], how="outer", suffixes=("", "_y"))               # :138
+            # Only the first six columns are ever used (:140,:150).  With K >= 3 the reference's second merge raises
+            # (pandas refuses the duplicate `_y` columns), i.e. the reference itself stops at K = 2 here; dropping the
+            # unused `_y` columns after every merge gives the same result for K = 2 and extends it to any K.
+            ref_df = ref_df[[c for c in ref_df.columns if not c.endswith("_y")]]
     ref_df = ref_df.sort_values(by=["Coordinate"])                                                       # :140
     ref = list(ref_df["Variant"])
     M = len(ref)

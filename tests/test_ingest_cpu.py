@@ -42,6 +42,45 @@ def test_k2_ld_bim_exchange_matches_reference(ref, tmp_path):
     assert Rs2[0].nnz > Rs[0].nnz and np.array_equal(Rs2[1].toarray(), Rs[1].toarray())
 
 
+def test_k3_merge_and_supplier_choice(tmp_path):
+    """K = 3 is beyond what the reference driver can run with the installed pandas (its second `.bim` merge raises on
+    duplicate `_y` columns), so there is no golden: the merge is checked on its definition (outer union, coordinate
+    order, SNPs unknown to cohort 1 last with NaN coordinate exactly as for K = 2) and the supplier choice against a
+    direct restatement of src/main.py:156-163."""
+    rng = np.random.default_rng(7)
+    snps = ["rs%d" % i for i in range(101, 113)]
+    coord = {rs: 5000 + 11 * i for i, rs in enumerate(snps)}
+    drop = [("rs103", "rs108"), ("rs105",), ("rs103", "rs110", "rs112")]
+    N_list, lists = [400, 900, 600], []
+    for k in range(3):
+        ss = [rs for rs in snps if rs not in drop[k]]
+        if k == 1:
+            ss = ss[3:] + ss[:3]
+        lists.append(ss)
+        with open(tmp_path / ("d%d.bim" % k), "w") as f:
+            for rs in ss:
+                f.write("2\t%s\t0\t%d\tC\tT\n" % (rs, coord[rs]))
+    mg = ingest.merge_bims([str(tmp_path / ("d%d.bim" % k)) for k in range(3)], N_list)
+    assert mg["M"] == 12 and set(mg["ref"]) == set(snps)
+    known = [rs for rs in mg["ref"] if rs in lists[0]]
+    assert known == sorted(known, key=lambda r: coord[r])             # cohort 1's SNPs in coordinate order ...
+    assert mg["ref"][len(known):] == [rs for rs in mg["ref"] if rs not in lists[0]]   # ... the others after them
+    assert list(mg["ref_df"].columns) == ingest.BIM_COLUMNS
+    for k in range(3):
+        assert [mg["ref"][i] for i in mg["i_maps"][k]] == lists[k]
+        src = np.ones(12) * k
+        for rs in set(snps) - set(lists[k]):
+            cand = [q for q in range(3) if q != k and rs in lists[q]]
+            src[mg["idx"][rs]] = int(np.argmax(np.array(N_list)[cand]))                 # the reference's rule (position)
+        assert np.array_equal(mg["sources"][k], src)
+    fixed = ingest.merge_bims([str(tmp_path / ("d%d.bim" % k)) for k in range(3)], N_list, source_quirk=False)
+    for k in range(3):
+        for rs in set(snps) - set(lists[k]):
+            q = int(fixed["sources"][k][fixed["idx"][rs]])
+            assert q != k and rs in lists[q]                                             # a cohort that really has the SNP
+            assert N_list[q] == max(N_list[c] for c in range(3) if c != k and rs in lists[c])
+
+
 def test_k1_ld_matches_reference(ref, tmp_path):
     M, Rs, rs, mg = ingest.load_all([p("c2.ld")], [p("c2.assoc.linear")], [p("c2.bim")], [900], [9])
     assert M == int(ref["k1_M"]) == 9
