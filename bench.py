@@ -407,6 +407,7 @@ def main():
                   else sgvamp.DiaWindow(host.numpy(), offsets, col0, M))
             h2d_ld = (2 * w + 1) * (hi - glo) * 4            # upper diagonals + the lower ones for the symmetry check
         v2 = new_solver()
+        v2.load_ld(0, Rh)                              # untimed warm-up of the upload path (staging buffers, first touch)
         barrier()
         t0 = time.perf_counter()
         v2.load_ld(0, Rh)
