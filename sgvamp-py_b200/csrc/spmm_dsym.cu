@@ -126,7 +126,15 @@ __global__ void __launch_bounds__(32 * RW * S, MINB)
 k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_t E, double2* __restrict__ ypart,
             double2* __restrict__ tails) {
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
-    const int tile = blockIdx.x;
+    // Tiles whose x window reaches into the right neighbour's rows stage their window over NVLink (a few
+    // microseconds of latency instead of an L2 hit): they go FIRST, so that this overlaps the streaming of the
+    // other tiles instead of stretching the tail of the kernel.  (The left-edge tiles are the first ones anyway.)
+    int tile = blockIdx.x;
+    if (a.v_right != nullptr) {
+        const int ntiles = gridDim.x;
+        const int nedge = min(ntiles, (Dp + 128 * RW - 1) / (128 * RW) + 1);
+        tile = (int)blockIdx.x < nedge ? ntiles - 1 - (int)blockIdx.x : (int)blockIdx.x - nedge;
+    }
     constexpr int TR = 128 * RW;
     constexpr int NT = 32 * RW * S;
     constexpr int NW = RW * S;
