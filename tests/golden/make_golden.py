@@ -272,6 +272,21 @@ def main():
     cases["dense_K3_L2_em"] = base(M=256, K=3, R=[f32(R_) for R_ in Rs], r=rs, N_list=Nl,
                                    prior_vars=[0, 0.5 / cm], prior_probs=[0.97, 0.03], layout="dense",
                                    iterations=6, x0=beta)
+    # K=2 cohorts with banded LD (different genotype samples and N, shared effects), L=3: the multi-cohort path on the
+    # sparse layouts
+    R1, r1, x01, N1 = ldgen.sim_banded(M=1000, w=30, N_ld=512, N=1500, lam=0.02, h2=0.5, seed=11)
+    R2, r2o, x02, N2 = ldgen.sim_banded(M=1000, w=30, N_ld=512, N=2500, lam=0.02, h2=0.5, seed=12)
+    beta = x01 / np.sqrt(N1)
+    r2 = R2 @ (beta * np.sqrt(N2)) + (r2o - R2 @ x02)
+    cm = max(1, int(1000 * 0.02))
+    cases["banded_K2_L3_em_s01"] = base(M=1000, K=2, R=[f32(R1), f32(R2)], r=[r1, r2], N_list=[N1, N2], s=0.1,
+                                        prior_vars=[0, 0.1 / cm, 1.0 / cm], prior_probs=[0.98, 0.01, 0.01],
+                                        layout="banded", iterations=6, x0=beta)
+    # CG that never reaches its tolerance (cg_maxit=4: every solve ends with info = maxiter), warm starts carry on
+    R, r, x0, N = ldgen.sim_banded(M=1200, w=25, N_ld=512, N=1200, lam=0.01, h2=0.5, seed=13)
+    cm = max(1, int(1200 * 0.01))
+    cases["banded_L2_em_cgmaxit4"] = base(M=1200, R=[f32(R)], r=[r], N_list=[N], s=0.1, prior_vars=[0, 0.5 / cm],
+                                          prior_probs=[0.99, 0.01], layout="banded", iterations=6, cg_maxit=4)
     # a fixture whose LD is NOT fp32-representable is produced at test time from dense_L2_em by
     # perturbing R; the reference perturbation study bounds that effect separately.
 
