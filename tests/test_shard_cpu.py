@@ -141,3 +141,32 @@ def test_torch_comm_gloo_world3(tmp_path):
                        capture_output=True, text=True, timeout=240, env=env)
     assert p.returncode == 0, p.stdout + p.stderr
     assert p.stdout.count("ok") == 3
+
+
+def test_partitions_fuzz():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(M=st.integers(1, 5_000_000), world=st.integers(1, 8))
+    def rows(M, world):
+        b = shd.partition_rows(M, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == M
+        assert all(b[r][1] == b[r + 1][0] for r in range(world - 1))
+        assert all(lo <= hi for lo, hi in b)
+        if M >= 8 * world:
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 8           # balanced up to the alignment of the cuts
+
+    @settings(max_examples=100, deadline=None)
+    @given(sizes=st.lists(st.integers(1, 400), min_size=8, max_size=60), world=st.integers(1, 8))
+    def blocks(sizes, world):
+        starts = np.concatenate([[0], np.cumsum(sizes)])
+        b = shd.partition_blocks(starts, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == starts[-1]
+        for r in range(world):
+            assert b[r][0] in starts and b[r][1] in starts and b[r][1] > b[r][0]
+            if r:
+                assert b[r][0] == b[r - 1][1]
+
+    rows()
+    blocks()
