@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--M", type=int, default=1_000_000)
     ap.add_argument("--w", type=int, default=500)
-    ap.add_argument("--cpu-sample-M", type=int, default=60_000)
+    ap.add_argument("--cpu-sample-M", type=int, default=80_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-format", default="dia", choices=["dia", "csr"],
@@ -109,7 +109,8 @@ def build_problem(torch, M, w, seed, dev, lo=0, hi=None, ext=0, keep_full=True):
     full = band if keep_full else None              # full band of the rows [glo, hi) (host-side legs)
     del band
     U = ldgen.dsym_tile(torch, U)                   # [ldb/128][Dp/4][4][128]: one contiguous stream per 128-row block
-    torch.cuda.synchronize()
+    if U.is_cuda:
+        torch.cuda.synchronize()
     return U, ldb, full, r.cpu().numpy(), x0_host, time.time() - t0
 
 
@@ -209,31 +210,85 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU leg: the oracle port of the reference on the host cores, on a bounded sample
+# CPU leg: the oracle port of the reference on the host cores, on a bounded sample of the SAME workload
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(M_full, w, sample_M, iterations, seed, threads):
-    """Time the CPU oracle (numpy/scipy restatement of src/sgvamp.py, same algorithm, same scipy CG)
-    on the leading sample_M x sample_M principal sub-band of the same kind of workload; scale the
-    per-iteration time linearly in M (every per-iteration cost is O(M w))."""
-    import ldgen
+def band_to_scipy_dia(band, M, w):
+    """Host band[k, i] = R[i, i + k - w] (numpy, (2w+1) x M) -> scipy DIA matrix in fp64 (data[k, j] = R[j - off_k, j])."""
+    import scipy.sparse
+    data = np.zeros((2 * w + 1, M))
+    for k in range(2 * w + 1):
+        off = k - w
+        if off >= 0:
+            data[k, off:] = band[k, : M - off]
+        else:
+            data[k, : M + off] = band[k, -off:]
+    return scipy.sparse.dia_matrix((data, np.arange(-w, w + 1)), shape=(M, M))
+
+
+def build_sample(torch, Ms, w, seed, dev):
+    """The bounded sample both arms run: the first Ms markers' worth of the benchmark workload, produced by the SAME
+    generator and parameters as the M-marker problem (ldgen.banded_dia_device, N_ld = 4096, Bartlett taper, s, h2).
+    Returns the device half band (for the GPU), Rused as scipy CSR in fp64 (what src/main.py:199-265 hands the
+    reference solver for an .npz LD file), r, x0."""
+    U, ldb, band, r, x0, _ = build_problem(torch, Ms, w, seed, dev)
+    R = band_to_scipy_dia(band.cpu().numpy(), Ms, w).tocsr()
+    del band
+    return U, ldb, R, r, x0
+
+
+def cpu_reference_run(R, r, M_full, iterations, probes, threads):
+    """Time the CPU oracle (numpy/scipy restatement of src/sgvamp.py: same algorithm, same scipy CG, A = gamw R + gam2 I
+    materialised every iteration as src/sgvamp.py:312 does) on the sample; the per-iteration time is scaled linearly in
+    M (every per-iteration cost is O(M w)).  The sparse matvec is row-split over `threads` host threads (scipy's own
+    csr_matvec is single-threaded); BLAS / OpenMP pools are limited to one thread while that pool is active, so the
+    arm behaves the same with and without OMP_NUM_THREADS in the environment."""
+    from threadpoolctl import threadpool_limits
     from oracle import sgvamp_oracle as orc
-    Ms = int(min(sample_M, M_full))
-    R, r, x0, N = ldgen.sim_banded(M=Ms, w=w, N_ld=256, N=n_gwas(Ms), lam=LAM_TRUE, h2=H2, seed=seed, exact_noise=True)
-    noise_R = r - R @ x0                                  # sqrt(1-h2) * N(0, R)
-    R = orc.regularise(R, S_REG)
-    r = R @ x0 + np.sqrt(1 - S_REG) * noise_R + np.sqrt((1 - H2) * S_REG) * np.random.default_rng(seed).standard_normal(Ms)
+    Ms = R.shape[0]
     p = vamp_params(Ms)
     o = orc.VAMPOracle([n_gwas(Ms)], Ms, p["rho"], p["gamw"], p["gam1"], p["prior_vars"], p["prior_probs"])
-    probes = make_probes(iterations, Ms, seed)
     tm = {}
-    t0 = time.perf_counter()
-    out = o.infer([R], [r], iterations, cg_maxit=p["cg_maxit"], em_prior_maxit=p["em_prior_maxit"],
-                  learn_gamw=True, lmmse_damp=False, prior_update="em", update_prior_from=1,
-                  probe_fn=lambda k, it, M_: probes[k, it], timers=tm, threads=threads)
-    dt = time.perf_counter() - t0
+    with threadpool_limits(limits=1):
+        t0 = time.perf_counter()
+        out = o.infer([R], [r], iterations, cg_maxit=p["cg_maxit"], em_prior_maxit=p["em_prior_maxit"],
+                      learn_gamw=True, lmmse_damp=False, prior_update="em", update_prior_from=1,
+                      probe_fn=lambda k, it, M_: probes[k, it], timers=tm, threads=threads, materialise_A=True)
+        dt = time.perf_counter() - t0
     its_per_s_sample = iterations / dt
     return dict(value=its_per_s_sample * Ms / M_full, sample_its_per_s=its_per_s_sample, sample_M=Ms,
-                seconds=dt, cg_iters=[list(x[0]) for x in out["cg_iters"]], timers=tm)
+                seconds=dt, cg_iters=[list(x[0]) for x in out["cg_iters"]], timers=tm, out=out)
+
+
+def cpu_sample_text(res, w, its, threads):
+    return ("oracle port of src/sgvamp.py (scipy CG semantics, A materialised per iteration, csr_matvec row-split over %d "
+            "threads, BLAS pools limited to 1), %d VAMP iterations from it=0 on the first M=%d markers of the same "
+            "generator (N_ld=%d, w=%d) (%.1f s), scaled by M_sample/M" % (threads, its, res["sample_M"], N_LD, w, res["seconds"]))
+
+
+def gpu_sample_parity(sgvamp, U, ldb, w, r, ref_out, iterations, probes, device, stream):
+    """Run the GPU path on the sample the CPU leg ran (same LD values, r, probes, parameters) and compare every
+    iteration: the north-star gate (xhat rel-L2 <= 1e-4, scalars <= 1e-4 relative) measured inside the bench run."""
+    Ms = len(r)
+    p = vamp_params(Ms)
+    v = sgvamp.VAMP(N=n_gwas(Ms), Nt=n_gwas(Ms), M=Ms, K=1, rho=p["rho"], gamw=p["gamw"], gam1=p["gam1"],
+                    a=np.array([1.0]), prior_vars=p["prior_vars"], prior_probs=p["prior_probs"], out_dir=None,
+                    out_name="parity", device=device, stream=stream)
+    xs = v.infer(sgvamp.DeviceDSYM(U.data_ptr(), w, ldb, 0, keepalive=U), r, iterations, cg_maxit=p["cg_maxit"],
+                 em_prior_maxit=p["em_prior_maxit"], learn_gamw=True, lmmse_damp=False, prior_update="em",
+                 update_prior_from=1, probes=probes)
+    xerr, serr, cg_equal = 0.0, 0.0, True
+    for it in range(iterations):
+        ref_x = ref_out["xhat1"][it]
+        xerr = max(xerr, float(np.linalg.norm(xs[it].ravel() - ref_x) / np.linalg.norm(ref_x)))
+        a_, b_ = np.array(v.history["rows"][it][0][1:7], dtype=np.float64), np.array(ref_out["rows"][it][0][1:7], dtype=np.float64)
+        serr = max(serr, float(np.max(np.abs(a_ - b_) / np.abs(b_))))
+        cg_equal = cg_equal and tuple(v.history["cg_iters"][it][0]) == tuple(ref_out["cg_iters"][it][0])
+    cg = [list(v.history["cg_iters"][it][0]) for it in range(iterations)]
+    v.close()
+    return {"xhat_rel_l2_max": xerr, "scalar_rel_max": serr, "cg_iters_equal": bool(cg_equal), "cg_iters_gpu": cg,
+            "cg_iters_ref": [list(x[0]) for x in ref_out["cg_iters"]], "iterations": iterations, "sample_M": Ms,
+            "what": "GPU (C ABI, DSYM fused CG) vs CPU oracle on the cpu_baseline sample: same LD, r, probes; "
+                    "scalars = gamw, gam1, gam2, alpha1, alpha2, lam"}
 
 
 def main():
@@ -249,19 +304,22 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
+        import torch
+        dev = torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
         its = max(2, min(a.steps + a.warmup, 3))
-        res = cpu_reference_run(a.M, a.w, a.cpu_sample_M, its, a.seed, threads=ncores)
+        Ms = int(min(a.cpu_sample_M, a.M))
+        _U, _ldb, Rs, rs_, _x0 = build_sample(torch, Ms, a.w, a.seed, dev)
+        del _U
+        res = cpu_reference_run(Rs, rs_, a.M, its, make_probes(its, Ms, a.seed), threads=ncores)
         line = {"impl": "reference", "metric": "VAMP iterations/s", "value": res["value"], "unit": "it/s",
                 "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1000.0 / res["value"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload},
                 "cpu_baseline": {"value": res["value"], "unit": "it/s", "cores": ncores, "kind": "port",
-                                 "sample": "oracle port of src/sgvamp.py (scipy CG, threaded row-split csr_matvec), "
-                                           "%d VAMP iterations from it=0 on an M=%d w=%d banded sample, "
-                                           "scaled by M_sample/M (all per-iteration costs are O(M w))" % (
-                                               its, res["sample_M"], a.w),
-                                 "sample_its_per_s": res["sample_its_per_s"], "cg_iters": res["cg_iters"]},
+                                 "sample": cpu_sample_text(res, a.w, its, ncores),
+                                 "sample_its_per_s": res["sample_its_per_s"], "cg_iters": res["cg_iters"],
+                                 "timers_s": {k: round(x, 3) for k, x in res["timers"].items()}},
                 "e2e": {"value": res["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -429,12 +487,17 @@ def main():
         v2.close()
         del Rh, keep
 
-    cpu = None
+    cpu, parity = None, None
     if not a.no_cpu_baseline and world == 1:
-        res = cpu_reference_run(M, w, a.cpu_sample_M, 2, a.seed, threads=ncores)
+        its_c = 2
+        Ms = int(min(a.cpu_sample_M, M))
+        Us, ldbs, Rs, rs_, _x0s = build_sample(torch, Ms, w, a.seed, dev)
+        probes_s = make_probes(its_c, Ms, a.seed)
+        res = cpu_reference_run(Rs, rs_, M, its_c, probes_s, threads=ncores)
         cpu = {"value": res["value"], "unit": "it/s", "cores": ncores, "kind": "port",
-               "sample": "oracle port of src/sgvamp.py, 2 VAMP iterations from it=0 on an M=%d w=%d banded sample "
-                         "(%.1f s), scaled by M_sample/M" % (res["sample_M"], w, res["seconds"])}
+               "sample": cpu_sample_text(res, w, its_c, ncores), "sample_its_per_s": res["sample_its_per_s"]}
+        parity = gpu_sample_parity(sgvamp, Us, ldbs, w, rs_, res["out"], its_c, probes_s, local_rank, stream)
+        del Us, Rs
     sampler.close()
     traffic = None
     try:   # dram bytes per launch of the dominant kernel from the committed ncu --set full capture (1 GPU, M=1M, w=500)
@@ -462,7 +525,7 @@ def main():
                      "launches_timed": spmm_launches, "isolated_launch_ms": iso_ms,
                      "isolated_gbs": (bytes_pass / (iso_ms * 1e-3) / 1e9) if iso_ms else None,
                      "peak_source": peak_src, "spmm_share_of_step": spmm_share},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(sum_over_ranks([launches["b"] - launches["a"]])[0]),
+        "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(sum_over_ranks([launches["b"] - launches["a"]])[0]),
         "clocks": clocks,
     }
     if rank == 0:

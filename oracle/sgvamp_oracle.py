@@ -123,8 +123,10 @@ def denoise_all(r1s, gam1s, a, prior, per_marker=False):
     return Num / Den, (DerNum * Den - DerDen * Num) / (Den * Den)
 
 
-def _denoise_one(rs, w, lam, omegas, sigmas):
-    """Literal single-marker evaluation of src/sgvamp.py:93-114 (derivative without w_rank)."""
+def _denoise_one(rs, w, lam, omegas, sigmas, w_rank=None):
+    """Literal single-marker evaluation of src/sgvamp.py:93-114.  Without ``w_rank`` the derivative is returned
+    without the factor a[rank]*gam1s[rank]; with ``w_rank = (a[rank], gam1s[rank])`` the two factors sit
+    inside the sums exactly where the reference puts them (:112-113): bit-identical to der_denoiser_meta."""
     sigma2_meta = 1.0 / (sum(w) + 1.0 / sigmas)
     mu_meta = np.inner(rs, w) * sigma2_meta
     max_ind = (np.array(mu_meta * mu_meta / sigma2_meta)).argmax()
@@ -134,6 +136,10 @@ def _denoise_one(rs, w, lam, omegas, sigmas):
     Num = lam * sum(omegas * EXP * mu_meta * np.sqrt(sigma2_meta / sigmas))
     EXP2 = np.exp(-0.5 * ((mu_meta[max_ind]) ** 2 / sigma2_meta[max_ind]))
     Den = (1 - lam) * EXP2 + lam * sum(omegas * EXP * np.sqrt(sigma2_meta / sigmas))
+    if w_rank is not None:
+        DerNum = lam * sum(omegas * EXP * (mu_meta * mu_meta + sigma2_meta) * w_rank[0] * w_rank[1] * np.sqrt(sigma2_meta / sigmas))
+        DerDen = lam * sum(omegas * mu_meta * EXP * w_rank[0] * w_rank[1] * np.sqrt(sigma2_meta / sigmas))
+        return Num / Den, (DerNum * Den - DerDen * Num) / (Den * Den)
     DerNum = lam * sum(omegas * EXP * (mu_meta * mu_meta + sigma2_meta) * np.sqrt(sigma2_meta / sigmas))
     DerDen = lam * sum(omegas * mu_meta * EXP * np.sqrt(sigma2_meta / sigmas))
     return Num / Den, (DerNum * Den - DerDen * Num) / (Den * Den)

@@ -23,6 +23,12 @@ extern "C" int sgv_version(void) { return 100; }
 __global__ void k_resolve(RedCtx rc);
 __global__ void k_scale_copy(int64_t M, const double* __restrict__ src, double* __restrict__ dst, double scale);
 
+int sgv_reset_cg_state(sgv_ctx* c) {
+    SGV_CUDA(cudaMemsetAsync(c->cg, 0, sizeof(CgState), c->stream));
+    SGV_CUDA(cudaMemcpyAsync(&c->cg->band_eps, &c->cg_band_eps, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
 extern "C" int sgv_create(int device, void* stream, sgv_handle* out) {
     SGV_CHECK(out != nullptr, "out is null");
     int ndev = 0;
@@ -52,7 +58,9 @@ extern "C" int sgv_create(int device, void* stream, sgv_handle* out) {
     SGV_CUDA(cudaMalloc(&c->counter, 64));
     SGV_CUDA(cudaMemset(c->counter, 0, 64));
     SGV_CUDA(cudaMalloc(&c->cg, sizeof(CgState)));
-    SGV_CUDA(cudaMemset(c->cg, 0, sizeof(CgState)));
+    if (const char* e = getenv("SGV_CG_BAND")) c->cg_band_eps = atof(e);
+    SGV_TRY(sgv_reset_cg_state(c));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
     SGV_CUDA(cudaMallocHost(&c->cg_host, sizeof(CgState)));
     memset(c->cg_host, 0, sizeof(CgState));
     SGV_CUDA(cudaMallocHost(&c->host_scal, 64 * sizeof(double)));
@@ -285,7 +293,7 @@ extern "C" int sgv_configure_part(sgv_handle c, int64_t M, int K, int rank, int 
     c->peer[rank].ipc = false;
     SGV_CUDA(cudaMalloc(&c->bb, v2));
     SGV_CUDA(cudaMemsetAsync(c->bb, 0, v2, c->stream));
-    SGV_CUDA(cudaMemsetAsync(c->cg, 0, sizeof(CgState), c->stream));
+    SGV_TRY(sgv_reset_cg_state(c));
     for (int i = 0; i < sgv_ctx::NSNAP; ++i) {   // allocated up front: cudaMalloc inside the loop would synchronise
         SGV_CUDA(cudaMalloc(&c->snap[i], vb));
         SGV_CUDA(cudaEventCreateWithFlags(&c->snap_ev[i], cudaEventDisableTiming));

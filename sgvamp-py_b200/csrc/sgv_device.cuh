@@ -101,6 +101,7 @@ __device__ __forceinline__ void apply_totals(const ApplyArgs& ap, CgState* s, co
             s->maxit = ap.maxit;
             s->step = 0;
             s->alpha[0] = s->alpha[1] = 0.0;
+            s->ambig[0] = s->ambig[1] = 0;
             for (int c = 0; c < 2; ++c) {
                 s->bnorm2[c] = t[c];
                 s->rho[c] = 0.0;
@@ -145,12 +146,27 @@ __device__ __forceinline__ void apply_totals(const ApplyArgs& ap, CgState* s, co
             // its window (or by the post kernel), but its effect on rho is known now:
             //     |r - alpha q|^2 = r.r - 2 alpha r.q + alpha^2 q.q
             // with r.r the exactly summed norm of the residual this step used (no drift accumulates).
+            // scipy sums r.r of the updated residual; the extrapolation cancels, so its error is bounded by
+            // ~eps (|r| + alpha |q|)^2.  When the extrapolated value lies within that band of the stopping threshold the
+            // decision is postponed (ambig): the step is taken tentatively and the NEXT pass - which sums r.r of the
+            // updated residual exactly, as scipy does - decides; if the column had in fact converged, the tentative
+            // step is discarded (alpha = 0, no count).  Iteration counts therefore follow the summed norm always.
             for (int c = 0; c < 2; ++c) {
                 if (s->done[c]) {
                     s->alpha[c] = 0.0;
                     continue;
                 }
                 const double rr = t[6 + c];
+                if (s->ambig[c]) {          // postponed loop-top test of this step, now with the exact sum
+                    s->ambig[c] = 0;
+                    s->rho[c] = rr;
+                    if (sqrt(rr) < 1e-5 * sqrt(s->bnorm2[c])) {
+                        s->done[c] = 1;
+                        s->info[c] = 0;
+                        s->alpha[c] = 0.0;  // the tentative step is void: nothing pending
+                        continue;
+                    }
+                }
                 const double al = rr / t[c];
                 double rn = rr - 2.0 * al * t[2 + c] + al * al * t[4 + c];
                 if (rn < 0.0) rn = 0.0;
@@ -159,6 +175,15 @@ __device__ __forceinline__ void apply_totals(const ApplyArgs& ap, CgState* s, co
                 s->rho[c] = rn;
                 s->iters[c] += 1;
                 cg_top_test(s, c);
+                if (s->iters[c] < s->maxit) {
+                    const double sr = sqrt(rr) + fabs(al) * sqrt(t[4 + c]);
+                    const double band = s->band_eps * sr * sr;                     // ~1e3 eps (|r| + alpha |q|)^2
+                    const double thr = 1e-10 * s->bnorm2[c];
+                    if (fabs(rn - thr) <= band) {
+                        s->ambig[c] = 1;
+                        s->done[c] = 0;
+                    }
+                }
             }
             s->step += 1;
             break;

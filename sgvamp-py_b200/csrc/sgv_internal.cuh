@@ -54,7 +54,9 @@ struct CgState {
     int    done[2], iters[2], info[2], zero_b[2];
     double alpha[2];       // fused CG (DSYM): step length of the update x += alpha p, r -= alpha q still to be applied (0: none)
     int    step;           // CG updates performed (0 -> p = r)
+    int    ambig[2];       // fused CG: the extrapolated |r|^2 was too close to the threshold to decide; the next pass's exact sum decides
     int    maxit;
+    double band_eps;       // relative half-width of the "ambiguous" band around the stopping threshold (~1e3 eps)
     int    error;          // != 0: a cross-rank wait timed out; bit q set = rank q's partial never arrived
     unsigned long long err_seq;   // sequence number of the reduction that timed out
     EmState em;
@@ -188,6 +190,7 @@ struct sgv_ctx {
     sgv_ctx*     peer_ctx[SGV_MAX_RANKS] = {};
     std::atomic<unsigned long long> host_seq{0};
     unsigned long long seq = 0;      // reductions issued so far (identical on all ranks)
+    double       cg_band_eps = 2.0e-13;   // CgState::band_eps (SGV_CG_BAND overrides: tests force the postponed path)
     bool         coop_ok = false;      // device supports cooperative launches (persistent EM loop kernel)
     int          em_loop_blocks_per_sm = 0;
     int          last_em_steps = 0;  // EM passes the previous prior update needed (first batch of the next one)
@@ -219,6 +222,8 @@ struct sgv_ctx {
     std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
     size_t       prof_n = 0;             // events used
 };
+
+int sgv_reset_cg_state(sgv_ctx* c);   // api.cu: zero the device state, keep the constants
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

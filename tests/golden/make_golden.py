@@ -94,8 +94,21 @@ def run_reference(case):
         c["it"] += 1
         return ((probes[_tls.rank, c["it"]] + 1) // 2).astype(np.int64)
 
+    def binomial_recorded(p=None, n=None, size=None):
+        # default-RNG case: the reference's own call (src/sgvamp.py:326) on numpy's legacy global state, only recorded
+        c = counters[_tls.rank]
+        c["it"] += 1
+        b = orig_binomial(p=p, n=n, size=size)
+        probes[_tls.rank, c["it"]] = b * 2 - 1
+        return b
+
     ref.con_grad = cg_wrapped
-    ref.binomial = binomial_injected
+    if case.get("rng_seed") is not None:
+        assert K == 1, "one global RNG stream: single cohort only"
+        np.random.seed(case["rng_seed"])
+        ref.binomial = binomial_recorded
+    else:
+        ref.binomial = binomial_injected
 
     def worker(k):
         _tls.rank = k
@@ -182,6 +195,8 @@ def save_case(name, case, out):
         final_lam=out["final_lam"], final_omegas=out["final_omegas"],
         layout=case["layout"],
     )
+    if case.get("rng_seed") is not None:
+        d["rng_seed"] = case["rng_seed"]
     if case.get("x0") is not None:
         d["x0"] = case["x0"]
         d["metrics"] = out["metrics"]
@@ -287,6 +302,30 @@ def main():
     cm = max(1, int(1200 * 0.01))
     cases["banded_L2_em_cgmaxit4"] = base(M=1200, R=[f32(R)], r=[r], N_list=[N], s=0.1, prior_vars=[0, 0.5 / cm],
                                           prior_probs=[0.99, 0.01], layout="banded", iterations=6, cg_maxit=4)
+    # probes NOT injected: np.random.seed + the reference's own binomial call (src/sgvamp.py:326) on the legacy global RNG
+    R, r, x0, N = ldgen.sim_banded(M=1500, w=20, N_ld=512, N=1500, lam=0.01, h2=0.5, seed=14)
+    cm = max(1, int(1500 * 0.01))
+    cases["banded_L2_em_defaultrng"] = base(M=1500, R=[f32(R)], r=[r], N_list=[N], s=0.1, prior_vars=[0, 0.5 / cm],
+                                            prior_probs=[0.99, 0.01], layout="banded", iterations=6, rng_seed=20261018)
+    # general sparse CSR in a stable regime (all iterations and the CG counts are compared): irregular symmetric
+    # pattern = banded sample LD with 60 % of the off-diagonal pairs dropped, diagonally loaded to stay PD
+    R, r, x0, N = ldgen.sim_banded(M=1600, w=24, N_ld=512, N=3200, lam=0.01, h2=0.5, seed=15)
+    rng = np.random.default_rng(150)
+    Ru = scipy.sparse.triu(R, 1).tocoo()
+    keep = rng.random(Ru.nnz) < 0.4
+    Ru = scipy.sparse.csr_matrix((Ru.data[keep], (Ru.row[keep], Ru.col[keep])), shape=R.shape)
+    Rk = (Ru + Ru.T).tocsr()
+    load = 0.3 - min(0.0, float(np.linalg.eigvalsh(Rk.toarray())[0]))      # diagonal load: smallest eigenvalue 0.3/load
+    Rk = ((Rk + load * scipy.sparse.identity(1600)) * (1.0 / load)).tocsr()  # unit diagonal again
+    Rk = f32(Rk)
+    Rk.sort_indices()
+    # r ~ N(Rk x0, (1-h2) Rk): the summary-statistic form of the reference recipe for this LD
+    Lc = np.linalg.cholesky(Rk.toarray())
+    r = Rk @ x0 + np.sqrt(0.5) * (Lc @ rng.standard_normal(1600))
+    cm = max(1, int(1600 * 0.01))
+    cases["csr_irregular_stable_L2_em"] = base(M=1600, R=[f32(Rk)], r=[r], N_list=[N], s=0.0,
+                                               prior_vars=[0, 0.5 / cm], prior_probs=[0.99, 0.01], layout="csr",
+                                               iterations=7, x0=x0 / np.sqrt(N))
     # a fixture whose LD is NOT fp32-representable is produced at test time from dense_L2_em by
     # perturbing R; the reference perturbation study bounds that effect separately.
 

@@ -36,6 +36,8 @@ def load_case(name):
     c["prior_vars"] = [float(v) for v in c["prior_vars"]]
     c["prior_probs"] = [float(v) for v in c["prior_probs"]]
     c["probes"] = c["probes"].astype(np.int64)
+    if "rng_seed" in c:     # probes were drawn by the reference itself (np.random.seed + src/sgvamp.py:326), not injected
+        c["rng_seed"] = int(c["rng_seed"])
     return c
 
 

@@ -365,9 +365,14 @@ def run_gpu(c, out_dir=None, layout="auto"):
     x0 = c["x0"] * np.sqrt(N_list[0]) if "x0" in c else None
     R = c["R"] if K > 1 else c["R"][0]
     r = list(c["r"]) if K > 1 else c["r"][0]
+    probes = c["probes"]
+    if "rng_seed" in c:
+        # the reference's own draw sequence (src/sgvamp.py:326): seed numpy's legacy global RNG and inject nothing
+        np.random.seed(c["rng_seed"])
+        probes = None
     xs = v.infer(R, r, c["iterations"], x0=x0, cg_maxit=c["cg_maxit"], em_prior_maxit=c["em_prior_maxit"],
                  learn_gamw=c["learn_gamw"], lmmse_damp=c["lmmse_damp"], prior_update=c["prior_update"],
-                 update_prior_from=c["update_prior_from"], s=c["s"], probes=c["probes"], layout=layout)
+                 update_prior_from=c["update_prior_from"], s=c["s"], probes=probes, layout=layout)
     info = [v.handle.ld_info(k) for k in range(K)]
     hist = v.history
     fin = (float(v.lam), np.array(v.omegas))

@@ -71,8 +71,15 @@ def test_denoiser_and_derivative(K, L, seed, tmp_path_factory):
         wder = ref.der_denoiser_meta(r1s[:, j], gam1s)
         assert np.isclose(xhat[j], want, rtol=1e-10, atol=1e-300)
         assert xh1[j] == want
-        assert np.isclose(a[rank] * gam1s[rank] * dfac[j], wder, rtol=1e-9, atol=1e-300)
-        assert np.isclose(a[rank] * gam1s[rank] * df1[j], wder, rtol=1e-12, atol=1e-300)
+        # literal form with the rank factor inside the sums, where the reference has it (:112-113): bit-identical
+        w = a * gam1s
+        lit = orc._denoise_one(r1s[:, j], w, prior.lam, prior.omegas, prior.sigmas, w_rank=(a[rank], gam1s[rank]))
+        assert lit[0] == want and lit[1] == wder
+        # factored form (what the kernels compute: a[rank]*gam1[rank] outside the sums): the derivative is a difference
+        # of two products (:114), so the bound scales with the cancelled magnitude DerDen*Num/Den^2 = xhat^2
+        scale = abs(wder) + a[rank] * gam1s[rank] * want * want
+        assert abs(a[rank] * gam1s[rank] * dfac[j] - wder) <= 1e-10 * scale + 1e-300
+        assert abs(a[rank] * gam1s[rank] * df1[j] - wder) <= 1e-12 * scale + 1e-300
 
 
 @settings(max_examples=40, deadline=None)
