@@ -7,6 +7,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsgvamp_b200.so")
+# development builds with other tuning macros: SGV_BUILD_FLAGS="-DX=1 ..." SGV_BUILD_OUT=/path/lib.so (loaded with SGV_LIB)
+EXTRA = os.environ.get("SGV_BUILD_FLAGS", "").split()
+OUT = os.environ.get("SGV_BUILD_OUT") or LIB
 
 
 def sources():
@@ -22,16 +25,17 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    if not force and not needs_build():
+    if not force and not needs_build() and OUT == LIB:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build" if OUT == LIB else "build_" + os.path.basename(OUT))
+    os.makedirs(bdir, exist_ok=True)
     procs = []
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         cmd = [nvcc, "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-               "--extended-lambda", "-Xcompiler", "-fPIC"] + (["-DSGV_EXPERIMENTS"] if os.environ.get("SGV_EXPERIMENTS") else []) + [ "-Xptxas", "-v" if verbose else "-O3",
+               "--extended-lambda", "-Xcompiler", "-fPIC"] + EXTRA + (["-DSGV_EXPERIMENTS"] if os.environ.get("SGV_EXPERIMENTS") else []) + [ "-Xptxas", "-v" if verbose else "-O3",
                "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
@@ -43,9 +47,9 @@ def build(force=False, verbose=False):
         failed = failed or p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
-    return LIB
+    return OUT
 
 
 if __name__ == "__main__":

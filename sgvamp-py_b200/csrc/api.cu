@@ -129,6 +129,9 @@ extern "C" int sgv_destroy(sgv_handle c) {
     cudaFree(c->ypartT);
     cudaFree(c->ds_ypart);
     cudaFree(c->ds_tails);
+    cudaFree(c->dsp_yhead);
+    cudaFree(c->dsp_tails);
+    cudaFree(c->dsp_flags);
     cudaFree(c->partials);
     cudaFree(c->counter);
     cudaFree(c->cg);

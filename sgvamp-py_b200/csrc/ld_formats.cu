@@ -126,8 +126,11 @@ __global__ void k_dsym_check(int64_t M, const int64_t* __restrict__ indptr, cons
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
     unsigned bad = 0;
+    long long delta = 0;   // stored non-zero entries above minus below the diagonal (own rows x own columns)
     for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) {
         const int64_t cl = (int64_t)indices[k] - col_base;
+        if (cl > row && cl < M && data[k] != (T)0) ++delta;
+        if (cl >= 0 && cl < row && data[k] != (T)0) --delta;
         if (cl >= 0 && cl < row) {
             // symmetric to fp32 rounding: relative to the entry, or (LD computed in fp32: the two triangles come
             // from different summation orders) to the largest diagonal entry
@@ -136,6 +139,9 @@ __global__ void k_dsym_check(int64_t M, const int64_t* __restrict__ indptr, cons
         }
     }
     if (bad) atomicAdd(mismatches, (unsigned long long)bad);
+    // a lower entry is compared with its mirror above; an UPPER entry without a stored mirror (triu-only input) is
+    // caught by the counts: all lower entries match and the counts are equal <=> the non-zero patterns mirror
+    if (delta) atomicAdd(mismatches + 1, (unsigned long long)delta);
 }
 
 template <typename T>
@@ -189,10 +195,96 @@ __global__ void k_dense_convert(const T* __restrict__ src, int64_t ld_src, float
 }
 
 // ---------------------------------------------------------------------------------------------
+// symmetry of dense panels.  The default dense / block-diagonal kernel (spmm_psym.cu) reads only the upper triangle
+// and the full-panel kernel computes P^T v, so both equal the reference's R @ v only for symmetric R.  Every panel is
+// therefore compared with its transpose once, at upload (32 x 32 tile pairs through shared memory, one read of the
+// panel); a panel store that is NOT symmetric is transposed in place and pinned to the full-panel kernel, whose
+// P^T v is then exactly R v.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_panel_asym(const float* __restrict__ P, int m, int ld, float abs_tol, unsigned long long* __restrict__ bad) {
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if (by > bx) return;
+    __shared__ float tB[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {                         // B = P[bx*32 + r][by*32 + c]
+        const int i = bx * 32 + r, j = by * 32 + tx;
+        tB[r][tx] = (i < m && j < m) ? P[(int64_t)i * ld + j] : 0.f;
+    }
+    __syncthreads();
+    unsigned n = 0;
+    for (int r = ty; r < 32; r += 8) {                         // A = P[by*32 + r][bx*32 + c]  vs  B[c][r]
+        const int i = by * 32 + r, j = bx * 32 + tx;
+        if (i < m && j < m && j > i) {
+            const float up = P[(int64_t)i * ld + j], lo = tB[tx][r];
+            if (fabsf(lo - up) > fmaxf(4e-7f * fmaxf(fabsf(lo), fabsf(up)), abs_tol)) ++n;
+        }
+    }
+    if (n) atomicAdd(bad, (unsigned long long)n);
+}
+
+__global__ void __launch_bounds__(256)
+k_panel_transpose(float* __restrict__ P, int m, int ld) {
+    const int bx = blockIdx.x, by = blockIdx.y;
+    if (by > bx) return;
+    __shared__ float tA[32][33], tB[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int ia = by * 32 + r, ja = bx * 32 + tx, ib = bx * 32 + r, jb = by * 32 + tx;
+        tA[r][tx] = (ia < m && ja < m) ? P[(int64_t)ia * ld + ja] : 0.f;
+        tB[r][tx] = (ib < m && jb < m) ? P[(int64_t)ib * ld + jb] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int ia = by * 32 + r, ja = bx * 32 + tx, ib = bx * 32 + r, jb = by * 32 + tx;
+        if (ia < m && ja < m) P[(int64_t)ia * ld + ja] = tB[tx][r];
+        if (bx != by && ib < m && jb < m) P[(int64_t)ib * ld + jb] = tA[tx][r];
+    }
+}
+
+// returns 0 and sets ld.panel_sym; a non-symmetric store that the library does not own cannot be transposed: error
+static int check_panel_symmetry(sgv_ctx* c, LdMatrix& ld, const std::vector<int64_t>& starts, const std::vector<int64_t>& offs,
+                                const std::vector<int>& lds) {
+    const int nb = (int)starts.size() - 1;
+    unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(c->counter + 8);
+    SGV_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
+    float diag0 = 1.f;
+    SGV_CUDA(cudaMemcpyAsync(&diag0, ld.panels + offs[0], sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    const float abs_tol = 2e-6f * fmaxf(fabsf(diag0), 1e-30f);
+    for (int b = 0; b < nb; ++b) {
+        const int m = (int)(starts[b + 1] - starts[b]);
+        if (m < 2) continue;
+        const unsigned nt = (unsigned)((m + 31) / 32);
+        k_panel_asym<<<dim3(nt, nt), 256, 0, c->stream>>>(ld.panels + offs[b], m, lds[b], abs_tol, d_bad);
+        c->launches++;
+    }
+    unsigned long long bad = 0;
+    SGV_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    SGV_CUDA(cudaGetLastError());
+    ld.panel_sym = bad == 0;
+    if (bad == 0) return 0;
+    SGV_CHECK(ld.owned, "adopted dense LD is not symmetric (%llu entries differ from their mirror): LD must be symmetric",
+              bad);
+    for (int b = 0; b < nb; ++b) {
+        const int m = (int)(starts[b + 1] - starts[b]);
+        if (m < 2) continue;
+        const unsigned nt = (unsigned)((m + 31) / 32);
+        k_panel_transpose<<<dim3(nt, nt), 256, 0, c->stream>>>(const_cast<float*>(ld.panels) + offs[b], m, lds[b]);
+        c->launches++;
+    }
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    SGV_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // panel work items
 // ---------------------------------------------------------------------------------------------
 int sgv_build_panel_items(sgv_ctx* c, LdMatrix& ld, const std::vector<int64_t>& starts,
                           const std::vector<int64_t>& offs, const std::vector<int>& lds) {
+    SGV_TRY(check_panel_symmetry(c, ld, starts, offs, lds));
     const int TI = 128 * ld.panel_rw;
     const int nb = (int)starts.size() - 1;
     int64_t tiles = 0;
@@ -369,7 +461,7 @@ static int convert_csr(sgv_ctx* c, LdMatrix& ld, int layout, const int64_t* d_in
         k_dsym_fill_diag<<<592, 256, 0, c->stream>>>(U, M, E, ngr, 0.5f * (float)s);   // absent diagonal entry (stored halved)
         k_csr_to_dsym<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, U, ngr, E, s, col_base);
         unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(c->counter + 8);   // spare words of the ticket block
-        SGV_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
+        SGV_CUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(unsigned long long), c->stream));
         // absolute tolerance 2e-6 x the scale of the diagonal (1 for a correlation matrix; read from row 0)
         float diag0 = 1.f;
         SGV_CUDA(cudaMemcpyAsync(&diag0, U + sgv_dsym_index(E, 0, ngr), sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -377,10 +469,10 @@ static int convert_csr(sgv_ctx* c, LdMatrix& ld, int layout, const int64_t* d_in
         const float abs_tol = 2e-6f * fmaxf(2.f * fabsf(diag0), 1e-30f);
         k_dsym_check<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, U, ngr, E, s, col_base, abs_tol, d_bad);
         c->launches += 3;
-        unsigned long long bad = 0;
-        SGV_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
+        unsigned long long bad2[2] = {0, 0};
+        SGV_CUDA(cudaMemcpyAsync(bad2, d_bad, sizeof(bad2), cudaMemcpyDeviceToHost, c->stream));
         SGV_CUDA(cudaStreamSynchronize(c->stream));
-        if (bad != 0) {   // not symmetric: the caller falls back to the full band
+        if (bad2[0] != 0 || bad2[1] != 0) {   // values or pattern not symmetric: the caller falls back to the full band
             sgv_ld_free(ld);
             return 1;
         }
@@ -467,6 +559,19 @@ struct PhaseTimer {
     }
 };
 
+// device staging buffer freed on every exit path unless released to a longer-lived owner
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    void* release() {
+        void* q = p;
+        p = nullptr;
+        return q;
+    }
+};
+
 extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr, const int32_t* indices,
                                  const void* data, int dtype, int64_t nnz, double s, int layout_hint) {
     SGV_TRY(check_cohort(c, cohort));
@@ -482,17 +587,16 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
     LdMatrix& ld = c->coh[cohort].ld;
     sgv_ld_free(ld);
     const size_t esz = dtype == SGV_F64 ? 8 : 4;
-    int64_t* d_indptr = nullptr;
-    int32_t* d_indices = nullptr;
-    void* d_data = nullptr;
-    int *d_lo = nullptr, *d_hi = nullptr, *d_dg = nullptr;
-    SGV_CUDA(cudaMalloc(&d_indptr, (M + 1) * sizeof(int64_t)));
-    SGV_CUDA(cudaMalloc(&d_indices, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
-    SGV_CUDA(cudaMalloc(&d_data, std::max<int64_t>(nnz, 1) * esz));
-    SGV_CUDA(cudaMalloc(&d_lo, 3 * M * sizeof(int)));
+    DevBuf b_indptr, b_indices, b_data, b_lo;   // freed on every return path (error paths included)
+    SGV_CUDA(cudaMalloc(&b_indptr.p, (M + 1) * sizeof(int64_t)));
+    SGV_CUDA(cudaMalloc(&b_indices.p, std::max<int64_t>(nnz, 1) * sizeof(int32_t)));
+    SGV_CUDA(cudaMalloc(&b_data.p, std::max<int64_t>(nnz, 1) * esz));
+    SGV_CUDA(cudaMalloc(&b_lo.p, 3 * M * sizeof(int)));
+    int64_t* d_indptr = static_cast<int64_t*>(b_indptr.p);
+    int32_t* d_indices = static_cast<int32_t*>(b_indices.p);
+    void* d_data = b_data.p;
+    int *d_lo = static_cast<int*>(b_lo.p), *d_hi = d_lo + M, *d_dg = d_hi + M;
     pt.lap("free old + cudaMalloc staging");
-    d_hi = d_lo + M;
-    d_dg = d_hi + M;
     SGV_CUDA(cudaMemcpyAsync(d_indptr, indptr, (M + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     SGV_CUDA(cudaMemcpyAsync(d_indices, indices, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     SGV_CUDA(cudaMemcpyAsync(d_data, data, nnz * esz, cudaMemcpyHostToDevice, c->stream));
@@ -582,14 +686,9 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
         }
     }
     pt.lap("layout conversion");
-    cudaFree(d_data);
-    cudaFree(d_lo);
-    if (rc == 0 && layout == SGV_LAYOUT_CSR) {
-        ld.indptr = d_indptr;
-        ld.indices = d_indices;
-    } else {
-        cudaFree(d_indptr);
-        cudaFree(d_indices);
+    if (rc == 0 && layout == SGV_LAYOUT_CSR) {   // the CSR layout keeps the index arrays
+        ld.indptr = static_cast<int64_t*>(b_indptr.release());
+        ld.indices = static_cast<int32_t*>(b_indices.release());
     }
     if (rc != 0) sgv_ld_free(ld);
     pt.lap("free staging");
@@ -717,6 +816,16 @@ static int upload_dia_t(sgv_ctx* c, LdMatrix& ld, const T* data, int64_t ldd, in
         else lowr.push_back(k);
     }
     const dim3 blk(256);
+    if (layout == SGV_LAYOUT_DSYM && !assume_symmetric) {
+        // an upper diagonal whose mirror is not among the containers' diagonals: the matrix is not symmetric (only
+        // stored diagonals can be compared below), the half band cannot hold it
+        for (int ku : up) {
+            if (offsets[ku] == 0) continue;
+            bool found = false;
+            for (int kl : lowr) found = found || offsets[kl] == -offsets[ku];
+            if (!found) return 1;
+        }
+    }
     if (layout == SGV_LAYOUT_DSYM) {
         const int64_t E = sgv_dsym_ext(c, w), Dp = round_up(w + 1, 4), ngr = Dp / 4;
         const int64_t n = round_up(Ml + E, 128), g0 = c->row_lo - E;

@@ -119,6 +119,7 @@ struct LdMatrix {
     const float* panels = nullptr;
     PanelItem*   items = nullptr;
     int      n_items = 0, s_cross = 1, panel_rw = 4;
+    bool     panel_sym = true;             // false: the store holds R^T of a non-symmetric R (full-panel kernel only)
     struct SymItem* sym_items = nullptr;   // upper-triangle work items of the symmetric panel kernel (spmm_psym.cu)
     int*     rowmeta = nullptr;            // per row: strip, strips of its block, forward slots of its strip
     int      n_sym_items = 0;
@@ -197,6 +198,12 @@ struct sgv_ctx {
     double2*     ds_ypart = nullptr; // DSYM kernel: per-row partial sums and per-tile tails
     double2*     ds_tails = nullptr;
     int64_t      ds_ypart_cap = 0, ds_tails_cap = 0;
+    // persistent DSYM kernel (spmm_dsymp.cu): head-row partial sums / carry-out per row range, hand-off flags
+    double2*     dsp_yhead = nullptr;
+    double2*     dsp_tails = nullptr;
+    int64_t      dsp_cap = 0;
+    unsigned long long* dsp_flags = nullptr;
+    unsigned long long  dsp_epoch = 0;
     double2*     ypart = nullptr;    // cross-CTA partial outputs of the panel kernel
     int64_t      ypart_cap = 0;      // in double2 elements
     double2*     ypartT = nullptr;   // transposed partial outputs of the symmetric panel kernel, per strip
@@ -281,7 +288,13 @@ size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s, int nst);
 bool   sgv_dsym_feasible(int64_t w);
 int    sgv_dsym_ensure_scratch(sgv_ctx* c, const LdMatrix& ld);
 int    sgv_launch_dsym(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a);
-int    sgv_launch_dsym_cg(sgv_ctx* c, Cohort& co, int n, double gamw, double gam2);   // CG step n (reads buffers (n+1)&1, writes n&1)
+int    sgv_launch_dsym_cg(sgv_ctx* c, Cohort& co, int n, double gamw, double gam2);
+// spmm_dsymp.cu (persistent form of the same product: one kernel per pass)
+int    sgv_preload_dsymp();
+bool   sgv_dsymp_feasible(int64_t w);
+size_t sgv_dsymp_smem_bytes(int64_t w, int rw, int s, int nst);
+int    sgv_dsymp_ensure_scratch(sgv_ctx* c, const LdMatrix& ld);
+int    sgv_launch_dsymp(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a);   // CG step n (reads buffers (n+1)&1, writes n&1)
 // element offset of diagonal d (0..Dp-1) at storage row j in the tiled DSYM layout (ngr = Dp/4)
 __host__ __device__ static inline int64_t sgv_dsym_index(int64_t j, int64_t d, int64_t ngr) {
     return ((j >> 7) * ngr + (d >> 2)) * 512 + (d & 3) * 128 + (j & 127);

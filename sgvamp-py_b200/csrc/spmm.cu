@@ -389,7 +389,7 @@ static int launch_epi(sgv_ctx* c, Cohort& co, SpmmArgs& a) {
     // Measured on B200 (2-RHS pass): dense M=50k 1.10 ms vs 1.53 ms for the full-panel kernel below (which runs at
     // the HBM roofline of the FULL matrix), M=10k 0.070 vs 0.086 ms, block-diagonal M=300k 0.45 vs 0.52 ms.
     // SGV_PANEL_FULL=1 selects the full-panel kernel.
-    if ((ld.layout == SGV_LAYOUT_DENSE || ld.layout == SGV_LAYOUT_BLOCKDIAG) && ld.sym_items != nullptr) {
+    if ((ld.layout == SGV_LAYOUT_DENSE || ld.layout == SGV_LAYOUT_BLOCKDIAG) && ld.sym_items != nullptr && ld.panel_sym) {
         const char* e = getenv("SGV_PANEL_FULL");
         if (e == nullptr || e[0] != '1') return sgv_launch_psym(c, ld, EPI, a);
     }

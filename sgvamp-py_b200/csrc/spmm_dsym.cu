@@ -48,66 +48,7 @@
 #include <cstring>
 #include "sgv_device.cuh"
 
-#define DS_FWD(C, XA, XB, XC, XD)                                                             \
-    do {                                                                                      \
-        const double v0 = (double)(C).x, v1 = (double)(C).y, v2 = (double)(C).z, v3 = (double)(C).w; \
-        acc0.x = fma(v0, (XA).x, acc0.x); acc0.y = fma(v0, (XA).y, acc0.y);                   \
-        acc1.x = fma(v1, (XB).x, acc1.x); acc1.y = fma(v1, (XB).y, acc1.y);                   \
-        acc2.x = fma(v2, (XC).x, acc2.x); acc2.y = fma(v2, (XC).y, acc2.y);                   \
-        acc3.x = fma(v3, (XD).x, acc3.x); acc3.y = fma(v3, (XD).y, acc3.y);                   \
-    } while (0)
-
-// transposed use of the 4 values of one diagonal: element e of diagonal d+k goes to target e+k
-#define DS_TRN(C, TA, TB, TC, TD)                                                             \
-    do {                                                                                      \
-        const double v0 = (double)(C).x, v1 = (double)(C).y, v2 = (double)(C).z, v3 = (double)(C).w; \
-        TA.x = fma(v0, O0.x, TA.x); TA.y = fma(v0, O0.y, TA.y);                               \
-        TB.x = fma(v1, O1.x, TB.x); TB.y = fma(v1, O1.y, TB.y);                               \
-        TC.x = fma(v2, O2.x, TC.x); TC.y = fma(v2, O2.y, TC.y);                               \
-        TD.x = fma(v3, O3.x, TD.x); TD.y = fma(v3, O3.y, TD.y);                               \
-    } while (0)
-
-__device__ __forceinline__ double2 shfl_down1(double2 v) {   // lane 31 gets its own value back
-    double2 r;
-    r.x = __shfl_down_sync(0xffffffffu, v.x, 1);
-    r.y = __shfl_down_sync(0xffffffffu, v.y, 1);
-    return r;
-}
-
-static inline int ds_per(int Dp, int S) { return (((Dp + S - 1) / S) + 3) & ~3; }
-
-
-// ---- per-warp TMA ring: the matrix stream goes global -> shared memory with bulk asynchronous copies
-// (cp.async.bulk, completion on an mbarrier), so the bytes in flight cost no registers.  One stage = one
-// group of 4 diagonals x the warp's 128 rows = 4 x 512 contiguous bytes.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-#define DS_STAGE_FLOATS 512   // 4 diagonals x 128 rows
-#ifndef DS_O_IN_REGS
-#define DS_O_IN_REGS 1
-#endif
+#include "dsym_common.cuh"
 
 size_t sgv_dsym_smem_bytes(int64_t w, int rw, int s, int nst) {
     const int Dp = (int)round_up(w + 1, 4);
@@ -273,6 +214,7 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
                     const float4 c0 = sp[0], c1 = sp[32], c2 = sp[64], c3 = sp[96];
                     __syncwarp();
                     if (lane == 0 && gi + NST < ngroups) {
+                        fence_proxy_async_smem();   // the stage's LDS reads (generic proxy) before its refill (async proxy)
                         mbar_expect_tx(bar0 + 8 * stage, DS_STAGE_FLOATS * 4);
                         bulk_g2s(ring0 + stage * DS_STAGE_FLOATS * 4, gsrc + (int64_t)(gi + NST) * DS_STAGE_FLOATS,
                                  DS_STAGE_FLOATS * 4, bar0 + 8 * stage);
@@ -422,6 +364,7 @@ static int preload_main() {
 int sgv_preload_dsym() {
     SGV_TRY(preload_main<false>());
     SGV_TRY(preload_main<true>());
+    SGV_TRY(sgv_preload_dsymp());
     cudaFuncAttributes fa;
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_dsym_finish<EPI_Q>));
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_dsym_finish<EPI_RESID>));
@@ -453,7 +396,7 @@ int sgv_dsym_ensure_scratch(sgv_ctx* c, const LdMatrix& ld) {
         SGV_CUDA(cudaMalloc(&c->ds_ypart, ld.ldb * sizeof(double2)));
         c->ds_ypart_cap = ld.ldb;
     }
-    return 0;
+    return sgv_dsymp_ensure_scratch(c, ld);
 }
 
 template <int RW, int S, bool CG>
@@ -483,6 +426,7 @@ static int launch_finish(sgv_ctx* c, const LdMatrix& ld, SpmmArgs& a, int TR, co
 // a: fully prepared SpmmArgs (vectors, halos, epilogue operands, reduction context)
 int sgv_launch_dsym(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a) {
     SGV_CHECK(c->ds_ypart != nullptr && c->ds_tails != nullptr, "DSYM scratch not allocated");
+    if ((epi == EPI_CG || epi == EPI_Q || epi == EPI_PLAIN) && sgv_dsymp_feasible(ld.w)) return sgv_launch_dsymp(c, ld, epi, a);
     const bool big = ds_use_big(c, ld);
     const int TR = big ? 128 * DS_BIG_RW : 128;
     if (epi == EPI_CG) {

@@ -1,0 +1,546 @@
+// Symmetric half-band SpMM, PERSISTENT form: one kernel per pass, no finish kernel, no ypart / tails round trip.
+//
+// Same arithmetic per stored value as spmm_dsym.cu (forward use from a sliding register window, transposed use as a
+// systolic pipeline over the lanes of a warp, matrix stream through a per-warp bulk-copy ring).  What changes is the
+// ownership of rows: a CTA does not own one tile but a contiguous RANGE of 128-row units (ticket order, balanced to
+// one unit) and walks down it tile by tile:
+//   * the transposed sums that reach past a tile (the `tails` of the one-tile kernel: Dp rows, 2/3 of a tile at w = 500)
+//     stay in shared memory as a carry and are consumed by the CTA's own next tiles; a row is complete as soon as its
+//     tile is combined, so the epilogue (q = gamw y + gam2 p, the four dot products of the fused CG step) runs right
+//     there and nothing but q is written;
+//   * the x window slides: only the TR new entries are staged per tile (the one-tile kernel re-stages TR + Dp entries
+//     per tile, in CG mode three vector loads each);
+//   * the bulk-copy ring runs ahead across tile boundaries, so the matrix stream never drains while a tile is being
+//     combined (one stage per warp is lent to hold the forward sums during the combine and re-armed right after).
+// Only the first Dp rows of a range need sums from the previous range: their partial sums are parked in `yhead`, the
+// range's own carry-out goes to `tails[range]` with a release flag, and each CTA finishes its head rows at the very
+// end, after an (almost always already satisfied) acquire on its predecessor's flag.  Ranges are handed out by an
+// atomic ticket, so a CTA's predecessor is always running or finished: no co-residency assumption, no deadlock.
+// Per-range dot-product partials are added in range order by the last CTA: results are bit-reproducible.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include "dsym_common.cuh"
+
+#ifndef DSP_UNROLL
+#define DSP_UNROLL 1     // unroll factor of the group loop (tuning knob)
+#endif
+#ifndef DSP_L2HINT
+#define DSP_L2HINT 1     // evict-first L2 policy on the matrix stream
+#endif
+#define DSP_STR2(x) #x
+#define DSP_STR(x) DSP_STR2(x)
+
+struct DsPersist {
+    const float*        U;
+    int                 Dp;       // stored diagonals (multiple of 4)
+    int                 units;    // ldb / 128
+    int64_t             E;        // extension rows stored before the first own row
+    double2*            yhead;    // [ranges][Dp] partial sums of the first Dp rows of a range
+    double2*            tails;    // [ranges][Dp] carry-out of a range (sums for the Dp rows after it)
+    unsigned long long* flags;    // [ranges] == epoch once tails[range] is complete
+    unsigned*           ticket;   // range ticket (reset by the last CTA)
+    unsigned long long  epoch;
+    int                 epi;      // non-CG instantiation: EPI_Q or EPI_PLAIN
+    int                 nph;      // phases of the drain step (1 when a segment spans >= 128 diagonals)
+};
+
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+static inline int dsp_per(int Dp, int S) { return (((Dp + S - 1) / S) + 3) & ~3; }
+
+size_t sgv_dsymp_smem_bytes(int64_t w, int rw, int s, int nst) {
+    const int Dp = (int)round_up(w + 1, 4);
+    const int TR = 128 * rw, NW = rw * s;
+    size_t b = (size_t)NW * nst * DS_STAGE_FLOATS * sizeof(float);         // per-warp rings
+    b += (size_t)4 * dia_plane_len(TR + Dp) * sizeof(double2);              // x window
+    b += (size_t)rw * (Dp + 128) * sizeof(double2);                         // transposed sums per row-warp
+    b += (size_t)Dp * sizeof(double2);                                      // carry
+    b += (size_t)NW * nst * 8;                                              // mbarriers
+    b += (size_t)NW * 8 * sizeof(double) + (size_t)NW * sizeof(int) + 16;   // dot slots, lent stages, misc
+    return b;
+}
+
+template <int RW, int S, int NST, bool CG>
+__global__ void __launch_bounds__(32 * RW * S, 2)
+k_dsym_persist(SpmmArgs a, DsPersist g) {
+    static_assert(S >= 4 && (NST & (NST - 1)) == 0, "one new window entry per thread; ring depth a power of two");
+    if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
+    constexpr int TR = 128 * RW, NT = 32 * RW * S, NW = RW * S;
+    constexpr int NV = CG ? 8 : 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int Dp = g.Dp;
+    const int W = TR + Dp;
+    const int PL = dia_plane_len(W);
+    const int AL = Dp + 128;
+    float* ring = reinterpret_cast<float*>(smem_raw);
+    double2* xw = reinterpret_cast<double2*>(smem_raw + (size_t)NW * NST * DS_STAGE_FLOATS * sizeof(float));
+    double2* Aall = xw + 4 * PL;
+    double2* carry = Aall + RW * AL;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(carry + Dp);
+    double* sdot = reinterpret_cast<double*>(bars + NW * NST);
+    int* s_lent = reinterpret_cast<int*>(sdot + NW * 8);
+    int* s_misc = s_lent + NW;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int rw = wid % RW, s = wid / RW;
+    const int G = gridDim.x;
+    if (tid == 0) s_misc[0] = (int)atomicAdd(g.ticket, 1u);
+    const unsigned bar0 = smem_u32(bars + wid * NST);
+    const unsigned ring0 = smem_u32(ring + (size_t)wid * NST * DS_STAGE_FLOATS);
+    if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < NST; ++t) mbar_init(bar0 + 8 * t, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int j = tid; j < NW * 8; j += NT) sdot[j] = 0.0;
+    __syncthreads();
+    const int c = s_misc[0];                                   // this CTA's range (ticket order)
+    const int u0 = (int)((int64_t)c * g.units / G), u1 = (int)((int64_t)(c + 1) * g.units / G);
+    const int nunits = u1 - u0;
+    const int ntiles = (nunits + RW - 1) / RW;
+    const int64_t rb = (int64_t)u0 * 128, re = (int64_t)u1 * 128;   // storage rows of the range
+
+    // this warp's diagonals [d0, d1): segments are laid out from the TOP of the band, so that every d1 is a multiple of
+    // `per` below Dp and the drain ranges [d1, d1 + 128) of different segments do not overlap when per >= 128
+    const int per = (((Dp + S - 1) / S) + 3) & ~3;
+    int d1 = Dp - (S - 1 - s) * per;
+    if (d1 < 0) d1 = 0;
+    const int d0 = max(0, d1 - per);
+    const int ngw = (d1 - d0) >> 2;                             // groups of 4 diagonals per tile
+    const int ntw = (ngw > 0 && nunits > rw) ? (nunits - rw + RW - 1) / RW : 0;   // tiles in which this warp has rows
+
+    // ring walker (warp-uniform): next group to request
+#if DSP_L2HINT
+    const unsigned long long pol = l2_policy_evict_first();
+#define DSP_COPY(DST, SRC, BYTES, BAR) bulk_g2s_hint(DST, SRC, BYTES, BAR, pol)
+#else
+#define DSP_COPY(DST, SRC, BYTES, BAR) bulk_g2s(DST, SRC, BYTES, BAR)
+#endif
+    int pf_left = ntw * ngw, pf_gi = 0;
+    const float* pf_ptr = g.U + ((int64_t)(u0 + rw) * (Dp >> 2) + (d0 >> 2)) * DS_STAGE_FLOATS;
+    const int64_t unit_stride = (int64_t)RW * (Dp >> 2) * DS_STAGE_FLOATS;
+#define DSP_ISSUE(STAGE)                                                                                         \
+    do {                                                                                                         \
+        if (lane == 0) {                                                                                         \
+            fence_proxy_async_smem();                                                                            \
+            mbar_expect_tx(bar0 + 8 * (STAGE), DS_STAGE_FLOATS * 4);                                             \
+            DSP_COPY(ring0 + (STAGE) * DS_STAGE_FLOATS * 4, pf_ptr + (int64_t)pf_gi * DS_STAGE_FLOATS,           \
+                     DS_STAGE_FLOATS * 4, bar0 + 8 * (STAGE));                                                   \
+        }                                                                                                        \
+        --pf_left;                                                                                               \
+        if (++pf_gi == ngw) {                                                                                    \
+            pf_gi = 0;                                                                                           \
+            pf_ptr += unit_stride;                                                                               \
+        }                                                                                                        \
+    } while (0)
+#pragma unroll
+    for (int t = 0; t < NST; ++t)
+        if (pf_left > 0) DSP_ISSUE(t);
+    int q = 0;                                                  // groups consumed so far (stage = q % NST)
+
+    // CG scalars of the step (see spmm_dsym.cu)
+    double al0 = 0.0, al1 = 0.0, beta0 = 0.0, beta1 = 0.0;
+    bool first = true, fz0 = false, fz1 = false;
+    if (CG) {
+        const CgState* st = a.rc.st;
+        first = st->step == 0;
+        fz0 = st->done[0] != 0;
+        fz1 = st->done[1] != 0;
+        if (!first) {
+            al0 = st->alpha[0];
+            al1 = st->alpha[1];
+            beta0 = st->rho[0] / st->rho_prev[0];
+            beta1 = st->rho[1] / st->rho_prev[1];
+        }
+    }
+    // Value of the input vector at local column `col` (0 = first own row of this rank): own memory, the left / right
+    // neighbour's arena, or zero outside the matrix.  CG mode: the new direction p = r + beta p_old with the pending
+    // update r -= alpha q applied on the fly; the rows this CTA owns get r, p and x += alpha p_old written.
+    auto stage_entry = [&](int64_t col) -> double2 {
+        double2 val = make_double2(0.0, 0.0);
+        const double2 *src = nullptr, *rsrc = nullptr, *qsrc = nullptr;
+        int64_t idx = col;
+        if (col >= 0 && col < a.M) {
+            src = a.v;
+            rsrc = a.r;
+            qsrc = a.q;
+        } else if (col < 0 && a.v_left != nullptr && a.n_left + col >= 0) {
+            src = a.v_left;
+            rsrc = a.r_left;
+            qsrc = a.q_left;
+            idx = a.n_left + col;
+        } else if (col >= a.M && a.v_right != nullptr) {
+            src = a.v_right;
+            rsrc = a.r_right;
+            qsrc = a.q_right;
+            idx = col - a.M;
+        }
+        if (src == nullptr) return val;
+        if (!CG) return ld_vec2(src + idx);
+        double2 rv = ld_vec2(rsrc + idx);
+        double2 po = make_double2(0.0, 0.0);
+        if (!first) {
+            po = ld_vec2(src + idx);
+            const double2 qo = ld_vec2(qsrc + idx);
+            if (al0 != 0.0) rv.x -= al0 * qo.x;                 // scipy: r -= alpha*q
+            if (al1 != 0.0) rv.y -= al1 * qo.y;
+        }
+        val.x = fz0 ? po.x : (first ? rv.x : po.x * beta0 + rv.x);   // scipy: p *= beta; p += r  (first step: p = r)
+        val.y = fz1 ? po.y : (first ? rv.y : po.y * beta1 + rv.y);
+        const int64_t js = col + g.E;
+        if (col >= 0 && col < a.M && js >= rb && js < re) {     // rows of this range: written exactly once
+            a.r_new[col] = rv;
+            a.p_new[col] = val;
+            if (al0 != 0.0 || al1 != 0.0) {
+                double2 xv = a.x[col];
+                if (al0 != 0.0) xv.x += al0 * po.x;             // scipy: x += alpha*p
+                if (al1 != 0.0) xv.y += al1 * po.y;
+                a.x[col] = xv;
+            }
+        }
+        return val;
+    };
+    // a finished row: fused epilogue, dot products into d[]
+    double d[NV];
+#pragma unroll
+    for (int k2 = 0; k2 < NV; ++k2) d[k2] = 0.0;
+    auto finish_row = [&](int64_t i, double2 y, double2 vi) {
+        double2 o;
+        o.x = a.gamw * y.x + a.gam2 * vi.x;
+        o.y = a.gamw * y.y + a.gam2 * vi.y;
+        a.out[i] = o;
+        if constexpr (CG) {
+            const double2 rv = a.r_new[i];
+            d[0] += vi.x * o.x; d[1] += vi.y * o.y;      // p.q
+            d[2] += rv.x * o.x; d[3] += rv.y * o.y;      // r.q
+            d[4] += o.x * o.x;  d[5] += o.y * o.y;       // q.q
+            d[6] += rv.x * rv.x; d[7] += rv.y * rv.y;    // r.r
+        } else {
+            d[0] += vi.x * o.x;
+            d[1] += vi.y * o.y;
+        }
+    };
+    auto flush_dots = [&]() {                                  // warp sums into the warp's slot (fixed order over tiles)
+#pragma unroll
+        for (int k2 = 0; k2 < NV; ++k2) {
+            const double v = warp_sum(d[k2]);
+            if (lane == 0) sdot[wid * 8 + k2] += v;
+            d[k2] = 0.0;
+        }
+    };
+
+    // first window [rb - E, rb - E + W) in local coordinates; carry and the untouched tail of the A ranges start at zero
+    for (int j = tid; j < 4 * PL; j += NT) {
+        double2 val = make_double2(0.0, 0.0);
+        if (j < W) val = stage_entry(rb - g.E + j);
+        xw[(j & 3) * PL + (j >> 2)] = val;
+    }
+    for (int j = tid; j < Dp; j += NT) carry[j] = make_double2(0.0, 0.0);
+    for (int j = tid; j < RW * 128; j += NT) Aall[(j >> 7) * AL + Dp + (j & 127)] = make_double2(0.0, 0.0);
+    __syncthreads();
+
+    const int g4 = rw * 32 + lane;                              // this thread's rows: 4*g4 .. 4*g4+3 of the tile
+    double2* Arw = Aall + rw * AL;
+    const double hm = lane == 31 ? 0.0 : 1.0;                   // lane 31 has no lane above: its incoming sums are zero
+    for (int k = 0; k < ntiles; ++k) {
+        const int64_t r0s = rb + (int64_t)k * TR;               // storage row of the tile's first row
+        const bool active = ngw > 0 && k * RW + rw < nunits;
+        const bool last = k == ntiles - 1;
+        double2 acc0 = make_double2(0.0, 0.0), acc1 = acc0, acc2 = acc0, acc3 = acc0;
+        double2 T0 = acc0, T1 = acc0, T2 = acc0, T3 = acc0;
+        int lent = -1;
+        if (active) {
+            double2 T4 = acc0, T5 = acc0, T6 = acc0;
+            const double2 O0 = xw[g4], O1 = xw[PL + g4], O2 = xw[2 * PL + g4], O3 = xw[3 * PL + g4];
+            int xi = g4 + (d0 >> 2);
+            double2 X0 = xw[xi], X1 = xw[PL + xi], X2 = xw[2 * PL + xi], X3 = xw[3 * PL + xi];
+            _Pragma(DSP_STR(unroll DSP_UNROLL))
+            for (int gi = 0; gi < ngw; ++gi) {
+                const int stage = q & (NST - 1);
+                mbar_wait(bar0 + 8 * stage, (unsigned)(q / NST) & 1u);
+                const float4* sp = reinterpret_cast<const float4*>(ring + ((size_t)wid * NST + stage) * DS_STAGE_FLOATS) + lane;
+                const float4 c0 = sp[0], c1 = sp[32], c2 = sp[64], c3 = sp[96];
+                __syncwarp();
+                // hand the stage straight back to the copy engine - except the tile's last one, which holds the
+                // forward sums during the combine and is re-armed after it
+                if (gi + 1 < ngw) {
+                    if (pf_left > 0) DSP_ISSUE(stage);
+                } else {
+                    lent = stage;
+                }
+                ++q;
+                const double2 N0 = xw[xi + 1], N1 = xw[PL + xi + 1], N2 = xw[2 * PL + xi + 1], N3 = xw[3 * PL + xi + 1];
+                DS_FWD(c0, X0, X1, X2, X3);
+                DS_TRN(c0, T0, T1, T2, T3);
+                DS_FWD(c1, X1, X2, X3, N0);
+                DS_TRN(c1, T1, T2, T3, T4);
+                DS_FWD(c2, X2, X3, N0, N1);
+                DS_TRN(c2, T2, T3, T4, T5);
+                DS_FWD(c3, X3, N0, N1, N2);
+                DS_TRN(c3, T3, T4, T5, T6);
+                X0 = N0; X1 = N1; X2 = N2; X3 = N3;
+                ++xi;
+                if (lane == 0) {                                 // lane 0's four sums are final for the warp
+                    double2* e = Arw + d0 + 4 * gi;
+                    e[0] = T0; e[1] = T1; e[2] = T2; e[3] = T3;
+                }
+                const double2 I0 = shfl_down1(T0), I1 = shfl_down1(T1), I2 = shfl_down1(T2), I3 = shfl_down1(T3);
+                T0 = make_double2(fma(I0.x, hm, T4.x), fma(I0.y, hm, T4.y));
+                T1 = make_double2(fma(I1.x, hm, T5.x), fma(I1.y, hm, T5.y));
+                T2 = make_double2(fma(I2.x, hm, T6.x), fma(I2.y, hm, T6.y));
+                T3 = make_double2(I3.x * hm, I3.y * hm);
+                T4 = T5 = T6 = make_double2(0.0, 0.0);
+            }
+            // forward sums of the warp's 128 rows into the lent ring stage (2 KB = 128 x double2)
+            double2* f = reinterpret_cast<double2*>(ring + ((size_t)wid * NST + lent) * DS_STAGE_FLOATS) + 4 * lane;
+            f[0] = acc0; f[1] = acc1; f[2] = acc2; f[3] = acc3;
+        }
+        if (lane == 0) s_lent[wid] = lent;
+        // the TR new window entries of the next tile: loads issued now, consumed after the combine
+        double2 nx = make_double2(0.0, 0.0);
+        if (!last && tid < TR) nx = stage_entry(r0s + TR - g.E + Dp + tid);
+        __syncthreads();                                        // S1: forward sums and lane-0 sums of every warp are in place
+        // drain: every lane holds finished sums for targets d1 + 4*lane + {0..3} (relative to the warp's first row)
+        for (int ph = 0; ph < g.nph; ++ph) {
+            if (active && (s % g.nph) == ph) {
+                double2* e = Arw + d1 + 4 * lane;
+                e[0].x += T0.x; e[0].y += T0.y;
+                e[1].x += T1.x; e[1].y += T1.y;
+                e[2].x += T2.x; e[2].y += T2.y;
+                e[3].x += T3.x; e[3].y += T3.y;
+            }
+            __syncthreads();                                    // S2
+        }
+        // combine, in fixed order: carry-in + forward sums of the S segments + the row-warps' transposed sums
+        const int t_end = last ? (int)(re - r0s) : TR;          // rows of this tile that belong to the range
+        const int act_rw = min(RW, nunits - k * RW);
+        double2 keep[4], xs[3];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int t = tid + m * NT;
+            keep[m] = make_double2(0.0, 0.0);
+            if (t < W) {
+                double2 sum = t < Dp ? carry[t] : make_double2(0.0, 0.0);
+                if (t < TR && (t >> 7) < act_rw) {
+#pragma unroll
+                    for (int s2 = 0; s2 < S; ++s2) {
+                        const int w2 = s2 * RW + (t >> 7);
+                        const int st2 = s_lent[w2];
+                        if (st2 >= 0) {
+                            const double2 v = reinterpret_cast<const double2*>(ring + ((size_t)w2 * NST + st2) * DS_STAGE_FLOATS)[t & 127];
+                            sum.x += v.x;
+                            sum.y += v.y;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int rw2 = 0; rw2 < RW; ++rw2) {
+                    const int rel = t - 128 * rw2;
+                    if (rw2 < act_rw && rel >= 0 && rel < AL) {
+                        const double2 v = Aall[rw2 * AL + rel];
+                        sum.x += v.x;
+                        sum.y += v.y;
+                    }
+                }
+                if (t < t_end) {                                // a row of this range
+                    const int64_t js = r0s + t, i = js - g.E;
+                    if (c > 0 && js - rb < Dp) g.yhead[(int64_t)c * Dp + (js - rb)] = sum;   // still lacks the previous range's carry
+                    else if (i >= 0 && i < a.M) finish_row(i, sum, xw[(t & 3) * PL + (t >> 2)]);
+                } else if (!last) {
+                    keep[m] = sum;                              // carry for the next tiles (index t - TR)
+                } else if (t - t_end < Dp) {
+                    g.tails[(int64_t)c * Dp + (t - t_end)] = sum;   // carry-out of the range
+                }
+            }
+        }
+        if (!last) {
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int j = tid + m * NT;
+                xs[m] = j < Dp ? xw[((j + TR) & 3) * PL + ((j + TR) >> 2)] : make_double2(0.0, 0.0);
+            }
+        }
+        flush_dots();
+        __syncthreads();                                        // S3: carry, window, A and the lent stages have been read
+        if (!last) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int t = tid + m * NT;
+                if (t >= TR && t < W) carry[t - TR] = keep[m];
+            }
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const int j = tid + m * NT;
+                if (j < Dp) xw[(j & 3) * PL + (j >> 2)] = xs[m];
+            }
+            if (tid < TR) {
+                const int j = Dp + tid;
+                xw[(j & 3) * PL + (j >> 2)] = nx;
+            }
+            for (int j = tid; j < RW * 128; j += NT) Aall[(j >> 7) * AL + Dp + (j & 127)] = make_double2(0.0, 0.0);
+        }
+        if (lent >= 0 && pf_left > 0) DSP_ISSUE(lent);          // re-arm the lent stage (warp-uniform)
+        __syncthreads();                                        // S4
+    }
+#undef DSP_ISSUE
+#undef DSP_COPY
+
+    // carry-out published; head rows: add the previous range's carry-out and finish them
+    if (tid == 0 && c + 1 < G) {
+        __threadfence();
+        st_release_gpu_u64(g.flags + c, g.epoch);
+    }
+    if (c > 0) {
+        if (tid == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu_u64(g.flags + (c - 1)) != g.epoch) {
+                if (clock64() - t0 > 8000000000LL) {            // ~4 s: cannot happen unless a CTA died; never hang
+                    a.rc.st->error = 1 << 30;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        for (int t = tid; t < Dp; t += NT) {
+            const int64_t js = rb + t, i = js - g.E;
+            if (js < re && i >= 0 && i < a.M) {
+                double2 y = g.yhead[(int64_t)c * Dp + t];
+                const double2 tl = ld_vec2(g.tails + (int64_t)(c - 1) * Dp + t);
+                y.x += tl.x;
+                y.y += tl.y;
+                finish_row(i, y, CG ? a.p_new[i] : ld_vec2(a.v + i));
+            }
+        }
+        flush_dots();
+    }
+    __syncthreads();
+    if (tid < NV) {
+        double tot = 0.0;
+        for (int w2 = 0; w2 < NW; ++w2) tot += sdot[w2 * 8 + tid];
+        a.rc.partials[(size_t)c * NV + tid] = tot;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const unsigned t = atomicAdd(a.rc.counter, 1u);
+        s_misc[1] = (t == (unsigned)G - 1u);
+    }
+    __syncthreads();
+    if (!s_misc[1]) return;
+    // last CTA: reset the tickets; add the per-range partials in range order; state transition / cross-rank exchange
+    __threadfence();
+    if (tid == 0) {
+        *a.rc.counter = 0u;
+        *g.ticket = 0u;
+    }
+    if (!CG && g.epi == EPI_PLAIN) return;
+    double acc[NV];
+#pragma unroll
+    for (int k2 = 0; k2 < NV; ++k2) acc[k2] = 0.0;
+    for (int b = tid; b < G; b += NT) {
+#pragma unroll
+        for (int k2 = 0; k2 < NV; ++k2) acc[k2] += __ldcg(&a.rc.partials[(size_t)b * NV + k2]);
+    }
+    double* red = reinterpret_cast<double*>(Aall);
+    block_reduce<NV>(acc, red);
+    if (tid == 0 && a.rc.world == 1) apply_totals(a.rc.ap, a.rc.st, acc);
+    if (a.rc.world > 1 && tid < 32) {
+        publish_warp<NV>(acc, a.rc, a.rc.seq, tid);
+        if (a.rc.inline_resolve) {
+            __syncwarp();
+            resolve_warp(a.rc, tid);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+#define DSP_RW 2
+#define DSP_S 4
+#define DSP_NST 4
+#define DSP_SMEM_LIMIT (113 * 1024)   // two CTAs per SM
+
+static int dsp_nph(int64_t w) {
+    const int Dp = (int)round_up(w + 1, 4);
+    const int per = dsp_per(Dp, DSP_S);
+    return per >= 128 ? 1 : (128 + per - 1) / per;
+}
+
+// The persistent kernel is used when its shared memory fits two CTAs per SM and the drain step needs at most 4
+// phases (w >= ~125); narrower or much wider bands keep the one-tile kernels.  SGV_DS_PERSIST=0 disables it (A/B).
+bool sgv_dsymp_feasible(int64_t w) {
+    static const bool off = getenv("SGV_DS_PERSIST") != nullptr && atoi(getenv("SGV_DS_PERSIST")) == 0;
+    if (off) return false;
+    return sgv_dsymp_smem_bytes(w, DSP_RW, DSP_S, DSP_NST) <= DSP_SMEM_LIMIT && dsp_nph(w) <= 4;
+}
+
+int sgv_preload_dsymp() {
+    SGV_CUDA(cudaFuncSetAttribute(k_dsym_persist<DSP_RW, DSP_S, DSP_NST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  DSP_SMEM_LIMIT));
+    SGV_CUDA(cudaFuncSetAttribute(k_dsym_persist<DSP_RW, DSP_S, DSP_NST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  DSP_SMEM_LIMIT));
+    return 0;
+}
+
+static int dsp_ranges(const sgv_ctx* c, const LdMatrix& ld) {
+    const int64_t Dp = round_up(ld.w + 1, 4);
+    const int64_t units = ld.ldb / 128, min_units = (Dp + 127) / 128;   // a range spans at least Dp rows
+    return (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)c->sm_count * 2, units / min_units));
+}
+
+int sgv_dsymp_ensure_scratch(sgv_ctx* c, const LdMatrix& ld) {
+    const int64_t Dp = round_up(ld.w + 1, 4);
+    const int64_t need = (int64_t)c->sm_count * 2 * Dp;
+    if (c->dsp_cap < need) {
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->dsp_yhead) cudaFree(c->dsp_yhead);
+        if (c->dsp_tails) cudaFree(c->dsp_tails);
+        c->dsp_yhead = c->dsp_tails = nullptr;
+        c->dsp_cap = 0;
+        SGV_CUDA(cudaMalloc(&c->dsp_yhead, need * sizeof(double2)));
+        SGV_CUDA(cudaMalloc(&c->dsp_tails, need * sizeof(double2)));
+        c->dsp_cap = need;
+    }
+    if (c->dsp_flags == nullptr) {
+        SGV_CUDA(cudaMalloc(&c->dsp_flags, (size_t)c->sm_count * 2 * sizeof(unsigned long long)));
+        SGV_CUDA(cudaMemset(c->dsp_flags, 0, (size_t)c->sm_count * 2 * sizeof(unsigned long long)));
+    }
+    return sgv_ensure_partials(c, (int64_t)c->sm_count * 2);
+}
+
+int sgv_launch_dsymp(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a) {
+    SGV_CHECK(c->dsp_yhead != nullptr && c->dsp_flags != nullptr, "DSYM persistent scratch not allocated");
+    SGV_CHECK(epi == EPI_CG || epi == EPI_Q || epi == EPI_PLAIN, "epilogue %d not available in the persistent kernel", epi);
+    DsPersist g;
+    g.U = ld.band;
+    g.Dp = (int)round_up(ld.w + 1, 4);
+    g.units = (int)(ld.ldb / 128);
+    g.E = ld.ext;
+    g.yhead = c->dsp_yhead;
+    g.tails = c->dsp_tails;
+    g.flags = c->dsp_flags;
+    g.ticket = c->counter + 12;
+    g.epoch = ++c->dsp_epoch;
+    g.epi = epi;
+    g.nph = dsp_nph(ld.w);
+    const int G = dsp_ranges(c, ld);
+    SGV_TRY(sgv_ensure_partials(c, G));
+    a.rc.partials = c->partials;
+    a.rc.counter = c->counter;
+    const size_t smem = sgv_dsymp_smem_bytes(ld.w, DSP_RW, DSP_S, DSP_NST);
+    if (epi == EPI_CG)
+        k_dsym_persist<DSP_RW, DSP_S, DSP_NST, true><<<G, 32 * DSP_RW * DSP_S, smem, c->stream>>>(a, g);
+    else
+        k_dsym_persist<DSP_RW, DSP_S, DSP_NST, false><<<G, 32 * DSP_RW * DSP_S, smem, c->stream>>>(a, g);
+    c->launches++;
+    return 0;
+}

@@ -206,6 +206,61 @@ def test_symmetric_and_full_panel_kernels_agree(nat, monkeypatch):
         h.close()
 
 
+def test_nonsymmetric_ld_is_not_mirrored_silently(nat):
+    """The reference computes R @ v for whatever R it is given (src/sgvamp.py:316,352).  The half-band and
+    upper-triangle kernels use symmetry, so every upload path verifies it on the device and routes a non-symmetric R
+    to a kernel that keeps R as given: dense / block-diagonal -> transposed store + full-panel kernel, banded -> full
+    band; an explicit request for the half band refuses."""
+    rng = np.random.default_rng(12)
+    # dense, not symmetric
+    M = 515
+    R = rng.standard_normal((M, M)).astype(np.float32).astype(np.float64)
+    X = rng.standard_normal((M, 2))
+    h = nat.Handle()
+    h.configure(M, 1)
+    h.upload_dense(0, R, s=0.0)
+    assert rel_l2(h.spmm(0, X, alpha=1.2, beta=0.4), 1.2 * (R @ X) + 0.4 * X) < 1e-13
+    # one entry off in an otherwise symmetric dense matrix
+    Rs = (R + R.T)
+    Rs[7, 300] += 0.5
+    h.upload_dense(0, Rs, s=0.0)
+    assert rel_l2(h.spmm(0, X), Rs @ X) < 1e-13
+    # block-diagonal from CSR with one non-symmetric block
+    blocks = []
+    for b in (40, 260, 33):
+        B = rng.standard_normal((b, b))
+        blocks.append((B + B.T).astype(np.float32).astype(np.float64))
+    blocks[1][3, 200] = 0.25
+    Rb = scipy.sparse.block_diag([scipy.sparse.csr_matrix(b) for b in blocks], format="csr")
+    Rb.sort_indices()
+    Mb = Rb.shape[0]
+    h.configure(Mb, 1)
+    h._ck(h.upload_csr(0, Rb.indptr, Rb.indices, Rb.data, layout=nat.LAYOUT_BLOCKDIAG))
+    Xb = rng.standard_normal((Mb, 2))
+    assert rel_l2(h.spmm(0, Xb), Rb @ Xb) < 1e-13
+    # banded CSR holding only the upper triangle: not symmetric -> full band; explicit half band refuses
+    Mt, w = 3000, 20
+    Rt = scipy.sparse.triu(_rand_sym_band(Mt, w, 31), 0).tocsr()
+    Rt.sort_indices()
+    h.configure(Mt, 1)
+    h._ck(h.upload_csr(0, Rt.indptr, Rt.indices, Rt.data))
+    assert h.ld_info(0)["layout"] == "dia"
+    Xt = rng.standard_normal((Mt, 2))
+    assert rel_l2(h.spmm(0, Xt), Rt @ Xt) < 1e-13
+    assert h.upload_csr(0, Rt.indptr, Rt.indices, Rt.data, layout=nat.LAYOUT_DSYM) != 0
+    # the same in scipy's DIA container (only non-negative offsets stored)
+    Rd = Rt.todia()
+    assert Rd.offsets.min() >= 0
+    h._ck(h.upload_dia(0, Rd.data, Rd.offsets))
+    assert h.ld_info(0)["layout"] == "dia"
+    assert rel_l2(h.spmm(0, Xt), Rt @ Xt) < 1e-13
+    assert h.upload_dia(0, Rd.data, Rd.offsets, layout=nat.LAYOUT_DSYM) != 0
+    h._ck(h.upload_dia(0, Rd.data, Rd.offsets, layout=nat.LAYOUT_DSYM, assume_symmetric=True))   # declared symmetric: mirrored
+    Rm = (Rt + scipy.sparse.triu(Rt, 1).T).tocsr()
+    assert rel_l2(h.spmm(0, Xt), Rm @ Xt) < 1e-13
+    h.close()
+
+
 def test_regularisation_at_upload(nat):
     """Rused = (1-s) R + s I (src/main.py:265) on every layout, including absent diagonal entries."""
     rng = np.random.default_rng(9)
