@@ -81,3 +81,8 @@ __device__ __forceinline__ void bulk_g2s_hint(unsigned dst, const void* src, uns
 // Orders this thread's earlier generic-proxy accesses of shared memory (the LDS reads of a ring stage, made visible
 // to it by __syncwarp) before its later async-proxy operations (the bulk copy that refills the stage).
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// pull `bytes` (multiple of 16) starting at a 16-byte aligned global address into L2 without a destination
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}

@@ -214,7 +214,6 @@ k_spmm_dsym(SpmmArgs a, const float* __restrict__ U, int Dp, int64_t ldb, int64_
                     const float4 c0 = sp[0], c1 = sp[32], c2 = sp[64], c3 = sp[96];
                     __syncwarp();
                     if (lane == 0 && gi + NST < ngroups) {
-                        fence_proxy_async_smem();   // the stage's LDS reads (generic proxy) before its refill (async proxy)
                         mbar_expect_tx(bar0 + 8 * stage, DS_STAGE_FLOATS * 4);
                         bulk_g2s(ring0 + stage * DS_STAGE_FLOATS * 4, gsrc + (int64_t)(gi + NST) * DS_STAGE_FLOATS,
                                  DS_STAGE_FLOATS * 4, bar0 + 8 * stage);

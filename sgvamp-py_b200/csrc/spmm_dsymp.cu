@@ -28,6 +28,11 @@
 #ifndef DSP_L2HINT
 #define DSP_L2HINT 1     // evict-first L2 policy on the matrix stream
 #endif
+// Measured and dropped (B200, M = 1M, w = 500, ms per pass isolated / in the CG loop; kept 0.383 / 0.416):
+//   cp.async.bulk.prefetch.L2 4-16 groups ahead of the ring        0.426-0.444 / 0.464-0.515
+//   group loop unrolled x2 / x4 (stage index still a run-time value) 0.391-0.408 / 0.448-0.450
+//   fence.proxy.async before every refill (see DSP_ISSUE)           0.392-0.401 / 0.432-0.433
+//   refill after the group's FMAs instead of right after its loads  0.383 / 0.425
 #define DSP_STR2(x) #x
 #define DSP_STR(x) DSP_STR2(x)
 
@@ -127,10 +132,10 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
     int pf_left = ntw * ngw, pf_gi = 0;
     const float* pf_ptr = g.U + ((int64_t)(u0 + rw) * (Dp >> 2) + (d0 >> 2)) * DS_STAGE_FLOATS;
     const int64_t unit_stride = (int64_t)RW * (Dp >> 2) * DS_STAGE_FLOATS;
-#define DSP_ISSUE(STAGE)                                                                                         \
+#define DSP_ISSUE(STAGE, FENCE)                                                                                       \
     do {                                                                                                         \
         if (lane == 0) {                                                                                         \
-            fence_proxy_async_smem();                                                                            \
+            if (FENCE) fence_proxy_async_smem();                                                                 \
             mbar_expect_tx(bar0 + 8 * (STAGE), DS_STAGE_FLOATS * 4);                                             \
             DSP_COPY(ring0 + (STAGE) * DS_STAGE_FLOATS * 4, pf_ptr + (int64_t)pf_gi * DS_STAGE_FLOATS,           \
                      DS_STAGE_FLOATS * 4, bar0 + 8 * (STAGE));                                                   \
@@ -143,7 +148,7 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
     } while (0)
 #pragma unroll
     for (int t = 0; t < NST; ++t)
-        if (pf_left > 0) DSP_ISSUE(t);
+        if (pf_left > 0) DSP_ISSUE(t, false);
     int q = 0;                                                  // groups consumed so far (stage = q % NST)
 
     // CG scalars of the step (see spmm_dsym.cu)
@@ -212,13 +217,12 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
     double d[NV];
 #pragma unroll
     for (int k2 = 0; k2 < NV; ++k2) d[k2] = 0.0;
-    auto finish_row = [&](int64_t i, double2 y, double2 vi) {
+    auto finish_row = [&](int64_t i, double2 y, double2 vi, double2 rv) {   // rv: r_new[i] (CG mode)
         double2 o;
         o.x = a.gamw * y.x + a.gam2 * vi.x;
         o.y = a.gamw * y.y + a.gam2 * vi.y;
         a.out[i] = o;
         if constexpr (CG) {
-            const double2 rv = a.r_new[i];
             d[0] += vi.x * o.x; d[1] += vi.y * o.y;      // p.q
             d[2] += rv.x * o.x; d[3] += rv.y * o.y;      // r.q
             d[4] += o.x * o.x;  d[5] += o.y * o.y;       // q.q
@@ -271,8 +275,11 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
                 __syncwarp();
                 // hand the stage straight back to the copy engine - except the tile's last one, which holds the
                 // forward sums during the combine and is re-armed after it
+                // (the lanes' LDS reads of the stage are ordered before lane 0's refill by __syncwarp, the same
+                // consumer-release -> producer hand-off CUTLASS' TMA pipelines use; a fence.proxy.async here costs 4 %
+                // of the pass - MEMBAR.ALL.CTA in SASS - and is kept only where generic WRITES precede a refill)
                 if (gi + 1 < ngw) {
-                    if (pf_left > 0) DSP_ISSUE(stage);
+                    if (pf_left > 0) DSP_ISSUE(stage, false);
                 } else {
                     lent = stage;
                 }
@@ -307,6 +314,13 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
         // the TR new window entries of the next tile: loads issued now, consumed after the combine
         double2 nx = make_double2(0.0, 0.0);
         if (!last && tid < TR) nx = stage_entry(r0s + TR - g.E + Dp + tid);
+        // r of the row this thread finishes in the combine (row tid of the tile): written when the row was staged, at
+        // least one barrier ago; requested here so that its latency hides behind the barriers below
+        double2 rpre = make_double2(0.0, 0.0);
+        if (CG && tid < TR) {
+            const int64_t i = r0s + tid - g.E;
+            if (i >= 0 && i < a.M && r0s + tid < re) rpre = a.r_new[i];
+        }
         __syncthreads();                                        // S1: forward sums and lane-0 sums of every warp are in place
         // drain: every lane holds finished sums for targets d1 + 4*lane + {0..3} (relative to the warp's first row)
         for (int ph = 0; ph < g.nph; ++ph) {
@@ -353,7 +367,7 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
                 if (t < t_end) {                                // a row of this range
                     const int64_t js = r0s + t, i = js - g.E;
                     if (c > 0 && js - rb < Dp) g.yhead[(int64_t)c * Dp + (js - rb)] = sum;   // still lacks the previous range's carry
-                    else if (i >= 0 && i < a.M) finish_row(i, sum, xw[(t & 3) * PL + (t >> 2)]);
+                    else if (i >= 0 && i < a.M) finish_row(i, sum, xw[(t & 3) * PL + (t >> 2)], rpre);   // t < TR: m == 0, t == tid
                 } else if (!last) {
                     keep[m] = sum;                              // carry for the next tiles (index t - TR)
                 } else if (t - t_end < Dp) {
@@ -387,7 +401,7 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
             }
             for (int j = tid; j < RW * 128; j += NT) Aall[(j >> 7) * AL + Dp + (j & 127)] = make_double2(0.0, 0.0);
         }
-        if (lent >= 0 && pf_left > 0) DSP_ISSUE(lent);          // re-arm the lent stage (warp-uniform)
+        if (lent >= 0 && pf_left > 0) DSP_ISSUE(lent, true);    // re-arm the lent stage (held generic writes: proxy fence)
         __syncthreads();                                        // S4
     }
 #undef DSP_ISSUE
@@ -416,7 +430,7 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
                 const double2 tl = ld_vec2(g.tails + (int64_t)(c - 1) * Dp + t);
                 y.x += tl.x;
                 y.y += tl.y;
-                finish_row(i, y, CG ? a.p_new[i] : ld_vec2(a.v + i));
+                finish_row(i, y, CG ? a.p_new[i] : ld_vec2(a.v + i), CG ? a.r_new[i] : make_double2(0.0, 0.0));
             }
         }
         flush_dots();

@@ -221,8 +221,8 @@ def test_nonsymmetric_ld_is_not_mirrored_silently(nat):
     h.upload_dense(0, R, s=0.0)
     assert rel_l2(h.spmm(0, X, alpha=1.2, beta=0.4), 1.2 * (R @ X) + 0.4 * X) < 1e-13
     # one entry off in an otherwise symmetric dense matrix
-    Rs = (R + R.T)
-    Rs[7, 300] += 0.5
+    Rs = (R + R.T).astype(np.float32).astype(np.float64)
+    Rs[7, 300] = 0.5 if Rs[300, 7] != 0.5 else 0.75
     h.upload_dense(0, Rs, s=0.0)
     assert rel_l2(h.spmm(0, X), Rs @ X) < 1e-13
     # block-diagonal from CSR with one non-symmetric block
