@@ -294,7 +294,10 @@ int    sgv_preload_dsymp();
 bool   sgv_dsymp_feasible(int64_t w);
 size_t sgv_dsymp_smem_bytes(int64_t w, int rw, int s, int nst);
 int    sgv_dsymp_ensure_scratch(sgv_ctx* c, const LdMatrix& ld);
-int    sgv_launch_dsymp(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a);   // CG step n (reads buffers (n+1)&1, writes n&1)
+int    sgv_launch_dsymp(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a);
+bool   sgv_dsymp_solve_usable(const sgv_ctx* c, const LdMatrix& ld);
+int    sgv_launch_dsymp_solve(sgv_ctx* c, const LdMatrix& ld, SpmmArgs& a, int max_steps);
+int    sgv_launch_dsym_solve(sgv_ctx* c, Cohort& co, double gamw, double gam2, int max_steps);   // spmm_dsym.cu: whole CG solve   // CG step n (reads buffers (n+1)&1, writes n&1)
 // element offset of diagonal d (0..Dp-1) at storage row j in the tiled DSYM layout (ngr = Dp/4)
 __host__ __device__ static inline int64_t sgv_dsym_index(int64_t j, int64_t d, int64_t ngr) {
     return ((j >> 7) * ngr + (d >> 2)) * 512 + (d & 3) * 128 + (j & 127);

@@ -500,3 +500,37 @@ int sgv_launch_dsym_cg(sgv_ctx* c, Cohort& co, int n, double gamw, double gam2) 
     SGV_CUDA(cudaGetLastError());
     return sgv_red_end(c, a.rc);
 }
+
+// The whole CG solve as ONE cooperative launch of the persistent kernel (spmm_dsymp.cu): no launch per step, no host
+// read-back inside the solve.  Reduction sequence numbers: step n uses seq0 + n; the caller advances c->seq by the
+// number of steps that ran (identical on every rank) once it has read the state back.
+int sgv_launch_dsym_solve(sgv_ctx* c, Cohort& co, double gamw, double gam2, int max_steps) {
+    const LdMatrix& ld = co.ld;
+    SGV_CHECK(sgv_dsymp_solve_usable(c, ld), "whole-solve kernel not usable for this cohort");
+    SpmmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.x = c->xx;
+    a.bb = c->bb;
+    a.gamw = gamw;
+    a.gam2 = gam2;
+    a.M = c->Ml;
+    a.rc = sgv_red_begin(c, AP_CGFUSED, 8, 0);
+    a.rc.st = c->cg;
+    if (c->prof) {
+        if (c->prof_n + 2 > c->prof_ev.size()) {
+            for (int i = 0; i < 256; ++i) {
+                cudaEvent_t e;
+                SGV_CUDA(cudaEventCreate(&e));
+                c->prof_ev.push_back(e);
+            }
+        }
+        SGV_CUDA(cudaEventRecord(c->prof_ev[c->prof_n], c->stream));
+    }
+    SGV_TRY(sgv_launch_dsymp_solve(c, ld, a, max_steps));
+    if (c->prof) {
+        SGV_CUDA(cudaEventRecord(c->prof_ev[c->prof_n + 1], c->stream));
+        c->prof_n += 2;
+    }
+    SGV_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -50,6 +50,17 @@ struct DsPersist {
     int                 nph;      // phases of the drain step (1 when a segment spans >= 128 diagonals)
 };
 
+// Whole-solve mode (SOLVE): one cooperative launch runs every CG step of an LMMSE solve; step n reads the vector
+// buffers (n+1)&1 - the neighbours' too - and writes n&1, exactly as the one-step launches do.
+struct DsSolve {
+    double2 *pp[2], *rr[2], *qq[2];                       // own arena buffers
+    const double2 *ppL[2], *rrL[2], *qqL[2];              // left neighbour's (null: none)
+    const double2 *ppR[2], *rrR[2], *qqR[2];              // right neighbour's
+    unsigned long long* gen;                              // step barrier: == epoch + n + 1 once step n's state transition is done
+    unsigned*           exit_ticket;
+    int                 max_steps;
+};
+
 __device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -73,11 +84,12 @@ size_t sgv_dsymp_smem_bytes(int64_t w, int rw, int s, int nst) {
     return b;
 }
 
-template <int RW, int S, int NST, bool CG>
+template <int RW, int S, int NST, bool CG, bool SOLVE>
 __global__ void __launch_bounds__(32 * RW * S, 2)
-k_dsym_persist(SpmmArgs a, DsPersist g) {
+k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
     static_assert(S >= 4 && (NST & (NST - 1)) == 0, "one new window entry per thread; ring depth a power of two");
-    if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
+    static_assert(CG || !SOLVE, "whole-solve mode is the CG instantiation");
+    if (!SOLVE && a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     constexpr int TR = 128 * RW, NT = 32 * RW * S, NW = RW * S;
     constexpr int NV = CG ? 8 : 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -129,8 +141,9 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
 #else
 #define DSP_COPY(DST, SRC, BYTES, BAR) bulk_g2s(DST, SRC, BYTES, BAR)
 #endif
-    int pf_left = ntw * ngw, pf_gi = 0;
-    const float* pf_ptr = g.U + ((int64_t)(u0 + rw) * (Dp >> 2) + (d0 >> 2)) * DS_STAGE_FLOATS;
+    int pf_left = 0, pf_gi = 0;
+    const float* const pf_start = g.U + ((int64_t)(u0 + rw) * (Dp >> 2) + (d0 >> 2)) * DS_STAGE_FLOATS;
+    const float* pf_ptr = pf_start;
     const int64_t unit_stride = (int64_t)RW * (Dp >> 2) * DS_STAGE_FLOATS;
 #define DSP_ISSUE(STAGE, FENCE)                                                                                       \
     do {                                                                                                         \
@@ -146,24 +159,44 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
             pf_ptr += unit_stride;                                                                               \
         }                                                                                                        \
     } while (0)
-#pragma unroll
-    for (int t = 0; t < NST; ++t)
-        if (pf_left > 0) DSP_ISSUE(t, false);
     int q = 0;                                                  // groups consumed so far (stage = q % NST)
+    // start of a pass: the walker goes back to the range's first group; the first NST groups are requested at once
+#define DSP_ARM_PASS()                                                                                           \
+    do {                                                                                                         \
+        pf_left = ntw * ngw;                                                                                     \
+        pf_gi = 0;                                                                                               \
+        pf_ptr = pf_start;                                                                                       \
+        _Pragma("unroll") for (int t = 0; t < NST; ++t)                                                          \
+            if (pf_left > 0) DSP_ISSUE((q + t) & (NST - 1), false);                                              \
+    } while (0)
+    bool prearmed = false;
 
     // CG scalars of the step (see spmm_dsym.cu)
     double al0 = 0.0, al1 = 0.0, beta0 = 0.0, beta1 = 0.0;
     bool first = true, fz0 = false, fz1 = false;
+    const volatile CgState* vst = a.rc.st;                      // SOLVE: rewritten between steps by the last CTA
+    unsigned long long seq = a.rc.seq, epoch = g.epoch;
+  for (int step_i = 0;; ++step_i, ++seq, ++epoch) {
+    if (SOLVE) {
+        if ((vst->done[0] && vst->done[1]) || step_i >= sv.max_steps) break;
+        const int n = vst->step, prev = (n + 1) & 1, cur = n & 1;
+        a.v = sv.pp[prev]; a.r = sv.rr[prev]; a.q = sv.qq[prev];
+        a.p_new = sv.pp[cur]; a.r_new = sv.rr[cur]; a.out = sv.qq[cur];
+        a.v_left = sv.ppL[prev]; a.r_left = sv.rrL[prev]; a.q_left = sv.qqL[prev];
+        a.v_right = sv.ppR[prev]; a.r_right = sv.rrR[prev]; a.q_right = sv.qqR[prev];
+    }
+    if (!prearmed) DSP_ARM_PASS();
+    prearmed = false;
     if (CG) {
-        const CgState* st = a.rc.st;
-        first = st->step == 0;
-        fz0 = st->done[0] != 0;
-        fz1 = st->done[1] != 0;
+        first = vst->step == 0;
+        fz0 = vst->done[0] != 0;
+        fz1 = vst->done[1] != 0;
+        al0 = al1 = beta0 = beta1 = 0.0;
         if (!first) {
-            al0 = st->alpha[0];
-            al1 = st->alpha[1];
-            beta0 = st->rho[0] / st->rho_prev[0];
-            beta1 = st->rho[1] / st->rho_prev[1];
+            al0 = vst->alpha[0];
+            al1 = vst->alpha[1];
+            beta0 = vst->rho[0] / vst->rho_prev[0];
+            beta1 = vst->rho[1] / vst->rho_prev[1];
         }
     }
     // Value of the input vector at local column `col` (0 = first own row of this rank): own memory, the left / right
@@ -249,6 +282,7 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
     }
     for (int j = tid; j < Dp; j += NT) carry[j] = make_double2(0.0, 0.0);
     for (int j = tid; j < RW * 128; j += NT) Aall[(j >> 7) * AL + Dp + (j & 127)] = make_double2(0.0, 0.0);
+    for (int j = tid; j < NW * 8; j += NT) sdot[j] = 0.0;
     __syncthreads();
 
     const int g4 = rw * 32 + lane;                              // this thread's rows: 4*g4 .. 4*g4+3 of the tile
@@ -404,18 +438,16 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
         if (lent >= 0 && pf_left > 0) DSP_ISSUE(lent, true);    // re-arm the lent stage (held generic writes: proxy fence)
         __syncthreads();                                        // S4
     }
-#undef DSP_ISSUE
-#undef DSP_COPY
 
     // carry-out published; head rows: add the previous range's carry-out and finish them
     if (tid == 0 && c + 1 < G) {
         __threadfence();
-        st_release_gpu_u64(g.flags + c, g.epoch);
+        st_release_gpu_u64(g.flags + c, epoch);
     }
     if (c > 0) {
         if (tid == 0) {
             const long long t0 = clock64();
-            while (ld_acquire_gpu_u64(g.flags + (c - 1)) != g.epoch) {
+            while (ld_acquire_gpu_u64(g.flags + (c - 1)) != epoch) {
                 if (clock64() - t0 > 8000000000LL) {            // ~4 s: cannot happen unless a CTA died; never hang
                     a.rc.st->error = 1 << 30;
                     break;
@@ -441,6 +473,10 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
         for (int w2 = 0; w2 < NW; ++w2) tot += sdot[w2 * 8 + tid];
         a.rc.partials[(size_t)c * NV + tid] = tot;
     }
+    if (SOLVE) {                                                // the matrix does not change: the next step's first
+        DSP_ARM_PASS();                                         // requests go out before the step barrier
+        prearmed = true;
+    }
     __syncthreads();
     if (tid == 0) {
         __threadfence();
@@ -448,29 +484,67 @@ k_dsym_persist(SpmmArgs a, DsPersist g) {
         s_misc[1] = (t == (unsigned)G - 1u);
     }
     __syncthreads();
-    if (!s_misc[1]) return;
-    // last CTA: reset the tickets; add the per-range partials in range order; state transition / cross-rank exchange
-    __threadfence();
-    if (tid == 0) {
-        *a.rc.counter = 0u;
-        *g.ticket = 0u;
-    }
-    if (!CG && g.epi == EPI_PLAIN) return;
-    double acc[NV];
+    if (s_misc[1]) {
+        // last CTA of the pass: add the per-range partials in range order; state transition / cross-rank exchange
+        __threadfence();
+        if (tid == 0) {
+            *a.rc.counter = 0u;
+            *g.ticket = 0u;                                     // every CTA has taken its range by now
+        }
+        if (CG || g.epi != EPI_PLAIN) {
+            double acc[NV];
 #pragma unroll
-    for (int k2 = 0; k2 < NV; ++k2) acc[k2] = 0.0;
-    for (int b = tid; b < G; b += NT) {
+            for (int k2 = 0; k2 < NV; ++k2) acc[k2] = 0.0;
+            for (int b = tid; b < G; b += NT) {
 #pragma unroll
-        for (int k2 = 0; k2 < NV; ++k2) acc[k2] += __ldcg(&a.rc.partials[(size_t)b * NV + k2]);
+                for (int k2 = 0; k2 < NV; ++k2) acc[k2] += __ldcg(&a.rc.partials[(size_t)b * NV + k2]);
+            }
+            double* red = reinterpret_cast<double*>(Aall);
+            block_reduce<NV>(acc, red);
+            RedCtx rcs = a.rc;
+            rcs.seq = seq;
+            if (tid == 0 && rcs.world == 1) apply_totals(rcs.ap, rcs.st, acc);
+            if (rcs.world > 1 && tid < 32) {
+                publish_warp<NV>(acc, rcs, rcs.seq, tid);
+                if (rcs.inline_resolve) {
+                    __syncwarp();
+                    resolve_warp(rcs, tid);
+                }
+            }
+        }
+        if (SOLVE && tid == 0) {
+            __threadfence();
+            st_release_gpu_u64(sv.gen, epoch + 1);              // step barrier: the new CG state is in place
+        }
     }
-    double* red = reinterpret_cast<double*>(Aall);
-    block_reduce<NV>(acc, red);
-    if (tid == 0 && a.rc.world == 1) apply_totals(a.rc.ap, a.rc.st, acc);
-    if (a.rc.world > 1 && tid < 32) {
-        publish_warp<NV>(acc, a.rc, a.rc.seq, tid);
-        if (a.rc.inline_resolve) {
-            __syncwarp();
-            resolve_warp(a.rc, tid);
+    if (!SOLVE) break;
+    if (!s_misc[1] && tid == 0) {
+        const long long t0 = clock64();
+        while (ld_acquire_gpu_u64(sv.gen) != epoch + 1) {
+            if (clock64() - t0 > 40000000000LL) {               // ~20 s (a cross-rank wait inside is bounded by the same)
+                a.rc.st->error = 1 << 29;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+  }
+#undef DSP_ARM_PASS
+#undef DSP_ISSUE
+#undef DSP_COPY
+    if (SOLVE) {
+        // requests made ahead for a step that does not happen must land before the CTA's shared memory is released
+        if (prearmed) {
+            const int n_armed = min(NST, ntw * ngw);
+            for (int t = 0; t < n_armed; ++t) mbar_wait(bar0 + 8 * ((q + t) & (NST - 1)), (unsigned)((q + t) / NST) & 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned t = atomicAdd(sv.exit_ticket, 1u);
+            if (t == (unsigned)G - 1u) {                        // also covers a solve that was over before its first step
+                *sv.exit_ticket = 0u;
+                *g.ticket = 0u;
+            }
         }
     }
 }
@@ -497,11 +571,19 @@ bool sgv_dsymp_feasible(int64_t w) {
     return sgv_dsymp_smem_bytes(w, DSP_RW, DSP_S, DSP_NST) <= DSP_SMEM_LIMIT && dsp_nph(w) <= 4;
 }
 
+static int g_dsp_coop_blocks = 0;   // co-resident CTAs per SM of the whole-solve instantiation (0: not usable)
+
 int sgv_preload_dsymp() {
-    SGV_CUDA(cudaFuncSetAttribute(k_dsym_persist<DSP_RW, DSP_S, DSP_NST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SGV_CUDA(cudaFuncSetAttribute(k_dsym_persist<DSP_RW, DSP_S, DSP_NST, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   DSP_SMEM_LIMIT));
-    SGV_CUDA(cudaFuncSetAttribute(k_dsym_persist<DSP_RW, DSP_S, DSP_NST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SGV_CUDA(cudaFuncSetAttribute(k_dsym_persist<DSP_RW, DSP_S, DSP_NST, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   DSP_SMEM_LIMIT));
+    SGV_CUDA(cudaFuncSetAttribute(k_dsym_persist<DSP_RW, DSP_S, DSP_NST, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  DSP_SMEM_LIMIT));
+    int nb = 0;
+    SGV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_dsym_persist<DSP_RW, DSP_S, DSP_NST, true, true>,
+                                                           32 * DSP_RW * DSP_S, DSP_SMEM_LIMIT));
+    g_dsp_coop_blocks = nb;
     return 0;
 }
 
@@ -524,17 +606,14 @@ int sgv_dsymp_ensure_scratch(sgv_ctx* c, const LdMatrix& ld) {
         SGV_CUDA(cudaMalloc(&c->dsp_tails, need * sizeof(double2)));
         c->dsp_cap = need;
     }
-    if (c->dsp_flags == nullptr) {
-        SGV_CUDA(cudaMalloc(&c->dsp_flags, (size_t)c->sm_count * 2 * sizeof(unsigned long long)));
-        SGV_CUDA(cudaMemset(c->dsp_flags, 0, (size_t)c->sm_count * 2 * sizeof(unsigned long long)));
+    if (c->dsp_flags == nullptr) {   // one hand-off flag per range + the step barrier word of the whole-solve kernel
+        SGV_CUDA(cudaMalloc(&c->dsp_flags, ((size_t)c->sm_count * 2 + 2) * sizeof(unsigned long long)));
+        SGV_CUDA(cudaMemset(c->dsp_flags, 0, ((size_t)c->sm_count * 2 + 2) * sizeof(unsigned long long)));
     }
     return sgv_ensure_partials(c, (int64_t)c->sm_count * 2);
 }
 
-int sgv_launch_dsymp(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a) {
-    SGV_CHECK(c->dsp_yhead != nullptr && c->dsp_flags != nullptr, "DSYM persistent scratch not allocated");
-    SGV_CHECK(epi == EPI_CG || epi == EPI_Q || epi == EPI_PLAIN, "epilogue %d not available in the persistent kernel", epi);
-    DsPersist g;
+static void dsp_fill(sgv_ctx* c, const LdMatrix& ld, int epi, DsPersist& g) {
     g.U = ld.band;
     g.Dp = (int)round_up(ld.w + 1, 4);
     g.units = (int)(ld.ldb / 128);
@@ -543,18 +622,81 @@ int sgv_launch_dsymp(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a) {
     g.tails = c->dsp_tails;
     g.flags = c->dsp_flags;
     g.ticket = c->counter + 12;
-    g.epoch = ++c->dsp_epoch;
     g.epi = epi;
     g.nph = dsp_nph(ld.w);
+}
+
+int sgv_launch_dsymp(sgv_ctx* c, const LdMatrix& ld, int epi, SpmmArgs& a) {
+    SGV_CHECK(c->dsp_yhead != nullptr && c->dsp_flags != nullptr, "DSYM persistent scratch not allocated");
+    SGV_CHECK(epi == EPI_CG || epi == EPI_Q || epi == EPI_PLAIN, "epilogue %d not available in the persistent kernel", epi);
+    DsPersist g;
+    dsp_fill(c, ld, epi, g);
+    g.epoch = ++c->dsp_epoch;
+    DsSolve sv;
+    memset(&sv, 0, sizeof(sv));
     const int G = dsp_ranges(c, ld);
     SGV_TRY(sgv_ensure_partials(c, G));
     a.rc.partials = c->partials;
     a.rc.counter = c->counter;
     const size_t smem = sgv_dsymp_smem_bytes(ld.w, DSP_RW, DSP_S, DSP_NST);
     if (epi == EPI_CG)
-        k_dsym_persist<DSP_RW, DSP_S, DSP_NST, true><<<G, 32 * DSP_RW * DSP_S, smem, c->stream>>>(a, g);
+        k_dsym_persist<DSP_RW, DSP_S, DSP_NST, true, false><<<G, 32 * DSP_RW * DSP_S, smem, c->stream>>>(a, g, sv);
     else
-        k_dsym_persist<DSP_RW, DSP_S, DSP_NST, false><<<G, 32 * DSP_RW * DSP_S, smem, c->stream>>>(a, g);
+        k_dsym_persist<DSP_RW, DSP_S, DSP_NST, false, false><<<G, 32 * DSP_RW * DSP_S, smem, c->stream>>>(a, g, sv);
+    c->launches++;
+    return 0;
+}
+
+// Whole CG solve in one cooperative launch (the state must have been initialised by the set-up kernel).  Usable when
+// every range CTA is co-resident and no rank shares its GPU with another (the step barrier spans the cross-rank
+// exchange).  SGV_DS_SOLVE=0 falls back to one launch per step.
+bool sgv_dsymp_solve_usable(const sgv_ctx* c, const LdMatrix& ld) {
+    static const bool off = getenv("SGV_DS_SOLVE") != nullptr && atoi(getenv("SGV_DS_SOLVE")) == 0;
+    if (off || !c->coop_ok || (c->world > 1 && c->host_barrier)) return false;
+    return ld.layout == SGV_LAYOUT_DSYM && sgv_dsymp_feasible(ld.w) &&
+           dsp_ranges(c, ld) <= g_dsp_coop_blocks * c->sm_count;
+}
+
+int sgv_launch_dsymp_solve(sgv_ctx* c, const LdMatrix& ld, SpmmArgs& a, int max_steps) {
+    SGV_CHECK(c->dsp_yhead != nullptr && c->dsp_flags != nullptr, "DSYM persistent scratch not allocated");
+    DsPersist g;
+    dsp_fill(c, ld, EPI_CG, g);
+    g.epoch = c->dsp_epoch + 1;
+    c->dsp_epoch += (unsigned long long)max_steps + 1;           // step n uses epoch + n (flags) / epoch + n + 1 (barrier)
+    DsSolve sv;
+    memset(&sv, 0, sizeof(sv));
+    for (int i = 0; i < 2; ++i) {
+        sv.pp[i] = c->pp[i];
+        sv.rr[i] = c->rr2[i];
+        sv.qq[i] = c->qq2[i];
+    }
+    if (c->world > 1 && c->halo) {
+        for (int side = 0; side < 2; ++side) {
+            const int q = side == 0 ? c->rank - 1 : c->rank + 1;
+            if (q < 0 || q >= c->world) continue;
+            const PeerView& pv = c->peer[q];
+            SGV_CHECK(pv.base != nullptr && pv.Ml >= ld.w, "neighbour %d not attached or shorter than the half-bandwidth", q);
+            for (int i = 0; i < 2; ++i) {
+                const double2* p = reinterpret_cast<double2*>(pv.base + arena_off_pp(pv.Ml, i));
+                const double2* r = reinterpret_cast<double2*>(pv.base + arena_off_rr(pv.Ml, i));
+                const double2* qv = reinterpret_cast<double2*>(pv.base + arena_off_qq(pv.Ml, i));
+                if (side == 0) { sv.ppL[i] = p; sv.rrL[i] = r; sv.qqL[i] = qv; }
+                else { sv.ppR[i] = p; sv.rrR[i] = r; sv.qqR[i] = qv; }
+            }
+            if (side == 0) a.n_left = pv.Ml;
+        }
+    }
+    sv.gen = c->dsp_flags + (size_t)c->sm_count * 2;
+    sv.exit_ticket = c->counter + 13;
+    sv.max_steps = max_steps;
+    const int G = dsp_ranges(c, ld);
+    SGV_TRY(sgv_ensure_partials(c, G));
+    a.rc.partials = c->partials;
+    a.rc.counter = c->counter;
+    size_t smem = sgv_dsymp_smem_bytes(ld.w, DSP_RW, DSP_S, DSP_NST);
+    void* args[] = {&a, &g, &sv};
+    SGV_CUDA(cudaLaunchCooperativeKernel((const void*)k_dsym_persist<DSP_RW, DSP_S, DSP_NST, true, true>, dim3(G),
+                                         dim3(32 * DSP_RW * DSP_S), args, smem, c->stream));
     c->launches++;
     return 0;
 }

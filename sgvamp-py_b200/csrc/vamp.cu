@@ -708,6 +708,13 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
     int launched = 0;
     int batch = co.last_cg_iters > 0 ? co.last_cg_iters + 2 : 4;   // see sgv_prior_em: counts drift slowly
     CgState* hs = c->cg_host;
+    if (fusedcg && in->cg_maxit > 0 && sgv_dsymp_solve_usable(c, co.ld)) {
+        // the whole solve in one cooperative launch: steps separated by a grid barrier, not by launches
+        SGV_TRY(sgv_launch_dsym_solve(c, co, in->gamw, in->gam2, in->cg_maxit));
+        SGV_TRY(fetch_state(c));
+        c->seq += (unsigned long long)std::max(hs->step - 1, 0);   // step n used sequence number seq0 + n
+        launched = in->cg_maxit;
+    }
     while (launched < in->cg_maxit) {
         const int nb = std::min(batch, in->cg_maxit - launched);
         for (int b = 0; b < nb; ++b) {
