@@ -161,6 +161,39 @@ int sgv_lmmse(sgv_handle h, int cohort, const sgv_lmmse_in* in, const int8_t* pr
 /* r1 <- (xhat2 - alpha2*r2)/(1-alpha2)  (src/sgvamp.py:348) */
 int sgv_update_r1(sgv_handle h, int cohort, double alpha2);
 
+/* ---- fused VAMP iteration (src/sgvamp.py:222-387 for every cohort of this process).  The scalar chain gam1 ->
+ * alpha1 -> gam2 -> alpha2 -> gam1', gamw (:285-374, Python floats in the reference) is kept on the device and advanced
+ * by the kernels' finalisers with separately rounded IEEE operations in the reference's order, so one VAMP iteration is
+ * enqueued without a host round trip (prior update by EM only; MLE needs scipy's fsolve on the host and uses the
+ * stepwise entry points above).  Usage: sgv_set_prior + sgv_set_weights + sgv_set_xty + sgv_reset_state, then
+ * sgv_vamp_begin once, then per iteration: fill the probe buffer of a slot (K x local rows, int8, cohort-major),
+ * sgv_iteration_enqueue, and - possibly after enqueueing the next iteration on another slot - sgv_iteration_wait. ---- */
+#define SGV_ITER_SLOTS 4
+typedef struct {
+    int    it;              /* iteration index: damping for it > 0 (:275,:290), x0 = 0 warm start for it == 0 */
+    int    update_prior;    /* run the EM loop first (:250-257) */
+    int    em_maxit;
+    double em_tol;          /* the reference uses 1e-6 */
+    double rho;
+    int    cg_maxit, lmmse_damp, learn_gamw, want_metrics;
+} sgv_iter_in;
+typedef struct {
+    double row[7];          /* it, gamw, gam1, gam2, alpha1, alpha2, lam: the CSV row of :377 */
+    int    cg_iters[2], cg_info[2], spmm_passes;
+} sgv_iter_cohort;
+typedef struct {
+    double lam, omegas[SGV_MAX_L], em_relerr, metrics[4];   /* metrics: see sgv_metrics */
+    int    em_steps;
+    sgv_iter_cohort coh[SGV_MAX_K];
+} sgv_iter_out;
+int sgv_iteration_supported(sgv_handle h);   /* 1 unless ranks share a GPU (host-barrier mode) or cooperative launch is missing */
+int sgv_vamp_begin(sgv_handle h, const double* gam1, const double* gamw, const double* N);   /* K entries each (:210-216, :352) */
+int sgv_set_truth(sgv_handle h, const double* x0);
+int sgv_iteration_probe_buffer(sgv_handle h, int slot, int8_t** buf);
+/* xhat_pinned / r1_pinned[k]: pinned destinations (sgv_pinned_alloc) of the iteration's xhat1 and incoming r1 dumps, or NULL */
+int sgv_iteration_enqueue(sgv_handle h, const sgv_iter_in* in, double* xhat_pinned, double* const* r1_pinned, int slot);
+int sgv_iteration_wait(sgv_handle h, int slot, sgv_iter_out* out);
+
 /* metrics vs truth (src/sgvamp.py:379-382): dots[0]=xhat1.x0, [1]=xhat1.xhat1, [2]=x0.x0, [3]=|xhat1-x0|^2 */
 int sgv_metrics(sgv_handle h, const double* x0, double* dots);
 

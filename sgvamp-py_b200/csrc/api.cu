@@ -142,6 +142,11 @@ extern "C" int sgv_destroy(sgv_handle c) {
     cudaEventDestroy(c->ev_b);
     cudaEventDestroy(c->ev_copy);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    for (int i = 0; i < sgv_ctx::NLOG; ++i) {
+        if (c->log_host[i]) cudaFreeHost(c->log_host[i]);
+        if (c->log_ev[i]) cudaEventDestroy(c->log_ev[i]);
+        if (c->probe_pin[i]) cudaFreeHost(c->probe_pin[i]);
+    }
     cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -255,6 +260,8 @@ extern "C" int sgv_configure_part(sgv_handle c, int64_t M, int K, int rank, int 
     c->halo = halo;
     c->K = K;
     c->seq = 0;
+    c->vamp_begun = false;
+    if (c->probe_pin_bytes < (int64_t)K * (row_hi - row_lo)) c->probe_pin_bytes = 0;   // re-allocated by sgv_vamp_begin
     c->host_seq.store(0);
     c->host_barrier = false;
     for (int q = 0; q < SGV_MAX_RANKS; ++q) c->peer_ctx[q] = nullptr;

@@ -78,6 +78,16 @@ __device__ __forceinline__ void cg_top_test(CgState* s, int c) {
     }
 }
 
+// gamw / gam2 of an SpMM launched from the fused VAMP iteration live on the device (first statement of every kernel
+// that applies them)
+#define SGV_LOAD_DEV_SCALARS(a)                                   \
+    do {                                                          \
+        if ((a).vs_cohort >= 0) {                                 \
+            (a).gamw = (a).rc.st->vs.gamw[(a).vs_cohort];         \
+            (a).gam2 = (a).rc.st->vs.gam2[(a).vs_cohort];         \
+        }                                                         \
+    } while (0)
+
 // The state transition that follows a completed reduction.  Executed by exactly one thread per
 // rank: the finaliser of the reducing kernel (world == 1) or the resolve kernel (world > 1).
 __device__ __forceinline__ void apply_totals(const ApplyArgs& ap, CgState* s, const double* t) {
@@ -186,6 +196,57 @@ __device__ __forceinline__ void apply_totals(const ApplyArgs& ap, CgState* s, co
                 }
             }
             s->step += 1;
+            break;
+        // ---- device-resident scalar chain of the VAMP loop.  Every operation is a separately rounded IEEE operation in the
+        // reference's order (no FMA contraction), so the values equal what the Python floats of src/sgvamp.py would hold.
+        case AP_DENOISE: {   // t[0] = sum_j d(j): alpha1 (:285-291) and gam2 (:305) of every cohort
+            VampScal& v = s->vs;
+            const double dmean = __ddiv_rn(t[0], ap.Mtot);
+            s->log.dmean = dmean;
+            for (int k = 0; k < v.K; ++k) {
+                double a1 = __dmul_rn(__dmul_rn(v.a[k], v.gam1[k]), dmean);
+                if (ap.it > 0) a1 = __dadd_rn(__dmul_rn(ap.rho, a1), __dmul_rn(__dsub_rn(1.0, ap.rho), v.alpha1[k]));
+                v.alpha1[k] = a1;
+                v.gam2[k] = __ddiv_rn(__dmul_rn(v.gam1[k], __dsub_rn(1.0, a1)), a1);
+            }
+            s->log.lam = s->em.lam;
+            for (int l = 0; l < v.Lm1; ++l) s->log.omegas[l] = s->em.omegas[l];
+            s->log.em_steps = s->em.steps;
+            s->log.em_relerr = s->em.relerr;
+            break;
+        }
+        case AP_POST: {      // t = [u.Sigma2u, xhat2.r, xhat2^T R xhat2, u^T R Sigma2u] of cohort ap.cohort
+            VampScal& v = s->vs;
+            const int k = ap.cohort;
+            const double gam2 = v.gam2[k];
+            double a2 = __ddiv_rn(__dmul_rn(gam2, t[0]), ap.Mtot);                                       // :338-340
+            if (ap.lmmse_damp) a2 = __dadd_rn(__dmul_rn(ap.rho, a2), __dmul_rn(__dsub_rn(1.0, ap.rho), v.alpha2[k]));   // :345-346
+            v.alpha2[k] = a2;
+            const double gam1 = __ddiv_rn(__dmul_rn(gam2, __dsub_rn(1.0, a2)), a2);                      // :347
+            v.gam1[k] = gam1;
+            double gw = v.gamw[k];
+            if (ap.learn_gamw) {                                                                         // :350-364
+                const double N = v.N[k];
+                double z = __dadd_rn(__dsub_rn(N, __dmul_rn(2.0, t[1])), t[2]);
+                if (z < 0.0) z = 0.0;
+                gw = __ddiv_rn(1.0, __dadd_rn(__ddiv_rn(z, N), __ddiv_rn(t[3], N)));
+            }
+            gw = fmax(gw, 1.0);                                                                          // :374
+            v.gamw[k] = gw;
+            IterLog& L = s->log;
+            L.row[k][0] = (double)ap.it; L.row[k][1] = gw; L.row[k][2] = gam1; L.row[k][3] = gam2;
+            L.row[k][4] = v.alpha1[k]; L.row[k][5] = a2; L.row[k][6] = s->em.lam;
+            for (int cidx = 0; cidx < 2; ++cidx) {
+                L.cg_iters[k][cidx] = s->iters[cidx];
+                L.cg_info[k][cidx] = s->done[cidx] ? s->info[cidx] : s->maxit;   // never passed the test: scipy reports maxiter
+            }
+            L.passes[k] = s->iters[0] > s->iters[1] ? s->iters[0] : s->iters[1];
+            L.error = s->error;
+            break;
+        }
+        case AP_METRICS:
+            for (int k = 0; k < 4; ++k) s->log.metrics[k] = t[k];
+            s->log.error = s->error;
             break;
         case AP_CGUPDATE:   // x, r updated: rho_prev <- rho, rho <- r.r, count, loop-top test
             for (int c = 0; c < 2; ++c) {

@@ -48,6 +48,22 @@ struct EmState {
     int    K, Lm1, steps, maxit, done;
 };
 
+// Device-resident scalar chain of the VAMP loop (src/sgvamp.py:285-374 keeps these in Python floats): the finalisers of
+// the denoiser and of the LMMSE post-processing update them, so a whole VAMP iteration is enqueued without a host
+// round trip; `IterLog` is what the host reads back once per iteration (CSV row, CG counts, prior, metrics).
+struct VampScal {
+    double gam1[SGV_MAX_K], gamw[SGV_MAX_K], alpha1[SGV_MAX_K], alpha2[SGV_MAX_K], gam2[SGV_MAX_K];
+    double a[SGV_MAX_K], N[SGV_MAX_K];     // cohort weights (src/main.py:287) and sample sizes (gamw update :352-363)
+    double sigmas[SGV_MAX_L];              // slab variances (already times Nt, :27)
+    int    K, Lm1;
+};
+struct IterLog {
+    double row[SGV_MAX_K][7];              // it, gamw, gam1, gam2, alpha1, alpha2, lam  (:377)
+    int    cg_iters[SGV_MAX_K][2], cg_info[SGV_MAX_K][2], passes[SGV_MAX_K];
+    double lam, omegas[SGV_MAX_L], em_relerr, dmean, metrics[4];
+    int    em_steps, error;
+};
+
 struct CgState {
     double rho[2], rho_prev[2], pq[2], bnorm2[2];
     double stats[16];      // results of non-CG reductions (read back by the host)
@@ -60,6 +76,8 @@ struct CgState {
     int    error;          // != 0: a cross-rank wait timed out; bit q set = rank q's partial never arrived
     unsigned long long err_seq;   // sequence number of the reduction that timed out
     EmState em;
+    VampScal vs;
+    IterLog  log;
 };
 
 // Cross-rank reduction mailbox.  Lives at the start of every rank's symmetric arena; rank r writes its
@@ -77,12 +95,17 @@ struct Inbox {
 };
 
 // What to do with the totals of a grid-wide (and, for world > 1, cross-rank) reduction.
-enum { AP_STATS = 0, AP_PQ = 1, AP_RESID = 2, AP_SETUP = 3, AP_CGUPDATE = 4, AP_EM = 5, AP_CGFUSED = 6 };
+enum { AP_STATS = 0, AP_PQ = 1, AP_RESID = 2, AP_SETUP = 3, AP_CGUPDATE = 4, AP_EM = 5, AP_CGFUSED = 6,
+       AP_DENOISE = 7 /* alpha1, gam2 of every cohort */, AP_POST = 8 /* alpha2, gam1, gamw, CSV row of one cohort */,
+       AP_METRICS = 9 };
 enum { SKIP_NEVER = 0, SKIP_CG_DONE = 1, SKIP_EM_DONE = 2 };
 struct ApplyArgs {
     int kind, nv, off;      // AP_STATS: stats[off + k] = total[k]
     int maxit, x0_zero;     // AP_SETUP
     int is_min;             // combine with min instead of +
+    // device-resident scalar chain (AP_DENOISE / AP_POST / AP_METRICS; AP_SETUP reads maxit from here as well)
+    int    cohort, it, lmmse_damp, learn_gamw;
+    double rho, Mtot;
 };
 
 struct RedCtx {
@@ -191,6 +214,14 @@ struct sgv_ctx {
     sgv_ctx*     peer_ctx[SGV_MAX_RANKS] = {};
     std::atomic<unsigned long long> host_seq{0};
     unsigned long long seq = 0;      // reductions issued so far (identical on all ranks)
+    // fused VAMP iteration (sgv_iteration_*): ring of pinned log slots, probe staging
+    static const int NLOG = 4;
+    IterLog*     log_host[NLOG] = {};
+    cudaEvent_t  log_ev[NLOG] = {};
+    int8_t*      probe_pin[NLOG] = {};
+    int64_t      probe_pin_bytes = 0;
+    bool         vamp_begun = false;
+    int          vs_active = -1;    // cohort whose device-resident gamw / gam2 the SpMM kernels read (-1: by-value arguments)
     double       cg_band_eps = 2.0e-13;   // CgState::band_eps (SGV_CG_BAND overrides: tests force the postponed path)
     bool         coop_ok = false;      // device supports cooperative launches (persistent EM loop kernel)
     int          em_loop_blocks_per_sm = 0;
@@ -264,6 +295,7 @@ struct SpmmArgs {
     double         gamw, gam2;
     int64_t        M;      // local number of markers
     int            check_done;   // 1: exit immediately when both CG columns are done
+    int            vs_cohort;    // >= 0: gamw / gam2 are read from the device-resident scalar chain (CgState::vs) of this cohort
     // fused CG step (EPI_CG): r_new = r - alpha q (pending update), p_new = r_new + beta p, x += alpha p are formed
     // while the window is staged; v = p_old, r = r_old, q = q_old (each with the neighbours' halos)
     const double2 *q, *q_left, *q_right;

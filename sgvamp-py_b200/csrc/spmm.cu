@@ -43,6 +43,7 @@ bool sgv_dia_feasible(int64_t w) { return sgv_dia_smem_bytes(w, 1, 8) <= 200 * 1
 template <int RW, int S, int EPI, int PF, int MINB>
 __global__ void __launch_bounds__(32 * RW * S, MINB)
 k_spmm_dia(SpmmArgs a, const float* __restrict__ band, int w, int64_t ldb) {
+    SGV_LOAD_DEV_SCALARS(a);
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     constexpr int TR = 128 * RW;
     constexpr int NT = 32 * RW * S;
@@ -300,6 +301,7 @@ k_spmm_panel(SpmmArgs a, const float* __restrict__ panels, const PanelItem* __re
 
 template <int EPI>
 __global__ void __launch_bounds__(256) k_panel_finish(SpmmArgs a, const double2* __restrict__ ypart, int nslots) {
+    SGV_LOAD_DEV_SCALARS(a);
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     __shared__ double red[2 * 32];
     double dots[2] = {0.0, 0.0};
@@ -323,6 +325,7 @@ template <int EPI>
 __global__ void __launch_bounds__(256)
 k_spmm_csr(SpmmArgs a, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
            const float* __restrict__ vals) {
+    SGV_LOAD_DEV_SCALARS(a);
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     __shared__ double red[2 * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -456,6 +459,7 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, doub
                     int fused_p) {
     SpmmArgs a;
     memset(&a, 0, sizeof(a));
+    a.vs_cohort = c->vs_active;   // >= 0 inside the fused VAMP iteration: gamw / gam2 come from the device
     a.v = vec == VEC_XX ? c->xx : c->pp[vec - VEC_PP0];
     a.fused_p = fused_p;
     if (fused_p) {

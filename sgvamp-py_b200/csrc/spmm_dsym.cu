@@ -299,6 +299,7 @@ template <int EPI>
 __global__ void __launch_bounds__(256)
 k_dsym_finish(SpmmArgs a, const double2* __restrict__ ypart, const double2* __restrict__ tails, int Dp, int TR, int64_t E,
               const double2* __restrict__ vin) {
+    SGV_LOAD_DEV_SCALARS(a);
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     constexpr int NV = EPI == EPI_CG ? 8 : 2;
     __shared__ double red[NV * 32];
@@ -450,6 +451,7 @@ int sgv_launch_dsym_cg(sgv_ctx* c, Cohort& co, int n, double gamw, double gam2) 
     const int prev = (n + 1) & 1, cur = n & 1;
     SpmmArgs a;
     memset(&a, 0, sizeof(a));
+    a.vs_cohort = c->vs_active;   // >= 0 inside the fused VAMP iteration: gamw / gam2 come from the device
     a.v = c->pp[prev];
     a.r = c->rr2[prev];
     a.q = c->qq2[prev];
@@ -509,6 +511,7 @@ int sgv_launch_dsym_solve(sgv_ctx* c, Cohort& co, double gamw, double gam2, int 
     SGV_CHECK(sgv_dsymp_solve_usable(c, ld), "whole-solve kernel not usable for this cohort");
     SpmmArgs a;
     memset(&a, 0, sizeof(a));
+    a.vs_cohort = c->vs_active;   // >= 0 inside the fused VAMP iteration: gamw / gam2 come from the device
     a.x = c->xx;
     a.bb = c->bb;
     a.gamw = gamw;

@@ -87,6 +87,7 @@ size_t sgv_dsymp_smem_bytes(int64_t w, int rw, int s, int nst) {
 template <int RW, int S, int NST, bool CG, bool SOLVE>
 __global__ void __launch_bounds__(32 * RW * S, 2)
 k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
+    SGV_LOAD_DEV_SCALARS(a);
     static_assert(S >= 4 && (NST & (NST - 1)) == 0, "one new window entry per thread; ring depth a power of two");
     static_assert(CG || !SOLVE, "whole-solve mode is the CG instantiation");
     if (!SOLVE && a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;

@@ -207,6 +207,7 @@ k_spmm_psym(SpmmArgs a, const float* __restrict__ panels, const SymItem* __restr
 template <int EPI>
 __global__ void __launch_bounds__(256)
 k_psym_finish(SpmmArgs a, const double2* __restrict__ ypart, const double2* __restrict__ ypartT, const int* __restrict__ rowmeta) {
+    SGV_LOAD_DEV_SCALARS(a);
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     __shared__ double red[2 * 32];
     double dots[2] = {0.0, 0.0};

@@ -33,10 +33,35 @@ struct DenoiseConsts {
     double one_minus_lam;
 };
 
+// the same constants from the device-resident scalar chain (fused VAMP iteration): gam1s from CgState::vs, the prior
+// from CgState::em; separately rounded operations in fill_denoise_consts' order
+__device__ void dev_denoise_consts(const CgState* st, DenoiseConsts& k) {
+    const VampScal& v = st->vs;
+    k.K = v.K;
+    k.Lm1 = v.Lm1;
+    double W = 0.0;
+    for (int q = 0; q < v.K; ++q) {
+        k.w[q] = __dmul_rn(v.a[q], v.gam1[q]);
+        W = __dadd_rn(W, k.w[q]);
+    }
+    for (int l = 0; l < v.Lm1; ++l) {
+        k.s2[l] = __ddiv_rn(1.0, __dadd_rn(W, __ddiv_rn(1.0, v.sigmas[l])));
+        k.sq[l] = sqrt(__ddiv_rn(k.s2[l], v.sigmas[l]));
+        k.lw[l] = __dmul_rn(st->em.lam, st->em.omegas[l]);
+    }
+    k.one_minus_lam = __dsub_rn(1.0, st->em.lam);
+}
+
 __global__ void __launch_bounds__(256)
-k_denoise(int64_t M, const double* __restrict__ r1_all, double* __restrict__ xhat1, DenoiseConsts k, double rho,
-          int damp, RedCtx rc) {
+k_denoise(int64_t M, const double* __restrict__ r1_all, double* __restrict__ xhat1, DenoiseConsts kval, double rho,
+          int damp, RedCtx rc, int dev) {
     __shared__ double red[32];
+    __shared__ DenoiseConsts k;
+    if (threadIdx.x == 0) {
+        if (dev) dev_denoise_consts(rc.st, k);
+        else k = kval;
+    }
+    __syncthreads();
     double dsum[1] = {0.0};
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
         double sw = 0.0;
@@ -93,7 +118,7 @@ extern "C" int sgv_denoise(sgv_handle c, const double* gam1s, double rho, int da
     const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 8);
     SGV_TRY(sgv_ensure_partials(c, grid));
     RedCtx rc = sgv_red_begin(c, AP_STATS, 1, 0);
-    k_denoise<<<grid, 256, 0, c->stream>>>(c->Ml, c->r1_all, c->xhat1, k, rho, damp, rc);
+    k_denoise<<<grid, 256, 0, c->stream>>>(c->Ml, c->r1_all, c->xhat1, k, rho, damp, rc, 0);
     c->launches++;
     SGV_CUDA(cudaGetLastError());
     SGV_TRY(sgv_red_end(c, rc));
@@ -160,6 +185,32 @@ k_em(int64_t M, const double* __restrict__ r1_all, EmConsts k, RedCtx rc) {
     grid_reduce<16>(acc, rc, red);
 }
 
+__device__ void dev_em_consts(const CgState* st, EmConsts& k) {
+    const VampScal& v = st->vs;
+    k.K = v.K;
+    k.Lm1 = v.Lm1;
+    for (int q = 0; q < v.K; ++q) {
+        const double ginv = __ddiv_rn(1.0, v.gam1[q]);
+        k.a[q] = v.a[q];
+        k.mhg[q] = __dmul_rn(-0.5, v.gam1[q]);
+        k.sqg[q] = __ddiv_rn(1.0, sqrt(ginv));
+        for (int l = 0; l < v.Lm1; ++l) {
+            k.ce[q][l] = __ddiv_rn(-0.5, __dadd_rn(v.sigmas[l], ginv));
+            k.isq[q][l] = __ddiv_rn(1.0, sqrt(__dadd_rn(ginv, v.sigmas[l])));
+        }
+    }
+}
+
+// start of a prior update inside the fused iteration: loop state reset, lam / omegas stay where the last update left them
+__global__ void k_em_begin(CgState* st, int maxit, double tol) {
+    EmState& e = st->em;
+    e.steps = 0;
+    e.maxit = maxit;
+    e.tol = tol;
+    e.relerr = 0.0;
+    e.done = maxit <= 0;
+}
+
 // The whole EM loop in ONE persistent (cooperative) kernel: per pass every block sums its markers, a grid
 // barrier, block 0 adds the block partials in index order, completes the reduction across ranks (LL inbox)
 // and applies the update + convergence test (AP_EM), a second grid barrier, next pass.  No kernel launch, no
@@ -181,8 +232,15 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
 }
 
 __global__ void __launch_bounds__(256)
-k_em_loop(int64_t M, const double* __restrict__ r1_all, EmConsts k, RedCtx rc, unsigned* __restrict__ bar, int maxit) {
+k_em_loop(int64_t M, const double* __restrict__ r1_all, EmConsts kval, RedCtx rc, unsigned* __restrict__ bar, int maxit,
+          int dev) {
     __shared__ double red[16 * 32];
+    __shared__ EmConsts k;
+    if (threadIdx.x == 0) {
+        if (dev) dev_em_consts(rc.st, k);
+        else k = kval;
+    }
+    __syncthreads();
     const volatile EmState* em = &rc.st->em;
     const unsigned nblk = gridDim.x;
     unsigned epoch = 0;
@@ -305,8 +363,8 @@ extern "C" int sgv_prior_em(sgv_handle c, const double* gam1s, int maxit, double
         RedCtx rc = sgv_red_begin(c, AP_EM, 16, 0);   // sequence number of pass 0; pass i uses seq + i
         int64_t Ml = c->Ml;
         const double* r1 = c->r1_all;
-        int mi = maxit;
-        void* args[] = {&Ml, &r1, &k, &rc, &bar, &mi};
+        int mi = maxit, dev0 = 0;
+        void* args[] = {&Ml, &r1, &k, &rc, &bar, &mi, &dev0};
         SGV_CUDA(cudaLaunchCooperativeKernel((const void*)k_em_loop, dim3(lgrid), dim3(256), args, 0, c->stream));
         c->launches++;
         SGV_TRY(fetch_state(c));
@@ -495,8 +553,13 @@ k_lmmse_setup(int64_t M, const double* __restrict__ xhat1, const double* __restr
               const double* __restrict__ xty, const int8_t* __restrict__ probe, const double* __restrict__ xhat2,
               const double* __restrict__ sig, const double2* __restrict__ rxs, double* __restrict__ r2,
               double2* __restrict__ bb, double2* __restrict__ xx, double2* __restrict__ rr, double alpha1, double gamw,
-              double gam2, int x0_zero, RedCtx rc) {
+              double gam2, int x0_zero, RedCtx rc, int vs_cohort) {
     __shared__ double red[4 * 32];
+    if (vs_cohort >= 0) {   // fused iteration: the denoiser's finaliser left alpha1 / gam2 on the device
+        alpha1 = rc.st->vs.alpha1[vs_cohort];
+        gamw = rc.st->vs.gamw[vs_cohort];
+        gam2 = rc.st->vs.gam2[vs_cohort];
+    }
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
         const double r2j = (xhat1[j] - alpha1 * r1[j]) / (1.0 - alpha1);
@@ -577,8 +640,12 @@ struct CgBufs {
 __global__ void __launch_bounds__(256)
 k_lmmse_post(int64_t M, double2* __restrict__ xx, CgBufs cb, const double2* __restrict__ bb,
              const double* __restrict__ xty, double* __restrict__ xhat2, double* __restrict__ sig,
-             double2* __restrict__ rxs, double gamw, double gam2, double rho, int damp, RedCtx rc) {
+             double2* __restrict__ rxs, double gamw, double gam2, double rho, int damp, RedCtx rc, int vs_cohort) {
     __shared__ double red[4 * 32];
+    if (vs_cohort >= 0) {
+        gamw = rc.st->vs.gamw[vs_cohort];
+        gam2 = rc.st->vs.gam2[vs_cohort];
+    }
     const int z0 = rc.st->zero_b[0], z1 = rc.st->zero_b[1];
     const double igw = 1.0 / gamw;
     const int step = rc.st->step;
@@ -633,7 +700,8 @@ k_pack_x0(int64_t M, const double* __restrict__ xhat2, const double* __restrict_
 
 __global__ void __launch_bounds__(256)
 k_update_r1(int64_t M, const double* __restrict__ xhat2, const double* __restrict__ r2, double* __restrict__ r1,
-            double alpha2) {
+            double alpha2, const CgState* __restrict__ st, int vs_cohort) {
+    if (vs_cohort >= 0) alpha2 = st->vs.alpha2[vs_cohort];
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x)
         r1[j] = (xhat2[j] - alpha2 * r2[j]) / (1.0 - alpha2);                       // :348
 }
@@ -643,7 +711,7 @@ extern "C" int sgv_update_r1(sgv_handle c, int cohort, double alpha2) {
     SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
     Cohort& co = c->coh[cohort];
     const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 8);
-    k_update_r1<<<grid, 256, 0, c->stream>>>(c->Ml, co.xhat2, co.r2, co.r1, alpha2);
+    k_update_r1<<<grid, 256, 0, c->stream>>>(c->Ml, co.xhat2, co.r2, co.r1, alpha2, c->cg, -1);
     c->launches++;
     SGV_CUDA(cudaGetLastError());
     return 0;
@@ -663,27 +731,31 @@ int sgv_preload_vamp() {
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_update_r1));
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_pack_x0));
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_em_loop));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_em_begin));
     return 0;
 }
 
-extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const int8_t* probe, sgv_lmmse_out* out) {
-    SGV_TRY(check_ready(c));
-    SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
-    SGV_CHECK(in && probe && out, "null argument");
+// The LMMSE step of one cohort, enqueued on the handle's stream.  dev == false: scalars by value (reference-style
+// stepwise API), the caller reads the state back afterwards.  dev == true (fused iteration): alpha1 / gamw / gam2 are read
+// from the device-resident chain, the post kernel's finaliser advances it (AP_POST) and nothing is read back here -
+// except by layouts whose CG loop is enqueued in batches (every layout but the whole-solve half-band kernel).
+static int lmmse_enqueue(sgv_ctx* c, int cohort, const sgv_lmmse_in* in, bool dev, int it, int* passes_out) {
     Cohort& co = c->coh[cohort];
     SGV_CHECK(co.ld.layout != 0, "cohort %d has no LD matrix", cohort);
     const int64_t M = c->Ml;
+    const int vsc = dev ? cohort : -1;
+    c->vs_active = vsc;
     const bool fused = co.ld.layout == SGV_LAYOUT_DIA;     // direction update fused into the SpMM staging
-    const bool fusedcg = co.ld.layout == SGV_LAYOUT_DSYM;  // whole CG step in one kernel   // direction update fused into the SpMM staging
+    const bool fusedcg = co.ld.layout == SGV_LAYOUT_DSYM;  // whole CG step in one kernel
     const unsigned vgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 8);
     SGV_TRY(sgv_ensure_partials(c, vgrid + 1));
-    SGV_CUDA(cudaMemcpyAsync(co.probe, probe, M, cudaMemcpyHostToDevice, c->stream));
     int passes = 0;
     if (in->x0_zero && !co.rxs_valid) {    // the caller states x0 = 0: so is R x0
         SGV_CUDA(cudaMemsetAsync(co.rxs, 0, (size_t)M * sizeof(double2), c->stream));
         co.rxs_valid = true;
     }
     if (!in->x0_zero && !co.rxs_valid) {   // injected warm start: R x0 by a real pass
+        c->vs_active = -1;                  // plain product: alpha = 1, beta = 0 by value
         RedCtx rc = sgv_red_begin(c, AP_STATS, 1, 15);
         k_pack_x0<<<vgrid, 256, 0, c->stream>>>(M, co.xhat2, co.sig, c->xx, rc);
         c->launches++;
@@ -697,22 +769,29 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
         }
         co.rxs_valid = true;
         passes++;
+        c->vs_active = vsc;
     }
     {   // b, x0, r = b - A x0 (no matrix pass: R x0 is kept from the previous solve), |b|^2, r.r, loop-top test of iteration 0
         RedCtx rc = sgv_red_begin(c, AP_SETUP, 4, 0, in->cg_maxit, in->x0_zero);
         k_lmmse_setup<<<vgrid, 256, 0, c->stream>>>(M, c->xhat1, co.r1, co.xty, co.probe, co.xhat2, co.sig, co.rxs, co.r2,
-                                                   c->bb, c->xx, c->rr, in->alpha1, in->gamw, in->gam2, in->x0_zero, rc);
+                                                   c->bb, c->xx, c->rr, in->alpha1, in->gamw, in->gam2, in->x0_zero, rc, vsc);
         c->launches++;
         SGV_TRY(sgv_red_end(c, rc));
     }
     int launched = 0;
     int batch = co.last_cg_iters > 0 ? co.last_cg_iters + 2 : 4;   // see sgv_prior_em: counts drift slowly
     CgState* hs = c->cg_host;
+    bool state_fetched = false;
     if (fusedcg && in->cg_maxit > 0 && sgv_dsymp_solve_usable(c, co.ld)) {
         // the whole solve in one cooperative launch: steps separated by a grid barrier, not by launches
         SGV_TRY(sgv_launch_dsym_solve(c, co, in->gamw, in->gam2, in->cg_maxit));
-        SGV_TRY(fetch_state(c));
-        c->seq += (unsigned long long)std::max(hs->step - 1, 0);   // step n used sequence number seq0 + n
+        if (dev) {
+            c->seq += (unsigned long long)(in->cg_maxit - 1);          // step n uses sequence number seq0 + n; the count
+        } else {                                                        // that ran is not known here (no read-back)
+            SGV_TRY(fetch_state(c));
+            state_fetched = true;
+            c->seq += (unsigned long long)std::max(hs->step - 1, 0);
+        }
         launched = in->cg_maxit;
     }
     while (launched < in->cg_maxit) {
@@ -741,19 +820,19 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
         }
         launched += nb;
         SGV_TRY(fetch_state(c));
+        state_fetched = true;
         if (hs->done[0] && hs->done[1]) break;
         batch = 8;
     }
-    if (in->cg_maxit == 0 || launched == 0) SGV_TRY(fetch_state(c));
-    out->cg_iters[0] = hs->iters[0];
-    out->cg_iters[1] = hs->iters[1];
-    co.last_cg_iters = std::max(hs->iters[0], hs->iters[1]);
-    // a column that ran out of iterations without ever passing the test reports maxiter (scipy)
-    out->cg_info[0] = hs->done[0] ? hs->info[0] : in->cg_maxit;
-    out->cg_info[1] = hs->done[1] ? hs->info[1] : in->cg_maxit;
-    passes += std::max(hs->iters[0], hs->iters[1]);
+    if (state_fetched) co.last_cg_iters = std::max(hs->iters[0], hs->iters[1]);
     {
-        RedCtx rc = sgv_red_begin(c, AP_STATS, 4, 0);
+        RedCtx rc = sgv_red_begin(c, dev ? AP_POST : AP_STATS, 4, 0);
+        rc.ap.cohort = cohort;
+        rc.ap.it = it;
+        rc.ap.lmmse_damp = in->lmmse_damp;
+        rc.ap.learn_gamw = in->learn_gamw;
+        rc.ap.rho = in->rho;
+        rc.ap.Mtot = (double)c->M;
         CgBufs cb;
         for (int i = 0; i < 2; ++i) {
             cb.rr[i] = c->rr2[i];
@@ -762,17 +841,227 @@ extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const
         }
         cb.fusedcg = fusedcg;
         k_lmmse_post<<<vgrid, 256, 0, c->stream>>>(M, c->xx, cb, c->bb, co.xty, co.xhat2, co.sig, co.rxs, in->gamw, in->gam2,
-                                                  in->rho, in->lmmse_damp, rc);
+                                                  in->rho, in->lmmse_damp, rc, vsc);
         c->launches++;
         SGV_TRY(sgv_red_end(c, rc));
     }
     co.rxs_valid = true;
+    c->vs_active = -1;
     SGV_CUDA(cudaGetLastError());
+    if (passes_out) *passes_out = passes;
+    return 0;
+}
+
+extern "C" int sgv_lmmse(sgv_handle c, int cohort, const sgv_lmmse_in* in, const int8_t* probe, sgv_lmmse_out* out) {
+    SGV_TRY(check_ready(c));
+    SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
+    SGV_CHECK(in && probe && out, "null argument");
+    Cohort& co = c->coh[cohort];
+    SGV_CUDA(cudaMemcpyAsync(co.probe, probe, c->Ml, cudaMemcpyHostToDevice, c->stream));
+    int passes = 0;
+    SGV_TRY(lmmse_enqueue(c, cohort, in, false, 0, &passes));
     SGV_TRY(fetch_state(c));
+    CgState* hs = c->cg_host;
+    out->cg_iters[0] = hs->iters[0];
+    out->cg_iters[1] = hs->iters[1];
+    co.last_cg_iters = std::max(hs->iters[0], hs->iters[1]);
+    // a column that ran out of iterations without ever passing the test reports maxiter (scipy)
+    out->cg_info[0] = hs->done[0] ? hs->info[0] : in->cg_maxit;
+    out->cg_info[1] = hs->done[1] ? hs->info[1] : in->cg_maxit;
+    passes += std::max(hs->iters[0], hs->iters[1]);
     out->u_sigma2u = hs->stats[0];
     out->xhat2_r = hs->stats[1];
     out->xhat2_R_xhat2 = hs->stats[2];      // (:352,:359) - no extra matrix pass, see k_lmmse_post
     out->u_R_sigma2u = hs->stats[3];
     out->spmm_passes = passes;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused VAMP iteration (src/sgvamp.py:222-387 for all cohorts of this process): prior update (EM), denoiser, the
+// LMMSE step of every cohort, r1 update, metrics - enqueued without a host round trip; the scalar chain
+// (alpha1, gam2, alpha2, gam1, gamw) advances on the device in the kernels' finalisers.  The host reads ONE small
+// record per iteration (sgv_iteration_wait) and may enqueue the next iteration before it does.
+// ---------------------------------------------------------------------------------------------
+extern "C" int sgv_iteration_supported(sgv_handle c) {
+    if (c == nullptr) return 0;
+    return c->coop_ok && !(c->world > 1 && c->host_barrier) ? 1 : 0;
+}
+
+extern "C" int sgv_vamp_begin(sgv_handle c, const double* gam1, const double* gamw, const double* N) {
+    SGV_TRY(check_ready(c));
+    SGV_CHECK(gam1 && gamw && N, "null argument");
+    const PriorParams& p = c->prior;
+    SGV_CHECK(p.L >= 2, "prior not set");
+    SGV_CHECK(sgv_iteration_supported(c), "fused iteration needs cooperative launches and one GPU per rank");
+    for (int i = 0; i < sgv_ctx::NLOG; ++i) {
+        if (c->log_host[i] == nullptr) {
+            SGV_CUDA(cudaMallocHost(&c->log_host[i], sizeof(IterLog)));
+            SGV_CUDA(cudaEventCreateWithFlags(&c->log_ev[i], cudaEventDisableTiming));
+        }
+    }
+    const int64_t pbytes = (int64_t)c->K * c->Ml;
+    if (c->probe_pin_bytes < pbytes) {
+        for (int i = 0; i < sgv_ctx::NLOG; ++i) {
+            if (c->probe_pin[i]) cudaFreeHost(c->probe_pin[i]);
+            c->probe_pin[i] = nullptr;
+            SGV_CUDA(cudaMallocHost(&c->probe_pin[i], pbytes));
+        }
+        c->probe_pin_bytes = pbytes;
+    }
+    CgState* hs = c->cg_host;
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    memset(&hs->vs, 0, sizeof(VampScal));
+    memset(&hs->em, 0, sizeof(EmState));
+    hs->vs.K = p.K;
+    hs->vs.Lm1 = p.L - 1;
+    hs->em.K = p.K;
+    hs->em.Lm1 = p.L - 1;
+    hs->em.lam = p.lam;
+    hs->em.Mtot = (double)c->M;
+    for (int l = 0; l < p.L - 1; ++l) {
+        hs->vs.sigmas[l] = p.sigmas[l];
+        hs->em.omegas[l] = p.omegas[l];
+    }
+    for (int k = 0; k < p.K; ++k) {
+        hs->vs.gam1[k] = gam1[k];
+        hs->vs.gamw[k] = gamw[k];
+        hs->vs.a[k] = p.a[k];
+        hs->vs.N[k] = N[k];
+        hs->em.a[k] = p.a[k];
+        hs->em.asum += p.a[k];
+    }
+    SGV_CUDA(cudaMemcpyAsync(&c->cg->vs, &hs->vs, sizeof(VampScal), cudaMemcpyHostToDevice, c->stream));
+    SGV_CUDA(cudaMemcpyAsync(&c->cg->em, &hs->em, sizeof(EmState), cudaMemcpyHostToDevice, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    c->vamp_begun = true;
+    return 0;
+}
+
+extern "C" int sgv_set_truth(sgv_handle c, const double* x0) {
+    SGV_TRY(check_ready(c));
+    SGV_CHECK(x0 != nullptr, "null argument");
+    SGV_CUDA(cudaMemcpyAsync(c->truth, x0, c->Ml * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    c->truth_set = true;
+    return 0;
+}
+
+extern "C" int sgv_iteration_probe_buffer(sgv_handle c, int slot, int8_t** buf) {
+    SGV_CHECK(c != nullptr && buf != nullptr && slot >= 0 && slot < sgv_ctx::NLOG, "bad arguments");
+    SGV_CHECK(c->vamp_begun && c->probe_pin[slot] != nullptr, "sgv_vamp_begin has not been called");
+    *buf = c->probe_pin[slot];
+    return 0;
+}
+
+extern "C" int sgv_iteration_enqueue(sgv_handle c, const sgv_iter_in* in, double* xhat_pinned, double* const* r1_pinned,
+                                     int slot) {
+    SGV_TRY(check_ready(c));
+    SGV_CHECK(in != nullptr && slot >= 0 && slot < sgv_ctx::NLOG, "bad arguments");
+    SGV_CHECK(c->vamp_begun, "sgv_vamp_begin has not been called");
+    const int K = c->K;
+    const int64_t M = c->Ml;
+    const unsigned vgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 8);
+    // ---- prior update: EM loop on the device (src/sgvamp.py:250-257); lam / omegas stay in CgState::em
+    if (in->update_prior && in->em_maxit > 0) {
+        if (c->em_loop_blocks_per_sm == 0) {
+            int nb = 0;
+            SGV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_loop, 256, 0));
+            c->em_loop_blocks_per_sm = std::max(1, std::min(nb, 4));
+        }
+        const unsigned lgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * c->em_loop_blocks_per_sm);
+        SGV_TRY(sgv_ensure_partials(c, lgrid + 1));
+        k_em_begin<<<1, 1, 0, c->stream>>>(c->cg, in->em_maxit, in->em_tol);
+        c->launches++;
+        unsigned* bar = c->counter + 4;
+        SGV_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), c->stream));
+        RedCtx rc = sgv_red_begin(c, AP_EM, 16, 0);
+        c->seq += (unsigned long long)(in->em_maxit - 1);          // pass i uses sequence number seq0 + i
+        int64_t Ml = M;
+        const double* r1 = c->r1_all;
+        EmConsts kdummy;
+        memset(&kdummy, 0, sizeof(kdummy));
+        int mi = in->em_maxit, dev1 = 1;
+        void* args[] = {&Ml, &r1, &kdummy, &rc, &bar, &mi, &dev1};
+        SGV_CUDA(cudaLaunchCooperativeKernel((const void*)k_em_loop, dim3(lgrid), dim3(256), args, 0, c->stream));
+        c->launches++;
+    } else {
+        k_em_begin<<<1, 1, 0, c->stream>>>(c->cg, 0, 0.0);          // steps = 0 for the log
+        c->launches++;
+    }
+    // ---- denoiser + derivative + damping (:270-293); its finaliser sets alpha1 / gam2 of every cohort
+    {
+        const unsigned grid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 8);
+        SGV_TRY(sgv_ensure_partials(c, grid));
+        RedCtx rc = sgv_red_begin(c, AP_DENOISE, 1, 0);
+        rc.ap.it = in->it;
+        rc.ap.rho = in->rho;
+        rc.ap.Mtot = (double)c->M;
+        DenoiseConsts kdummy;
+        memset(&kdummy, 0, sizeof(kdummy));
+        k_denoise<<<grid, 256, 0, c->stream>>>(M, c->r1_all, c->xhat1, kdummy, in->rho, in->it > 0, rc, 1);
+        c->launches++;
+        SGV_CUDA(cudaGetLastError());
+        SGV_TRY(sgv_red_end(c, rc));
+    }
+    // ---- output snapshots (the xhat1 of this iteration, the r1 that entered it: :280-283)
+    if (xhat_pinned) SGV_TRY(sgv_get_vec_async(c, 0, SGV_VEC_XHAT1, 1.0, xhat_pinned));
+    if (r1_pinned)
+        for (int k = 0; k < K; ++k)
+            if (r1_pinned[k]) SGV_TRY(sgv_get_vec_async(c, k, SGV_VEC_R1, 1.0, r1_pinned[k]));
+    // ---- LMMSE + Hutchinson + gamw + r1 update, cohort by cohort (:301-374)
+    for (int k = 0; k < K; ++k) {
+        Cohort& co = c->coh[k];
+        SGV_CUDA(cudaMemcpyAsync(co.probe, c->probe_pin[slot] + (size_t)k * M, M, cudaMemcpyHostToDevice, c->stream));
+        sgv_lmmse_in li;
+        memset(&li, 0, sizeof(li));
+        li.rho = in->rho;
+        li.cg_maxit = in->cg_maxit;
+        li.lmmse_damp = in->lmmse_damp;
+        li.learn_gamw = in->learn_gamw;
+        li.x0_zero = in->it == 0;
+        SGV_TRY(lmmse_enqueue(c, k, &li, true, in->it, nullptr));
+        k_update_r1<<<vgrid, 256, 0, c->stream>>>(M, co.xhat2, co.r2, co.r1, 0.0, c->cg, k);
+        c->launches++;
+    }
+    // ---- metrics vs truth (:379-387)
+    if (in->want_metrics) {
+        SGV_CHECK(c->truth_set, "truth vector not uploaded (sgv_set_truth)");
+        const unsigned grid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 4);
+        SGV_TRY(sgv_ensure_partials(c, grid + 1));
+        RedCtx rc = sgv_red_begin(c, AP_METRICS, 4, 0);
+        k_metrics<<<grid, 256, 0, c->stream>>>(M, c->xhat1, c->truth, rc);
+        c->launches++;
+        SGV_TRY(sgv_red_end(c, rc));
+    }
+    SGV_CUDA(cudaGetLastError());
+    SGV_CUDA(cudaMemcpyAsync(c->log_host[slot], &c->cg->log, sizeof(IterLog), cudaMemcpyDeviceToHost, c->stream));
+    SGV_CUDA(cudaEventRecord(c->log_ev[slot], c->stream));
+    return 0;
+}
+
+extern "C" int sgv_iteration_wait(sgv_handle c, int slot, sgv_iter_out* out) {
+    SGV_CHECK(c != nullptr && out != nullptr && slot >= 0 && slot < sgv_ctx::NLOG, "bad arguments");
+    SGV_CUDA(cudaSetDevice(c->device));
+    SGV_CUDA(cudaEventSynchronize(c->log_ev[slot]));
+    const IterLog* L = c->log_host[slot];
+    SGV_CHECK(L->error == 0, "cross-rank reduction timed out on rank %d of %d (mask 0x%x)", c->rank, c->world, L->error);
+    memset(out, 0, sizeof(*out));
+    out->lam = L->lam;
+    out->em_steps = L->em_steps;
+    out->em_relerr = L->em_relerr;
+    for (int l = 0; l < SGV_MAX_L; ++l) out->omegas[l] = L->omegas[l];
+    for (int i = 0; i < 4; ++i) out->metrics[i] = L->metrics[i];
+    for (int k = 0; k < c->K; ++k) {
+        for (int j = 0; j < 7; ++j) out->coh[k].row[j] = L->row[k][j];
+        for (int j = 0; j < 2; ++j) {
+            out->coh[k].cg_iters[j] = L->cg_iters[k][j];
+            out->coh[k].cg_info[j] = L->cg_info[k][j];
+        }
+        out->coh[k].spmm_passes = L->passes[k];
+    }
+    // keep the host copy of the prior in step (the stepwise entry points read it)
+    c->prior.lam = L->lam;
+    for (int l = 0; l < c->prior.L - 1; ++l) c->prior.omegas[l] = L->omegas[l];
     return 0;
 }

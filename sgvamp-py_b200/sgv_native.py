@@ -28,7 +28,10 @@ SYMBOLS = [
     "sgv_launch_count", "sgv_profile", "sgv_profile_read", "sgv_configure_part", "sgv_ipc_export", "sgv_ipc_import",
     "sgv_peer_attach_local", "sgv_partition_info", "sgv_ld_set_bandwidth_hint", "sgv_spmm_stage", "sgv_spmm_run",
     "sgv_ld_adopt_dsym", "sgv_dsym_extension", "sgv_set_host_barrier", "sgv_device_id", "sgv_ld_upload_dia",
+    "sgv_iteration_supported", "sgv_vamp_begin", "sgv_set_truth", "sgv_iteration_probe_buffer", "sgv_iteration_enqueue",
+    "sgv_iteration_wait",
 ]
+MAX_K, MAX_L, ITER_SLOTS = 8, 8, 4
 
 
 class LmmseIn(C.Structure):
@@ -40,6 +43,21 @@ class LmmseOut(C.Structure):
     _fields_ = [("u_sigma2u", C.c_double), ("xhat2_r", C.c_double), ("xhat2_R_xhat2", C.c_double),
                 ("u_R_sigma2u", C.c_double), ("cg_iters", C.c_int * 2), ("cg_info", C.c_int * 2),
                 ("spmm_passes", C.c_int)]
+
+
+class IterIn(C.Structure):
+    _fields_ = [("it", C.c_int), ("update_prior", C.c_int), ("em_maxit", C.c_int), ("em_tol", C.c_double),
+                ("rho", C.c_double), ("cg_maxit", C.c_int), ("lmmse_damp", C.c_int), ("learn_gamw", C.c_int),
+                ("want_metrics", C.c_int)]
+
+
+class IterCohort(C.Structure):
+    _fields_ = [("row", C.c_double * 7), ("cg_iters", C.c_int * 2), ("cg_info", C.c_int * 2), ("spmm_passes", C.c_int)]
+
+
+class IterOut(C.Structure):
+    _fields_ = [("lam", C.c_double), ("omegas", C.c_double * MAX_L), ("em_relerr", C.c_double), ("metrics", C.c_double * 4),
+                ("em_steps", C.c_int), ("coh", IterCohort * MAX_K)]
 
 
 class SgvError(RuntimeError):
@@ -284,6 +302,45 @@ class Handle:
         p = _dp(_f64(x0).ravel()) if x0 is not None else None
         self._ck(self.lib.sgv_metrics(self.h, p, _dp(d)))
         return d
+
+    # -- fused VAMP iteration (device-resident scalar chain) -------------------------------------
+    def iteration_supported(self):
+        return bool(self.lib.sgv_iteration_supported(self.h))
+
+    def vamp_begin(self, gam1, gamw, N):
+        g1, gw, n = _f64(gam1), _f64(gamw), _f64(N)
+        assert g1.shape[0] == gw.shape[0] == n.shape[0] == self.K
+        self._ck(self.lib.sgv_vamp_begin(self.h, _dp(g1), _dp(gw), _dp(n)))
+
+    def set_truth(self, x0):
+        x0 = _f64(x0).ravel()
+        assert x0.shape[0] == self.M
+        self._ck(self.lib.sgv_set_truth(self.h, _dp(x0)))
+
+    def iteration_probe_buffer(self, slot):
+        """The pinned (K, local rows) int8 staging buffer of a slot: write the iteration's probes into it."""
+        p = C.POINTER(C.c_int8)()
+        self._ck(self.lib.sgv_iteration_probe_buffer(self.h, C.c_int(slot), C.byref(p)))
+        n = self.K * self.M
+        return np.ctypeslib.as_array(p, shape=(n,)).reshape(self.K, self.M)
+
+    def iteration_enqueue(self, it, update_prior, em_maxit, em_tol, rho, cg_maxit, lmmse_damp, learn_gamw, want_metrics,
+                          xhat_pinned, r1_pinned, slot):
+        pin = IterIn(int(it), int(bool(update_prior)), int(em_maxit), float(em_tol), float(rho), int(cg_maxit),
+                     int(bool(lmmse_damp)), int(bool(learn_gamw)), int(bool(want_metrics)))
+        xp = _dp(xhat_pinned) if xhat_pinned is not None else None
+        rp = None
+        if r1_pinned is not None:
+            arr = (C.POINTER(C.c_double) * self.K)()
+            for k in range(self.K):
+                arr[k] = _dp(r1_pinned[k]) if r1_pinned[k] is not None else None
+            rp = arr
+        self._ck(self.lib.sgv_iteration_enqueue(self.h, C.byref(pin), xp, rp, C.c_int(slot)))
+
+    def iteration_wait(self, slot):
+        out = IterOut()
+        self._ck(self.lib.sgv_iteration_wait(self.h, C.c_int(slot), C.byref(out)))
+        return out
 
     # -- hooks ---------------------------------------------------------------------------------
     def spmm(self, cohort, X, alpha=1.0, beta=0.0):

@@ -408,6 +408,10 @@ class VAMP:
                 raise Exception("no LD matrix for cohort %d" % k)
             h.set_xty(k, self._local(rs[idx]))
         h.reset_state()                                                 # :199-217
+        if (not self.rank_mode and prior_update != "mle" and h.iteration_supported()
+                and os.environ.get("SGV_STEPWISE", "0") != "1"):
+            return self._infer_fused(rs, Ns, iterations, x0, cg_maxit, em_prior_maxit, learn_gamw, lmmse_damp,
+                                     prior_update, update_prior_from, probes, write_outputs, iter_hook, gather_outputs)
         write = write_outputs and self.out_dir is not None
         sharded = self.shard.world > 1
         r1_keep = {}
@@ -582,6 +586,150 @@ class VAMP:
                         self.write_xhat_to_file(it, xhat1s[it] / sqrtNt)
                         for idx, k in enumerate(mine):
                             self.write_r1_to_file(it, r1_full[it, idx] / sqrtNt, k + 1)
+        return xhat1s
+
+    def _infer_fused(self, rs, Ns, iterations, x0, cg_maxit, em_prior_maxit, learn_gamw, lmmse_damp, prior_update,
+                     update_prior_from, probes, write_outputs, iter_hook, gather_outputs):
+        """The same loop with the scalar chain on the device (sgv_iteration_*): one VAMP iteration is enqueued without a
+        host round trip and the host reads one small record per iteration, one iteration behind the GPU.  Used whenever
+        the prior update does not need the host (EM or none) and this process drives all cohorts."""
+        M, K, Nt, rho = self.M, self.K, self.Nt, self.rho
+        h = self.handle
+        rank = self.shard.rank
+        mine = self.my_cohorts
+        write = write_outputs and self.out_dir is not None
+        sharded = self.shard.world > 1
+        sqrtNt = np.sqrt(Nt)
+        NS = nat.ITER_SLOTS
+        worker = _Worker()
+        tm = self.timers = dict(enqueue=0.0, wait=0.0, host_tail=0.0)
+        pc = time.perf_counter
+        probe_src = None
+        if probes is None:
+            probe_src = _ProbeSource([(it, k) for it in range(iterations) for k in mine], M)
+        self._push_prior()
+        h.vamp_begin([self.gam1] * K, [self.gamw] * K, Ns)
+        truth = None
+        if x0 is not None:
+            truth = self._local(x0)
+            h.set_truth(truth)
+        xhat1s = [None] * iterations
+        r1_keep = {}
+        self.history = dict(rows=[], cg_iters=[], cg_info=[], em_steps=[], spmm_passes=[], lam=[], omegas=[])
+        pin_x = self._pinned_ring("x", NS, 1)
+        pin_r = self._pinned_ring("r", NS, K) if write else None
+        slot_done = [None] * NS
+        if rank == 0:
+            logging.debug(f"a = {self.a}")
+        h.sync()
+        self.shard.barrier()       # every rank's state is initialised before any kernel touches peer memory
+
+        def finish(it):
+            slot = it % NS
+            t0 = pc()
+            out = h.iteration_wait(slot)
+            tm["wait"] += pc() - t0
+            self.lam = out.lam
+            self.omegas = np.array(out.omegas[: self.L - 1], dtype=np.float64)
+            if rank == 0:
+                logging.info(f"\n -----ITERATION {it} -----")
+                if prior_update == "em" and it >= update_prior_from:
+                    logging.info(f"... prior-learning EM algorithm performed {out.em_steps} steps and had final relative error = {out.em_relerr:0.9f}")
+            rows_it, iters_it, info_it, passes_it = {}, {}, {}, 0
+            for k in mine:
+                ck = out.coh[k]
+                row = [it] + [np.float64(v) for v in ck.row[1:6]] + [float(ck.row[6])]
+                row[1] = float(row[1])
+                for c_ in range(2):
+                    if ck.cg_info[c_] > 0:
+                        logging.info(f"Rank {k} WARNING: CG {c_ + 1} convergence after {ck.cg_info[c_]} iterations not achieved!")
+                rows_it[k] = row
+                iters_it[k] = (ck.cg_iters[0], ck.cg_iters[1])
+                info_it[k] = (ck.cg_info[0], ck.cg_info[1])
+                passes_it += ck.spmm_passes
+                if write and self.root:
+                    self.write_params_to_file(row, k)                    # :377
+            if truth is not None:                                        # :379-387
+                d = out.metrics
+                alignment = d[0] / np.sqrt(d[1]) / np.sqrt(d[2])
+                l2 = np.sqrt(d[3]) / np.sqrt(d[2])
+                if rank == 0:
+                    logging.debug(f"Alignment(xhat1, x0) = {alignment:0.9f} \n")
+                    logging.debug(f"L2_error(xhat1, x0) = {l2:0.9f} \n")
+                    if write and self.root:
+                        self.write_metrics_to_file([it, alignment, l2])
+                self.history.setdefault("metrics", []).append((it, alignment, l2))
+            self.history["rows"].append(rows_it)
+            self.history["cg_iters"].append(iters_it)
+            self.history["cg_info"].append(info_it)
+            self.history["em_steps"].append(int(out.em_steps) if (prior_update == "em" and it >= update_prior_from) else 0)
+            self.history["spmm_passes"].append(passes_it)
+            self.history["lam"].append(float(self.lam))
+            self.history["omegas"].append(np.array(self.omegas, dtype=np.float64).copy())
+
+            def drain(it=it, slot=slot):
+                h.wait_copies()
+                xh = pin_x[slot][0].copy()
+                xhat1s[it] = xh.reshape(-1, 1)
+                if write and sharded:                                    # dumps are assembled after the loop
+                    r1_keep[it] = [pin_r[slot][k].copy() for k in range(K)]
+                elif write:
+                    (xh / sqrtNt).tofile(os.path.join(self.out_dir, "%s_xhat_it_%d.bin" % (self.out_name, it)))
+                    for k in mine:
+                        (pin_r[slot][k] / sqrtNt).tofile(
+                            os.path.join(self.out_dir, "%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k + 1, it)))
+
+            slot_done[slot] = worker.submit(drain)
+
+        for it in range(iterations):
+            if iter_hook is not None:
+                iter_hook(it)
+            t0 = pc()
+            slot = it % NS
+            if slot_done[slot] is not None:
+                slot_done[slot].wait()                                   # the worker has drained this slot's host buffers
+            pb = h.iteration_probe_buffer(slot)
+            for k in mine:
+                if probes is None:
+                    u = probe_src.get((it, k))                           # :326 (same RNG calls, same order)
+                elif callable(probes):
+                    u = probes(k, it, M)
+                else:
+                    u = np.asarray(probes)[k, it]
+                if sharded and len(u) == M:
+                    u = u[self.lo:self.hi]                               # every rank draws the same global probe
+                pb[k, :] = u
+            h.iteration_enqueue(it, prior_update == "em" and it >= update_prior_from, em_prior_maxit, 1e-6, rho, cg_maxit,
+                                lmmse_damp, learn_gamw, truth is not None, pin_x[slot][0],
+                                pin_r[slot] if write else None, slot)
+            tm["enqueue"] += pc() - t0
+            if it >= 1:
+                t1 = pc()
+                finish(it - 1)                                           # one iteration behind the GPU
+                tm["host_tail"] += pc() - t1
+        if iterations > 0:
+            finish(iterations - 1)
+        if iter_hook is not None:
+            iter_hook(iterations)
+        h.sync()
+        worker.close()
+        if iterations > 0:
+            last = self.history["rows"][-1]
+            self.gam1_final = [last[k][2] for k in mine]
+            self.gamw_final = [last[k][1] for k in mine]
+        if sharded and gather_outputs:
+            full = shd.gather_rows(self.shard, np.stack([x.ravel() for x in xhat1s]) if iterations else np.zeros((0, self.Ml)),
+                                   self.bounds)
+            xhat1s = [full[it].reshape(M, 1) for it in range(iterations)]
+            if write:
+                r1_full = shd.gather_rows(self.shard, np.array([[r1_keep[it][k] for k in range(K)]
+                                                                for it in range(iterations)]).reshape(iterations, K, self.Ml),
+                                          self.bounds)
+                if self.root:
+                    for it in range(iterations):
+                        self.write_xhat_to_file(it, xhat1s[it] / sqrtNt)
+                        for k in mine:
+                            self.write_r1_to_file(it, r1_full[it, k] / sqrtNt, k + 1)
         return xhat1s
 
     def _local(self, v):

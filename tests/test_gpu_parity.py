@@ -471,6 +471,26 @@ def test_trajectory_matches_reference(nat, name):
             assert rel_err(m[:n_check, 1:], c["metrics"][:n_check, 1:]) <= tol
 
 
+@pytest.mark.parametrize("name", ["banded_L2_em_s01", "dense_K3_L2_em", "dense_noprior_fixedgamw_damp", "blockdiag_L3_em_s01"])
+def test_stepwise_and_fused_loops_agree(nat, name, monkeypatch):
+    """VAMP.infer runs the loop either stepwise (scalars on the host, as the reference keeps them; always used for the
+    MLE prior update and the rank-per-cohort mode) or fused (scalar chain advanced on the device by the kernels'
+    finalisers with the reference's operation order): same trajectories, scalars equal to the last bits."""
+    c = load_case(name)
+    monkeypatch.setenv("SGV_STEPWISE", "1")
+    xs_s, hist_s, _, fin_s = run_gpu(c)
+    monkeypatch.delenv("SGV_STEPWISE")
+    xs_f, hist_f, _, fin_f = run_gpu(c)
+    n_check = c["iterations"] if name not in UNSTABLE else 3
+    for it in range(n_check):
+        assert rel_l2(xs_f[it], xs_s[it]) <= 1e-12, (name, it)
+        for k in range(c["K"]):
+            assert rel_err(hist_f["rows"][it][k][1:7], hist_s["rows"][it][k][1:7]) <= 1e-12, (name, it, k)
+            assert tuple(hist_f["cg_iters"][it][k]) == tuple(hist_s["cg_iters"][it][k])
+            assert tuple(hist_f["cg_info"][it][k]) == tuple(hist_s["cg_info"][it][k])
+        assert hist_f["em_steps"][it] == hist_s["em_steps"][it]
+
+
 @pytest.mark.parametrize("layout", ["csr", "dense", "dia"])
 def test_banded_case_other_layouts(nat, layout):
     c = load_case("banded_L2_em_s01")
