@@ -124,6 +124,16 @@ extern "C" int sgv_destroy(sgv_handle c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
+    if (c->dsp_dbg) {   // SGV_DS_DEBUG: where a CG step of the whole-solve kernel spends its time (range 0 / last CTA), per rank
+        unsigned long long d[16];
+        if (cudaMemcpy(d, c->dsp_dbg, sizeof(d), cudaMemcpyDeviceToHost) == cudaSuccess && d[7] > 0) {
+            const double n = (double)d[7];
+            fprintf(stderr, "[sgv solve clock] rank %d/%d steps %llu | us per step: stage %.1f tiles %.1f headfix %.1f wait(range0) %.1f | "
+                            "last CTA: reduce %.1f exchange %.1f\n", c->rank, c->world, d[7], d[0] / n / 1e3, d[1] / n / 1e3,
+                    d[2] / n / 1e3, d[3] / n / 1e3, d[4] / n / 1e3, d[5] / n / 1e3);
+        }
+        cudaFree(c->dsp_dbg);
+    }
     free_vectors(c);
     cudaFree(c->ypart);
     cudaFree(c->ypartT);

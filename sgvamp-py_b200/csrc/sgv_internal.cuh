@@ -235,6 +235,7 @@ struct sgv_ctx {
     int64_t      dsp_cap = 0;
     unsigned long long* dsp_flags = nullptr;
     unsigned long long  dsp_epoch = 0;
+    unsigned long long* dsp_dbg = nullptr;   // SGV_DS_DEBUG=1: phase clock of the whole-solve kernel (printed by sgv_destroy)
     double2*     ypart = nullptr;    // cross-CTA partial outputs of the panel kernel
     int64_t      ypart_cap = 0;      // in double2 elements
     double2*     ypartT = nullptr;   // transposed partial outputs of the symmetric panel kernel, per strip

@@ -33,6 +33,9 @@
 //   group loop unrolled x2 / x4 (stage index still a run-time value) 0.391-0.408 / 0.448-0.450
 //   fence.proxy.async before every refill (see DSP_ISSUE)           0.392-0.401 / 0.432-0.433
 //   refill after the group's FMAs instead of right after its loads  0.383 / 0.425
+#ifndef DSP_DEBUG
+#define DSP_DEBUG 0      // 1: compile the phase clock of the whole-solve kernel in (development builds; costs registers)
+#endif
 #define DSP_STR2(x) #x
 #define DSP_STR(x) DSP_STR2(x)
 
@@ -40,6 +43,7 @@ struct DsPersist {
     const float*        U;
     int                 Dp;       // stored diagonals (multiple of 4)
     int                 units;    // ldb / 128
+    int                 upr;      // > 0: fixed units per range, the last range takes what is left; 0: even split over the grid
     int64_t             E;        // extension rows stored before the first own row
     double2*            yhead;    // [ranges][Dp] partial sums of the first Dp rows of a range
     double2*            tails;    // [ranges][Dp] carry-out of a range (sums for the Dp rows after it)
@@ -59,7 +63,14 @@ struct DsSolve {
     unsigned long long* gen;                              // step barrier: == epoch + n + 1 once step n's state transition is done
     unsigned*           exit_ticket;
     int                 max_steps;
+    unsigned long long* dbg;                              // SGV_DS_DEBUG: accumulated phase durations in ns (see DSP_T)
 };
+
+__device__ __forceinline__ unsigned long long dsp_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -121,7 +132,9 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
     for (int j = tid; j < NW * 8; j += NT) sdot[j] = 0.0;
     __syncthreads();
     const int c = s_misc[0];                                   // this CTA's range (ticket order)
-    const int u0 = (int)((int64_t)c * g.units / G), u1 = (int)((int64_t)(c + 1) * g.units / G);
+    // every range but the last spans >= Dp rows (the host chooses the split, see dsp_units_per_range)
+    const int u0 = g.upr > 0 ? c * g.upr : (int)((int64_t)c * g.units / G);
+    const int u1 = g.upr > 0 ? min(g.units, (c + 1) * g.upr) : (int)((int64_t)(c + 1) * g.units / G);
     const int nunits = u1 - u0;
     const int ntiles = (nunits + RW - 1) / RW;
     const int64_t rb = (int64_t)u0 * 128, re = (int64_t)u1 * 128;   // storage rows of the range
@@ -177,34 +190,44 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
     bool first = true, fz0 = false, fz1 = false;
     const volatile CgState* vst = a.rc.st;                      // SOLVE: rewritten between steps by the last CTA
     unsigned long long seq = a.rc.seq, epoch = g.epoch;
+    // phase clock of the whole-solve kernel (SGV_DS_DEBUG=1; thread 0 of range 0 and of the last-arriving CTA):
+    // dbg[0] stage window, [1] tiles, [2] head fix-up + partials, [3] wait for the slowest CTA, [4] local reduction,
+    // [5] cross-rank exchange, [6] barrier release seen by range 0, [7] steps
+    unsigned long long tp = 0;
+#define DSP_T(SLOT)                                                                  \
+    do {                                                                             \
+        if (DSP_DEBUG && SOLVE && sv.dbg != nullptr && tid == 0 && c == 0) {                      \
+            const unsigned long long tn = dsp_now();                                 \
+            atomicAdd(sv.dbg + (SLOT), tn - tp);                                     \
+            tp = tn;                                                                 \
+        }                                                                            \
+    } while (0)
   for (int step_i = 0;; ++step_i, ++seq, ++epoch) {
-    if (SOLVE) {
-        if ((vst->done[0] && vst->done[1]) || step_i >= sv.max_steps) break;
-        const int n = vst->step, prev = (n + 1) & 1, cur = n & 1;
+    if (SOLVE) {                                                // the set-up kernel leaves step = 0: step n of the solve is
+        const int n = step_i, prev = (n + 1) & 1, cur = n & 1;  // this loop's n-th turn, known without reading the state
         a.v = sv.pp[prev]; a.r = sv.rr[prev]; a.q = sv.qq[prev];
         a.p_new = sv.pp[cur]; a.r_new = sv.rr[cur]; a.out = sv.qq[cur];
         a.v_left = sv.ppL[prev]; a.r_left = sv.rrL[prev]; a.q_left = sv.qqL[prev];
         a.v_right = sv.ppR[prev]; a.r_right = sv.rrR[prev]; a.q_right = sv.qqR[prev];
+        first = n == 0;
     }
     if (!prearmed) DSP_ARM_PASS();
     prearmed = false;
-    if (CG) {
-        first = vst->step == 0;
-        fz0 = vst->done[0] != 0;
-        fz1 = vst->done[1] != 0;
-        al0 = al1 = beta0 = beta1 = 0.0;
-        if (!first) {
-            al0 = vst->alpha[0];
-            al1 = vst->alpha[1];
-            beta0 = vst->rho[0] / vst->rho_prev[0];
-            beta1 = vst->rho[1] / vst->rho_prev[1];
-        }
-    }
+    if (DSP_DEBUG && SOLVE && sv.dbg != nullptr && tid == 0 && c == 0) tp = dsp_now();
     // Value of the input vector at local column `col` (0 = first own row of this rank): own memory, the left / right
     // neighbour's arena, or zero outside the matrix.  CG mode: the new direction p = r + beta p_old with the pending
     // update r -= alpha q applied on the fly; the rows this CTA owns get r, p and x += alpha p_old written.
-    auto stage_entry = [&](int64_t col) -> double2 {
-        double2 val = make_double2(0.0, 0.0);
+    // Split into a load half and a compute / store half, so that a thread can put the loads of several entries in
+    // flight before it touches any of them (the stores in between would otherwise serialise the round trips).
+    struct Stg {
+        double2 rv, po, qo, xv;
+        int64_t col;
+        int     kind;     // 0: outside the matrix, 1: loaded, 2: loaded + a row of this range (to be written)
+    };
+    auto stage_load = [&](int64_t col, Stg& t) {
+        t.col = col;
+        t.kind = 0;
+        t.rv = t.po = t.qo = t.xv = make_double2(0.0, 0.0);
         const double2 *src = nullptr, *rsrc = nullptr, *qsrc = nullptr;
         int64_t idx = col;
         if (col >= 0 && col < a.M) {
@@ -222,31 +245,90 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
             qsrc = a.q_right;
             idx = col - a.M;
         }
-        if (src == nullptr) return val;
-        if (!CG) return ld_vec2(src + idx);
-        double2 rv = ld_vec2(rsrc + idx);
-        double2 po = make_double2(0.0, 0.0);
-        if (!first) {
-            po = ld_vec2(src + idx);
-            const double2 qo = ld_vec2(qsrc + idx);
-            if (al0 != 0.0) rv.x -= al0 * qo.x;                 // scipy: r -= alpha*q
-            if (al1 != 0.0) rv.y -= al1 * qo.y;
+        if (src == nullptr) return;
+        t.kind = 1;
+        if (!CG) {
+            t.po = ld_vec2(src + idx);
+            return;
         }
-        val.x = fz0 ? po.x : (first ? rv.x : po.x * beta0 + rv.x);   // scipy: p *= beta; p += r  (first step: p = r)
-        val.y = fz1 ? po.y : (first ? rv.y : po.y * beta1 + rv.y);
+        t.rv = ld_vec2(rsrc + idx);
+        if (!first) {
+            t.po = ld_vec2(src + idx);
+            t.qo = ld_vec2(qsrc + idx);
+        }
         const int64_t js = col + g.E;
         if (col >= 0 && col < a.M && js >= rb && js < re) {     // rows of this range: written exactly once
-            a.r_new[col] = rv;
-            a.p_new[col] = val;
+            t.kind = 2;
+            if (!first && (SOLVE || al0 != 0.0 || al1 != 0.0)) t.xv = ld_vec2(a.x + col);   // (whole-solve: alpha not read yet)
+        }
+    };
+    auto stage_finish = [&](const Stg& t) -> double2 {
+        if (t.kind == 0) return make_double2(0.0, 0.0);
+        if (!CG) return t.po;
+        double2 rv = t.rv;
+        if (al0 != 0.0) rv.x -= al0 * t.qo.x;                   // scipy: r -= alpha*q
+        if (al1 != 0.0) rv.y -= al1 * t.qo.y;
+        double2 val;
+        val.x = fz0 ? t.po.x : (first ? rv.x : t.po.x * beta0 + rv.x);   // scipy: p *= beta; p += r  (first step: p = r)
+        val.y = fz1 ? t.po.y : (first ? rv.y : t.po.y * beta1 + rv.y);
+        if (t.kind == 2) {
+            a.r_new[t.col] = rv;
+            a.p_new[t.col] = val;
             if (al0 != 0.0 || al1 != 0.0) {
-                double2 xv = a.x[col];
-                if (al0 != 0.0) xv.x += al0 * po.x;             // scipy: x += alpha*p
-                if (al1 != 0.0) xv.y += al1 * po.y;
-                a.x[col] = xv;
+                double2 xv = t.xv;
+                if (al0 != 0.0) xv.x += al0 * t.po.x;           // scipy: x += alpha*p
+                if (al1 != 0.0) xv.y += al1 * t.po.y;
+                a.x[t.col] = xv;
             }
         }
         return val;
     };
+    // first window [rb - E, rb - E + W) in local coordinates: up to 4 entries per thread, their loads issued back to
+    // back; in whole-solve mode BEFORE the step's CG state is read (one memory round trip less per step)
+    Stg st4[4];
+    auto window_loads = [&]() {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int j = tid + m * NT;
+            st4[m].kind = 0;
+            if (j < W) stage_load(rb - g.E + j, st4[m]);
+        }
+    };
+    if (SOLVE) window_loads();
+    // the CG state of the step: ONE thread reads it and hands it round in shared memory (every thread of every CTA
+    // reading the same cache line at the same moment costs ~10 us per step at the L2 slice that holds it)
+    {
+        double* s_st = reinterpret_cast<double*>(Aall);        // free between passes
+        if (tid == 0) {
+            s_st[0] = (double)vst->step;
+            s_st[1] = (double)vst->done[0];
+            s_st[2] = (double)vst->done[1];
+            s_st[3] = vst->alpha[0];
+            s_st[4] = vst->alpha[1];
+            s_st[5] = vst->rho[0];
+            s_st[6] = vst->rho_prev[0];
+            s_st[7] = vst->rho[1];
+            s_st[8] = vst->rho_prev[1];
+        }
+        __syncthreads();
+        const int st_step = (int)s_st[0];
+        fz0 = s_st[1] != 0.0;
+        fz1 = s_st[2] != 0.0;
+        al0 = al1 = beta0 = beta1 = 0.0;
+        if (CG && st_step != 0) {
+            al0 = s_st[3];
+            al1 = s_st[4];
+            beta0 = s_st[5] / s_st[6];
+            beta1 = s_st[7] / s_st[8];
+        }
+        if (!SOLVE) first = st_step == 0;
+        __syncthreads();                                        // the A region is written again below
+    }
+    if (SOLVE && ((fz0 && fz1) || step_i >= sv.max_steps)) {
+        prearmed = true;                                        // the ring holds this step's first requests: drained below
+        break;
+    }
+    if (!SOLVE) window_loads();
     // a finished row: fused epilogue, dot products into d[]
     double d[NV];
 #pragma unroll
@@ -275,16 +357,20 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
         }
     };
 
-    // first window [rb - E, rb - E + W) in local coordinates; carry and the untouched tail of the A ranges start at zero
-    for (int j = tid; j < 4 * PL; j += NT) {
-        double2 val = make_double2(0.0, 0.0);
-        if (j < W) val = stage_entry(rb - g.E + j);
-        xw[(j & 3) * PL + (j >> 2)] = val;
+    // the window goes into shared memory; carry and the untouched tail of the A ranges start at zero
+    {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int j = tid + m * NT;
+            if (j < 4 * PL) xw[(j & 3) * PL + (j >> 2)] = j < W ? stage_finish(st4[m]) : make_double2(0.0, 0.0);
+        }
+        for (int j = tid + 4 * NT; j < 4 * PL; j += NT) xw[(j & 3) * PL + (j >> 2)] = make_double2(0.0, 0.0);
     }
     for (int j = tid; j < Dp; j += NT) carry[j] = make_double2(0.0, 0.0);
     for (int j = tid; j < RW * 128; j += NT) Aall[(j >> 7) * AL + Dp + (j & 127)] = make_double2(0.0, 0.0);
     for (int j = tid; j < NW * 8; j += NT) sdot[j] = 0.0;
     __syncthreads();
+    DSP_T(0);
 
     const int g4 = rw * 32 + lane;                              // this thread's rows: 4*g4 .. 4*g4+3 of the tile
     double2* Arw = Aall + rw * AL;
@@ -348,7 +434,11 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
         if (lane == 0) s_lent[wid] = lent;
         // the TR new window entries of the next tile: loads issued now, consumed after the combine
         double2 nx = make_double2(0.0, 0.0);
-        if (!last && tid < TR) nx = stage_entry(r0s + TR - g.E + Dp + tid);
+        if (!last && tid < TR) {
+            Stg t1;
+            stage_load(r0s + TR - g.E + Dp + tid, t1);
+            nx = stage_finish(t1);
+        }
         // r of the row this thread finishes in the combine (row tid of the tile): written when the row was staged, at
         // least one barrier ago; requested here so that its latency hides behind the barriers below
         double2 rpre = make_double2(0.0, 0.0);
@@ -440,6 +530,7 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
         __syncthreads();                                        // S4
     }
 
+    DSP_T(1);
     // carry-out published; head rows: add the previous range's carry-out and finish them
     if (tid == 0 && c + 1 < G) {
         __threadfence();
@@ -479,12 +570,18 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
         prearmed = true;
     }
     __syncthreads();
+    DSP_T(2);
     if (tid == 0) {
         __threadfence();
         const unsigned t = atomicAdd(a.rc.counter, 1u);
         s_misc[1] = (t == (unsigned)G - 1u);
     }
     __syncthreads();
+    unsigned long long tl = 0;
+    if (DSP_DEBUG && SOLVE && sv.dbg != nullptr && tid == 0 && s_misc[1]) {
+        tl = dsp_now();
+        if (c == 0) { atomicAdd(sv.dbg + 3, tl - tp); tp = tl; }
+    }
     if (s_misc[1]) {
         // last CTA of the pass: add the per-range partials in range order; state transition / cross-rank exchange
         __threadfence();
@@ -504,6 +601,11 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
             block_reduce<NV>(acc, red);
             RedCtx rcs = a.rc;
             rcs.seq = seq;
+            if (DSP_DEBUG && SOLVE && sv.dbg != nullptr && tid == 0) {
+                const unsigned long long tn = dsp_now();
+                atomicAdd(sv.dbg + 4, tn - tl);
+                tl = tn;
+            }
             if (tid == 0 && rcs.world == 1) apply_totals(rcs.ap, rcs.st, acc);
             if (rcs.world > 1 && tid < 32) {
                 publish_warp<NV>(acc, rcs, rcs.seq, tid);
@@ -515,6 +617,10 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
         }
         if (SOLVE && tid == 0) {
             __threadfence();
+            if (DSP_DEBUG && sv.dbg != nullptr) {
+                atomicAdd(sv.dbg + 5, dsp_now() - tl);
+                atomicAdd(sv.dbg + 7, 1ull);
+            }
             st_release_gpu_u64(sv.gen, epoch + 1);              // step barrier: the new CG state is in place
         }
     }
@@ -529,7 +635,13 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
         }
     }
     __syncthreads();
+    if (DSP_DEBUG && SOLVE && sv.dbg != nullptr && tid == 0 && c == 0) {
+        const unsigned long long tn = dsp_now();
+        atomicAdd(sv.dbg + (s_misc[1] ? 6 : 3), s_misc[1] ? 0ull : tn - tp);   // range 0 waiting = slowest CTA + reduction + exchange
+        tp = tn;
+    }
   }
+#undef DSP_T
 #undef DSP_ARM_PASS
 #undef DSP_ISSUE
 #undef DSP_COPY
@@ -588,10 +700,20 @@ int sgv_preload_dsymp() {
     return 0;
 }
 
-static int dsp_ranges(const sgv_ctx* c, const LdMatrix& ld) {
+// Row ranges.  A range must span at least Dp rows (min_units 128-row units), so that its carry-out ends inside the next
+// one.  Enough rows for two ranges per SM: the units are split evenly over 2 x SMs ranges (sizes differ by one unit).
+// Fewer rows (a shard of a multi-GPU partition): ranges of exactly min_units units and a LAST range that takes the
+// remainder - nothing follows it, so it may be shorter - which keeps the makespan at min_units units where an even split
+// over fewer ranges would hand one of them an extra unit (+25 % at M = 125k, w = 500).
+static int dsp_units_per_range(const sgv_ctx* c, const LdMatrix& ld) {
     const int64_t Dp = round_up(ld.w + 1, 4);
-    const int64_t units = ld.ldb / 128, min_units = (Dp + 127) / 128;   // a range spans at least Dp rows
-    return (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)c->sm_count * 2, units / min_units));
+    const int64_t units = ld.ldb / 128, min_units = (Dp + 127) / 128, slots = (int64_t)c->sm_count * 2;
+    return units >= slots * min_units ? 0 : (int)min_units;
+}
+static int dsp_ranges(const sgv_ctx* c, const LdMatrix& ld) {
+    const int64_t units = ld.ldb / 128, upr = dsp_units_per_range(c, ld);
+    if (upr == 0) return c->sm_count * 2;
+    return (int)std::max<int64_t>(1, (units + upr - 1) / upr);
 }
 
 int sgv_dsymp_ensure_scratch(sgv_ctx* c, const LdMatrix& ld) {
@@ -607,6 +729,10 @@ int sgv_dsymp_ensure_scratch(sgv_ctx* c, const LdMatrix& ld) {
         SGV_CUDA(cudaMalloc(&c->dsp_tails, need * sizeof(double2)));
         c->dsp_cap = need;
     }
+    if (c->dsp_dbg == nullptr && getenv("SGV_DS_DEBUG") != nullptr) {
+        SGV_CUDA(cudaMalloc(&c->dsp_dbg, 16 * sizeof(unsigned long long)));
+        SGV_CUDA(cudaMemset(c->dsp_dbg, 0, 16 * sizeof(unsigned long long)));
+    }
     if (c->dsp_flags == nullptr) {   // one hand-off flag per range + the step barrier word of the whole-solve kernel
         SGV_CUDA(cudaMalloc(&c->dsp_flags, ((size_t)c->sm_count * 2 + 2) * sizeof(unsigned long long)));
         SGV_CUDA(cudaMemset(c->dsp_flags, 0, ((size_t)c->sm_count * 2 + 2) * sizeof(unsigned long long)));
@@ -618,6 +744,7 @@ static void dsp_fill(sgv_ctx* c, const LdMatrix& ld, int epi, DsPersist& g) {
     g.U = ld.band;
     g.Dp = (int)round_up(ld.w + 1, 4);
     g.units = (int)(ld.ldb / 128);
+    g.upr = dsp_units_per_range(c, ld);
     g.E = ld.ext;
     g.yhead = c->dsp_yhead;
     g.tails = c->dsp_tails;
@@ -690,6 +817,7 @@ int sgv_launch_dsymp_solve(sgv_ctx* c, const LdMatrix& ld, SpmmArgs& a, int max_
     sv.gen = c->dsp_flags + (size_t)c->sm_count * 2;
     sv.exit_ticket = c->counter + 13;
     sv.max_steps = max_steps;
+    sv.dbg = c->dsp_dbg;
     const int G = dsp_ranges(c, ld);
     SGV_TRY(sgv_ensure_partials(c, G));
     a.rc.partials = c->partials;

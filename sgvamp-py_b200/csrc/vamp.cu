@@ -969,7 +969,8 @@ extern "C" int sgv_iteration_enqueue(sgv_handle c, const sgv_iter_in* in, double
             SGV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_em_loop, 256, 0));
             c->em_loop_blocks_per_sm = std::max(1, std::min(nb, 4));
         }
-        const unsigned lgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * c->em_loop_blocks_per_sm);
+        // a pass is two grid barriers and a partial-sum sweep: at least 1024 markers per block keeps both short
+        const unsigned lgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((M + 1023) / 1024, (int64_t)c->sm_count * c->em_loop_blocks_per_sm));
         SGV_TRY(sgv_ensure_partials(c, lgrid + 1));
         k_em_begin<<<1, 1, 0, c->stream>>>(c->cg, in->em_maxit, in->em_tol);
         c->launches++;
