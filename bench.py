@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--e2e-format", default="dia", choices=["dia", "csr"],
                     help="host container of the LD matrix in the end-to-end leg (scipy DIA arrays or CSR)")
     ap.add_argument("--seed", type=int, default=5)
+    ap.add_argument("--config", default="c5", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configuration: c5 (default, the headline metric) = M=1M banded LD row-partitioned "
+                         "over the GPUs; c1..c4 = the dense / block-diagonal shapes on one GPU (bench_configs.py)")
     return ap.parse_args()
 
 
@@ -293,6 +296,11 @@ def gpu_sample_parity(sgvamp, U, ldb, w, r, ref_out, iterations, probes, device,
 
 def main():
     a = parse()
+    if a.config != "c5":
+        import bench_configs
+        if a.impl == "reference":
+            return bench_configs.run_reference(a, sys.modules[__name__])
+        return bench_configs.run_config(a, sys.modules[__name__])
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -103,6 +103,11 @@ int sgv_ld_adopt_dia(sgv_handle h, int cohort, const float* band_dev, int64_t w,
 int sgv_ld_adopt_dsym(sgv_handle h, int cohort, const float* U_dev, int64_t w, int64_t ldb, int64_t ext);
 int sgv_dsym_extension(sgv_handle h, int64_t w, int64_t* ext);
 int sgv_ld_adopt_dense(sgv_handle h, int cohort, const float* R_dev, int64_t ld);
+/* block-diagonal LD (per-chromosome LD blocks, BASELINE.json configs[2]) already in HBM: block b holds the rows
+ * [starts[b], starts[b+1]) of this handle (starts[nblocks] = local rows) as a dense row-major panel at
+ * panels_dev + offs[b] with leading dimension lds[b] (offs, lds multiples of 4 elements).  Symmetry is verified. */
+int sgv_ld_adopt_blockdiag(sgv_handle h, int cohort, const float* panels_dev, int nblocks, const int64_t* starts,
+                           const int64_t* offs, const int* lds);
 /* layout actually chosen + stored bytes + algorithmic bytes of one SpMM pass at nrhs */
 int sgv_ld_info(sgv_handle h, int cohort, int* layout, int64_t* nnz_stored, int64_t* bandwidth,
                 int64_t* nblocks, double* bytes_per_pass_nrhs2);

@@ -399,6 +399,30 @@ extern "C" int sgv_ld_adopt_dense(sgv_handle c, int cohort, const float* R_dev, 
     return sgv_build_panel_items(c, ld, {0, c->M}, {0}, {(int)ldd});
 }
 
+extern "C" int sgv_ld_adopt_blockdiag(sgv_handle c, int cohort, const float* panels_dev, int nblocks, const int64_t* starts,
+                                      const int64_t* offs, const int* lds) {
+    SGV_TRY(check_cohort(c, cohort));
+    SGV_CHECK(panels_dev != nullptr && ((uintptr_t)panels_dev & 15) == 0, "device pointer must be 16-byte aligned");
+    SGV_CHECK(nblocks >= 1 && starts && offs && lds, "null / empty block description");
+    SGV_CHECK(starts[0] == 0 && starts[nblocks] == c->Ml, "blocks must cover the local rows [0,%lld)", (long long)c->Ml);
+    SGV_CHECK(c->world == 1 || !c->halo, "block-diagonal LD is sharded at block boundaries (halo = 0)");
+    std::vector<int64_t> st(starts, starts + nblocks + 1), of(offs, offs + nblocks);
+    std::vector<int> ld_(lds, lds + nblocks);
+    LdMatrix& ld = c->coh[cohort].ld;
+    sgv_ld_free(ld);
+    ld.nnz_stored = 0;
+    for (int b = 0; b < nblocks; ++b) {
+        const int64_t m = st[b + 1] - st[b];
+        SGV_CHECK(m >= 1 && ld_[b] >= m && ld_[b] % 4 == 0 && of[b] % 4 == 0, "block %d: ld must be >= size and a multiple of 4, "
+                  "offset a multiple of 4", b);
+        ld.nnz_stored += m * m;
+    }
+    ld.panels = panels_dev;
+    ld.owned = false;
+    ld.layout = nblocks == 1 ? SGV_LAYOUT_DENSE : SGV_LAYOUT_BLOCKDIAG;
+    return sgv_build_panel_items(c, ld, st, of, ld_);
+}
+
 extern "C" int sgv_ld_adopt_dia(sgv_handle c, int cohort, const float* band_dev, int64_t w, int64_t ldb) {
     SGV_TRY(check_cohort(c, cohort));
     SGV_CHECK(band_dev != nullptr && ((uintptr_t)band_dev & 15) == 0, "device pointer must be 16-byte aligned");

@@ -29,7 +29,7 @@ SYMBOLS = [
     "sgv_peer_attach_local", "sgv_partition_info", "sgv_ld_set_bandwidth_hint", "sgv_spmm_stage", "sgv_spmm_run",
     "sgv_ld_adopt_dsym", "sgv_dsym_extension", "sgv_set_host_barrier", "sgv_device_id", "sgv_ld_upload_dia",
     "sgv_iteration_supported", "sgv_vamp_begin", "sgv_set_truth", "sgv_iteration_probe_buffer", "sgv_iteration_enqueue",
-    "sgv_iteration_wait",
+    "sgv_iteration_wait", "sgv_ld_adopt_blockdiag",
 ]
 MAX_K, MAX_L, ITER_SLOTS = 8, 8, 4
 
@@ -208,6 +208,16 @@ class Handle:
 
     def adopt_dense(self, cohort, ptr, ld):
         self._ck(self.lib.sgv_ld_adopt_dense(self.h, C.c_int(cohort), C.c_void_p(ptr), C.c_int64(ld)))
+
+    def adopt_blockdiag(self, cohort, ptr, starts, offs, lds):
+        st = np.ascontiguousarray(starts, dtype=np.int64)
+        of = np.ascontiguousarray(offs, dtype=np.int64)
+        ld = np.ascontiguousarray(lds, dtype=np.int32)
+        nb = len(of)
+        assert len(st) == nb + 1 and len(ld) == nb
+        self._ck(self.lib.sgv_ld_adopt_blockdiag(self.h, C.c_int(cohort), C.c_void_p(ptr), C.c_int(nb),
+                                                 st.ctypes.data_as(C.POINTER(C.c_int64)), of.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                 ld.ctypes.data_as(C.POINTER(C.c_int32))))
 
     def ld_info(self, cohort):
         layout = C.c_int()

@@ -60,6 +60,14 @@ class DeviceDense:
         self.ptr, self.ld, self.keepalive = int(ptr), int(ld), keepalive
 
 
+class DeviceBlockDiag:
+    """Block-diagonal LD already resident in HBM: dense row-major panels (see sgv_ld_adopt_blockdiag); `starts` are the
+    local block boundaries of this rank (0 ... local rows)."""
+
+    def __init__(self, ptr, starts, offs, lds, keepalive=None):
+        self.ptr, self.starts, self.offs, self.lds, self.keepalive = int(ptr), starts, offs, lds, keepalive
+
+
 class _SoloComm:
     def Get_rank(self):
         return 0
@@ -228,6 +236,10 @@ class VAMP:
         elif isinstance(R, DeviceDense):
             assert s == 0.0, "device-resident LD must already be regularised"
             h.adopt_dense(cohort, R.ptr, R.ld)
+            self._keep.append(R)
+        elif isinstance(R, DeviceBlockDiag):
+            assert s == 0.0, "device-resident LD must already be regularised"
+            h.adopt_blockdiag(cohort, R.ptr, R.starts, R.offs, R.lds)
             self._keep.append(R)
         elif isinstance(R, DiaWindow) or (scipy.sparse.issparse(R) and R.format == "dia"):
             # banded LD in DIA form: diagonals travel as they are (no index arrays; half of them for symmetric LD)
