@@ -426,7 +426,6 @@ class VAMP:
                                      prior_update, update_prior_from, probes, write_outputs, iter_hook, gather_outputs)
         write = write_outputs and self.out_dir is not None
         sharded = self.shard.world > 1
-        r1_keep = {}
         worker = _Worker()
         tm = self.timers = dict(prior=0.0, denoise=0.0, lmmse=0.0, host_tail=0.0)
         pc = time.perf_counter
@@ -551,8 +550,10 @@ class VAMP:
                 h.wait_copies()
                 xh = pin_x[slot][0].copy()
                 xhat1s[it] = xh.reshape(-1, 1)
-                if write and sharded:                                    # dumps are assembled after the loop
-                    r1_keep[it] = [pin_r[slot][idx].copy() for idx in range(len(mine))]
+                if write and sharded:                                    # this rank's slices; assembled after the loop
+                    self._write_part("%s_xhat_it_%d.bin" % (self.out_name, it), xh / sqrtNt)
+                    for idx, k in enumerate(mine):
+                        self._write_part("%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k + 1, it), pin_r[slot][idx] / sqrtNt)
                 elif write:
                     if rank == 0:
                         (xh / sqrtNt).tofile(os.path.join(self.out_dir, "%s_xhat_it_%d.bin" % (self.out_name, it)))
@@ -589,15 +590,9 @@ class VAMP:
             full = shd.gather_rows(self.shard, np.stack([x.ravel() for x in xhat1s]) if iterations else np.zeros((0, self.Ml)),
                                    self.bounds)
             xhat1s = [full[it].reshape(M, 1) for it in range(iterations)]
-            if write:
-                r1_full = shd.gather_rows(self.shard, np.array([[r1_keep[it][idx] for idx in range(len(mine))]
-                                                                for it in range(iterations)]).reshape(iterations, len(mine), self.Ml),
-                                          self.bounds)
-                if self.root:
-                    for it in range(iterations):
-                        self.write_xhat_to_file(it, xhat1s[it] / sqrtNt)
-                        for idx, k in enumerate(mine):
-                            self.write_r1_to_file(it, r1_full[it, idx] / sqrtNt, k + 1)
+        if sharded and write:
+            self._assemble_parts(["%s_xhat_it_%d.bin" % (self.out_name, it) for it in range(iterations)] +
+                                 ["%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k + 1, it) for it in range(iterations) for k in mine])
         return xhat1s
 
     def _infer_fused(self, rs, Ns, iterations, x0, cg_maxit, em_prior_maxit, learn_gamw, lmmse_damp, prior_update,
@@ -626,7 +621,6 @@ class VAMP:
             truth = self._local(x0)
             h.set_truth(truth)
         xhat1s = [None] * iterations
-        r1_keep = {}
         self.history = dict(rows=[], cg_iters=[], cg_info=[], em_steps=[], spmm_passes=[], lam=[], omegas=[])
         pin_x = self._pinned_ring("x", NS, 1)
         pin_r = self._pinned_ring("r", NS, K) if write else None
@@ -683,8 +677,10 @@ class VAMP:
                 h.wait_copies()
                 xh = pin_x[slot][0].copy()
                 xhat1s[it] = xh.reshape(-1, 1)
-                if write and sharded:                                    # dumps are assembled after the loop
-                    r1_keep[it] = [pin_r[slot][k].copy() for k in range(K)]
+                if write and sharded:                                    # this rank's slices; assembled after the loop
+                    self._write_part("%s_xhat_it_%d.bin" % (self.out_name, it), xh / sqrtNt)
+                    for k in mine:
+                        self._write_part("%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k + 1, it), pin_r[slot][k] / sqrtNt)
                 elif write:
                     (xh / sqrtNt).tofile(os.path.join(self.out_dir, "%s_xhat_it_%d.bin" % (self.out_name, it)))
                     for k in mine:
@@ -733,16 +729,34 @@ class VAMP:
             full = shd.gather_rows(self.shard, np.stack([x.ravel() for x in xhat1s]) if iterations else np.zeros((0, self.Ml)),
                                    self.bounds)
             xhat1s = [full[it].reshape(M, 1) for it in range(iterations)]
-            if write:
-                r1_full = shd.gather_rows(self.shard, np.array([[r1_keep[it][k] for k in range(K)]
-                                                                for it in range(iterations)]).reshape(iterations, K, self.Ml),
-                                          self.bounds)
-                if self.root:
-                    for it in range(iterations):
-                        self.write_xhat_to_file(it, xhat1s[it] / sqrtNt)
-                        for k in mine:
-                            self.write_r1_to_file(it, r1_full[it, k] / sqrtNt, k + 1)
+        if sharded and write:
+            self._assemble_parts(["%s_xhat_it_%d.bin" % (self.out_name, it) for it in range(iterations)] +
+                                 ["%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k + 1, it) for it in range(iterations) for k in mine])
         return xhat1s
+
+    # sharded output dumps: every rank streams its row slice of a dump into a part file while the loop runs; after the
+    # loop rank 0 concatenates the parts in rank order (nothing of size iterations x M is ever held in host memory)
+    def _part_path(self, name, rank):
+        return os.path.join(self.out_dir, ".%s.part%d" % (name, rank))
+
+    def _write_part(self, name, vec):
+        np.ascontiguousarray(vec, dtype=np.float64).ravel().tofile(self._part_path(name, self.shard.rank))
+
+    def _assemble_parts(self, names):
+        self.shard.barrier()                                    # every rank's parts are on disk
+        if self.root:
+            for name in names:
+                with open(os.path.join(self.out_dir, name), "wb") as out:
+                    for q in range(self.shard.world):
+                        pp = self._part_path(name, q)
+                        with open(pp, "rb") as f:
+                            while True:
+                                buf = f.read(1 << 24)
+                                if not buf:
+                                    break
+                                out.write(buf)
+                        os.remove(pp)
+        self.shard.barrier()
 
     def _local(self, v):
         """This rank's rows of a marker vector given either globally (length M) or already sliced."""

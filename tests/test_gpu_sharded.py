@@ -147,6 +147,41 @@ def test_sharded_banded_trajectory_matches_reference(nat, world):
         assert raw.count(b"\r\n") == c["iterations"] + 1
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_multi_cohort_banded(nat, world):
+    """K = 2 cohorts, every cohort's LD row-partitioned over all ranks (cohorts as a batch dimension): the
+    r1 / gam1 all-gather of src/sgvamp.py:228-233 is a no-op because every rank holds its rows of every cohort."""
+    import sgvamp
+    import shard as shd
+    c = load_case("banded_K2_L3_em_s01")
+    K, M = c["K"], c["M"]
+    Nt = sum(c["N_list"])
+    bounds = shd.partition_rows(M, world)
+
+    def fn(sh, dev):
+        v = sgvamp.VAMP(N=c["N_list"], Nt=Nt, M=M, K=K, rho=c["rho"], gamw=c["gamw"], gam1=c["gam1"],
+                        a=np.array(c["N_list"]) / Nt, prior_vars=c["prior_vars"], prior_probs=c["prior_probs"], out_dir=None,
+                        out_name="g", device=dev, shard=sh, shard_rows=bounds, halo=True)
+        xs = v.infer(c["R"], list(c["r"]), c["iterations"], x0=c["x0"] * np.sqrt(c["N_list"][0]), cg_maxit=c["cg_maxit"],
+                     em_prior_maxit=c["em_prior_maxit"], learn_gamw=c["learn_gamw"], lmmse_damp=c["lmmse_damp"],
+                     prior_update=c["prior_update"], update_prior_from=c["update_prior_from"], s=c["s"], probes=c["probes"])
+        res = (xs, v.history, [v.handle.ld_info(k)["layout"] for k in range(K)])
+        sh.barrier()
+        v.close()
+        return res
+
+    res = run_ranks(world, fn)
+    for r in range(world):
+        xs, hist, lays = res[r]
+        assert lays == ["dsym"] * K
+        for it in range(c["iterations"]):
+            assert rel_l2(xs[it], c["xhat"][it]) <= 1e-4
+            for k in range(K):
+                assert rel_err(hist["rows"][it][k][1:6], c["rows"][it, k, 1:6]) <= 1e-4
+                assert tuple(hist["cg_iters"][it][k]) == tuple(c["cg_iters"][it, k])
+                assert hist["rows"][it][k] == res[0][1]["rows"][it][k]          # bit-identical scalars on all ranks
+
+
 def test_sharded_banded_from_scipy_dia(nat):
     """Every rank is handed the whole matrix in scipy's DIA format and uploads only the diagonals' entries of
     its own rows (+ extension): same trajectory as from CSR."""
