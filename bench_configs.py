@@ -101,10 +101,7 @@ def gen_dense_cohort(torch, M, N, beta, seed, dev, out=None, chunk=8192):
     return G, r.cpu().numpy()
 
 
-def gen_blockdiag(torch, M, seed, dev, s, N_gwas, N_ld=4096):
-    """Block-diagonal LD: panels (one dense R_b = X_b^T X_b per LD block, Rused applied), block starts / offsets / lds,
-    r and x0."""
-    import ldgen
+def block_sizes(M, seed):
     rng = np.random.default_rng(seed)
     sizes, left = [], M
     while left > 0:
@@ -113,6 +110,20 @@ def gen_blockdiag(torch, M, seed, dev, s, N_gwas, N_ld=4096):
             b = left
         sizes.append(b)
         left -= b
+    return sizes
+
+
+def gen_blockdiag(torch, M, seed, dev, s, N_gwas, N_ld=4096, row_lo=0, row_hi=None):
+    """Block-diagonal LD: panels (one dense R_b = X_b^T X_b per LD block, Rused applied), block starts / offsets / lds,
+    r and x0.  With a row range (a rank of a block partition: boundaries are block boundaries) only the blocks inside it
+    are generated; starts are then local.  Every block depends only on (seed, block index)."""
+    import ldgen
+    row_hi = M if row_hi is None else row_hi
+    all_sizes = block_sizes(M, seed)
+    all_starts = np.concatenate([[0], np.cumsum(all_sizes)]).astype(np.int64)
+    mine = [b for b in range(len(all_sizes)) if all_starts[b] >= row_lo and all_starts[b + 1] <= row_hi]
+    assert mine and all_starts[mine[0]] == row_lo and all_starts[mine[-1] + 1] == row_hi, "row range must consist of whole blocks"
+    sizes = [all_sizes[b] for b in mine]
     starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     lds = np.array([(m + 3) // 4 * 4 for m in sizes], dtype=np.int32)
     offs = np.concatenate([[0], np.cumsum(np.array(sizes, dtype=np.int64) * lds)])[:-1].astype(np.int64)
@@ -120,13 +131,15 @@ def gen_blockdiag(torch, M, seed, dev, s, N_gwas, N_ld=4096):
     P = torch.zeros(total, device=dev, dtype=torch.float32)
     beta = causal_beta(M, seed)
     x0 = beta * np.sqrt(N_gwas)
-    x0d = torch.from_numpy(x0).to(dev)
-    r = torch.zeros(M, device=dev, dtype=torch.float64)
+    x0d = torch.from_numpy(x0[row_lo:row_hi]).to(dev)
+    r = torch.zeros(row_hi - row_lo, device=dev, dtype=torch.float64)
     g = torch.Generator(device=dev)
-    g.manual_seed(seed * 31 + 17)
     for b, m in enumerate(sizes):
         lo = int(starts[b])
-        X = ldgen.genotypes_device(torch, N_ld, lo + b * 4096, lo + b * 4096 + m, seed, dev)   # offset: blocks independent
+        gb = mine[b]                                                        # global block index
+        glo = int(all_starts[gb]) + gb * 4096                               # offset: blocks independent
+        g.manual_seed(seed * 31 + 17 + gb * 1009)
+        X = ldgen.genotypes_device(torch, N_ld, glo, glo + m, seed, dev)
         Rb = X.t() @ X
         Rb = torch.triu(Rb) + torch.triu(Rb, 1).t()
         Rb.fill_diagonal_(1.0)
@@ -217,13 +230,37 @@ def run_config(a, bench):
     cfg = CONFIGS[a.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    if world > 1:
-        # these shapes are measured on one GPU; further ranks have nothing to do (the row-partitioned shape is c5)
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sharded = world > 1 and cfg["kind"] == "blockdiag"       # c3: LD blocks sharded over the GPUs, scalar-only exchange
+    if world > 1 and not sharded:
+        # the dense shapes are measured on one GPU; further ranks have nothing to do
         if rank != 0:
             return
+        local_rank = 0
     ncores = len(os.sched_getaffinity(0))
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(local_rank)
+    import shard as shd
+    shard = shd.SoloShard()
+    if sharded:
+        import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+        shard = shd.TorchShard()
+
+    def max_over_ranks(x):
+        if not sharded:
+            return float(x)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor(np.atleast_1d(np.asarray(x, dtype=np.float64)), device=dev)
+        if sharded:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
     M, Ns, L, s, K = cfg["M"], cfg["N"], cfg["L"], cfg["s"], len(cfg["N"])
     Nt = float(sum(Ns))
     pv, pp = prior_for(M, L)
@@ -240,7 +277,13 @@ def run_config(a, bench):
             rs_.append(r)
         x0 = beta * np.sqrt(Ns[0])
     else:
-        P, starts, offs, lds, r, x0 = gen_blockdiag(torch, M, seed, dev, s, Ns[0])
+        bounds = None
+        lo, hi = 0, M
+        if sharded:
+            gstarts = np.concatenate([[0], np.cumsum(block_sizes(M, seed))])
+            bounds = shd.partition_blocks(gstarts, world)                   # whole LD blocks per GPU, balanced by sum m_b^2
+            lo, hi = bounds[rank]
+        P, starts, offs, lds, r, x0 = gen_blockdiag(torch, M, seed, dev, s, Ns[0], row_lo=lo, row_hi=hi)
         keep.append(P)
         Rs.append(sgvamp.DeviceBlockDiag(P.data_ptr(), starts, offs, lds, keepalive=P))
         rs_.append(r)
@@ -250,17 +293,18 @@ def run_config(a, bench):
     torch.cuda.set_stream(solver_stream)
     stream = solver_stream.cuda_stream
 
-    def new_solver(Mx=M, Nsx=Ns):
+    def new_solver(Mx=M, Nsx=Ns, solo=False):
+        kw = dict(shard=shard, shard_rows=bounds, halo=False) if (sharded and not solo) else {}
         return sgvamp.VAMP(N=Nsx if K > 1 else Nsx[0], Nt=float(sum(Nsx)), M=Mx, K=K, rho=cfg.get("rho", 0.5), gamw=2.0, gam1=1e-6,
                            a=np.array(Nsx) / float(sum(Nsx)), prior_vars=prior_for(Mx, L)[0], prior_probs=prior_for(Mx, L)[1],
-                           out_dir=None, out_name="bench", device=0, stream=stream)
+                           out_dir=None, out_name="bench", device=local_rank, stream=stream, **kw)
 
     def run(v, R, r, n_it, pr, hook=None):
         return v.infer(R if K > 1 else R[0], list(r) if K > 1 else r[0], n_it, cg_maxit=cfg["cg_maxit"], em_prior_maxit=100,
                        learn_gamw=True, lmmse_damp=False, prior_update="em", update_prior_from=1, probes=pr, iter_hook=hook,
-                       s=0.0)
+                       s=0.0, gather_outputs=False)
 
-    sampler = bench.ClockSampler(0)
+    sampler = bench.ClockSampler(local_rank)
     v0 = new_solver()
     run(v0, Rs, rs_, 2, probes)                                       # process-level warm-up
     v0.close()
@@ -270,6 +314,8 @@ def run_config(a, bench):
     def hook(it):
         if it == a.warmup:
             torch.cuda.synchronize()
+            if sharded:
+                dist.barrier()
             v.handle.profile(True)
             launches["a"] = v.handle.launch_count()
             wall["a"] = time.time()
@@ -279,18 +325,21 @@ def run_config(a, bench):
 
     xs = run(v, Rs, rs_, iterations, probes, hook)
     torch.cuda.synchronize()
+    if sharded:
+        dist.barrier()
     wall["b"] = time.time()
     spmm_ms, spmm_launches = v.handle.profile_read()
     v.handle.profile(False)
     launches["b"] = v.handle.launch_count()
     clocks = sampler.window(wall["a"], wall["b"])
-    ms_total = events[a.warmup].elapsed_time(events[iterations])
+    ms_total = max_over_ranks(events[a.warmup].elapsed_time(events[iterations]))
     hist = v.history
     passes = sum(hist["spmm_passes"][a.warmup:])
     infos = [v.handle.ld_info(k) for k in range(K)]
     # algorithmic bytes of one 2-RHS pass over a SYMMETRIC dense store: the upper triangle once (2 bytes per matrix
     # entry on average) + vector pair in and out
-    bytes_pass = float(np.mean([2.0 * i["nnz_stored"] + 32.0 * M for i in infos]))
+    Ml = v.Ml
+    bytes_pass = float(np.mean([2.0 * i["nnz_stored"] + 32.0 * Ml for i in infos]))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(bench.REPO, "MEASURED_PEAKS.json")))
@@ -298,9 +347,20 @@ def run_config(a, bench):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     avg_ms = spmm_ms / max(passes, 1)
-    achieved = bytes_pass / (avg_ms * 1e-3) / 1e9
-    iso_ms = v.handle.spmm_bench(0, 20)
-    aligns = [float(np.dot(x.ravel(), x0) / max(np.linalg.norm(x) * np.linalg.norm(x0), 1e-300)) for x in xs]
+    achieved = -max_over_ranks(-(bytes_pass / (avg_ms * 1e-3) / 1e9))     # the slowest rank
+    avg_ms = max_over_ranks(avg_ms)
+    iso_ms = v.handle.spmm_bench(0, 20) if not sharded else None
+    xl = x0[v.lo:v.hi]
+    dots = sum_over_ranks([[float(np.dot(x.ravel(), xl)), float(np.dot(x.ravel(), x.ravel()))] for x in xs] + [[float(np.dot(xl, xl)), 0.0]])
+    dots = dots.reshape(-1, 2)
+    aligns = [float(dots[i, 0] / max(np.sqrt(dots[i, 1] * dots[-1, 0]), 1e-300)) for i in range(iterations)]
+    nlaunch = int(sum_over_ranks([launches["b"] - launches["a"]])[0])
+    nnz_all = [int(x) for x in sum_over_ranks([i["nnz_stored"] for i in infos])] if sharded else [i["nnz_stored"] for i in infos]
+    if rank != 0:
+        v.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     sys.stderr.write("trajectory (it gamw gam1 gam2 alpha1 alpha2 lam | cg | align):\n")
     for i in range(iterations):
         rw = hist["rows"][i][0]
@@ -309,10 +369,14 @@ def run_config(a, bench):
     value = a.steps / (ms_total / 1e3)
     layout = infos[0]["layout"]
     v.close()
+    if sharded:
+        torch.cuda.synchronize()
 
     # ---- end-to-end leg: host LD (fp32, pinned where it fits) -> VAMP.load_ld -> VAMP.infer -> host xhat
     e2e = None
     host_bytes = sum(4.0 * M * M for _ in range(K)) if cfg["kind"] == "dense" else 8.0 * infos[0]["nnz_stored"]
+    if sharded:
+        a.no_e2e = a.no_cpu_baseline = True        # rank 0 only prints; the one-GPU run of the shape carries those legs
     if not a.no_e2e and host_bytes < 48e9:
         import scipy.sparse
         hostR = []
@@ -383,21 +447,27 @@ def run_config(a, bench):
     kernel = {"dense": "k_spmm_psym (2-RHS upper-triangle symmetric dense SpMM) + k_psym_finish",
               "blockdiag": "k_spmm_psym (2-RHS upper-triangle SpMM over the LD blocks' panels) + k_psym_finish"}[cfg["kind"]]
     line = {
-        "metric": "VAMP iterations/s", "value": value, "unit": "it/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
+        "metric": "VAMP iterations/s", "value": value, "unit": "it/s", "n_gpus": world if sharded else 1, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "%s: %s, cg_maxit=%d, rho=%.1f" % (a.config, cfg["text"], cfg["cg_maxit"], cfg.get("rho", 0.5)), "M": M, "K": K, "layout": layout,
-                   "nnz_stored": [i["nnz_stored"] for i in infos], "nblocks": infos[0]["nblocks"],
+                   "nnz_stored": nnz_all, "nblocks_rank0": infos[0]["nblocks"],
+                   "partition": ("%d GPUs, whole LD blocks per GPU balanced by sum m_b^2 (shard.partition_blocks); SpMM local, "
+                                 "scalar reductions exchanged in-kernel through peer memory" % world) if sharded else "single GPU",
                    "l2_policy": "inputs (%.1f GB of LD in HBM) larger than L2" % (sum(i["nnz_stored"] for i in infos) * 4 / 1e9),
                    "timed_iterations": "VAMP iterations %d..%d of one trajectory" % (a.warmup, iterations - 1),
                    "cg_iters_timed": [[list(hist["cg_iters"][i][k]) for k in range(K)] for i in range(a.warmup, iterations)],
                    "spmm_passes_timed": passes, "alignment_with_truth": aligns[-1], "gen_seconds": t_gen,
-                   "note": "single-GPU shape; under torchrun only rank 0 runs it" if world > 1 else None},
+                   "note": "single-GPU shape; under torchrun only rank 0 runs it" if (world > 1 and not sharded) else None},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "kernel": kernel, "bytes_per_launch": bytes_pass, "avg_launch_ms": avg_ms, "launches_timed": spmm_launches,
-                     "isolated_launch_ms": iso_ms, "isolated_gbs": bytes_pass / (iso_ms * 1e-3) / 1e9,
+                     "isolated_launch_ms": iso_ms, "isolated_gbs": (bytes_pass / (iso_ms * 1e-3) / 1e9) if iso_ms else None,
+                     "per": "GPU (slowest rank)",
                      "bytes_definition": "upper triangle of the symmetric fp32 store (2 B per matrix entry) + 32 B per marker",
                      "spmm_share_of_step": spmm_ms / ms_total},
-        "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches["b"] - launches["a"]), "clocks": clocks,
+        "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": nlaunch, "clocks": clocks,
     }
     print(json.dumps(line))
+    if sharded:
+        dist.barrier()
+        dist.destroy_process_group()
