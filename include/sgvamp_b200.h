@@ -108,6 +108,17 @@ int sgv_ld_adopt_dense(sgv_handle h, int cohort, const float* R_dev, int64_t ld)
  * panels_dev + offs[b] with leading dimension lds[b] (offs, lds multiples of 4 elements).  Symmetry is verified. */
 int sgv_ld_adopt_blockdiag(sgv_handle h, int cohort, const float* panels_dev, int nblocks, const int64_t* starts,
                            const int64_t* offs, const int* lds);
+/* On-GPU LD construction (simulation/sim_gen_phen_mult.py:39-55: X column-standardised genotypes / sqrt(N), R = X^T X,
+ * r = X^T y; scripts/plink2np.py builds the same kind of matrix from PLINK output): banded R with half-bandwidth w from
+ * int8 genotypes in {0,1,2}, marker-major (one row of N samples per marker, as in a .bed file; rows `ldg` bytes apart,
+ * ldg a multiple of 16, padding zero).  G holds the markers [g0, g0+nmark), which must cover this handle's rows, the
+ * w markers after them and (ranks > 0 of a row partition) the sgv_dsym_extension rows before them; host or device
+ * pointer (on_device).  The integer Gram sums are exact; standardisation, the optional Bartlett taper
+ * 1-|i-j|/(w+1), Rused = (1-s) R + s I and the fp32 rounding are applied once, and the result is written directly in
+ * the symmetric half-band layout (see sgv_ld_adopt_dsym).  y (host, N entries) != NULL: xty_out (host, local rows)
+ * receives r = X^T y of the same standardised X. */
+int sgv_ld_build_banded(sgv_handle h, int cohort, const int8_t* G, int on_device, int64_t g0, int64_t nmark, int64_t N,
+                        int64_t ldg, int64_t w, double s, int taper, const double* y, double* xty_out);
 /* layout actually chosen + stored bytes + algorithmic bytes of one SpMM pass at nrhs */
 int sgv_ld_info(sgv_handle h, int cohort, int* layout, int64_t* nnz_stored, int64_t* bandwidth,
                 int64_t* nblocks, double* bytes_per_pass_nrhs2);

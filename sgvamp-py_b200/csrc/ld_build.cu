@@ -1,0 +1,202 @@
+// On-GPU LD construction: banded R = X^T X and r = X^T y from int8 genotypes, written straight into
+// the tiled symmetric half-band layout the SpMM kernels stream (sgv_ld_adopt_dsym) - no dense M x M product, no host pass.
+//
+// Reference recipe (simulation/sim_gen_phen_mult.py:39-55): X = genotypes {0,1,2}, column-standardised with the
+// population standard deviation, divided by sqrt(N); R = X^T X, r = X^T y.  With integer genotypes g,
+//     S_ij = sum_n g_ni g_nj   (exact int32),   mu_i = sum_n g_ni / N,   sd_i = sqrt(S_ii / N - mu_i^2),
+//     R_ij = (S_ij - N mu_i mu_j) / (N sd_i sd_j),        r_j = (sum_n g_nj y_n - mu_j sum_n y_n) / (sd_j sqrt(N)),
+// so the whole contraction is an integer Gram product restricted to the band |i - j| <= w; the standardisation, the
+// optional Bartlett taper 1 - |i-j|/(w+1) (keeps a truncated band positive semi-definite), Rused = (1-s) R + s I
+// (src/main.py:265) and the fp32 rounding happen once, in the epilogue, from exact integers in fp64.
+//
+// Genotypes are marker-major (one row of N samples per marker, as in a PLINK .bed), int8, rows padded with zeros to a
+// multiple of 16 bytes.  Kernel: a CTA owns 64 markers (rows i) x 64 markers (columns j) of the band and sweeps the
+// samples in chunks of 256 through shared memory; a thread accumulates a 4 x 4 block of S with IDP4A (4 samples per
+// instruction), operands fetched as 128-bit shared-memory loads (8 LDS.128 per 64 IDP4A).
+#include <algorithm>
+#include <cstring>
+#include "sgv_device.cuh"
+
+#define LB_T 64        // markers per tile side
+#define LB_KC 256      // samples per shared-memory chunk (bytes per marker row in the chunk)
+#define LB_PAD 16      // row padding in shared memory (bytes): rows 272 B apart -> conflict-free 128-bit loads
+
+__global__ void __launch_bounds__(256)
+k_ld_col_stats(const int8_t* __restrict__ G, int64_t ldg, int64_t nmark, int64_t N, double* __restrict__ mu, double* __restrict__ sd) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= nmark) return;
+    const int* row = reinterpret_cast<const int*>(G + j * ldg);
+    int s1 = 0, s2 = 0;
+    for (int64_t k = lane; k < ldg / 4; k += 32) {
+        const int v = row[k];
+        s1 = __dp4a(v, 0x01010101, s1);
+        s2 = __dp4a(v, v, s2);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+        const double m = (double)s1 / (double)N;
+        mu[j] = m;
+        sd[j] = sqrt(fmax((double)s2 / (double)N - m * m, 0.0));
+    }
+}
+
+// G: markers [g0, g0 + nmark) of the matrix (global indices), row jb of the buffer = marker g0 + jb.
+// Output rows: storage row t <-> global marker row_lo - E + t, t in [0, rows_st); diagonals d in [0, w].
+__global__ void __launch_bounds__(256)
+k_ld_band_gram(const int8_t* __restrict__ G, int64_t ldg, int64_t g0, int64_t nmark, int64_t N, const double* __restrict__ mu,
+               const double* __restrict__ sd, float* __restrict__ U, int64_t ngr, int64_t w, int64_t row_lo, int64_t E,
+               int64_t rows_st, int64_t M, double s, int taper) {
+    __shared__ __align__(16) int8_t sa[LB_T][LB_KC + LB_PAD];
+    __shared__ __align__(16) int8_t sb[LB_T][LB_KC + LB_PAD];
+    const int tid = threadIdx.x;
+    const int ti = tid >> 4, tj = tid & 15;                       // 16 x 16 threads, 4 x 4 outputs each
+    const int64_t t0 = (int64_t)blockIdx.x * LB_T;                // first storage row of the tile
+    const int64_t i0 = row_lo - E + t0;                           // its global marker
+    const int64_t j0 = i0 + (int64_t)blockIdx.y * LB_T;           // first column marker of the tile
+    if (j0 - (i0 + LB_T - 1) > w) return;                         // tile entirely outside the band
+    int acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0;
+    for (int64_t k0 = 0; k0 < ldg; k0 += LB_KC) {
+        const int kc = (int)min((int64_t)LB_KC, ldg - k0);        // multiple of 16
+        // stage 64 rows of A and of B: 16-byte pieces, zero outside the buffer / beyond kc
+        for (int p = tid; p < LB_T * (LB_KC / 16); p += 256) {
+            const int r = p / (LB_KC / 16), c16 = p % (LB_KC / 16);
+            int4 va = make_int4(0, 0, 0, 0), vb = va;
+            if (c16 * 16 < kc) {
+                const int64_t ia = i0 + r - g0, jb = j0 + r - g0;
+                if (ia >= 0 && ia < nmark) va = *reinterpret_cast<const int4*>(G + ia * ldg + k0 + c16 * 16);
+                if (jb >= 0 && jb < nmark) vb = *reinterpret_cast<const int4*>(G + jb * ldg + k0 + c16 * 16);
+            }
+            *reinterpret_cast<int4*>(&sa[r][c16 * 16]) = va;
+            *reinterpret_cast<int4*>(&sb[r][c16 * 16]) = vb;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < LB_KC; kk += 16) {
+            int4 a4[4], b4[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) a4[a] = *reinterpret_cast<const int4*>(&sa[ti + 16 * a][kk]);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) b4[b] = *reinterpret_cast<const int4*>(&sb[tj + 16 * b][kk]);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    acc[a][b] = __dp4a(a4[a].x, b4[b].x, acc[a][b]);
+                    acc[a][b] = __dp4a(a4[a].y, b4[b].y, acc[a][b]);
+                    acc[a][b] = __dp4a(a4[a].z, b4[b].z, acc[a][b]);
+                    acc[a][b] = __dp4a(a4[a].w, b4[b].w, acc[a][b]);
+                }
+        }
+        __syncthreads();
+    }
+    // epilogue: standardise, taper, regularise, round once, scatter into the tiled half band
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int64_t t = t0 + ti + 16 * a, i = row_lo - E + t;   // storage row / global marker
+        if (t >= rows_st || i < 0 || i >= M) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int64_t j = j0 + tj + 16 * b, d = j - i;
+            if (d < 0 || d > w || j >= M) continue;
+            if (t < E && j < row_lo) continue;                    // extension rows keep only their couplings to own rows
+            const double mi = mu[i - g0], mj = mu[j - g0], si = sd[i - g0], sj = sd[j - g0];
+            double r = 0.0;
+            if (si > 0.0 && sj > 0.0) r = ((double)acc[a][b] - (double)N * mi * mj) / ((double)N * si * sj);
+            if (d == 0) r = 1.0;                                   // unit diagonal (a monomorphic marker is left uncoupled)
+            if (taper) r *= 1.0 - (double)d / (double)(w + 1);
+            r = (1.0 - s) * r + (d == 0 ? s : 0.0);
+            if (d == 0) r *= 0.5;                                  // the layout stores half of the diagonal
+            U[sgv_dsym_index(t, d, ngr)] = (float)r;
+        }
+    }
+}
+
+// r_j = (sum_n g_nj y_n - mu_j sum_n y_n) / (sd_j sqrt(N)) for the own markers
+__global__ void __launch_bounds__(256)
+k_ld_xty(const int8_t* __restrict__ G, int64_t ldg, int64_t g0, int64_t N, const double* __restrict__ mu, const double* __restrict__ sd,
+         const double* __restrict__ y, double ysum, int64_t row_lo, int64_t rows, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= rows) return;
+    const int64_t jb = row_lo + t - g0;
+    const int8_t* row = G + jb * ldg;
+    double acc = 0.0;
+    for (int64_t n = lane; n < N; n += 32) acc += (double)row[n] * y[n];
+    acc = warp_sum(acc);
+    if (lane == 0) out[t] = sd[jb] > 0.0 ? (acc - mu[jb] * ysum) / (sd[jb] * sqrt((double)N)) : 0.0;
+}
+
+extern "C" int sgv_ld_build_banded(sgv_handle c, int cohort, const int8_t* G, int on_device, int64_t g0, int64_t nmark,
+                                   int64_t N, int64_t ldg, int64_t w, double s, int taper, const double* y, double* xty_out) {
+    SGV_CHECK(c != nullptr && c->M > 0, "handle not configured");
+    SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort index %d out of range [0,%d)", cohort, c->K);
+    SGV_CUDA(cudaSetDevice(c->device));
+    SGV_CHECK(G != nullptr && N > 0 && ldg >= N && ldg % 16 == 0, "genotype rows must be padded to a multiple of 16 bytes (ldg >= N)");
+    SGV_CHECK(w >= 0 && w < c->M && sgv_dsym_feasible(w), "half-bandwidth %lld not supported by the half-band layout", (long long)w);
+    SGV_CHECK(N < (1LL << 29), "N too large for exact int32 Gram sums of genotypes in {0,1,2}");
+    SGV_CHECK(c->world == 1 || c->halo, "banded LD construction needs a halo partition when sharded");
+    const int64_t E = sgv_dsym_ext(c, w), Ml = c->Ml, row_lo = c->row_lo, M = c->M;
+    const int64_t need_lo = std::max<int64_t>(0, row_lo - E), need_hi = std::min<int64_t>(M, row_lo + Ml + w);
+    SGV_CHECK(g0 <= need_lo && g0 + nmark >= need_hi, "genotype window [%lld,%lld) must cover markers [%lld,%lld) (own rows, "
+              "the extension rows before them and w markers after them)", (long long)g0, (long long)(g0 + nmark),
+              (long long)need_lo, (long long)need_hi);
+    const int8_t* dG = G;
+    int8_t* owned = nullptr;
+    if (!on_device) {
+        SGV_CUDA(cudaMalloc(&owned, (size_t)nmark * ldg));
+        SGV_CUDA(cudaMemcpyAsync(owned, G, (size_t)nmark * ldg, cudaMemcpyHostToDevice, c->stream));
+        dG = owned;
+    }
+    double *mu = nullptr, *sd = nullptr, *dy = nullptr, *dout = nullptr;
+    int rc = 0;
+    LdMatrix& ld = c->coh[cohort].ld;
+    do {
+        if (cudaMalloc(&mu, 2 * (size_t)nmark * sizeof(double)) != cudaSuccess) { sgv_set_error("out of device memory"); rc = -2; break; }
+        sd = mu + nmark;
+        k_ld_col_stats<<<(unsigned)((nmark * 32 + 255) / 256), 256, 0, c->stream>>>(dG, ldg, nmark, N, mu, sd);
+        c->launches++;
+        sgv_ld_free(ld);
+        const int64_t Dp = round_up(w + 1, 4), ngr = Dp / 4, ldb = round_up(Ml + E, 128);
+        float* U = nullptr;
+        if (cudaMalloc(&U, (size_t)Dp * ldb * sizeof(float)) != cudaSuccess) { sgv_set_error("out of device memory"); rc = -2; break; }
+        ld.band = U;
+        ld.owned = true;
+        ld.w = w;
+        ld.ldb = ldb;
+        ld.ext = E;
+        ld.nnz_stored = (w + 1) * Ml;
+        cudaMemsetAsync(U, 0, (size_t)Dp * ldb * sizeof(float), c->stream);
+        const dim3 grid((unsigned)((Ml + E + LB_T - 1) / LB_T), (unsigned)((w + LB_T - 1) / LB_T + 1));
+        k_ld_band_gram<<<grid, 256, 0, c->stream>>>(dG, ldg, g0, nmark, N, mu, sd, U, ngr, w, row_lo, E, Ml + E, M, s, taper);
+        c->launches++;
+        ld.layout = SGV_LAYOUT_DSYM;
+        if ((rc = sgv_dsym_ensure_scratch(c, ld)) != 0) break;
+        if (y != nullptr && xty_out != nullptr) {
+            if (cudaMalloc(&dy, (size_t)(N + Ml) * sizeof(double)) != cudaSuccess) { sgv_set_error("out of device memory"); rc = -2; break; }
+            dout = dy + N;
+            cudaMemcpyAsync(dy, y, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+            double ysum = 0.0;
+            for (int64_t n = 0; n < N; ++n) ysum += y[n];
+            k_ld_xty<<<(unsigned)((Ml * 32 + 255) / 256), 256, 0, c->stream>>>(dG, ldg, g0, N, mu, sd, dy, ysum, row_lo, Ml, dout);
+            c->launches++;
+            cudaMemcpyAsync(xty_out, dout, (size_t)Ml * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        }
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            sgv_set_error("LD construction kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = -2;
+        }
+    } while (0);
+    cudaFree(mu);
+    cudaFree(dy);
+    cudaFree(owned);
+    if (rc != 0) sgv_ld_free(ld);
+    return rc;
+}

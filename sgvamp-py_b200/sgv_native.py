@@ -29,7 +29,7 @@ SYMBOLS = [
     "sgv_peer_attach_local", "sgv_partition_info", "sgv_ld_set_bandwidth_hint", "sgv_spmm_stage", "sgv_spmm_run",
     "sgv_ld_adopt_dsym", "sgv_dsym_extension", "sgv_set_host_barrier", "sgv_device_id", "sgv_ld_upload_dia",
     "sgv_iteration_supported", "sgv_vamp_begin", "sgv_set_truth", "sgv_iteration_probe_buffer", "sgv_iteration_enqueue",
-    "sgv_iteration_wait", "sgv_ld_adopt_blockdiag",
+    "sgv_iteration_wait", "sgv_ld_adopt_blockdiag", "sgv_ld_build_banded",
 ]
 MAX_K, MAX_L, ITER_SLOTS = 8, 8, 4
 
@@ -218,6 +218,27 @@ class Handle:
         self._ck(self.lib.sgv_ld_adopt_blockdiag(self.h, C.c_int(cohort), C.c_void_p(ptr), C.c_int(nb),
                                                  st.ctypes.data_as(C.POINTER(C.c_int64)), of.ctypes.data_as(C.POINTER(C.c_int64)),
                                                  ld.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def build_banded(self, cohort, G, N, w, s=0.0, taper=True, y=None, g0=0, device_ptr=None, nmark=None, ldg=None):
+        """Banded LD (and XTy) from int8 genotypes, marker-major.  G: (nmark, ldg) int8 host array with ldg % 16 == 0 and
+        zero padding beyond N - or device_ptr/nmark/ldg for a buffer already in HBM."""
+        out = None
+        yp = None
+        if y is not None:
+            y = _f64(y).ravel()
+            assert y.shape[0] == N
+            out = np.empty(self.M, dtype=np.float64)
+            yp = _dp(y)
+        if device_ptr is None:
+            G = np.ascontiguousarray(G, dtype=np.int8)
+            nmark, ldg = G.shape
+            ptr, on_dev = G.ctypes.data_as(C.c_void_p), 0
+        else:
+            ptr, on_dev = C.c_void_p(int(device_ptr)), 1
+        self._ck(self.lib.sgv_ld_build_banded(self.h, C.c_int(cohort), ptr, C.c_int(on_dev), C.c_int64(g0), C.c_int64(nmark),
+                                              C.c_int64(N), C.c_int64(ldg), C.c_int64(w), C.c_double(s), C.c_int(int(bool(taper))),
+                                              yp, _dp(out) if out is not None else None))
+        return out
 
     def ld_info(self, cohort):
         layout = C.c_int()

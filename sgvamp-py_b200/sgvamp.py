@@ -315,6 +315,14 @@ class VAMP:
         self._ld_loaded[cohort] = True
         return h.ld_info(cohort)
 
+    def build_ld_from_genotypes(self, cohort, G, N, w, s=0.0, taper=True, y=None, g0=0, device_ptr=None, nmark=None, ldg=None):
+        """Banded LD of one cohort (and r = X^T y when y is given) computed on the GPU from int8 genotypes in {0,1,2},
+        marker-major, following simulation/sim_gen_phen_mult.py:39-55 restricted to |i-j| <= w (see sgv_ld_build_banded).
+        Returns r (this rank's rows) or None."""
+        r = self.handle.build_banded(cohort, G, N, w, s=s, taper=taper, y=y, g0=g0, device_ptr=device_ptr, nmark=nmark, ldg=ldg)
+        self._ld_loaded[cohort] = True
+        return r
+
     # ------------------------------------------------------------------------------------------
     # per-step methods kept for API compatibility (reference src/sgvamp.py:93-194)
     # ------------------------------------------------------------------------------------------
