@@ -69,10 +69,11 @@ def make_probes(iterations, M, seed):
 # ------------------------------------------------------------------------------------------------
 # synthetic banded LD + XTy on the device (torch as a data-generation utility)
 # ------------------------------------------------------------------------------------------------
-def build_problem(torch, M, w, seed, dev, lo=0, hi=None, ext=0, keep_full=True):
+def build_problem(torch, M, w, seed, dev, lo=0, hi=None, ext=0, keep_full=True, use_library=True):
     """Rows [lo, hi) of the workload.  Returns the symmetric half band of Rused in the DSYM layout
     (fp32, device; with `ext` leading extension rows for ranks > 0, sgv_ld_adopt_dsym), the full band
-    of the rows [lo-ext, hi) (for the host-side end-to-end leg; None unless keep_full), r (host), x0 (host, global)."""
+    of the rows [lo-ext, hi) (for the host-side end-to-end leg; None unless keep_full; the extension rows hold only their
+    couplings to the own rows), r (host), x0 (host, global)."""
     import ldgen
     t0 = time.time()
     hi = M if hi is None else hi
@@ -80,11 +81,33 @@ def build_problem(torch, M, w, seed, dev, lo=0, hi=None, ext=0, keep_full=True):
     glo = lo - ext                                  # first generated row (extension rows included)
     assert glo >= 0
     n = hi - glo
-    band, noise = ldgen.banded_dia_device(torch, M, w, glo, hi, seed, dev, N_ld=N_LD)   # (2w+1) x n
-    for d in range(1, w + 1):                       # exactly symmetric: the lower triangle mirrors the upper one
-        band[w - d, d:] = band[w + d, : n - d]      # (fp32 sample LD differs in the last bit between the triangles)
-    band *= (1.0 - S_REG)                           # Rused = (1-s) R + s I  (src/main.py:265)
-    band[w, :] += S_REG
+    # LD by the library's own construction kernel (sgv_ld_build_banded: exact integer Gram sums of the int8 genotypes,
+    # standardisation + Bartlett taper + Rused = (1-s) R + s I in its epilogue, tiled half band as output); torch only
+    # synthesises the genotypes and the noise
+    Dp = (w + 1 + 3) // 4 * 4
+    if use_library:
+        import sgv_native as nat
+        part = lo > 0 or hi < M
+        U, ldb, ext_lib, noise_own = ldgen.banded_dsym_library(torch, nat, M, w, lo, hi, 1 if ext > 0 else 0, 2 if part else 1,
+                                                                seed, dev, S_REG, N_ld=N_LD)
+        assert ext_lib == ext, (ext_lib, ext)
+        Ud = ldgen.dsym_untile(torch, U, Dp, ldb)[: w + 1, :n]
+        band = torch.zeros((2 * w + 1, n), device=dev, dtype=torch.float32)   # full band of the rows [glo, hi) (r, host legs)
+        band[w:, :] = Ud
+        band[w] *= 2.0                              # the layout stores half of the diagonal
+        for d in range(1, w + 1):
+            band[w - d, d:] = Ud[d, : n - d]
+        del Ud
+    else:
+        # the same workload from torch matmuls (reference arm: nothing of this library on its path; CPU-only boxes)
+        band, noise = ldgen.banded_dia_device(torch, M, w, glo, hi, seed, dev, N_ld=N_LD)   # (2w+1) x n
+        for d in range(1, w + 1):                   # exactly symmetric: the lower triangle mirrors the upper one
+            band[w - d, d:] = band[w + d, : n - d]
+        band *= (1.0 - S_REG)                       # Rused = (1-s) R + s I  (src/main.py:265)
+        band[w, :] += S_REG
+        noise_own = noise[ext:]
+        ldb = (n + 127) // 128 * 128
+        U = None
     x0_host = ldgen.causal_effects(M, n_gwas(M), LAM_TRUE, H2, seed)
     # r = Rused x0 + n,  n ~ N(0, (1-h2) Rused): the summary-statistic form of the reference recipe
     # (simulation/sim_gen_phen_mult.py:39-55: r = X^T y, R = X^T X  =>  r ~ N(R x0, (1-h2) R))
@@ -98,21 +121,10 @@ def build_problem(torch, M, w, seed, dev, lo=0, hi=None, ext=0, keep_full=True):
     g = torch.Generator(device=dev)
     g.manual_seed(seed * 31 + 17)
     z = torch.randn((M,), generator=g, device=dev, dtype=torch.float64)[lo:hi]
-    r += float(np.sqrt(1.0 - H2)) * (float(np.sqrt(1.0 - S_REG)) * noise[ext:] + float(np.sqrt(S_REG)) * z)
-    # half band: U[d, j] = Rused[i, i+d], i = glo + j; extension rows keep only their couplings to own rows
-    Dp = (w + 1 + 3) // 4 * 4
-    ldb = (n + 127) // 128 * 128
-    U = torch.zeros((Dp, ldb), device=dev, dtype=torch.float32)
-    U[: w + 1, :n] = band[w:, :]
-    U[0] *= 0.5                                     # DSYM convention: the diagonal is stored halved
-    if ext:
-        jj = torch.arange(ext, device=dev)[None, :]
-        dd = torch.arange(Dp, device=dev)[:, None]
-        U[:, :ext] *= (jj + dd >= ext).to(torch.float32)
+    r += float(np.sqrt(1.0 - H2)) * (float(np.sqrt(1.0 - S_REG)) * noise_own + float(np.sqrt(S_REG)) * z)
     full = band if keep_full else None              # full band of the rows [glo, hi) (host-side legs)
     del band
-    U = ldgen.dsym_tile(torch, U)                   # [ldb/128][Dp/4][4][128]: one contiguous stream per 128-row block
-    if U.is_cuda:
+    if dev.type == "cuda":
         torch.cuda.synchronize()
     return U, ldb, full, r.cpu().numpy(), x0_host, time.time() - t0
 
@@ -228,12 +240,12 @@ def band_to_scipy_dia(band, M, w):
     return scipy.sparse.dia_matrix((data, np.arange(-w, w + 1)), shape=(M, M))
 
 
-def build_sample(torch, Ms, w, seed, dev):
+def build_sample(torch, Ms, w, seed, dev, use_library=True):
     """The bounded sample both arms run: the first Ms markers' worth of the benchmark workload, produced by the SAME
     generator and parameters as the M-marker problem (ldgen.banded_dia_device, N_ld = 4096, Bartlett taper, s, h2).
     Returns the device half band (for the GPU), Rused as scipy CSR in fp64 (what src/main.py:199-265 hands the
     reference solver for an .npz LD file), r, x0."""
-    U, ldb, band, r, x0, _ = build_problem(torch, Ms, w, seed, dev)
+    U, ldb, band, r, x0, _ = build_problem(torch, Ms, w, seed, dev, use_library=use_library)
     R = band_to_scipy_dia(band.cpu().numpy(), Ms, w).tocsr()
     del band
     return U, ldb, R, r, x0
@@ -316,7 +328,7 @@ def main():
         dev = torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
         its = max(2, min(a.steps + a.warmup, 3))
         Ms = int(min(a.cpu_sample_M, a.M))
-        _U, _ldb, Rs, rs_, _x0 = build_sample(torch, Ms, a.w, a.seed, dev)
+        _U, _ldb, Rs, rs_, _x0 = build_sample(torch, Ms, a.w, a.seed, dev, use_library=False)
         del _U
         res = cpu_reference_run(Rs, rs_, a.M, its, make_probes(its, Ms, a.seed), threads=ncores)
         line = {"impl": "reference", "metric": "VAMP iterations/s", "value": res["value"], "unit": "it/s",

@@ -119,6 +119,9 @@ int sgv_ld_adopt_blockdiag(sgv_handle h, int cohort, const float* panels_dev, in
  * receives r = X^T y of the same standardised X. */
 int sgv_ld_build_banded(sgv_handle h, int cohort, const int8_t* G, int on_device, int64_t g0, int64_t nmark, int64_t N,
                         int64_t ldg, int64_t w, double s, int taper, const double* y, double* xty_out);
+/* copy a cohort's half band (tiled layout of sgv_ld_adopt_dsym, roundup(w+1,4) x ldb floats) into a device buffer of the
+ * caller, e.g. to adopt one constructed matrix in several handles; dst_dev == NULL only returns w / ldb / ext */
+int sgv_ld_copy_band(sgv_handle h, int cohort, float* dst_dev, int64_t nfloats, int64_t* w, int64_t* ldb, int64_t* ext);
 /* layout actually chosen + stored bytes + algorithmic bytes of one SpMM pass at nrhs */
 int sgv_ld_info(sgv_handle h, int cohort, int* layout, int64_t* nnz_stored, int64_t* bandwidth,
                 int64_t* nblocks, double* bytes_per_pass_nrhs2);

@@ -200,3 +200,21 @@ extern "C" int sgv_ld_build_banded(sgv_handle c, int cohort, const int8_t* G, in
     if (rc != 0) sgv_ld_free(ld);
     return rc;
 }
+
+// Copy a cohort's half band (tiled layout, Dp x ldb floats) into a caller's device buffer: lets one constructed matrix
+// be adopted by several handles (benchmarks build once and run several solvers).
+extern "C" int sgv_ld_copy_band(sgv_handle c, int cohort, float* dst_dev, int64_t nfloats, int64_t* w, int64_t* ldb, int64_t* ext) {
+    SGV_CHECK(c != nullptr && cohort >= 0 && cohort < c->K, "bad handle / cohort");
+    SGV_CUDA(cudaSetDevice(c->device));
+    const LdMatrix& ld = c->coh[cohort].ld;
+    SGV_CHECK(ld.layout == SGV_LAYOUT_DSYM, "cohort %d does not hold a half band", cohort);
+    const int64_t need = round_up(ld.w + 1, 4) * ld.ldb;
+    if (w) *w = ld.w;
+    if (ldb) *ldb = ld.ldb;
+    if (ext) *ext = ld.ext;
+    if (dst_dev == nullptr) return 0;                             // size query
+    SGV_CHECK(nfloats >= need, "destination holds %lld floats, %lld needed", (long long)nfloats, (long long)need);
+    SGV_CUDA(cudaMemcpyAsync(dst_dev, ld.band, (size_t)need * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}

@@ -170,8 +170,9 @@ def _latent_block(torch, n, lo, hi, seed, hap, B, kern, dev):
     return z
 
 
-def genotypes_device(torch, n, lo, hi, seed, dev, rho=0.97, B=256):
-    """Standardised genotype columns [lo, hi) (n x (hi-lo), fp32, already / sqrt(n))."""
+def genotype_counts_device(torch, n, lo, hi, seed, dev, rho=0.97, B=256):
+    """Genotype counts in {0,1,2} of the markers [lo, hi) for n samples (n x (hi-lo), fp32): two thresholded latent
+    AR(1)-like Gaussian haplotypes with a per-marker allele frequency; depends only on (seed, marker index)."""
     kern = (rho ** torch.arange(B + 1, device=dev, dtype=torch.float32))
     kern = kern / kern.norm()
     j = torch.arange(lo, hi, device=dev, dtype=torch.float64)
@@ -183,6 +184,12 @@ def genotypes_device(torch, n, lo, hi, seed, dev, rho=0.97, B=256):
     for hap in range(2):
         z = _latent_block(torch, n, lo, hi, seed, hap, B, kern, dev)
         G += (z < thr[None, :]).to(torch.float32)
+    return G
+
+
+def genotypes_device(torch, n, lo, hi, seed, dev, rho=0.97, B=256):
+    """Standardised genotype columns [lo, hi) (n x (hi-lo), fp32, already / sqrt(n))."""
+    G = genotype_counts_device(torch, n, lo, hi, seed, dev, rho, B)
     mu = G.mean(dim=0, keepdim=True)
     sd = G.std(dim=0, unbiased=False, keepdim=True)
     sd = torch.where(sd == 0, torch.ones_like(sd), sd)
@@ -225,6 +232,55 @@ def banded_dia_device(torch, M, w, lo, hi, seed, dev, N_ld=4096, chunk=4096):
         del X, P, E, C, F
     band[w, :] = 1.0
     return band, noise
+
+
+def banded_dsym_library(torch, nat, M, w, lo, hi, rank, world, seed, dev, s, N_ld=4096, chunk=8192):
+    """Rows [lo, hi) of the same workload as banded_dia_device, with the LD matrix built by the LIBRARY's kernel
+    (sgv_ld_build_banded: integer Gram sums of the int8 genotypes, standardisation, Bartlett taper and Rused = (1-s) R + s I
+    in its epilogue, written straight into the tiled half-band layout) instead of torch matmuls.  torch only synthesises
+    the genotypes and the exact N(0, R) noise.  Returns (U tiled fp32 tensor, ldb, ext, noise fp64 for rows [lo, hi))."""
+    h = nat.Handle(device=dev.index or 0)
+    if world > 1:
+        h.configure_part(M, 1, rank, world, lo, hi, True)
+    else:
+        h.configure(M, 1)
+    ext = h.dsym_extension(w)
+    g0, g1 = max(0, lo - ext), min(M, hi + w)
+    ldg = (N_ld + 15) // 16 * 16
+    Gt = torch.zeros((g1 - g0, ldg), device=dev, dtype=torch.int8)
+    noise = torch.empty((hi - lo,), device=dev, dtype=torch.float64)
+    for c0 in range(g0, g1, chunk):
+        c1 = min(g1, c0 + chunk)
+        G = genotype_counts_device(torch, N_ld, c0, c1, seed, dev)            # N_ld x (c1-c0)
+        Gt[c0 - g0: c1 - g0, :N_ld] = G.t().to(torch.int8)
+        a0, a1 = max(c0, lo), min(c1, hi)                                      # own rows of this chunk: their noise
+        if a1 > a0:
+            Gi = G[:, a0 - c0: a1 - c0].to(torch.float64)
+            mu = Gi.mean(dim=0, keepdim=True)
+            sd = Gi.std(dim=0, unbiased=False, keepdim=True)
+            sd = torch.where(sd == 0, torch.ones_like(sd), sd)
+            Xi = (Gi - mu) / sd / float(np.sqrt(N_ld))
+            E = _chunked_randn(torch, N_ld, a0 - w, a1, seed, 5, dev)
+            Cs = torch.cumsum(E.to(torch.float64), dim=1)
+            F = Cs[:, w:].clone()
+            F[:, 1:] -= Cs[:, : a1 - a0 - 1]
+            noise[a0 - lo: a1 - lo] = (Xi * F).sum(dim=0) / float(np.sqrt(w + 1.0))
+            del Gi, Xi, E, Cs, F
+        del G
+    h.build_banded(0, None, N_ld, w, s=s, taper=True, g0=g0, device_ptr=Gt.data_ptr(), nmark=g1 - g0, ldg=ldg)
+    _w, ldb, ext2 = h.band_shape(0)
+    assert ext2 == ext
+    Dp = (w + 1 + 3) // 4 * 4
+    U = torch.empty((Dp * ldb,), device=dev, dtype=torch.float32)
+    h.copy_band(0, U.data_ptr(), U.numel())
+    h.close()
+    del Gt
+    return U, ldb, ext, noise
+
+
+def dsym_untile(torch, U, Dp, ldb):
+    """Inverse of dsym_tile: the tiled buffer -> (Dp, ldb) diagonal-major half band."""
+    return U.view(ldb // 128, Dp // 4, 4, 128).permute(1, 2, 0, 3).reshape(Dp, ldb)
 
 
 def dsym_tile(torch, U):

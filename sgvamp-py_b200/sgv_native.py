@@ -29,7 +29,7 @@ SYMBOLS = [
     "sgv_peer_attach_local", "sgv_partition_info", "sgv_ld_set_bandwidth_hint", "sgv_spmm_stage", "sgv_spmm_run",
     "sgv_ld_adopt_dsym", "sgv_dsym_extension", "sgv_set_host_barrier", "sgv_device_id", "sgv_ld_upload_dia",
     "sgv_iteration_supported", "sgv_vamp_begin", "sgv_set_truth", "sgv_iteration_probe_buffer", "sgv_iteration_enqueue",
-    "sgv_iteration_wait", "sgv_ld_adopt_blockdiag", "sgv_ld_build_banded",
+    "sgv_iteration_wait", "sgv_ld_adopt_blockdiag", "sgv_ld_build_banded", "sgv_ld_copy_band",
 ]
 MAX_K, MAX_L, ITER_SLOTS = 8, 8, 4
 
@@ -239,6 +239,14 @@ class Handle:
                                               C.c_int64(N), C.c_int64(ldg), C.c_int64(w), C.c_double(s), C.c_int(int(bool(taper))),
                                               yp, _dp(out) if out is not None else None))
         return out
+
+    def band_shape(self, cohort):
+        w, ldb, ext = C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self.lib.sgv_ld_copy_band(self.h, C.c_int(cohort), None, C.c_int64(0), C.byref(w), C.byref(ldb), C.byref(ext)))
+        return w.value, ldb.value, ext.value
+
+    def copy_band(self, cohort, dst_ptr, nfloats):
+        self._ck(self.lib.sgv_ld_copy_band(self.h, C.c_int(cohort), C.c_void_p(int(dst_ptr)), C.c_int64(nfloats), None, None, None))
 
     def ld_info(self, cohort):
         layout = C.c_int()
