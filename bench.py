@@ -550,7 +550,9 @@ def main():
                    "spmm_passes_timed": passes, "its_per_s_from_it0": iterations / (ms_from0 / 1e3),
                    "alignment_with_truth": aligns[-1], "gen_seconds": t_gen},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "k_spmm_dsym (2-RHS symmetric half-band SpMM, fused CG direction update) + k_dsym_finish (q, p.q)",
+                     "traffic": traffic, "kernel": "k_dsym_persist (2-RHS symmetric half-band SpMM over persistent row ranges with the whole CG step fused: direction / "
+                               "residual / solution updates while the window is staged, q and the four dot products in the epilogue; one "
+                               "cooperative launch per solve, avg_launch_ms = solve kernel time / CG steps)",
                      "per": "GPU (slowest rank)", "bytes_per_launch": bytes_pass, "avg_launch_ms": avg_ms_max,
                      "launches_timed": spmm_launches, "isolated_launch_ms": iso_ms,
                      "isolated_gbs": (bytes_pass / (iso_ms * 1e-3) / 1e9) if iso_ms else None,
