@@ -207,6 +207,7 @@ typedef struct {
 } sgv_iter_out;
 int sgv_iteration_supported(sgv_handle h);   /* 1 unless ranks share a GPU (host-barrier mode) or cooperative launch is missing */
 int sgv_vamp_begin(sgv_handle h, const double* gam1, const double* gamw, const double* N);   /* K entries each (:210-216, :352) */
+int sgv_vamp_set_alphas(sgv_handle h, const double* alpha1, const double* alpha2);   /* resume: previous alpha1 / alpha2 (K each) */
 int sgv_set_truth(sgv_handle h, const double* x0);
 int sgv_iteration_probe_buffer(sgv_handle h, int slot, int8_t** buf);
 /* xhat_pinned / r1_pinned[k]: pinned destinations (sgv_pinned_alloc) of the iteration's xhat1 and incoming r1 dumps, or NULL */

@@ -938,6 +938,17 @@ extern "C" int sgv_vamp_begin(sgv_handle c, const double* gam1, const double* ga
     return 0;
 }
 
+// resume (no reference counterpart: the reference cannot restart): the damping terms of :290-291 / :345-346
+// need the previous iteration's alpha1 / alpha2
+extern "C" int sgv_vamp_set_alphas(sgv_handle c, const double* alpha1, const double* alpha2) {
+    SGV_TRY(check_ready(c));
+    SGV_CHECK(c->vamp_begun && alpha1 && alpha2, "sgv_vamp_begin has not been called");
+    SGV_CUDA(cudaMemcpyAsync(c->cg->vs.alpha1, alpha1, c->K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SGV_CUDA(cudaMemcpyAsync(c->cg->vs.alpha2, alpha2, c->K * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 extern "C" int sgv_set_truth(sgv_handle c, const double* x0) {
     SGV_TRY(check_ready(c));
     SGV_CHECK(x0 != nullptr, "null argument");

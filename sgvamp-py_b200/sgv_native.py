@@ -29,7 +29,7 @@ SYMBOLS = [
     "sgv_peer_attach_local", "sgv_partition_info", "sgv_ld_set_bandwidth_hint", "sgv_spmm_stage", "sgv_spmm_run",
     "sgv_ld_adopt_dsym", "sgv_dsym_extension", "sgv_set_host_barrier", "sgv_device_id", "sgv_ld_upload_dia",
     "sgv_iteration_supported", "sgv_vamp_begin", "sgv_set_truth", "sgv_iteration_probe_buffer", "sgv_iteration_enqueue",
-    "sgv_iteration_wait", "sgv_ld_adopt_blockdiag", "sgv_ld_build_banded", "sgv_ld_copy_band",
+    "sgv_iteration_wait", "sgv_ld_adopt_blockdiag", "sgv_ld_build_banded", "sgv_ld_copy_band", "sgv_vamp_set_alphas",
 ]
 MAX_K, MAX_L, ITER_SLOTS = 8, 8, 4
 
@@ -350,6 +350,10 @@ class Handle:
         g1, gw, n = _f64(gam1), _f64(gamw), _f64(N)
         assert g1.shape[0] == gw.shape[0] == n.shape[0] == self.K
         self._ck(self.lib.sgv_vamp_begin(self.h, _dp(g1), _dp(gw), _dp(n)))
+
+    def vamp_set_alphas(self, alpha1, alpha2):
+        a1, a2 = _f64(alpha1), _f64(alpha2)
+        self._ck(self.lib.sgv_vamp_set_alphas(self.h, _dp(a1), _dp(a2)))
 
     def set_truth(self, x0):
         x0 = _f64(x0).ravel()

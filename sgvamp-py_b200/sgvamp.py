@@ -121,13 +121,17 @@ class _ProbeSource:
 
     def __init__(self, order, M):
         self.q = queue.Queue(maxsize=2)
+        self.states = {}            # RNG state before the draw of (it, k): what a checkpoint needs to continue the sequence
+        self.end_state = None
         self.t = threading.Thread(target=self._run, args=(order, M), daemon=True)
         self.t.start()
 
     def _run(self, order, M):
         for key in order:
+            self.states[key] = np.random.get_state()
             u = (np.random.binomial(p=1 / 2, n=1, size=M) * 2 - 1).astype(np.int8)
             self.q.put((key, u))
+        self.end_state = np.random.get_state()
 
     def get(self, key):
         k, u = self.q.get()
@@ -407,7 +411,12 @@ class VAMP:
     # ------------------------------------------------------------------------------------------
     def infer(self, R, r, iterations, x0=None, cg_maxit=500, em_prior_maxit=100, learn_gamw=True, lmmse_damp=True,
               prior_update=None, update_prior_from=1, *, s=0.0, probes=None, layout="auto", write_outputs=True,
-              iter_hook=None, gather_outputs=True):
+              iter_hook=None, gather_outputs=True, checkpoint_path=None, checkpoint_every=0, resume_from=None):
+        """checkpoint_path / checkpoint_every / resume_from (no reference counterpart: the reference cannot restart,
+        SURVEY 5.4): every `checkpoint_every` iterations the state needed to continue (r1, xhat1, xhat2, Sigma2_u, the
+        scalar chain, the prior, the legacy RNG state of the probe sequence) is written to `checkpoint_path` (one .npz per
+        row shard); `resume_from` continues such a run at the iteration after the checkpoint - the entries of the returned
+        list before it are None."""
         M, K, Nt, rho = self.M, self.K, self.Nt, self.rho
         h = self.handle
         rank = self.rank if self.shard.world == 1 else self.shard.rank   # only gates logging / rank-per-cohort mode
@@ -428,10 +437,12 @@ class VAMP:
                 raise Exception("no LD matrix for cohort %d" % k)
             h.set_xty(k, self._local(rs[idx]))
         h.reset_state()                                                 # :199-217
+        ck = dict(path=checkpoint_path, every=int(checkpoint_every or 0))
+        st0 = self._restore(resume_from) if resume_from is not None else None
         if (not self.rank_mode and prior_update != "mle" and h.iteration_supported()
                 and os.environ.get("SGV_STEPWISE", "0") != "1"):
             return self._infer_fused(rs, Ns, iterations, x0, cg_maxit, em_prior_maxit, learn_gamw, lmmse_damp,
-                                     prior_update, update_prior_from, probes, write_outputs, iter_hook, gather_outputs)
+                                     prior_update, update_prior_from, probes, write_outputs, iter_hook, gather_outputs, ck, st0)
         write = write_outputs and self.out_dir is not None
         sharded = self.shard.world > 1
         worker = _Worker()
@@ -439,7 +450,9 @@ class VAMP:
         pc = time.perf_counter
         probe_src = None
         if probes is None:
-            probe_src = _ProbeSource([(it, k) for it in range(iterations) for k in mine], M)
+            if st0 is not None and st0.get("rng_state") is not None:
+                np.random.set_state(st0["rng_state"])
+            probe_src = _ProbeSource([(it, k) for it in range(st0["it_next"] if st0 else 0, iterations) for k in mine], M)
         sqrtNt = np.sqrt(Nt)
         truth = None
         if x0 is not None:
@@ -448,6 +461,11 @@ class VAMP:
         gamw = [self.gamw] * K
         alpha1 = [np.float64(0.0)] * K
         alpha2 = [np.float64(0.0)] * K
+        it0 = 0
+        if st0 is not None:
+            it0 = st0["it_next"]
+            gam1, gamw = [np.float64(v) for v in st0["gam1"]], [float(v) for v in st0["gamw"]]
+            alpha1, alpha2 = [np.float64(v) for v in st0["alpha1"]], [np.float64(v) for v in st0["alpha2"]]
         xhat1s = [None] * iterations
         self.history = dict(rows=[], cg_iters=[], cg_info=[], em_steps=[], spmm_passes=[], lam=[], omegas=[])
         NS = 3                                                          # host-copy ring depth
@@ -459,7 +477,7 @@ class VAMP:
             logging.debug(f"a = {self.a}")
         h.sync()
         self.shard.barrier()       # every rank's state is initialised before any kernel touches peer memory
-        for it in range(iterations):
+        for it in range(it0, iterations):
             if iter_hook is not None:
                 iter_hook(it)
             if rank == 0:
@@ -571,7 +589,7 @@ class VAMP:
 
             slot_done[slot] = worker.submit(drain)
             if truth is not None:                                        # :379-387
-                d = h.metrics(truth if it == 0 else None)
+                d = h.metrics(truth if it == it0 else None)
                 alignment = d[0] / np.sqrt(d[1]) / np.sqrt(d[2])
                 l2 = np.sqrt(d[3]) / np.sqrt(d[2])
                 if rank == 0:
@@ -587,6 +605,8 @@ class VAMP:
             self.history["spmm_passes"].append(passes_it)
             self.history["lam"].append(float(self.lam))
             self.history["omegas"].append(np.array(self.omegas, dtype=np.float64).copy())
+            if ck["path"] and ck["every"] > 0 and (it + 1) % ck["every"] == 0:
+                self._checkpoint(ck["path"], it + 1, gam1, gamw, alpha1, alpha2, probe_src, mine)
             tm["host_tail"] += pc() - t_lm
         if iter_hook is not None:
             iter_hook(iterations)
@@ -595,16 +615,18 @@ class VAMP:
         self.gam1_final, self.gamw_final = gam1, gamw
         if sharded and gather_outputs:
             # the data path has no host collective; the per-rank output slices are assembled once, here
-            full = shd.gather_rows(self.shard, np.stack([x.ravel() for x in xhat1s]) if iterations else np.zeros((0, self.Ml)),
+            have = [i for i in range(iterations) if xhat1s[i] is not None]
+            full = shd.gather_rows(self.shard, np.stack([xhat1s[i].ravel() for i in have]) if have else np.zeros((0, self.Ml)),
                                    self.bounds)
-            xhat1s = [full[it].reshape(M, 1) for it in range(iterations)]
+            for j, i in enumerate(have):
+                xhat1s[i] = full[j].reshape(M, 1)
         if sharded and write:
-            self._assemble_parts(["%s_xhat_it_%d.bin" % (self.out_name, it) for it in range(iterations)] +
-                                 ["%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k + 1, it) for it in range(iterations) for k in mine])
+            self._assemble_parts(["%s_xhat_it_%d.bin" % (self.out_name, it) for it in range(it0, iterations)] +
+                                 ["%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k + 1, it) for it in range(it0, iterations) for k in mine])
         return xhat1s
 
     def _infer_fused(self, rs, Ns, iterations, x0, cg_maxit, em_prior_maxit, learn_gamw, lmmse_damp, prior_update,
-                     update_prior_from, probes, write_outputs, iter_hook, gather_outputs):
+                     update_prior_from, probes, write_outputs, iter_hook, gather_outputs, ck=None, st0=None):
         """The same loop with the scalar chain on the device (sgv_iteration_*): one VAMP iteration is enqueued without a
         host round trip and the host reads one small record per iteration, one iteration behind the GPU.  Used whenever
         the prior update does not need the host (EM or none) and this process drives all cohorts."""
@@ -619,11 +641,19 @@ class VAMP:
         worker = _Worker()
         tm = self.timers = dict(enqueue=0.0, wait=0.0, host_tail=0.0)
         pc = time.perf_counter
+        ck = ck or dict(path=None, every=0)
+        it0 = st0["it_next"] if st0 is not None else 0
         probe_src = None
         if probes is None:
-            probe_src = _ProbeSource([(it, k) for it in range(iterations) for k in mine], M)
+            if st0 is not None and st0.get("rng_state") is not None:
+                np.random.set_state(st0["rng_state"])
+            probe_src = _ProbeSource([(it, k) for it in range(it0, iterations) for k in mine], M)
         self._push_prior()
-        h.vamp_begin([self.gam1] * K, [self.gamw] * K, Ns)
+        if st0 is None:
+            h.vamp_begin([self.gam1] * K, [self.gamw] * K, Ns)
+        else:
+            h.vamp_begin(st0["gam1"], st0["gamw"], Ns)
+            h.vamp_set_alphas(st0["alpha1"], st0["alpha2"])
         truth = None
         if x0 is not None:
             truth = self._local(x0)
@@ -697,7 +727,8 @@ class VAMP:
 
             slot_done[slot] = worker.submit(drain)
 
-        for it in range(iterations):
+        finished = it0 - 1
+        for it in range(it0, iterations):
             if iter_hook is not None:
                 iter_hook(it)
             t0 = pc()
@@ -719,11 +750,18 @@ class VAMP:
                                 lmmse_damp, learn_gamw, truth is not None, pin_x[slot][0],
                                 pin_r[slot] if write else None, slot)
             tm["enqueue"] += pc() - t0
-            if it >= 1:
-                t1 = pc()
+            t1 = pc()
+            if finished < it - 1:
                 finish(it - 1)                                           # one iteration behind the GPU
-                tm["host_tail"] += pc() - t1
-        if iterations > 0:
+                finished = it - 1
+            if ck["path"] and ck["every"] > 0 and (it + 1) % ck["every"] == 0:
+                finish(it)                                               # a checkpoint needs this iteration's results now
+                finished = it
+                row = self.history["rows"][-1]
+                self._checkpoint(ck["path"], it + 1, [row[k][2] for k in range(K)], [row[k][1] for k in range(K)],
+                                 [row[k][4] for k in range(K)], [row[k][5] for k in range(K)], probe_src, mine)
+            tm["host_tail"] += pc() - t1
+        if finished < iterations - 1:
             finish(iterations - 1)
         if iter_hook is not None:
             iter_hook(iterations)
@@ -734,13 +772,62 @@ class VAMP:
             self.gam1_final = [last[k][2] for k in mine]
             self.gamw_final = [last[k][1] for k in mine]
         if sharded and gather_outputs:
-            full = shd.gather_rows(self.shard, np.stack([x.ravel() for x in xhat1s]) if iterations else np.zeros((0, self.Ml)),
+            have = [i for i in range(iterations) if xhat1s[i] is not None]
+            full = shd.gather_rows(self.shard, np.stack([xhat1s[i].ravel() for i in have]) if have else np.zeros((0, self.Ml)),
                                    self.bounds)
-            xhat1s = [full[it].reshape(M, 1) for it in range(iterations)]
+            for j, i in enumerate(have):
+                xhat1s[i] = full[j].reshape(M, 1)
         if sharded and write:
-            self._assemble_parts(["%s_xhat_it_%d.bin" % (self.out_name, it) for it in range(iterations)] +
-                                 ["%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k + 1, it) for it in range(iterations) for k in mine])
+            self._assemble_parts(["%s_xhat_it_%d.bin" % (self.out_name, it) for it in range(it0, iterations)] +
+                                 ["%s_r1_cohort_%d_it_%d.bin" % (self.out_name, k + 1, it) for it in range(it0, iterations) for k in mine])
         return xhat1s
+
+    # checkpoint / resume
+    def _ckpt_file(self, path):
+        return path if self.shard.world == 1 else "%s.rank%d" % (path, self.shard.rank)
+
+    def _checkpoint(self, path, it_next, gam1, gamw, alpha1, alpha2, probe_src, mine):
+        h = self.handle
+        h.sync()
+        d = dict(it_next=it_next, M=self.M, lo=self.lo, hi=self.hi, K=self.K, gam1=np.array(gam1, dtype=np.float64),
+                 gamw=np.array(gamw, dtype=np.float64), alpha1=np.array(alpha1, dtype=np.float64),
+                 alpha2=np.array(alpha2, dtype=np.float64), lam=float(self.lam), omegas=np.array(self.omegas, dtype=np.float64),
+                 gam=np.float64(np.nan if self.gam is None else self.gam), xhat1=h.get_vec(0, nat.VEC_XHAT1))
+        for k in mine:
+            d["r1_%d" % k] = h.get_vec(k, nat.VEC_R1)
+            d["xhat2_%d" % k] = h.get_vec(k, nat.VEC_XHAT2)
+            d["sig_%d" % k] = h.get_vec(k, nat.VEC_SIGMA2U)
+        if probe_src is not None:
+            t0 = time.time()
+            st = None
+            while st is None and time.time() - t0 < 30:     # the producer thread runs at most two draws ahead
+                st = probe_src.states.get((it_next, mine[0])) or probe_src.end_state
+                if st is None:
+                    time.sleep(0.001)
+            if st is not None:
+                d["rng_name"], d["rng_keys"], d["rng_pos"], d["rng_has_gauss"], d["rng_gauss"] = st[0], st[1], st[2], st[3], st[4]
+        f = self._ckpt_file(path)
+        with open(f + ".tmp", "wb") as fh:
+            np.savez(fh, **d)
+        os.replace(f + ".tmp", f)
+
+    def _restore(self, path):
+        z = np.load(self._ckpt_file(path), allow_pickle=False)
+        if int(z["M"]) != self.M or int(z["lo"]) != self.lo or int(z["hi"]) != self.hi or int(z["K"]) != self.K:
+            raise Exception("checkpoint %s does not match this problem / row partition" % path)
+        h = self.handle
+        h.set_vec(0, nat.VEC_XHAT1, z["xhat1"])
+        for k in self.my_cohorts:
+            h.set_vec(k, nat.VEC_R1, z["r1_%d" % k])
+            h.set_vec(k, nat.VEC_XHAT2, z["xhat2_%d" % k])       # injected warm starts: R x0 is re-formed by one real pass
+            h.set_vec(k, nat.VEC_SIGMA2U, z["sig_%d" % k])
+        self.lam = float(z["lam"])
+        self.omegas = np.array(z["omegas"], dtype=np.float64)
+        self.gam = None if np.isnan(z["gam"]) else float(z["gam"])
+        st = dict(it_next=int(z["it_next"]), gam1=z["gam1"], gamw=z["gamw"], alpha1=z["alpha1"], alpha2=z["alpha2"], rng_state=None)
+        if "rng_keys" in z.files:
+            st["rng_state"] = (str(z["rng_name"]), z["rng_keys"], int(z["rng_pos"]), int(z["rng_has_gauss"]), float(z["rng_gauss"]))
+        return st
 
     # sharded output dumps: every rank streams its row slice of a dump into a part file while the loop runs; after the
     # loop rank 0 concatenates the parts in rank order (nothing of size iterations x M is ever held in host memory)

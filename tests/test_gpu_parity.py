@@ -491,6 +491,52 @@ def test_stepwise_and_fused_loops_agree(nat, name, monkeypatch):
         assert hist_f["em_steps"][it] == hist_s["em_steps"][it]
 
 
+@pytest.mark.parametrize("name,stepwise", [("banded_L2_em_s01", False), ("banded_L2_em_defaultrng", False),
+                                           ("dense_K3_L2_em", False), ("dense_L2_mle", True)])
+def test_checkpoint_and_resume(nat, name, stepwise, tmp_path, monkeypatch):
+    """A run checkpointed after half of its iterations and continued by a fresh solver follows the reference's golden
+    trajectory to the end (warm starts, damping terms, prior, MLE multiplier and - for un-injected probes - the position
+    in numpy's legacy RNG sequence all travel in the checkpoint)."""
+    import sgvamp
+    c = load_case(name)
+    if stepwise:
+        monkeypatch.setenv("SGV_STEPWISE", "1")
+    K, M, its = c["K"], c["M"], c["iterations"]
+    half = its // 2
+    Nt = sum(c["N_list"])
+    path = str(tmp_path / "ck.npz")
+
+    def solver():
+        return sgvamp.VAMP(N=c["N_list"] if K > 1 else c["N_list"][0], Nt=Nt, M=M, K=K, rho=c["rho"], gamw=c["gamw"], gam1=c["gam1"],
+                           a=np.array(c["N_list"]) / Nt, prior_vars=c["prior_vars"], prior_probs=c["prior_probs"], out_dir=None,
+                           out_name="g")
+
+    def run(v, n_it, **kw):
+        probes = c["probes"]
+        if "rng_seed" in c:
+            probes = None
+        return v.infer(c["R"] if K > 1 else c["R"][0], list(c["r"]) if K > 1 else c["r"][0], n_it, cg_maxit=c["cg_maxit"],
+                       em_prior_maxit=c["em_prior_maxit"], learn_gamw=c["learn_gamw"], lmmse_damp=c["lmmse_damp"],
+                       prior_update=c["prior_update"], update_prior_from=c["update_prior_from"], s=c["s"], probes=probes, **kw)
+
+    if "rng_seed" in c:
+        np.random.seed(c["rng_seed"])
+    v1 = solver()
+    run(v1, half, checkpoint_path=path, checkpoint_every=half)
+    v1.close()
+    np.random.seed(12345)                      # the sequence position must come from the checkpoint, not from this process
+    v2 = solver()
+    xs = run(v2, its, resume_from=path)
+    hist = v2.history
+    v2.close()
+    assert all(x is None for x in xs[:half])
+    for it in range(half, its):
+        assert rel_l2(xs[it], c["xhat"][it]) <= 1e-4, (name, it)
+        for k in range(K):
+            assert rel_err(hist["rows"][it - half][k][1:6], c["rows"][it, k, 1:6]) <= 1e-4
+            assert tuple(hist["cg_iters"][it - half][k]) == tuple(c["cg_iters"][it, k])
+
+
 @pytest.mark.parametrize("layout", ["csr", "dense", "dia"])
 def test_banded_case_other_layouts(nat, layout):
     c = load_case("banded_L2_em_s01")
