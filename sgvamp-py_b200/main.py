@@ -57,7 +57,26 @@ def build_parser():
     p.add_argument("--row-partition", help="under torchrun with N ranks: 1 = split the marker rows of every cohort over the "
                    "N GPUs (banded LD; halos and reductions exchanged inside the kernels) instead of one rank per cohort; "
                    "default: 1 when K == 1", default=None)
+    p.add_argument("--probe-seed", help="deterministic Hutchinson probes: the probe of cohort k in iteration it is the it-th draw "
+                   "of numpy RandomState(seed + k).binomial(p=1/2, n=1, size=M) (default: the reference's draws from numpy's "
+                   "global RNG, src/sgvamp.py:326)", default=None)
+    p.add_argument("--checkpoint-path", help="write a restart file here every --checkpoint-every iterations", default=None)
+    p.add_argument("--checkpoint-every", help="iterations between restart files (0: never)", default=0)
+    p.add_argument("--resume-from", help="continue the run stored in this restart file", default=None)
     return p
+
+
+class _SeededProbes:
+    """probes(k, it, M): the it-th draw of RandomState(seed + k), drawn in order and cached."""
+
+    def __init__(self, seed, K):
+        self.rs = [np.random.RandomState(seed + k) for k in range(K)]
+        self.have = [[] for _ in range(K)]
+
+    def __call__(self, k, it, M):
+        while len(self.have[k]) <= it:
+            self.have[k].append((self.rs[k].binomial(p=1 / 2, n=1, size=M) * 2 - 1).astype(np.int8))
+        return self.have[k][it]
 
 
 def main(argv=None):
@@ -147,7 +166,9 @@ def main(argv=None):
     xhat1 = solver.infer(Rs[0] if one else Rs, rs[0] if one else rs, int(a.iterations), x0=x0,
                          cg_maxit=int(a.cg_maxit), em_prior_maxit=int(a.em_prior_maxit), learn_gamw=learn_gamw,
                          lmmse_damp=lmmse_damp, prior_update=a.prior_update,
-                         update_prior_from=int(a.update_prior_from), s=s, layout=a.layout)
+                         update_prior_from=int(a.update_prior_from), s=s, layout=a.layout,
+                         probes=_SeededProbes(int(a.probe_seed), K) if a.probe_seed is not None else None,
+                         checkpoint_path=a.checkpoint_path, checkpoint_every=int(a.checkpoint_every), resume_from=a.resume_from)
     logging.info(f"sgVAMP inference running time: {(time.time() - ts):0.4f}s\n")
     # README names the dump {out}__xhat_it_{it}.bin, the code writes {out}_xhat_it_{it}.bin: provide both
     is_root = (comm is None or comm.Get_rank() == 0) and (shard_obj is None or shard_obj.rank == 0)

@@ -57,6 +57,8 @@ class FakeComm:
         self.local = threading.local()
         self.q = {}
         self.lock = threading.Lock()
+        self.bar = threading.Barrier(K)
+        self.slot = None
 
     def _chan(self, src, dst, tag):
         with self.lock:
@@ -75,7 +77,72 @@ class FakeComm:
         return self._chan(source, self.local.rank, tag).get(timeout=60)
 
     def bcast(self, obj, root=0):
-        return obj
+        if self.K == 1:
+            return obj
+        if self.local.rank == root:
+            self.slot = np.array(obj, copy=True) if isinstance(obj, np.ndarray) else obj
+        self.bar.wait()
+        out = self.slot
+        out = out.copy() if isinstance(out, np.ndarray) else out
+        self.bar.wait()
+        return out
+
+
+def run_reference_solver(argv, K, probe_seed, iterations, M):
+    """The unmodified reference driver AND the unmodified reference solver (src/sgvamp.py), one thread per rank, with the
+    probe of (rank k, iteration it) injected as the it-th draw of RandomState(probe_seed + k) by rebinding the solver
+    module's `binomial` (src/sgvamp.py:5,326) - what `main.py --probe-seed` reproduces."""
+    import importlib.util
+    comm = FakeComm(K)
+    mpi = types.ModuleType("mpi4py")
+    MPI = types.ModuleType("mpi4py.MPI")
+    MPI.COMM_WORLD = comm
+    MPI.Finalize = lambda: None
+    mpi.MPI = MPI
+    spec = importlib.util.spec_from_file_location("sgvamp", "/root/reference/src/sgvamp.py")
+    sg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sg)
+    streams = [np.random.RandomState(probe_seed + k) for k in range(K)]
+    sg.binomial = lambda p=None, n=None, size=None: streams[comm.local.rank].binomial(p=p, n=n, size=size)
+    saved = {n: sys.modules.get(n) for n in ("mpi4py", "mpi4py.MPI", "sgvamp")}
+    sys.modules.update({"mpi4py": mpi, "mpi4py.MPI": MPI, "sgvamp": sg})
+    old_argv = sys.argv
+    sys.argv = ["main.py"] + argv
+    errs = []
+
+    def body(k):
+        comm.local.rank = k
+        try:
+            runpy.run_path(REF_MAIN, run_name="__main__")
+        except BaseException as e:   # noqa: BLE001
+            errs.append((k, e))
+            comm.bar.abort()
+
+    ts = [threading.Thread(target=body, args=(k,)) for k in range(K)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    sys.argv = old_argv
+    for n, m in saved.items():
+        if m is None:
+            sys.modules.pop(n, None)
+        else:
+            sys.modules[n] = m
+    if errs:
+        raise errs[0][1]
+    out_dir = argv[argv.index("--out-dir") + 1]
+    name = argv[argv.index("--out-name") + 1]
+    res = dict(xhat=np.stack([np.fromfile(os.path.join(out_dir, "%s_xhat_it_%d.bin" % (name, it))) for it in range(iterations)]))
+    import csv
+    rows = np.zeros((iterations, K, 7))
+    for k in range(K):
+        with open(os.path.join(out_dir, "%s_cohort_%d.csv" % (name, k + 1)), newline="") as f:
+            rd = list(csv.reader(f, delimiter="\t"))
+        for it in range(iterations):
+            rows[it, k] = [float(v) for v in rd[1 + it]]
+    res["rows"] = rows
+    res["r1"] = np.stack([[np.fromfile(os.path.join(out_dir, "%s_r1_cohort_%d_it_%d.bin" % (name, k + 1, it))) for k in range(K)]
+                          for it in range(iterations)])
+    return res
 
 
 def run_reference(argv, K):
@@ -147,9 +214,16 @@ def main():
                          "--iterations", "1", "--s", "0.0"], 1)
     out["k1_R_0"], out["k1_r_0"], out["k1_M"] = cap[0]["R"], cap[0]["r"], cap[0]["M"]
     out["k1_bim"] = open(p("ref_k1.bim")).read()
+    # K = 2 end to end: reference driver + reference solver, 4 iterations, probes from RandomState(77 + k)
+    run = run_reference_solver(["--ld-files", p("c1.ld") + "," + p("c2.ld"), "--r-files", p("c1.assoc.linear") + "," + p("c2.assoc.linear"),
+                                "--bim-files", p("c1.bim") + "," + p("c2.bim"), "--true-signal-file", p("x0.npy"),
+                                "--out-dir", OUT, "--out-name", "ref_run", "--N", "400,900", "--M", "8,9", "--K", "2",
+                                "--iterations", "4", "--s", "0.3", "--prior-vars", "0,0.001", "--prior-probs", "0.7,0.3",
+                                "--gamw", "2"], 2, 77, 4, 10)
+    out["k2run_xhat"], out["k2run_rows"], out["k2run_r1"] = run["xhat"], run["rows"], run["r1"]
     np.savez_compressed(os.path.join(OUT, "reference.npz"), **out)
     for n in os.listdir(OUT):
-        if n.startswith("ref_k"):
+        if n.startswith("ref_k") or n.startswith("ref_run"):
             os.remove(p(n))
     print("wrote", os.path.join(OUT, "reference.npz"), {k: getattr(v, "shape", None) for k, v in out.items()})
 

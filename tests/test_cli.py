@@ -95,3 +95,21 @@ def test_cli_two_cohorts_from_plink_ld_and_bim():
             for it in range(3):
                 assert os.path.getsize(os.path.join(d, "k2_r1_cohort_%d_it_%d.bin" % (k, it))) == 80
         assert os.path.getsize(os.path.join(d, "k2_xhat_it_2.bin")) == 80
+    # the same files through the reference driver AND the reference solver (tests/golden/make_ingest_golden.py, probes of
+    # cohort k from RandomState(77 + k)): values, not just shapes
+    ref = np.load(p("reference.npz"))
+    with tempfile.TemporaryDirectory() as d:
+        xs = cli.main(["--ld-files", p("c1.ld") + "," + p("c2.ld"), "--r-files", p("c1.assoc.linear") + "," + p("c2.assoc.linear"),
+                       "--bim-files", p("c1.bim") + "," + p("c2.bim"), "--true-signal-file", p("x0.npy"),
+                       "--out-dir", d, "--out-name", "k2", "--N", "400,900", "--M", "8,9", "--K", "2", "--iterations", "4",
+                       "--s", "0.3", "--prior-vars", "0,0.001", "--prior-probs", "0.7,0.3", "--gamw", "2", "--probe-seed", "77"])
+        for it in range(3):                                  # (iteration 3 of this tiny case has lam -> 1e-11: compared absolutely)
+            dump = np.fromfile(os.path.join(d, "k2_xhat_it_%d.bin" % it))
+            assert rel_l2(dump, ref["k2run_xhat"][it]) <= 1e-4, it
+            for k in (1, 2):
+                r1 = np.fromfile(os.path.join(d, "k2_r1_cohort_%d_it_%d.bin" % (k, it)))
+                assert rel_l2(r1, ref["k2run_r1"][it, k - 1]) <= 1e-4
+                raw = open(os.path.join(d, "k2_cohort_%d.csv" % k), "rb").read()
+                row = np.array([float(v) for v in raw.split(b"\r\n")[1 + it].split(b"\t")])
+                assert rel_err(row[1:7], ref["k2run_rows"][it, k - 1, 1:7]) <= 1e-4, (it, k, row, ref["k2run_rows"][it, k - 1])
+        assert np.abs(np.fromfile(os.path.join(d, "k2_xhat_it_3.bin")) - ref["k2run_xhat"][3]).max() <= 1e-6
