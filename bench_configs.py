@@ -222,7 +222,108 @@ def run_reference(a, bench):
     print(json.dumps(line))
 
 
+def run_rank_per_cohort(a, bench):
+    """c4 under torchrun with WORLD_SIZE == K: the reference's own deployment shape, one rank (here: one GPU) per cohort
+    (src/main.py:85,173-174); r1 / gam1 of every cohort are exchanged once per iteration (src/sgvamp.py:228-233) through
+    shard.TorchComm over NCCL.  Each rank generates and holds only its cohort's LD (40 GB at M = 100k)."""
+    import torch
+    import torch.distributed as dist
+    import build_native
+    cfg = CONFIGS[a.config]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build_native.build()
+    dist.barrier()
+    import sgvamp
+    import shard as shd
+    M, Ns, L, K = cfg["M"], cfg["N"], cfg["L"], len(cfg["N"])
+    assert world == K
+    iterations = a.warmup + a.steps
+    beta = causal_beta(M, a.seed)
+    t0 = time.time()
+    G, r = gen_dense_cohort(torch, M, Ns[rank], beta, a.seed + rank, dev)
+    t_gen = time.time() - t0
+    probes = bench.make_probes(iterations, M, a.seed + rank)[0]
+    solver_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(solver_stream)
+    pv, pp = prior_for(M, L)
+
+    def new_solver():
+        return sgvamp.VAMP(N=Ns[rank], Nt=float(sum(Ns)), M=M, K=K, rho=cfg.get("rho", 0.5), gamw=2.0, gam1=1e-6,
+                           a=np.array(Ns) / float(sum(Ns)), prior_vars=pv, prior_probs=pp, out_dir=None, out_name="bench",
+                           comm=shd.TorchComm(), device=local_rank, stream=solver_stream.cuda_stream)
+
+    def run(v, n_it, hook=None):
+        return v.infer(sgvamp.DeviceDense(G.data_ptr(), M, keepalive=G), r, n_it, cg_maxit=cfg["cg_maxit"], em_prior_maxit=100,
+                       learn_gamw=True, lmmse_damp=False, prior_update="em", update_prior_from=1,
+                       probes=lambda k, it, M_: probes[it], iter_hook=hook, s=0.0)
+
+    v0 = new_solver()
+    run(v0, 2)
+    v0.close()
+    v = new_solver()
+    events, launches = {}, {}
+
+    def hook(it):
+        if it == a.warmup:
+            torch.cuda.synchronize()
+            dist.barrier()
+            v.handle.profile(True)
+            launches["a"] = v.handle.launch_count()
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        events[it] = e
+
+    xs = run(v, iterations, hook)
+    torch.cuda.synchronize()
+    dist.barrier()
+    spmm_ms, _n = v.handle.profile_read()
+    launches["b"] = v.handle.launch_count()
+    t = torch.tensor([events[a.warmup].elapsed_time(events[iterations]), float(launches["b"] - launches["a"])], device=dev, dtype=torch.float64)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    ms_total = float(tmax[0].item())
+    passes = sum(v.history["spmm_passes"][a.warmup:])
+    info = v.handle.ld_info(rank)
+    bytes_pass = 2.0 * info["nnz_stored"] + 32.0 * M
+    avg_ms = spmm_ms / max(passes, 1)
+    x0 = beta * np.sqrt(Ns[0])
+    align = float(np.dot(xs[-1].ravel(), x0) / (np.linalg.norm(xs[-1]) * np.linalg.norm(x0)))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(bench.REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    if rank == 0:
+        print(json.dumps({
+            "metric": "VAMP iterations/s", "value": a.steps / (ms_total / 1e3), "unit": "it/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s, cg_maxit=%d" % (a.config, cfg["text"], cfg["cg_maxit"]), "M": M, "K": K,
+                       "partition": "one cohort per GPU (rank = cohort, the reference's deployment shape); r1 / gam1 exchanged per "
+                                    "iteration over NCCL (shard.TorchComm)", "layout": info["layout"],
+                       "cg_iters_timed_rank0": [list(v.history["cg_iters"][i][rank]) for i in range(a.warmup, iterations)],
+                       "alignment_with_truth": align, "gen_seconds": t_gen},
+            "roofline": {"bound": "hbm", "achieved": bytes_pass / (avg_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bytes_pass / (avg_ms * 1e-3) / 1e9 / peak, "traffic": None, "per": "GPU (rank 0)",
+                         "kernel": "k_spmm_psym + k_psym_finish", "bytes_per_launch": bytes_pass, "avg_launch_ms": avg_ms},
+            "cpu_baseline": None, "parity": None, "e2e": None, "gpu_launches": int(t[1].item())}))
+    v.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def run_config(a, bench):
+    if a.config == "c4" and int(os.environ.get("WORLD_SIZE", "1")) == len(CONFIGS["c4"]["N"]):
+        return run_rank_per_cohort(a, bench)
     import torch
     import build_native
     build_native.build()
