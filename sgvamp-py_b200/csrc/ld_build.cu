@@ -14,6 +14,7 @@
 // samples in chunks of 256 through shared memory; a thread accumulates a 4 x 4 block of S with IDP4A (4 samples per
 // instruction), operands fetched as 128-bit shared-memory loads (8 LDS.128 per 64 IDP4A).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include "sgv_device.cuh"
 
@@ -119,6 +120,139 @@ k_ld_band_gram(const int8_t* __restrict__ G, int64_t ldg, int64_t g0, int64_t nm
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same Gram tile on the 5th-generation tensor cores: tcgen05.mma kind::i8 (int8 x int8 -> int32, exact), accumulator
+// in tensor memory.  A CTA of 4 warps owns a 128 x 128 tile of S; per chunk of 128 samples its threads copy the 128 A rows
+// and 128 B rows (128 bytes each, K-major) into shared memory in the canonical 128-byte-swizzled UMMA layout (16-byte chunk
+// c of row r at chunk c ^ (r & 7) of the 1 KB atom that holds rows 8*(r/8) .. +7), one elected thread issues four
+// M128 x N128 x K32 MMAs and commits them to an mbarrier, everybody waits for it before the next chunk overwrites the
+// operands.  Epilogue: tcgen05.ld 32 lanes x 32 columns per warp, then the same standardisation / taper / scatter as above.
+// ---------------------------------------------------------------------------------------------
+#define TC_T 128
+__device__ __forceinline__ unsigned tc_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long tc_desc_k_sw128(unsigned smem_addr) {
+    // K-major, SWIZZLE_128B: start address >> 4, LBO = 16 B (1), SBO = 1024 B between 8-row groups (64), version 1 (sm_100),
+    // layout type 2 at bits 61..63
+    return (unsigned long long)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(128)
+k_ld_band_gram_tc(const int8_t* __restrict__ G, int64_t ldg, int64_t g0, int64_t nmark, int64_t N, const double* __restrict__ mu,
+                  const double* __restrict__ sd, float* __restrict__ U, int64_t ngr, int64_t w, int64_t row_lo, int64_t E,
+                  int64_t rows_st, int64_t M, double s, int taper) {
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sA = base;                 // 128 rows x 128 B
+    unsigned char* sB = base + 16384;
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ unsigned tmem_base_s;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int64_t t0 = (int64_t)blockIdx.x * TC_T;
+    const int64_t i0 = row_lo - E + t0;
+    const int64_t j0 = i0 + (int64_t)blockIdx.y * TC_T;
+    if (j0 - (i0 + TC_T - 1) > w) return;
+    const unsigned bar = tc_smem_u32(&mbar);
+    if (wid == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(tc_smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem_d = tmem_base_s;
+    // instruction descriptor: D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TC_T >> 3) << 17) | ((unsigned)(TC_T >> 4) << 24);
+    const int64_t ia = i0 + tid - g0, jb = j0 + tid - g0;            // this thread's A row / B row in the genotype buffer
+    const bool va = ia >= 0 && ia < nmark, vb = jb >= 0 && jb < nmark;
+    unsigned phase = 0;
+    int nchunk = 0;
+    for (int64_t k0 = 0; k0 < ldg; k0 += 128, ++nchunk) {
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) {
+            int4 a4 = make_int4(0, 0, 0, 0), b4 = a4;
+            if (k0 + cidx * 16 < ldg) {
+                if (va) a4 = *reinterpret_cast<const int4*>(G + ia * ldg + k0 + cidx * 16);
+                if (vb) b4 = *reinterpret_cast<const int4*>(G + jb * ldg + k0 + cidx * 16);
+            }
+            const int off = tid * 128 + ((cidx ^ (tid & 7)) << 4);
+            *reinterpret_cast<int4*>(sA + off) = a4;
+            *reinterpret_cast<int4*>(sB + off) = b4;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned long long da = tc_desc_k_sw128(tc_smem_u32(sA)), db = tc_desc_k_sw128(tc_smem_u32(sB));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {                            // K = 32 bytes per MMA: + 2 in the 16-byte start address
+                const unsigned acc = (nchunk > 0 || kk > 0) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p;\n\t"
+                    "setp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+                    "}\n" ::"r"(tmem_d), "l"(da + 2ull * kk), "l"(db + 2ull * kk), "r"(idesc), "r"(acc)
+                    : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+        }
+        // everybody waits until the tensor core has consumed the operands (and, after the last chunk, produced D)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "TC_WAIT:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+            "@P1 bra TC_DONE;\n\t"
+            "bra TC_WAIT;\n\t"
+            "TC_DONE:\n\t"
+            "}" ::"r"(bar), "r"(phase)
+            : "memory");
+        phase ^= 1u;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: warp w reads TMEM lanes 32w .. 32w+31 (= rows of the tile), 32 columns at a time
+    const int64_t t = t0 + tid, i = row_lo - E + t;
+    const bool row_ok = t < rows_st && i >= 0 && i < M;
+    const double mi = row_ok ? mu[i - g0] : 0.0, si = row_ok ? sd[i - g0] : 0.0;
+    for (int c0 = 0; c0 < TC_T; c0 += 32) {
+        unsigned v[32];
+        const unsigned taddr = tmem_d + ((unsigned)(32 * wid) << 16) + (unsigned)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+            "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+              "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+              "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row_ok) {
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                const int64_t j = j0 + c0 + b, d = j - i;
+                if (d < 0 || d > w || j >= M) continue;
+                if (t < E && j < row_lo) continue;
+                const double mj = mu[j - g0], sj = sd[j - g0];
+                double r = 0.0;
+                if (si > 0.0 && sj > 0.0) r = ((double)(int)v[b] - (double)N * mi * mj) / ((double)N * si * sj);
+                if (d == 0) r = 1.0;
+                if (taper) r *= 1.0 - (double)d / (double)(w + 1);
+                r = (1.0 - s) * r + (d == 0 ? s : 0.0);
+                if (d == 0) r *= 0.5;
+                U[sgv_dsym_index(t, d, ngr)] = (float)r;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_d) : "memory");
+}
+
 // r_j = (sum_n g_nj y_n - mu_j sum_n y_n) / (sd_j sqrt(N)) for the own markers
 __global__ void __launch_bounds__(256)
 k_ld_xty(const int8_t* __restrict__ G, int64_t ldg, int64_t g0, int64_t N, const double* __restrict__ mu, const double* __restrict__ sd,
@@ -174,8 +308,16 @@ extern "C" int sgv_ld_build_banded(sgv_handle c, int cohort, const int8_t* G, in
         ld.ext = E;
         ld.nnz_stored = (w + 1) * Ml;
         cudaMemsetAsync(U, 0, (size_t)Dp * ldb * sizeof(float), c->stream);
-        const dim3 grid((unsigned)((Ml + E + LB_T - 1) / LB_T), (unsigned)((w + LB_T - 1) / LB_T + 1));
-        k_ld_band_gram<<<grid, 256, 0, c->stream>>>(dG, ldg, g0, nmark, N, mu, sd, U, ngr, w, row_lo, E, Ml + E, M, s, taper);
+        // tensor-core Gram tiles (tcgen05, kind::i8) by default; SGV_LD_DP4A=1 selects the IDP4A kernel (A/B, cross-check)
+        const bool use_dp4a = getenv("SGV_LD_DP4A") != nullptr && atoi(getenv("SGV_LD_DP4A")) != 0;
+        if (use_dp4a) {
+            const dim3 grid((unsigned)((Ml + E + LB_T - 1) / LB_T), (unsigned)((w + LB_T - 1) / LB_T + 1));
+            k_ld_band_gram<<<grid, 256, 0, c->stream>>>(dG, ldg, g0, nmark, N, mu, sd, U, ngr, w, row_lo, E, Ml + E, M, s, taper);
+        } else {
+            const dim3 grid((unsigned)((Ml + E + TC_T - 1) / TC_T), (unsigned)((w + TC_T - 1) / TC_T + 1));
+            k_ld_band_gram_tc<<<grid, 128, 32768 + 1024, c->stream>>>(dG, ldg, g0, nmark, N, mu, sd, U, ngr, w, row_lo, E, Ml + E, M, s,
+                                                                      taper);
+        }
         c->launches++;
         ld.layout = SGV_LAYOUT_DSYM;
         if ((rc = sgv_dsym_ensure_scratch(c, ld)) != 0) break;

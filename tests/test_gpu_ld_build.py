@@ -125,3 +125,22 @@ def test_ld_build_row_partition(nat, world):
     Y = np.concatenate([o[0] for o in out], axis=0)
     rr = np.concatenate([o[1] for o in out])
     assert rel_l2(Y, R @ X) < 5e-7 and rel_l2(rr, r) < 1e-12
+
+
+def test_ld_build_tensor_core_and_dp4a_kernels_identical(nat, monkeypatch):
+    """The Gram sums are exact integers in both kernels (tcgen05.mma kind::i8 with TMEM accumulators; IDP4A on the CUDA
+    cores), and the epilogue is the same arithmetic: the two constructed matrices must be bit-identical."""
+    N, M, w = 1000, 3000, 300
+    G = _genotypes(N, M, seed=21)
+    Gt = _marker_major(G)
+    X = np.random.default_rng(3).standard_normal((M, 2))
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SGV_LD_DP4A", flag)
+        h = nat.Handle()
+        h.configure(M, 1)
+        h.build_banded(0, Gt, N, w, s=0.1, taper=True)
+        outs.append(h.spmm(0, X))
+        h.close()
+    monkeypatch.delenv("SGV_LD_DP4A")
+    assert np.array_equal(outs[0], outs[1])
