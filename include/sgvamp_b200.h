@@ -58,8 +58,10 @@ int sgv_configure(sgv_handle h, int64_t M, int K);
  * cohort; all vectors are local.  Every grid reduction is completed across ranks inside the
  * kernels: partial sums are written into every rank's inbox through peer memory (NVLink) and
  * added in rank order, so all ranks obtain identical scalars without host collectives.
- * halo != 0: banded LD - the SpMM reads the w halo entries of its input vector directly from the
+ * halo == 1: banded LD - the SpMM reads the w halo entries of its input vector directly from the
  * neighbouring ranks' memory.  halo == 0: block-diagonal LD sharded by block (scalar-only exchange).
+ * halo == 2: dense LD partitioned by rows (sgv_ld_upload_dense_rows): every product gathers the input vector pair of
+ * all ranks from their memory; outputs and all other vectors stay with the owner of the rows.
  * All ranks must issue the same sequence of calls. ---- */
 int sgv_configure_part(sgv_handle h, int64_t M, int K, int rank, int world, int64_t row_lo, int64_t row_hi, int halo);
 int sgv_ipc_export(sgv_handle h, void* handle64);                                   /* 64-byte CUDA IPC handle of the arena */
@@ -103,6 +105,14 @@ int sgv_ld_adopt_dia(sgv_handle h, int cohort, const float* band_dev, int64_t w,
 int sgv_ld_adopt_dsym(sgv_handle h, int cohort, const float* U_dev, int64_t w, int64_t ldb, int64_t ext);
 int sgv_dsym_extension(sgv_handle h, int64_t w, int64_t* ext);
 int sgv_ld_adopt_dense(sgv_handle h, int cohort, const float* R_dev, int64_t ld);
+/* Dense LD partitioned by ROWS over the ranks (sgv_configure_part with halo = 2; no reference counterpart: the
+ * reference holds a dense cohort on one rank, src/main.py:255-268).  `rows`: this rank's rows [row_lo, row_hi) of R,
+ * row-major with M columns.  The device store is the column panel P[j][i] = Rused[row_lo + i][j] (M rows of
+ * roundup(Ml,4) floats), so a product is exactly Rused v also for a non-symmetric R; the vector pair of all ranks is
+ * gathered from the peers' memory before each product (the CG direction update fused into the gather).  `adopt`:
+ * the column panel already in HBM (fp32, regularised, pad columns readable). */
+int sgv_ld_upload_dense_rows(sgv_handle h, int cohort, const void* rows, int dtype, int64_t ld_src, double s);
+int sgv_ld_adopt_dense_colpanel(sgv_handle h, int cohort, const float* P_dev, int64_t ld);
 /* block-diagonal LD (per-chromosome LD blocks, BASELINE.json configs[2]) already in HBM: block b holds the rows
  * [starts[b], starts[b+1]) of this handle (starts[nblocks] = local rows) as a dense row-major panel at
  * panels_dev + offs[b] with leading dimension lds[b] (offs, lds multiples of 4 elements).  Symmetry is verified. */

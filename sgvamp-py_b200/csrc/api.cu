@@ -58,6 +58,8 @@ extern "C" int sgv_create(int device, void* stream, sgv_handle* out) {
     SGV_CUDA(cudaMalloc(&c->counter, 64));
     SGV_CUDA(cudaMemset(c->counter, 0, 64));
     SGV_CUDA(cudaMalloc(&c->cg, sizeof(CgState)));
+    SGV_CUDA(cudaMalloc(&c->pubseq, sizeof(unsigned long long)));
+    SGV_CUDA(cudaMemset(c->pubseq, 0, sizeof(unsigned long long)));
     if (const char* e = getenv("SGV_CG_BAND")) c->cg_band_eps = atof(e);
     SGV_TRY(sgv_reset_cg_state(c));
     SGV_CUDA(cudaStreamSynchronize(c->stream));
@@ -102,6 +104,8 @@ static void free_vectors(sgv_ctx* c) {
     detach_peers(c);
     cudaFree(c->arena);
     cudaFree(c->bb);
+    cudaFree(c->vfull);
+    c->vfull = nullptr;
     c->arena = nullptr;
     c->bb = c->qq = c->xx = c->rr = c->pp[0] = c->pp[1] = c->rr2[0] = c->rr2[1] = c->qq2[0] = c->qq2[1] = nullptr;
     cudaFree(c->r1_all);
@@ -145,6 +149,7 @@ extern "C" int sgv_destroy(sgv_handle c) {
     cudaFree(c->partials);
     cudaFree(c->counter);
     cudaFree(c->cg);
+    cudaFree(c->pubseq);
     cudaFree(c->stage);
     cudaFreeHost(c->cg_host);
     cudaFreeHost(c->host_scal);
@@ -216,6 +221,7 @@ RedCtx sgv_red_begin(sgv_ctx* c, int kind, int nv, int off, int maxit, int x0_ze
     rc.world = c->world;
     rc.rank = c->rank;
     rc.seq = ++c->seq;
+    rc.pubseq = c->pubseq;
     rc.inline_resolve = c->world > 1 && !c->host_barrier;
     for (int q = 0; q < c->world; ++q) rc.inbox[q] = reinterpret_cast<Inbox*>(c->peer[q].base);
     rc.ap.kind = kind;
@@ -267,7 +273,9 @@ extern "C" int sgv_configure_part(sgv_handle c, int64_t M, int K, int rank, int 
     c->row_lo = row_lo;
     c->rank = rank;
     c->world = world;
-    c->halo = halo;
+    SGV_CHECK(halo >= 0 && halo <= 2, "halo must be 0 (block-diagonal shards), 1 (banded halos) or 2 (dense rows)");
+    c->halo = halo == 1;
+    c->rowpart = halo == 2;
     c->K = K;
     c->seq = 0;
     c->vamp_begun = false;
@@ -300,6 +308,7 @@ extern "C" int sgv_configure_part(sgv_handle c, int64_t M, int K, int rank, int 
     c->arena_bytes = arena_size(Ml);
     SGV_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
     SGV_CUDA(cudaMemsetAsync(c->arena, 0, c->arena_bytes, c->stream));
+    SGV_CUDA(cudaMemsetAsync(c->pubseq, 0, sizeof(unsigned long long), c->stream));   // slot numbering restarts with the zeroed inbox
     c->xx = reinterpret_cast<double2*>(c->arena + arena_off_xx(Ml));
     for (int i = 0; i < 2; ++i) {
         c->rr2[i] = reinterpret_cast<double2*>(c->arena + arena_off_rr(Ml, i));
@@ -313,6 +322,10 @@ extern "C" int sgv_configure_part(sgv_handle c, int64_t M, int K, int rank, int 
     c->peer[rank].ipc = false;
     SGV_CUDA(cudaMalloc(&c->bb, v2));
     SGV_CUDA(cudaMemsetAsync(c->bb, 0, v2, c->stream));
+    if (c->rowpart) {
+        SGV_CUDA(cudaMalloc(&c->vfull, (size_t)M * sizeof(double2)));
+        SGV_CUDA(cudaMemsetAsync(c->vfull, 0, (size_t)M * sizeof(double2), c->stream));
+    }
     SGV_TRY(sgv_reset_cg_state(c));
     for (int i = 0; i < sgv_ctx::NSNAP; ++i) {   // allocated up front: cudaMalloc inside the loop would synchronise
         SGV_CUDA(cudaMalloc(&c->snap[i], vb));

@@ -355,7 +355,7 @@ extern "C" int sgv_ld_upload_dense(sgv_handle c, int cohort, const void* R, int 
     SGV_TRY(check_cohort(c, cohort));
     SGV_CHECK(R != nullptr, "R is null");
     SGV_CHECK(dtype == SGV_F32 || dtype == SGV_F64, "bad dtype %d", dtype);
-    SGV_CHECK(c->world == 1, "dense LD upload is single-rank (shard dense LD by cohort, not by row)");
+    SGV_CHECK(c->world == 1 && !c->rowpart, "whole-matrix dense upload is single-rank; a rows partition takes sgv_ld_upload_dense_rows");
     SGV_CHECK(ld_src >= c->M, "leading dimension %lld < M", (long long)ld_src);
     SGV_CUDA(cudaSetDevice(c->device));
     LdMatrix& ld = c->coh[cohort].ld;
@@ -385,10 +385,131 @@ extern "C" int sgv_ld_upload_dense(sgv_handle c, int cohort, const void* R, int 
     return sgv_build_panel_items(c, ld, {0, M}, {0}, {(int)ldd});
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dense LD partitioned by ROWS over the ranks (sgv_configure_part with halo = 2).  Rank r owns the markers
+// [row_lo, row_hi) and holds the rows R[row_lo:row_hi, :] as the COLUMN PANEL  P[j][i] = R[row_lo + i][j]
+// (M stored rows of Ml values): the full-panel kernel's column sweep  y[i] = sum_j P[j][i] v[j]  is then exactly
+// (R v)[row_lo + i] - also for a non-symmetric R - with v the vector pair of ALL ranks (gathered from the peers'
+// symmetric arenas by k_gather_rows, spmm.cu) and the outputs owned locally: no partial sums cross the ranks.
+// ---------------------------------------------------------------------------------------------
+// src: rows [r0, r0+nr) of this rank's slice (nr x M, row-major, leading dimension ld_src) -> dst[j][r0 + r]
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_rows_to_colpanel(const T* __restrict__ src, int64_t ld_src, float* __restrict__ dst, int64_t ld_dst, int64_t r0,
+                   int64_t nr, int64_t M, int64_t row_lo, double s) {
+    __shared__ float t[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t jt = (int64_t)blockIdx.x * 32, rt = (int64_t)blockIdx.y * 32;   // column tile of src, row tile of src
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t rr = rt + r, j = jt + tx;
+        t[r][tx] = (rr < nr && j < M) ? reg_value(src[rr * ld_src + j], (row_lo + r0 + rr) == j, s) : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t j = jt + r, i = r0 + rt + tx;
+        if (j < M && rt + tx < nr) dst[j * ld_dst + i] = t[tx][r];
+    }
+}
+
+static int build_colpanel_items(sgv_ctx* c, LdMatrix& ld, int64_t ldd) {
+    const int TI = 128 * ld.panel_rw;
+    const int64_t M = c->M, Ml = c->Ml;
+    const int64_t tiles = (Ml + TI - 1) / TI;
+    const int64_t target = (int64_t)c->sm_count * 4;
+    int s_cross = (int)std::min<int64_t>(64, std::max<int64_t>(1, (target + tiles - 1) / tiles));
+    while (s_cross > 1 && M / s_cross < 64) --s_cross;
+    const int64_t per = (M + s_cross - 1) / s_cross;
+    std::vector<PanelItem> items;
+    for (int64_t i0 = 0; i0 < Ml; i0 += TI) {
+        for (int sl = 0; sl < s_cross; ++sl) {
+            PanelItem it;
+            const int64_t j0 = std::min<int64_t>(M, (int64_t)sl * per);
+            it.ld = (int)ldd;
+            it.off = j0 * ldd + i0;
+            it.i0 = (int)i0;
+            it.ni = (int)std::min<int64_t>(TI, Ml - i0);
+            it.j0 = (int)j0;                       // GLOBAL marker index: the kernel reads the gathered vector
+            it.nj = (int)std::max<int64_t>(0, std::min<int64_t>(per, M - j0));
+            it.navail = (int)std::min<int64_t>(TI, ldd - i0);
+            it.slot = sl;
+            items.push_back(it);
+        }
+    }
+    std::stable_sort(items.begin(), items.end(), [](const PanelItem& x, const PanelItem& y) {
+        return (int64_t)x.ni * x.nj > (int64_t)y.ni * y.nj;
+    });
+    SGV_CUDA(cudaMalloc(&ld.items, items.size() * sizeof(PanelItem)));
+    SGV_CUDA(cudaMemcpy(ld.items, items.data(), items.size() * sizeof(PanelItem), cudaMemcpyHostToDevice));
+    ld.n_items = (int)items.size();
+    ld.s_cross = s_cross;
+    ld.nblocks = 1;
+    ld.rowpart = true;
+    ld.panel_sym = false;                          // never the upper-triangle kernel
+    const int64_t need = (int64_t)s_cross * Ml;
+    if (c->ypart_cap < need) {
+        SGV_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->ypart) cudaFree(c->ypart);
+        c->ypart = nullptr;
+        c->ypart_cap = 0;
+        SGV_CUDA(cudaMalloc(&c->ypart, need * sizeof(double2)));
+        c->ypart_cap = need;
+    }
+    return 0;
+}
+
+extern "C" int sgv_ld_upload_dense_rows(sgv_handle c, int cohort, const void* rows, int dtype, int64_t ld_src, double s) {
+    SGV_TRY(check_cohort(c, cohort));
+    SGV_CHECK(rows != nullptr, "rows is null");
+    SGV_CHECK(dtype == SGV_F32 || dtype == SGV_F64, "bad dtype %d", dtype);
+    SGV_CHECK(c->rowpart, "the handle is not configured for the dense rows partition (sgv_configure_part halo = 2)");
+    SGV_CHECK(ld_src >= c->M, "leading dimension %lld < M", (long long)ld_src);
+    LdMatrix& ld = c->coh[cohort].ld;
+    sgv_ld_free(ld);
+    const int64_t M = c->M, Ml = c->Ml, ldd = round_up(Ml, 4);
+    float* P = nullptr;
+    SGV_CUDA(cudaMalloc(&P, (size_t)M * ldd * sizeof(float)));
+    SGV_CUDA(cudaMemsetAsync(P, 0, (size_t)M * ldd * sizeof(float), c->stream));
+    ld.panels = P;
+    ld.owned = true;
+    ld.layout = SGV_LAYOUT_DENSE;
+    ld.nnz_stored = M * Ml;
+    const size_t esz = dtype == SGV_F64 ? 8 : 4;
+    const int64_t chunk_rows = std::max<int64_t>(1, std::min<int64_t>(Ml, (int64_t)(256 << 20) / (int64_t)(ld_src * esz)));
+    SGV_TRY(sgv_ensure_stage(c, chunk_rows * ld_src * esz));
+    for (int64_t r0 = 0; r0 < Ml; r0 += chunk_rows) {
+        const int64_t nr = std::min(chunk_rows, Ml - r0);
+        SGV_CUDA(cudaMemcpyAsync(c->stage, (const char*)rows + (size_t)r0 * ld_src * esz, (size_t)nr * ld_src * esz,
+                                 cudaMemcpyHostToDevice, c->stream));
+        const dim3 grid((unsigned)((M + 31) / 32), (unsigned)((nr + 31) / 32));
+        if (dtype == SGV_F64)
+            k_rows_to_colpanel<double><<<grid, 256, 0, c->stream>>>((const double*)c->stage, ld_src, P, ldd, r0, nr, M, c->row_lo, s);
+        else
+            k_rows_to_colpanel<float><<<grid, 256, 0, c->stream>>>((const float*)c->stage, ld_src, P, ldd, r0, nr, M, c->row_lo, s);
+        c->launches++;
+        SGV_CUDA(cudaStreamSynchronize(c->stream));   // the staging buffer is reused
+    }
+    SGV_CUDA(cudaGetLastError());
+    return build_colpanel_items(c, ld, ldd);
+}
+
+extern "C" int sgv_ld_adopt_dense_colpanel(sgv_handle c, int cohort, const float* P_dev, int64_t ldd) {
+    SGV_TRY(check_cohort(c, cohort));
+    SGV_CHECK(P_dev != nullptr && ((uintptr_t)P_dev & 15) == 0, "device pointer must be 16-byte aligned");
+    SGV_CHECK(c->rowpart, "the handle is not configured for the dense rows partition (sgv_configure_part halo = 2)");
+    SGV_CHECK(ldd >= c->Ml && ldd % 4 == 0, "ld must be >= the local row count and a multiple of 4");
+    LdMatrix& ld = c->coh[cohort].ld;
+    sgv_ld_free(ld);
+    ld.panels = P_dev;
+    ld.owned = false;
+    ld.layout = SGV_LAYOUT_DENSE;
+    ld.nnz_stored = c->M * c->Ml;
+    return build_colpanel_items(c, ld, ldd);
+}
+
 extern "C" int sgv_ld_adopt_dense(sgv_handle c, int cohort, const float* R_dev, int64_t ldd) {
     SGV_TRY(check_cohort(c, cohort));
     SGV_CHECK(R_dev != nullptr && ((uintptr_t)R_dev & 15) == 0, "device pointer must be 16-byte aligned");
-    SGV_CHECK(c->world == 1, "dense LD is single-rank");
+    SGV_CHECK(c->world == 1 && !c->rowpart, "whole-matrix dense LD is single-rank; a rows partition takes sgv_ld_adopt_dense_colpanel");
     SGV_CHECK(ldd >= c->M && ldd % 4 == 0, "ld must be >= M and a multiple of 4");
     LdMatrix& ld = c->coh[cohort].ld;
     sgv_ld_free(ld);

@@ -285,13 +285,25 @@ __device__ __forceinline__ bool ld_entry(const InboxEntry* p, unsigned long long
     return f1 == f && f2 == f;
 }
 
-// Wait (bounded) until every rank's partial sums of reduction rc.seq are in this rank's inbox, add the
+// Sequence number of the cross-rank exchange in flight: one more than the number of exchanges this rank has
+// COMPLETED, counted on the device (RedCtx::pubseq).  Launches that exit early (CG / EM loop already converged) do
+// not exchange and do not advance it, so the inbox slot index (seq % SGV_INBOX_SLOTS) only moves with real
+// exchanges: every rank completes exchange s before any rank can publish s + 1, hence no rank is ever more than one
+// slot ahead of a peer that is still reading.  All ranks run the same sequence of exchanges (the skip decisions
+// depend on flags that are bit-identical everywhere), so the counters agree without being communicated.
+__device__ __forceinline__ unsigned long long red_next_seq(const RedCtx& rc) {
+    return *reinterpret_cast<volatile unsigned long long*>(rc.pubseq) + 1ull;
+}
+
+// Wait (bounded) until every rank's partial sums of the exchange in flight are in this rank's inbox, add the
 // rows in rank order (bit-identical on all ranks) and apply the state transition.  Called by one full
 // warp: lane q collects rank q's row.  On time-out the error flag is raised and the CG / EM loops are
 // marked done, so that nothing hangs.
 __device__ __forceinline__ void resolve_warp(const RedCtx& rc, int lane) {
     Inbox* me = rc.inbox[rc.rank];
-    const int slot = (int)(rc.seq % SGV_INBOX_SLOTS);
+    const unsigned long long seq = red_next_seq(rc);
+    __syncwarp();                                       // every lane has read the counter before lane 0 advances it
+    const int slot = (int)(seq % SGV_INBOX_SLOTS);
     const int nv = rc.ap.nv;
     double mine[SGV_MAX_PARTIAL_VALUES];
     bool good = true;
@@ -303,7 +315,7 @@ __device__ __forceinline__ void resolve_warp(const RedCtx& rc, int lane) {
         for (int e = lane; e < total; e += 32) {
             const InboxEntry* p = &me->e[slot][e / nv][e % nv];
             double dummy;
-            while (!ld_entry(p, rc.seq, dummy)) {
+            while (!ld_entry(p, seq, dummy)) {
                 if (clock64() - t0 > 40000000000LL) {   // ~20 s
                     good = false;
                     break;
@@ -317,7 +329,7 @@ __device__ __forceinline__ void resolve_warp(const RedCtx& rc, int lane) {
 #pragma unroll
         for (int k = 0; k < SGV_MAX_PARTIAL_VALUES; ++k) {
             mine[k] = 0.0;
-            if (k < nv) ld_entry(&me->e[slot][lane][k], rc.seq, mine[k]);
+            if (k < nv) ld_entry(&me->e[slot][lane][k], seq, mine[k]);
         }
     }
     const unsigned bad = __ballot_sync(0xffffffffu, !good);
@@ -332,10 +344,11 @@ __device__ __forceinline__ void resolve_warp(const RedCtx& rc, int lane) {
         t[k] = acc;
     }
     if (lane == 0) {
+        *rc.pubseq = seq;                               // this exchange is complete on this rank
         if (bad) {
             if (!rc.st->error) {
                 rc.st->error = (int)bad;
-                rc.st->err_seq = rc.seq;
+                rc.st->err_seq = seq;
             }
             rc.st->done[0] = rc.st->done[1] = 1;
             rc.st->em.done = 1;
@@ -348,7 +361,8 @@ __device__ __forceinline__ void resolve_warp(const RedCtx& rc, int lane) {
 // Write this rank's NV partial sums of reduction `seq` into every rank's inbox; called by a full warp, lane e
 // handles entry e = (peer, value) so that the peer stores are issued in parallel.
 template <int NV>
-__device__ __forceinline__ void publish_warp(const double (&acc)[NV], const RedCtx& rc, unsigned long long seq, int lane) {
+__device__ __forceinline__ void publish_warp(const double (&acc)[NV], const RedCtx& rc, int lane) {
+    const unsigned long long seq = red_next_seq(rc);
     const int slot = (int)(seq % SGV_INBOX_SLOTS);
     __threadfence();
     for (int e = lane; e < rc.world * NV; e += 32) {
@@ -402,7 +416,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], const RedCtx& rc, d
         // entries) are already ordered: every block fenced at GPU scope before taking its ticket, and peers read
         // this memory through this GPU's L2.  The world x NV entries are written by the 32 lanes in parallel: a
         // single thread issuing them one after the other costs ~0.25 us per peer store (16 us at 8 ranks x 8 sums).
-        publish_warp<NV>(acc, rc, rc.seq, threadIdx.x);
+        publish_warp<NV>(acc, rc, threadIdx.x);
         // one GPU per rank: this block completes the cross-rank reduction itself (the kernel ends when every
         // rank has published, which is also the ordering point for the halo reads of the next kernel)
         if (rc.inline_resolve) {

@@ -81,7 +81,7 @@ struct CgState {
 };
 
 // Cross-rank reduction mailbox.  Lives at the start of every rank's symmetric arena; rank r writes its
-// partial sums of reduction `seq` into slot seq % SLOTS, row r, of EVERY rank's inbox with peer stores
+// partial sums of exchange `seq` (counted on the device, see red_next_seq) into slot seq % SLOTS, row r, of EVERY rank's inbox with peer stores
 // over NVLink.  Every value travels with the sequence number in ONE 16-byte store, laid out as in NCCL's
 // low-latency (LL) protocol: each 8-byte half carries 32 bits of the double and its own 32-bit copy of the
 // sequence number, so the scheme only relies on 8-byte store atomicity.  A reader that sees the right
@@ -113,7 +113,8 @@ struct RedCtx {
     unsigned*          counter;    // "last block" ticket
     CgState*           st;
     Inbox*             inbox[SGV_MAX_RANKS];   // every rank's inbox, mapped into this rank's address space
-    unsigned long long seq;
+    unsigned long long seq;        // host-side launch ordinal (diagnostics only)
+    unsigned long long* pubseq;    // device counter of completed cross-rank exchanges: numbers the inbox slots (sgv_device.cuh)
     int                world, rank;
     int                inline_resolve; // world > 1, one GPU per rank: the finalising block itself waits for the other ranks
     int                skip_if_done;   // SKIP_*: the reducing kernel exits early in this state, and so does the resolve
@@ -143,6 +144,8 @@ struct LdMatrix {
     PanelItem*   items = nullptr;
     int      n_items = 0, s_cross = 1, panel_rw = 4;
     bool     panel_sym = true;             // false: the store holds R^T of a non-symmetric R (full-panel kernel only)
+    bool     rowpart = false;              // DENSE, rows partition: the store is the column panel R[:, row_lo:row_hi) (M x Ml),
+                                           // the product reads the vector pair of ALL ranks (gathered into sgv_ctx::vfull)
     struct SymItem* sym_items = nullptr;   // upper-triangle work items of the symmetric panel kernel (spmm_psym.cu)
     int*     rowmeta = nullptr;            // per row: strip, strips of its block, forward slots of its strip
     int      n_sym_items = 0;
@@ -191,6 +194,8 @@ struct sgv_ctx {
     int          rank = 0, world = 1;
     int64_t      bandwidth_hint = 0; // common half-bandwidth agreed by all ranks (0: detect)
     int          halo = 0;           // banded row partition: SpMM reads w-element halos from the neighbours
+    bool         rowpart = false;    // dense row partition (sgv_configure_part halo = 2): every rank holds Ml rows of a dense R
+    double2*     vfull = nullptr;    // rows partition: the input vector pair of all ranks, gathered before each product (M entries)
     int          K = 0;
     Cohort       coh[SGV_MAX_K];
     double*      r1_all = nullptr;   // K x Ml, cohort k's r1 at r1_all + k*Ml (coh[k].r1 aliases it)
@@ -214,6 +219,7 @@ struct sgv_ctx {
     sgv_ctx*     peer_ctx[SGV_MAX_RANKS] = {};
     std::atomic<unsigned long long> host_seq{0};
     unsigned long long seq = 0;      // reductions issued so far (identical on all ranks)
+    unsigned long long* pubseq = nullptr;   // device: cross-rank exchanges completed (zeroed with the arena)
     // fused VAMP iteration (sgv_iteration_*): ring of pinned log slots, probe staging
     static const int NLOG = 4;
     IterLog*     log_host[NLOG] = {};

@@ -227,7 +227,8 @@ k_spmm_dia(SpmmArgs a, const float* __restrict__ band, int w, int64_t ldb) {
 
 template <int RW, int S>
 __global__ void __launch_bounds__(32 * RW * S, 2)
-k_spmm_panel(SpmmArgs a, const float* __restrict__ panels, const PanelItem* __restrict__ items, double2* ypart) {
+k_spmm_panel(SpmmArgs a, const float* __restrict__ panels, const PanelItem* __restrict__ items, double2* ypart,
+             const double2* __restrict__ vin) {
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     constexpr int TI = 128 * RW;
     constexpr int NT = 32 * RW * S;
@@ -245,7 +246,7 @@ k_spmm_panel(SpmmArgs a, const float* __restrict__ panels, const PanelItem* __re
     for (int jb = 0; jb < it.nj; jb += PANEL_JC) {
         const int cnt = min(PANEL_JC, it.nj - jb);
         __syncthreads();
-        for (int t = threadIdx.x; t < cnt; t += NT) xs[t] = a.v[(int64_t)it.j0 + jb + t];
+        for (int t = threadIdx.x; t < cnt; t += NT) xs[t] = vin[(int64_t)it.j0 + jb + t];
         __syncthreads();
         const int per = (cnt + S - 1) / S;
         const int lo = s * per, hi = min(cnt, lo + per);
@@ -296,6 +297,49 @@ k_spmm_panel(SpmmArgs a, const float* __restrict__ panels, const PanelItem* __re
         if (left > 1) yp[1] = acc1;
         if (left > 2) yp[2] = acc2;
         if (left > 3) yp[3] = acc3;
+    }
+}
+
+// Rows partition of a dense R (ld.rowpart): the input vector pair of ALL ranks, read from the peers' symmetric arenas
+// into this rank's `vfull` (M entries, 16 B each: 1.6 MB at M = 100k against the 5 GB panel the product then streams).
+// fused: the CG direction update is formed on the way, p_new = r + beta p_old (scipy: p *= beta; p += z) from every
+// rank's r and p_old - the same values every owner computes - and the own slice of p_new is stored; p is double-
+// buffered, so a peer still gathering p_old is never overtaken.  Ordering: r, p_old and x of every rank are complete
+// once the previous cross-rank reduction has resolved (k_cg_update / k_lmmse_setup / k_pack_x0), as for the halos of
+// the banded partition.
+struct GatherArgs {
+    const double2* v[SGV_MAX_RANKS];
+    const double2* r[SGV_MAX_RANKS];
+    int64_t        lo[SGV_MAX_RANKS + 1];
+    int            world, rank;
+};
+__global__ void __launch_bounds__(256)
+k_gather_rows(GatherArgs g, double2* __restrict__ vfull, double2* __restrict__ p_new, int fused, int check_done,
+              const CgState* __restrict__ st) {
+    const int d0 = st->done[0], d1 = st->done[1];
+    if (check_done && d0 && d1) return;
+    const bool first = st->step == 0;
+    double b0 = 0.0, b1 = 0.0;
+    if (fused && !first) {
+        b0 = st->rho[0] / st->rho_prev[0];
+        b1 = st->rho[1] / st->rho_prev[1];
+    }
+    const int64_t M = g.lo[g.world];
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M; t += (int64_t)gridDim.x * blockDim.x) {
+        int q = 0;
+        while (q + 1 < g.world && t >= g.lo[q + 1]) ++q;
+        const int64_t i = t - g.lo[q];
+        double2 p;
+        if (fused) {
+            const double2 r = ld_vec2(g.r[q] + i);
+            p = first ? make_double2(0.0, 0.0) : ld_vec2(g.v[q] + i);
+            if (!d0) p.x = first ? r.x : (p.x * b0 + r.x);
+            if (!d1) p.y = first ? r.y : (p.y * b1 + r.y);
+            if (q == g.rank) p_new[i] = p;
+        } else {
+            p = ld_vec2(g.v[q] + i);
+        }
+        vfull[t] = p;
     }
 }
 
@@ -397,7 +441,7 @@ static int launch_epi(sgv_ctx* c, Cohort& co, SpmmArgs& a) {
         if (e == nullptr || e[0] != '1') return sgv_launch_psym(c, ld, EPI, a);
     }
     if (ld.layout == SGV_LAYOUT_DENSE || ld.layout == SGV_LAYOUT_BLOCKDIAG) {
-        k_spmm_panel<4, 2><<<ld.n_items, 256, 0, c->stream>>>(a, ld.panels, ld.items, c->ypart);
+        k_spmm_panel<4, 2><<<ld.n_items, 256, 0, c->stream>>>(a, ld.panels, ld.items, c->ypart, ld.rowpart ? c->vfull : a.v);
         c->launches++;
         const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 255) / 256, (int64_t)c->sm_count * 6);
         SGV_TRY(sgv_ensure_partials(c, grid));
@@ -444,6 +488,7 @@ int sgv_preload_spmm() {
     SGV_TRY(preload_epi<EPI_PLAIN>());
     cudaFuncAttributes fa;
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_spmm_panel<4, 2>));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_gather_rows));
     return 0;
 }
 
@@ -462,10 +507,38 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, doub
     a.vs_cohort = c->vs_active;   // >= 0 inside the fused VAMP iteration: gamw / gam2 come from the device
     a.v = vec == VEC_XX ? c->xx : c->pp[vec - VEC_PP0];
     a.fused_p = fused_p;
+    const bool rowpart = co.ld.layout == SGV_LAYOUT_DENSE && co.ld.rowpart;
+    SGV_CHECK(!c->rowpart || rowpart, "a handle configured for the dense rows partition holds dense column panels only");
     if (fused_p) {
-        SGV_CHECK(co.ld.layout == SGV_LAYOUT_DIA && vec != VEC_XX, "fused direction update needs the DIA layout");
+        SGV_CHECK((co.ld.layout == SGV_LAYOUT_DIA || rowpart) && vec != VEC_XX,
+                  "fused direction update needs the DIA layout or the dense rows partition");
         a.r = c->rr;
         a.p_new = c->pp[1 - (vec - VEC_PP0)];
+    }
+    if (rowpart) {
+        // all-gather of the input vector pair (with the direction update when fused); the epilogue then works on
+        // the own slice: p_new when fused
+        GatherArgs g;
+        memset(&g, 0, sizeof(g));
+        g.world = c->world;
+        g.rank = c->rank;
+        int64_t lo = 0;
+        for (int q = 0; q < c->world; ++q) {
+            const PeerView& pv = c->peer[q];
+            SGV_CHECK(pv.base != nullptr, "rank %d not attached (rows partition reads every rank's vectors)", q);
+            g.v[q] = arena_vec(c, q, vec);
+            g.r[q] = reinterpret_cast<const double2*>(pv.base + arena_off_rr(pv.Ml, 1));
+            g.lo[q] = lo;
+            if (q == c->rank) SGV_CHECK(lo == c->row_lo, "rows partition must be contiguous in rank order");
+            lo += pv.Ml;
+        }
+        g.lo[c->world] = lo;
+        SGV_CHECK(lo == c->M, "the ranks' row ranges do not add up to M");
+        const unsigned ggrid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 8);
+        k_gather_rows<<<ggrid, 256, 0, c->stream>>>(g, c->vfull, a.p_new, fused_p, check_done, c->cg);
+        c->launches++;
+        if (fused_p) a.v = a.p_new;
+        a.fused_p = 0;
     }
     if (c->world > 1 && c->halo && (co.ld.layout == SGV_LAYOUT_DIA || co.ld.layout == SGV_LAYOUT_DSYM)) {
         if (c->rank > 0) {

@@ -504,8 +504,7 @@ int sgv_launch_dsym_cg(sgv_ctx* c, Cohort& co, int n, double gamw, double gam2) 
 }
 
 // The whole CG solve as ONE cooperative launch of the persistent kernel (spmm_dsymp.cu): no launch per step, no host
-// read-back inside the solve.  Reduction sequence numbers: step n uses seq0 + n; the caller advances c->seq by the
-// number of steps that ran (identical on every rank) once it has read the state back.
+// read-back inside the solve.  The cross-rank exchanges of its steps are numbered on the device (RedCtx::pubseq).
 int sgv_launch_dsym_solve(sgv_ctx* c, Cohort& co, double gamw, double gam2, int max_steps) {
     const LdMatrix& ld = co.ld;
     SGV_CHECK(sgv_dsymp_solve_usable(c, ld), "whole-solve kernel not usable for this cohort");

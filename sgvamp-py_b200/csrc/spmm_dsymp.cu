@@ -189,7 +189,7 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
     double al0 = 0.0, al1 = 0.0, beta0 = 0.0, beta1 = 0.0;
     bool first = true, fz0 = false, fz1 = false;
     const volatile CgState* vst = a.rc.st;                      // SOLVE: rewritten between steps by the last CTA
-    unsigned long long seq = a.rc.seq, epoch = g.epoch;
+    unsigned long long epoch = g.epoch;
     // phase clock of the whole-solve kernel (SGV_DS_DEBUG=1; thread 0 of range 0 and of the last-arriving CTA):
     // dbg[0] stage window, [1] tiles, [2] head fix-up + partials, [3] wait for the slowest CTA, [4] local reduction,
     // [5] cross-rank exchange, [6] barrier release seen by range 0, [7] steps
@@ -202,7 +202,7 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
             tp = tn;                                                                 \
         }                                                                            \
     } while (0)
-  for (int step_i = 0;; ++step_i, ++seq, ++epoch) {
+  for (int step_i = 0;; ++step_i, ++epoch) {
     if (SOLVE) {                                                // the set-up kernel leaves step = 0: step n of the solve is
         const int n = step_i, prev = (n + 1) & 1, cur = n & 1;  // this loop's n-th turn, known without reading the state
         a.v = sv.pp[prev]; a.r = sv.rr[prev]; a.q = sv.qq[prev];
@@ -599,8 +599,7 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
             }
             double* red = reinterpret_cast<double*>(Aall);
             block_reduce<NV>(acc, red);
-            RedCtx rcs = a.rc;
-            rcs.seq = seq;
+            const RedCtx& rcs = a.rc;
             if (DSP_DEBUG && SOLVE && sv.dbg != nullptr && tid == 0) {
                 const unsigned long long tn = dsp_now();
                 atomicAdd(sv.dbg + 4, tn - tl);
@@ -608,7 +607,7 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
             }
             if (tid == 0 && rcs.world == 1) apply_totals(rcs.ap, rcs.st, acc);
             if (rcs.world > 1 && tid < 32) {
-                publish_warp<NV>(acc, rcs, rcs.seq, tid);
+                publish_warp<NV>(acc, rcs, tid);
                 if (rcs.inline_resolve) {
                     __syncwarp();
                     resolve_warp(rcs, tid);

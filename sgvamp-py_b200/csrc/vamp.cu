@@ -296,13 +296,11 @@ k_em_loop(int64_t M, const double* __restrict__ r1_all, EmConsts kval, RedCtx rc
                 for (int t = 0; t < 16; ++t) tot[t] += __ldcg(&rc.partials[(size_t)b * 16 + t]);
             }
             block_reduce<16>(tot, red);
-            RedCtx rp = rc;
-            rp.seq = rc.seq + (unsigned long long)pass;
-            if (threadIdx.x == 0 && rc.world == 1) apply_totals(rp.ap, rp.st, tot);
+            if (threadIdx.x == 0 && rc.world == 1) apply_totals(rc.ap, rc.st, tot);
             if (rc.world > 1 && threadIdx.x < 32) {     // totals are valid in every lane of warp 0
-                publish_warp<16>(tot, rp, rp.seq, threadIdx.x);
+                publish_warp<16>(tot, rc, threadIdx.x);
                 __syncwarp();
-                resolve_warp(rp, threadIdx.x);
+                resolve_warp(rc, threadIdx.x);
             }
             __threadfence();
         }
@@ -368,7 +366,6 @@ extern "C" int sgv_prior_em(sgv_handle c, const double* gam1s, int maxit, double
         SGV_CUDA(cudaLaunchCooperativeKernel((const void*)k_em_loop, dim3(lgrid), dim3(256), args, 0, c->stream));
         c->launches++;
         SGV_TRY(fetch_state(c));
-        c->seq += (unsigned long long)std::max(he->steps - 1, 0);   // every rank ran the same number of passes
         SGV_CHECK(he->done, "EM loop kernel ended without its done flag");
         maxit = 0;                                  // skip the batched path below
         c->last_em_steps = he->steps;
@@ -745,7 +742,8 @@ static int lmmse_enqueue(sgv_ctx* c, int cohort, const sgv_lmmse_in* in, bool de
     const int64_t M = c->Ml;
     const int vsc = dev ? cohort : -1;
     c->vs_active = vsc;
-    const bool fused = co.ld.layout == SGV_LAYOUT_DIA;     // direction update fused into the SpMM staging
+    // direction update fused into the SpMM staging (DIA) / into the all-gather of the dense rows partition
+    const bool fused = co.ld.layout == SGV_LAYOUT_DIA || (co.ld.layout == SGV_LAYOUT_DENSE && co.ld.rowpart);
     const bool fusedcg = co.ld.layout == SGV_LAYOUT_DSYM;  // whole CG step in one kernel
     const unsigned vgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 8);
     SGV_TRY(sgv_ensure_partials(c, vgrid + 1));
@@ -785,12 +783,9 @@ static int lmmse_enqueue(sgv_ctx* c, int cohort, const sgv_lmmse_in* in, bool de
     if (fusedcg && in->cg_maxit > 0 && sgv_dsymp_solve_usable(c, co.ld)) {
         // the whole solve in one cooperative launch: steps separated by a grid barrier, not by launches
         SGV_TRY(sgv_launch_dsym_solve(c, co, in->gamw, in->gam2, in->cg_maxit));
-        if (dev) {
-            c->seq += (unsigned long long)(in->cg_maxit - 1);          // step n uses sequence number seq0 + n; the count
-        } else {                                                        // that ran is not known here (no read-back)
+        if (!dev) {
             SGV_TRY(fetch_state(c));
             state_fetched = true;
-            c->seq += (unsigned long long)std::max(hs->step - 1, 0);
         }
         launched = in->cg_maxit;
     }
@@ -988,7 +983,6 @@ extern "C" int sgv_iteration_enqueue(sgv_handle c, const sgv_iter_in* in, double
         unsigned* bar = c->counter + 4;
         SGV_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), c->stream));
         RedCtx rc = sgv_red_begin(c, AP_EM, 16, 0);
-        c->seq += (unsigned long long)(in->em_maxit - 1);          // pass i uses sequence number seq0 + i
         int64_t Ml = M;
         const double* r1 = c->r1_all;
         EmConsts kdummy;

@@ -30,6 +30,7 @@ SYMBOLS = [
     "sgv_ld_adopt_dsym", "sgv_dsym_extension", "sgv_set_host_barrier", "sgv_device_id", "sgv_ld_upload_dia",
     "sgv_iteration_supported", "sgv_vamp_begin", "sgv_set_truth", "sgv_iteration_probe_buffer", "sgv_iteration_enqueue",
     "sgv_iteration_wait", "sgv_ld_adopt_blockdiag", "sgv_ld_build_banded", "sgv_ld_copy_band", "sgv_vamp_set_alphas",
+    "sgv_ld_upload_dense_rows", "sgv_ld_adopt_dense_colpanel",
 ]
 MAX_K, MAX_L, ITER_SLOTS = 8, 8, 4
 
@@ -168,6 +169,21 @@ class Handle:
         self._ck(self.lib.sgv_ld_upload_dense(self.h, C.c_int(cohort), R.ctypes.data_as(C.c_void_p),
                                               C.c_int(F64 if R.dtype == np.float64 else F32),
                                               C.c_int64(R.shape[1]), C.c_double(s)))
+
+    def upload_dense_rows(self, cohort, rows, s=0.0):
+        """Rows [row_lo, row_hi) of a dense R (this rank's slice of the rows partition, see sgv_ld_upload_dense_rows)."""
+        rows = np.asarray(rows)
+        if rows.dtype not in (np.float32, np.float64):
+            rows = rows.astype(np.float64)
+        if not rows.flags.c_contiguous:
+            rows = np.ascontiguousarray(rows)
+        assert rows.ndim == 2 and rows.shape[1] == self.M_global, rows.shape
+        self._ck(self.lib.sgv_ld_upload_dense_rows(self.h, C.c_int(cohort), rows.ctypes.data_as(C.c_void_p),
+                                                   C.c_int(F64 if rows.dtype == np.float64 else F32),
+                                                   C.c_int64(rows.shape[1]), C.c_double(s)))
+
+    def adopt_dense_colpanel(self, cohort, ptr, ld):
+        self._ck(self.lib.sgv_ld_adopt_dense_colpanel(self.h, C.c_int(cohort), C.c_void_p(ptr), C.c_int64(ld)))
 
     def upload_csr(self, cohort, indptr, indices, data, s=0.0, layout=LAYOUT_AUTO):
         indptr = np.ascontiguousarray(indptr, dtype=np.int64)

@@ -60,6 +60,14 @@ class DeviceDense:
         self.ptr, self.ld, self.keepalive = int(ptr), int(ld), keepalive
 
 
+class DeviceDenseCols:
+    """This rank's slice of a dense LD partitioned by rows, already resident in HBM as the fp32 column panel
+    P[j][i] = R[row_lo + i][j] (M rows of `ld` floats; see sgv_ld_adopt_dense_colpanel)."""
+
+    def __init__(self, ptr, ld, keepalive=None):
+        self.ptr, self.ld, self.keepalive = int(ptr), int(ld), keepalive
+
+
 class DeviceBlockDiag:
     """Block-diagonal LD already resident in HBM: dense row-major panels (see sgv_ld_adopt_blockdiag); `starts` are the
     local block boundaries of this rank (0 ... local rows)."""
@@ -171,7 +179,12 @@ class VAMP:
         self.lo, self.hi = self.bounds[self.shard.rank]
         self.Ml = self.hi - self.lo
         self.root = self.shard.rank == 0
-        self.halo = bool(halo)
+        # halo: True - banded LD, neighbours' halos; False - block-diagonal LD sharded at block boundaries;
+        # "rows" - dense LD, every rank holds its rows and gathers the vector pair of all ranks before a product
+        self.rows = isinstance(halo, str) and halo == "rows"
+        self.halo = (not self.rows) and bool(halo)
+        if self.rows and self.shard.world == 1:
+            raise Exception('halo="rows" partitions a dense LD over the ranks of a shard (world > 1)')
         self.device = device
         self.out_dir, self.out_name = out_dir, out_name
         if out_dir is not None and self.root:
@@ -185,7 +198,8 @@ class VAMP:
         if self.shard.world == 1:
             self.handle.configure(self.M, self.K)
         else:
-            self.handle.configure_part(self.M, self.K, self.shard.rank, self.shard.world, self.lo, self.hi, halo)
+            self.handle.configure_part(self.M, self.K, self.shard.rank, self.shard.world, self.lo, self.hi,
+                                       2 if self.rows else int(self.halo))
             shd.attach_peers(self.handle, self.shard)
         self.handle.set_weights(self.a)
         self._ld_loaded = [False] * self.K
@@ -245,6 +259,18 @@ class VAMP:
             assert s == 0.0, "device-resident LD must already be regularised"
             h.adopt_blockdiag(cohort, R.ptr, R.starts, R.offs, R.lds)
             self._keep.append(R)
+        elif isinstance(R, DeviceDenseCols):
+            assert s == 0.0, "device-resident LD must already be regularised"
+            h.adopt_dense_colpanel(cohort, R.ptr, R.ld)
+            self._keep.append(R)
+        elif self.rows:
+            # dense LD partitioned by rows: the whole matrix or this rank's rows [lo, hi)
+            Rd = R.toarray() if scipy.sparse.issparse(R) else np.asarray(R)
+            if Rd.shape == (self.M, self.M):
+                Rd = Rd[self.lo:self.hi]
+            if Rd.shape != (self.Ml, self.M):
+                raise Exception("LD rows of shape %s do not match rows [%d,%d) of M=%d" % (Rd.shape, self.lo, self.hi, self.M))
+            h.upload_dense_rows(cohort, Rd, s=s)
         elif isinstance(R, DiaWindow) or (scipy.sparse.issparse(R) and R.format == "dia"):
             # banded LD in DIA form: diagonals travel as they are (no index arrays; half of them for symmetric LD)
             if isinstance(R, DiaWindow):

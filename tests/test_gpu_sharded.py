@@ -218,6 +218,78 @@ def test_sharded_blockdiag_trajectory_matches_reference(nat, world):
         assert rel_err(om, c["final_omegas"]) <= 1e-4
 
 
+@pytest.mark.parametrize("M,world,symmetric", [(1000, 2, True), (777, 3, False), (2048, 4, True), (4100, 8, False)])
+def test_sharded_spmm_dense_rows(nat, M, world, symmetric):
+    """Dense R partitioned by rows: every rank holds rows [lo, hi) as a column panel and gathers the input pair of all
+    ranks from their memory; exact also for a non-symmetric R (the panel is the transposed row slice)."""
+    import shard as shd
+    rng = np.random.default_rng(M)
+    A = rng.standard_normal((M, M)).astype(np.float32).astype(np.float64)
+    R = (np.triu(A) + np.triu(A, 1).T) if symmetric else A
+    X = rng.standard_normal((M, 2))
+    bounds = shd.partition_rows(M, world)
+
+    def fn(sh, dev):
+        lo, hi = bounds[sh.rank]
+        h = nat.Handle(device=dev)
+        h.configure_part(M, 1, sh.rank, world, lo, hi, 2)
+        shd.attach_peers(h, sh)
+        h.upload_dense_rows(0, R[lo:hi] if sh.rank % 2 else R[lo:hi].astype(np.float32), s=0.25)
+        assert h.ld_info(0)["layout"] == "dense"
+        h.spmm_stage(X[lo:hi])
+        sh.barrier()                       # every rank's vector is in place before anyone gathers it
+        Y = h.spmm_run(0, 2, alpha=1.3, beta=-0.7)
+        sh.barrier()
+        with pytest.raises(Exception):     # whole-matrix upload is refused on a partitioned handle
+            h.upload_dense(0, R)
+        h.close()
+        return Y
+
+    Y = np.concatenate(run_ranks(world, fn), axis=0)
+    Ru = (0.75 * R + 0.25 * np.eye(M)).astype(np.float32).astype(np.float64)     # the store is fp32 (src/main.py:265 in fp64)
+    assert rel_l2(Y, 1.3 * (Ru @ X) - 0.7 * X) < 1e-13
+
+
+@pytest.mark.parametrize("case,world", [("dense_L2_em", 2), ("dense_L4_em_s01", 4), ("dense_K3_L2_em", 3)])
+def test_sharded_dense_rows_trajectory_matches_reference(nat, case, world):
+    """Whole runs with every cohort's dense LD partitioned by rows over all ranks (K = 3: cohorts as a batch dimension on
+    every rank): trajectory vs the reference golden, CG counts equal, scalars bit-identical on all ranks."""
+    import sgvamp
+    import shard as shd
+    c = load_case(case)
+    K, M = c["K"], c["M"]
+    Nl = c["N_list"]
+    Nt = sum(Nl) if K > 1 else Nl[0]
+    bounds = shd.partition_rows(M, world)
+
+    def fn(sh, dev):
+        v = sgvamp.VAMP(N=Nl if K > 1 else Nl[0], Nt=Nt, M=M, K=K, rho=c["rho"], gamw=c["gamw"], gam1=c["gam1"],
+                        a=np.array(Nl) / Nt if K > 1 else np.array([1.0]), prior_vars=c["prior_vars"],
+                        prior_probs=c["prior_probs"], out_dir=None, out_name="g", device=dev, shard=sh, shard_rows=bounds,
+                        halo="rows")
+        x0 = c["x0"] * np.sqrt(Nl[0]) if "x0" in c else None
+        R = c["R"] if K > 1 else c["R"][0]
+        r = list(c["r"]) if K > 1 else c["r"][0]
+        xs = v.infer(R, r, c["iterations"], x0=x0, cg_maxit=c["cg_maxit"], em_prior_maxit=c["em_prior_maxit"],
+                     learn_gamw=c["learn_gamw"], lmmse_damp=c["lmmse_damp"], prior_update=c["prior_update"],
+                     update_prior_from=c["update_prior_from"], s=c["s"], probes=c["probes"])
+        res = (xs, v.history, [v.handle.ld_info(k)["layout"] for k in range(K)])
+        sh.barrier()
+        v.close()
+        return res
+
+    res = run_ranks(world, fn)
+    for r in range(world):
+        xs, hist, lays = res[r]
+        assert lays == ["dense"] * K
+        for it in range(c["iterations"]):
+            assert rel_l2(xs[it], c["xhat"][it]) <= 1e-4
+            for k in range(K):
+                assert rel_err(hist["rows"][it][k][1:6], c["rows"][it, k, 1:6]) <= 1e-4
+                assert tuple(hist["cg_iters"][it][k]) == tuple(c["cg_iters"][it, k])
+                assert hist["rows"][it][k] == res[0][1]["rows"][it][k]          # bit-identical scalars on all ranks
+
+
 def test_sharded_rejects_coupled_blocks_and_short_shards(nat):
     import sgvamp
     import shard as shd
