@@ -48,10 +48,14 @@ def causal_beta(M, seed):
     return beta
 
 
-def gen_dense_cohort(torch, M, N, beta, seed, dev, out=None, chunk=8192):
+def gen_dense_cohort(torch, M, N, beta, seed, dev, out=None, chunk=8192, cols=None):
     """R = X^T X / N (fp32, M x M on the device, exactly symmetric) and r = X^T y / sqrt(N) (host fp64) of the reference
-    recipe, in two passes over seeded row chunks of X (pass 1: column sums and the raw Gram matrix; pass 2: y and r)."""
+    recipe, in two passes over seeded row chunks of X (pass 1: column sums and the raw Gram matrix; pass 2: y and r).
+    cols = (lo, hi): only the column panel R[:, lo:hi] (M x roundup(hi-lo, 4), what one rank of the dense rows partition
+    holds; the same X on every rank), standardised with a formula that is symmetric in (i, j) to the last bit."""
     torch.backends.cuda.matmul.allow_tf32 = True        # entries 0/1/2: products and fp32 sums are exact
+    if cols is not None:
+        return _gen_dense_colpanel(torch, M, N, beta, seed, dev, chunk, cols)
     G = out if out is not None else torch.empty((M, M), device=dev, dtype=torch.float32)
     G.zero_()
     s1 = torch.zeros(M, device=dev, dtype=torch.float64)
@@ -99,6 +103,53 @@ def gen_dense_cohort(torch, M, N, beta, seed, dev, out=None, chunk=8192):
     if dev.type == "cuda":
         torch.cuda.synchronize()
     return G, r.cpu().numpy()
+
+
+def _dense_chunk(torch, M, N, seed, dev, chunk, c0):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed * 7919 + c0)
+    n = min(chunk, N - c0)
+    u = torch.rand((n, M), generator=g, device=dev, dtype=torch.float32)
+    return (u < 0.4).to(torch.float32) + (torch.rand((n, M), generator=g, device=dev, dtype=torch.float32) < 0.4).to(torch.float32)
+
+
+def _gen_dense_colpanel(torch, M, N, beta, seed, dev, chunk, cols):
+    lo, hi = cols
+    Ml = hi - lo
+    ldd = (Ml + 3) // 4 * 4
+    P = torch.zeros((M, ldd), device=dev, dtype=torch.float32)
+    s1 = torch.zeros(M, device=dev, dtype=torch.float64)
+    s2 = torch.zeros(M, device=dev, dtype=torch.float64)
+    for c0 in range(0, N, chunk):
+        X = _dense_chunk(torch, M, N, seed, dev, chunk, c0)
+        P[:, :Ml].addmm_(X.t(), X[:, lo:hi])
+        s1 += X.sum(dim=0, dtype=torch.float64)
+        s2 += (X * X).sum(dim=0, dtype=torch.float64)
+        del X
+    mu = s1 / N
+    sd = torch.sqrt(torch.clamp(s2 / N - mu * mu, min=1e-12))
+    bt = torch.from_numpy(beta).to(dev)
+    r = torch.zeros(M, device=dev, dtype=torch.float64)
+    gn = torch.Generator(device=dev)
+    gn.manual_seed(seed * 31 + 5)
+    for c0 in range(0, N, chunk):
+        X = _dense_chunk(torch, M, N, seed, dev, chunk, c0).to(torch.float64)
+        Xs = (X - mu[None, :]) / sd[None, :]
+        y = Xs @ bt + float(np.sqrt(1 - H2)) * torch.randn((Xs.shape[0],), generator=gn, device=dev, dtype=torch.float64)
+        r += Xs.t() @ y
+        del X, Xs
+    r /= float(np.sqrt(N))
+    mu32, sd32 = mu.to(torch.float32), sd.to(torch.float32)
+    for i0 in range(0, M, 4096):
+        i1 = min(M, i0 + 4096)
+        blk = P[i0:i1, :Ml]
+        blk -= float(N) * (mu32[i0:i1, None] * mu32[None, lo:hi])          # products commute: R[i][j] == R[j][i] bit for bit
+        blk /= (float(N) * (sd32[i0:i1, None] * sd32[None, lo:hi]))
+    idx = torch.arange(lo, hi, device=dev)
+    P[idx, idx - lo] = 1.0
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    return P, r.cpu().numpy()
 
 
 def block_sizes(M, seed):
@@ -332,7 +383,10 @@ def run_config(a, bench):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    sharded = world > 1 and cfg["kind"] == "blockdiag"       # c3: LD blocks sharded over the GPUs, scalar-only exchange
+    # c3: LD blocks sharded over the GPUs, scalar-only exchange; dense shapes: every cohort partitioned by rows over all
+    # GPUs, the vector pair gathered from the peers before each product (SGV_DENSE_ROWS=0: rank 0 alone runs the shape)
+    rows_part = world > 1 and cfg["kind"] == "dense" and os.environ.get("SGV_DENSE_ROWS", "1") != "0"
+    sharded = world > 1 and (cfg["kind"] == "blockdiag" or rows_part)
     if world > 1 and not sharded:
         # the dense shapes are measured on one GPU; further ranks have nothing to do
         if rank != 0:
@@ -370,7 +424,17 @@ def run_config(a, bench):
     t0 = time.time()
     keep, Rs, rs_, x0 = [], [], [], None
     beta = causal_beta(M, seed)
-    if cfg["kind"] == "dense":
+    bounds = None
+    if cfg["kind"] == "dense" and rows_part:
+        bounds = shd.partition_rows(M, world)
+        lo, hi = bounds[rank]
+        for k, N in enumerate(Ns):
+            P, r = gen_dense_cohort(torch, M, N, beta, seed + k, dev, cols=(lo, hi))
+            keep.append(P)
+            Rs.append(sgvamp.DeviceDenseCols(P.data_ptr(), P.shape[1], keepalive=P))
+            rs_.append(r[lo:hi])
+        x0 = beta * np.sqrt(Ns[0])
+    elif cfg["kind"] == "dense":
         for k, N in enumerate(Ns):
             G, r = gen_dense_cohort(torch, M, N, beta, seed + k, dev)
             keep.append(G)
@@ -378,7 +442,6 @@ def run_config(a, bench):
             rs_.append(r)
         x0 = beta * np.sqrt(Ns[0])
     else:
-        bounds = None
         lo, hi = 0, M
         if sharded:
             gstarts = np.concatenate([[0], np.cumsum(block_sizes(M, seed))])
@@ -395,7 +458,7 @@ def run_config(a, bench):
     stream = solver_stream.cuda_stream
 
     def new_solver(Mx=M, Nsx=Ns, solo=False):
-        kw = dict(shard=shard, shard_rows=bounds, halo=False) if (sharded and not solo) else {}
+        kw = dict(shard=shard, shard_rows=bounds, halo="rows" if rows_part else False) if (sharded and not solo) else {}
         return sgvamp.VAMP(N=Nsx if K > 1 else Nsx[0], Nt=float(sum(Nsx)), M=Mx, K=K, rho=cfg.get("rho", 0.5), gamw=2.0, gam1=1e-6,
                            a=np.array(Nsx) / float(sum(Nsx)), prior_vars=prior_for(Mx, L)[0], prior_probs=prior_for(Mx, L)[1],
                            out_dir=None, out_name="bench", device=local_rank, stream=stream, **kw)
@@ -440,7 +503,10 @@ def run_config(a, bench):
     # algorithmic bytes of one 2-RHS pass over a SYMMETRIC dense store: the upper triangle once (2 bytes per matrix
     # entry on average) + vector pair in and out
     Ml = v.Ml
-    bytes_pass = float(np.mean([2.0 * i["nnz_stored"] + 32.0 * Ml for i in infos]))
+    if rows_part:      # the rank's column panel once (no symmetry to use across ranks) + the gathered pair + pair in / out
+        bytes_pass = float(np.mean([4.0 * i["nnz_stored"] + 16.0 * M + 32.0 * Ml for i in infos]))
+    else:
+        bytes_pass = float(np.mean([2.0 * i["nnz_stored"] + 32.0 * Ml for i in infos]))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(bench.REPO, "MEASURED_PEAKS.json")))
@@ -545,7 +611,8 @@ def run_config(a, bench):
                   "what": "GPU (C ABI, host LD upload) vs CPU oracle on the cpu_baseline sample: same LD, r, probes"}
         vs.close()
     sampler.close()
-    kernel = {"dense": "k_spmm_psym (2-RHS upper-triangle symmetric dense SpMM) + k_psym_finish",
+    kernel = {"dense": "k_gather_rows + k_spmm_panel (2-RHS column sweep over the rank's column panel) + k_panel_finish" if rows_part else
+                       "k_spmm_psym (2-RHS upper-triangle symmetric dense SpMM) + k_psym_finish",
               "blockdiag": "k_spmm_psym (2-RHS upper-triangle SpMM over the LD blocks' panels) + k_psym_finish"}[cfg["kind"]]
     line = {
         "metric": "VAMP iterations/s", "value": value, "unit": "it/s", "n_gpus": world if sharded else 1, "steps": a.steps, "warmup": a.warmup,
@@ -553,7 +620,10 @@ def run_config(a, bench):
         "data": "synthetic",
         "config": {"workload": "%s: %s, cg_maxit=%d, rho=%.1f" % (a.config, cfg["text"], cfg["cg_maxit"], cfg.get("rho", 0.5)), "M": M, "K": K, "layout": layout,
                    "nnz_stored": nnz_all, "nblocks_rank0": infos[0]["nblocks"],
-                   "partition": ("%d GPUs, whole LD blocks per GPU balanced by sum m_b^2 (shard.partition_blocks); SpMM local, "
+                   "partition": ("%d GPUs, every cohort's dense LD partitioned by rows (column panel R[:, lo:hi] per GPU); the vector "
+                                 "pair of all ranks is gathered from peer memory before each product (CG direction update fused "
+                                 "into the gather), reductions exchanged in-kernel" % world) if rows_part else
+                                ("%d GPUs, whole LD blocks per GPU balanced by sum m_b^2 (shard.partition_blocks); SpMM local, "
                                  "scalar reductions exchanged in-kernel through peer memory" % world) if sharded else "single GPU",
                    "l2_policy": "inputs (%.1f GB of LD in HBM) larger than L2" % (sum(i["nnz_stored"] for i in infos) * 4 / 1e9),
                    "timed_iterations": "VAMP iterations %d..%d of one trajectory" % (a.warmup, iterations - 1),
@@ -564,7 +634,8 @@ def run_config(a, bench):
                      "kernel": kernel, "bytes_per_launch": bytes_pass, "avg_launch_ms": avg_ms, "launches_timed": spmm_launches,
                      "isolated_launch_ms": iso_ms, "isolated_gbs": (bytes_pass / (iso_ms * 1e-3) / 1e9) if iso_ms else None,
                      "per": "GPU (slowest rank)",
-                     "bytes_definition": "upper triangle of the symmetric fp32 store (2 B per matrix entry) + 32 B per marker",
+                     "bytes_definition": "the rank's fp32 column panel once (4 B per entry) + 16 B per gathered marker + 32 B per own marker" if rows_part
+                                         else "upper triangle of the symmetric fp32 store (2 B per matrix entry) + 32 B per marker",
                      "spmm_share_of_step": spmm_ms / ms_total},
         "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": nlaunch, "clocks": clocks,
     }

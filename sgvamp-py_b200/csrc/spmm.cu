@@ -515,31 +515,6 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, doub
         a.r = c->rr;
         a.p_new = c->pp[1 - (vec - VEC_PP0)];
     }
-    if (rowpart) {
-        // all-gather of the input vector pair (with the direction update when fused); the epilogue then works on
-        // the own slice: p_new when fused
-        GatherArgs g;
-        memset(&g, 0, sizeof(g));
-        g.world = c->world;
-        g.rank = c->rank;
-        int64_t lo = 0;
-        for (int q = 0; q < c->world; ++q) {
-            const PeerView& pv = c->peer[q];
-            SGV_CHECK(pv.base != nullptr, "rank %d not attached (rows partition reads every rank's vectors)", q);
-            g.v[q] = arena_vec(c, q, vec);
-            g.r[q] = reinterpret_cast<const double2*>(pv.base + arena_off_rr(pv.Ml, 1));
-            g.lo[q] = lo;
-            if (q == c->rank) SGV_CHECK(lo == c->row_lo, "rows partition must be contiguous in rank order");
-            lo += pv.Ml;
-        }
-        g.lo[c->world] = lo;
-        SGV_CHECK(lo == c->M, "the ranks' row ranges do not add up to M");
-        const unsigned ggrid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 8);
-        k_gather_rows<<<ggrid, 256, 0, c->stream>>>(g, c->vfull, a.p_new, fused_p, check_done, c->cg);
-        c->launches++;
-        if (fused_p) a.v = a.p_new;
-        a.fused_p = 0;
-    }
     if (c->world > 1 && c->halo && (co.ld.layout == SGV_LAYOUT_DIA || co.ld.layout == SGV_LAYOUT_DSYM)) {
         if (c->rank > 0) {
             const PeerView& pv = c->peer[c->rank - 1];
@@ -577,6 +552,31 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, doub
             }
         }
         SGV_CUDA(cudaEventRecord(c->prof_ev[c->prof_n], c->stream));
+    }
+    if (rowpart) {
+        // all-gather of the input vector pair (with the direction update when fused); the epilogue then works on
+        // the own slice: p_new when fused
+        GatherArgs g;
+        memset(&g, 0, sizeof(g));
+        g.world = c->world;
+        g.rank = c->rank;
+        int64_t lo = 0;
+        for (int q = 0; q < c->world; ++q) {
+            const PeerView& pv = c->peer[q];
+            SGV_CHECK(pv.base != nullptr, "rank %d not attached (rows partition reads every rank's vectors)", q);
+            g.v[q] = arena_vec(c, q, vec);
+            g.r[q] = reinterpret_cast<const double2*>(pv.base + arena_off_rr(pv.Ml, 1));
+            g.lo[q] = lo;
+            if (q == c->rank) SGV_CHECK(lo == c->row_lo, "rows partition must be contiguous in rank order");
+            lo += pv.Ml;
+        }
+        g.lo[c->world] = lo;
+        SGV_CHECK(lo == c->M, "the ranks' row ranges do not add up to M");
+        const unsigned ggrid = (unsigned)std::min<int64_t>((c->M + 255) / 256, (int64_t)c->sm_count * 8);
+        k_gather_rows<<<ggrid, 256, 0, c->stream>>>(g, c->vfull, a.p_new, fused_p, check_done, c->cg);
+        c->launches++;
+        if (fused_p) a.v = a.p_new;
+        a.fused_p = 0;
     }
     switch (epi) {
         case EPI_Q: rc = launch_epi<EPI_Q>(c, co, a); break;
