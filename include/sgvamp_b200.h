@@ -110,7 +110,8 @@ int sgv_ld_adopt_dense(sgv_handle h, int cohort, const float* R_dev, int64_t ld)
  * row-major with M columns.  The device store is the column panel P[j][i] = Rused[row_lo + i][j] (M rows of
  * roundup(Ml,4) floats), so a product is exactly Rused v also for a non-symmetric R; the vector pair of all ranks is
  * gathered from the peers' memory before each product (the CG direction update fused into the gather).  `adopt`:
- * the column panel already in HBM (fp32, regularised, pad columns readable). */
+ * the column panel already in HBM (fp32, regularised, pad columns readable).  General sparse LD on such a handle:
+ * sgv_ld_upload_csr with this rank's rows and GLOBAL column indices (layout hint auto / csr). */
 int sgv_ld_upload_dense_rows(sgv_handle h, int cohort, const void* rows, int dtype, int64_t ld_src, double s);
 int sgv_ld_adopt_dense_colpanel(sgv_handle h, int cohort, const float* P_dev, int64_t ld);
 /* block-diagonal LD (per-chromosome LD blocks, BASELINE.json configs[2]) already in HBM: block b holds the rows

@@ -173,12 +173,12 @@ __global__ void k_panel_diag(int64_t M, float* __restrict__ panels, const int* _
 
 template <typename T>
 __global__ void k_csr_vals(int64_t M, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-                           const T* __restrict__ data, float* __restrict__ vals, double s) {
+                           const T* __restrict__ data, float* __restrict__ vals, double s, int col_base) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
     for (int64_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32)
-        vals[k] = reg_value(data[k], indices[k] == row, s);
+        vals[k] = reg_value(data[k], indices[k] - col_base == row, s);
 }
 
 // dense chunk: src rows [r0, r0+nr) of an M-column row-major matrix with leading dimension ld_src
@@ -680,7 +680,8 @@ static int convert_csr(sgv_ctx* c, LdMatrix& ld, int layout, const int64_t* d_in
         ld.vals = vals;
         ld.nnz = nnz;
         ld.nnz_stored = nnz;
-        k_csr_vals<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, vals, s);
+        k_csr_vals<T><<<wgrid, 256, 0, c->stream>>>(M, d_indptr, d_indices, d_data, vals, s, c->rowpart ? (int)c->row_lo : 0);
+        ld.rowpart = c->rowpart;     // rows partition: global column indices, the product reads the gathered vector pair
         c->launches++;
     }
     SGV_CUDA(cudaStreamSynchronize(c->stream));
@@ -725,8 +726,10 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
     SGV_CHECK(dtype == SGV_F32 || dtype == SGV_F64, "bad dtype %d", dtype);
     SGV_CHECK(c->M < INT_MAX, "M too large for int32 column indices");
     SGV_CUDA(cudaSetDevice(c->device));
-    const int64_t M = c->Ml;   // local rows; columns are global when the partition has halos
-    const int col_base = c->halo ? (int)c->row_lo : 0;
+    const int64_t M = c->Ml;   // local rows; columns are global when the partition has halos / is the rows partition
+    const int col_base = (c->halo || c->rowpart) ? (int)c->row_lo : 0;
+    SGV_CHECK(!c->rowpart || layout_hint == SGV_LAYOUT_AUTO || layout_hint == SGV_LAYOUT_CSR,
+              "the rows partition keeps sparse LD in CSR form (dense LD: sgv_ld_upload_dense_rows)");
     SGV_CHECK(indptr[0] == 0 && indptr[M] == nnz, "indptr[0]=%lld indptr[M]=%lld inconsistent with nnz=%lld",
               (long long)indptr[0], (long long)indptr[M], (long long)nnz);
     LdMatrix& ld = c->coh[cohort].ld;
@@ -761,7 +764,7 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
     for (int64_t i = 0; i < M; ++i) {
         if (hi[i] < 0) { all_diag = false; continue; }
         SGV_CHECK(lo[i] + col_base >= 0 && hi[i] + col_base < c->M, "column index out of range in row %lld", (long long)i);
-        SGV_CHECK(c->halo || (lo[i] >= 0 && hi[i] < M), "row %lld has columns outside this rank's shard", (long long)i);
+        SGV_CHECK(c->halo || c->rowpart || (lo[i] >= 0 && hi[i] < M), "row %lld has columns outside this rank's shard", (long long)i);
         w = std::max<int64_t>(w, std::max<int64_t>(i - lo[i], hi[i] - i));
         all_diag = all_diag && dg[i];
     }
@@ -798,6 +801,7 @@ extern "C" int sgv_ld_upload_csr(sgv_handle c, int cohort, const int64_t* indptr
             dsym_fallback = dsym_ok;
         }
     }
+    if (c->rowpart) layout = SGV_LAYOUT_CSR;      // rows of a general sparse R: any column of the matrix, indices stay global
     if (layout == SGV_LAYOUT_AUTO) {
         layout = SGV_LAYOUT_CSR;
         const bool blk_good = blk_fits && fill_blk >= (nb == 1 ? 0.25 : 0.5);

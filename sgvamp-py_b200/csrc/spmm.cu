@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(256) k_panel_finish(SpmmArgs a, const double2*
 template <int EPI>
 __global__ void __launch_bounds__(256)
 k_spmm_csr(SpmmArgs a, const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
-           const float* __restrict__ vals) {
+           const float* __restrict__ vals, const double2* __restrict__ vin) {
     SGV_LOAD_DEV_SCALARS(a);
     if (a.check_done && a.rc.st->done[0] && a.rc.st->done[1]) return;
     __shared__ double red[2 * 32];
@@ -382,15 +382,15 @@ k_spmm_csr(SpmmArgs a, const int64_t* __restrict__ indptr, const int32_t* __rest
         for (; k + 32 < end; k += 64) {
             const float v0 = ldg_stream_f1(vals + k), v1 = ldg_stream_f1(vals + k + 32);
             const int c0 = ldg_stream_i1(indices + k), c1 = ldg_stream_i1(indices + k + 32);
-            const double2 x0 = __ldg(&a.v[c0]);
-            const double2 x1 = __ldg(&a.v[c1]);
+            const double2 x0 = __ldg(&vin[c0]);
+            const double2 x1 = __ldg(&vin[c1]);
             ax = fma((double)v0, x0.x, ax); ay = fma((double)v0, x0.y, ay);
             bx = fma((double)v1, x1.x, bx); by = fma((double)v1, x1.y, by);
         }
         if (k < end) {
             const float v0 = ldg_stream_f1(vals + k);
             const int c0 = ldg_stream_i1(indices + k);
-            const double2 x0 = __ldg(&a.v[c0]);
+            const double2 x0 = __ldg(&vin[c0]);
             ax = fma((double)v0, x0.x, ax); ay = fma((double)v0, x0.y, ay);
         }
         ax = warp_sum(ax + bx);
@@ -454,7 +454,7 @@ static int launch_epi(sgv_ctx* c, Cohort& co, SpmmArgs& a) {
         const unsigned grid = (unsigned)std::min<int64_t>((c->Ml + 7) / 8, (int64_t)c->sm_count * 32);
         SGV_TRY(sgv_ensure_partials(c, grid));
         a.rc.partials = c->partials;
-        k_spmm_csr<EPI><<<grid, 256, 0, c->stream>>>(a, ld.indptr, ld.indices, ld.vals);
+        k_spmm_csr<EPI><<<grid, 256, 0, c->stream>>>(a, ld.indptr, ld.indices, ld.vals, ld.rowpart ? c->vfull : a.v);
         c->launches++;
         return 0;
     }
@@ -507,11 +507,11 @@ int sgv_launch_spmm(sgv_ctx* c, Cohort& co, int epi, int vec, double2* out, doub
     a.vs_cohort = c->vs_active;   // >= 0 inside the fused VAMP iteration: gamw / gam2 come from the device
     a.v = vec == VEC_XX ? c->xx : c->pp[vec - VEC_PP0];
     a.fused_p = fused_p;
-    const bool rowpart = co.ld.layout == SGV_LAYOUT_DENSE && co.ld.rowpart;
-    SGV_CHECK(!c->rowpart || rowpart, "a handle configured for the dense rows partition holds dense column panels only");
+    const bool rowpart = co.ld.rowpart;   // DENSE column panel or CSR rows with global column indices
+    SGV_CHECK(!c->rowpart || rowpart, "a handle configured for the rows partition holds dense column panels or CSR rows only");
     if (fused_p) {
         SGV_CHECK((co.ld.layout == SGV_LAYOUT_DIA || rowpart) && vec != VEC_XX,
-                  "fused direction update needs the DIA layout or the dense rows partition");
+                  "fused direction update needs the DIA layout or the rows partition");
         a.r = c->rr;
         a.p_new = c->pp[1 - (vec - VEC_PP0)];
     }

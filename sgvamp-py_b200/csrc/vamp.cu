@@ -743,7 +743,7 @@ static int lmmse_enqueue(sgv_ctx* c, int cohort, const sgv_lmmse_in* in, bool de
     const int vsc = dev ? cohort : -1;
     c->vs_active = vsc;
     // direction update fused into the SpMM staging (DIA) / into the all-gather of the dense rows partition
-    const bool fused = co.ld.layout == SGV_LAYOUT_DIA || (co.ld.layout == SGV_LAYOUT_DENSE && co.ld.rowpart);
+    const bool fused = co.ld.layout == SGV_LAYOUT_DIA || co.ld.rowpart;
     const bool fusedcg = co.ld.layout == SGV_LAYOUT_DSYM;  // whole CG step in one kernel
     const unsigned vgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 8);
     SGV_TRY(sgv_ensure_partials(c, vgrid + 1));

@@ -263,6 +263,24 @@ class VAMP:
             assert s == 0.0, "device-resident LD must already be regularised"
             h.adopt_dense_colpanel(cohort, R.ptr, R.ld)
             self._keep.append(R)
+        elif self.rows and scipy.sparse.issparse(R) and (lay == nat.LAYOUT_CSR or (
+                lay == nat.LAYOUT_AUTO and R.nnz < 0.25 * R.shape[0] * R.shape[1])):
+            # general sparse LD partitioned by rows: CSR rows with global column indices
+            R = R.tocsr()
+            if R.shape == (self.M, self.M):
+                R = R[self.lo:self.hi]
+            if R.shape != (self.Ml, self.M):
+                raise Exception("LD rows of shape %s do not match rows [%d,%d) of M=%d" % (R.shape, self.lo, self.hi, self.M))
+            if not R.has_canonical_format:
+                R = R.copy()
+                R.sum_duplicates()
+            rc = h.upload_csr(cohort, R.indptr, R.indices, R.data, s=s, layout=nat.LAYOUT_CSR)
+            if rc == -3:   # the CSR layout needs an explicitly stored diagonal when s != 0
+                R = R.copy()
+                R.setdiag(R.diagonal(k=self.lo), k=self.lo)     # inserts the missing entries (as explicit zeros)
+                R.sort_indices()
+                rc = h.upload_csr(cohort, R.indptr, R.indices, R.data, s=s, layout=nat.LAYOUT_CSR)
+            h._ck(rc)
         elif self.rows:
             # dense LD partitioned by rows: the whole matrix or this rank's rows [lo, hi)
             Rd = R.toarray() if scipy.sparse.issparse(R) else np.asarray(R)

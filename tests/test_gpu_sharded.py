@@ -250,6 +250,71 @@ def test_sharded_spmm_dense_rows(nat, M, world, symmetric):
     assert rel_l2(Y, 1.3 * (Ru @ X) - 0.7 * X) < 1e-13
 
 
+@pytest.mark.parametrize("M,world", [(3000, 2), (5001, 3), (4096, 8)])
+def test_sharded_spmm_csr_rows(nat, M, world):
+    """General sparse R (entries coupling arbitrary, distant markers) partitioned by rows: CSR rows with global column
+    indices, the input pair of all ranks gathered before the product."""
+    import shard as shd
+    A = scipy.sparse.random(M, M, density=0.004, format="csr", random_state=M, dtype=np.float64)
+    R = (A + A.T + scipy.sparse.identity(M)).tocsr()
+    R.data = R.data.astype(np.float32).astype(np.float64)        # the store is fp32
+    R.sort_indices()
+    X = np.random.default_rng(3).standard_normal((M, 2))
+    bounds = shd.partition_rows(M, world)
+
+    def fn(sh, dev):
+        lo, hi = bounds[sh.rank]
+        h = nat.Handle(device=dev)
+        h.configure_part(M, 1, sh.rank, world, lo, hi, 2)
+        shd.attach_peers(h, sh)
+        ip, ix, data = shd.slice_rows_csr(R, lo, hi)
+        h._ck(h.upload_csr(0, ip, ix, data, s=0.0, layout=nat.LAYOUT_AUTO))
+        assert h.ld_info(0)["layout"] == "csr"
+        h.spmm_stage(X[lo:hi])
+        sh.barrier()
+        Y = h.spmm_run(0, 2, alpha=0.9, beta=0.3)
+        sh.barrier()
+        h.close()
+        return Y
+
+    Y = np.concatenate(run_ranks(world, fn), axis=0)
+    assert rel_l2(Y, 0.9 * (R @ X) + 0.3 * X) < 1e-13
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_csr_rows_trajectory_matches_reference(nat, world):
+    """The irregular-sparsity golden (entries far from the diagonal: no band / block layout applies) with its rows
+    partitioned over the ranks."""
+    import sgvamp
+    import shard as shd
+    c = load_case("csr_irregular_stable_L2_em")
+    M, N = c["M"], c["N_list"][0]
+    bounds = shd.partition_rows(M, world)
+
+    def fn(sh, dev):
+        v = sgvamp.VAMP(N=N, Nt=N, M=M, K=1, rho=c["rho"], gamw=c["gamw"], gam1=c["gam1"], a=np.array([1.0]),
+                        prior_vars=c["prior_vars"], prior_probs=c["prior_probs"], out_dir=None, out_name="g",
+                        device=dev, shard=sh, shard_rows=bounds, halo="rows")
+        x0 = c["x0"] * np.sqrt(N) if "x0" in c else None
+        xs = v.infer(c["R"][0], c["r"][0], c["iterations"], x0=x0, cg_maxit=c["cg_maxit"], em_prior_maxit=c["em_prior_maxit"],
+                     learn_gamw=c["learn_gamw"], lmmse_damp=c["lmmse_damp"], prior_update=c["prior_update"],
+                     update_prior_from=c["update_prior_from"], s=c["s"], probes=c["probes"], layout="csr")
+        res = (xs, v.history, v.handle.ld_info(0)["layout"])
+        sh.barrier()
+        v.close()
+        return res
+
+    res = run_ranks(world, fn)
+    for r in range(world):
+        xs, hist, lay = res[r]
+        assert lay == "csr"
+        for it in range(c["iterations"]):
+            assert rel_l2(xs[it], c["xhat"][it]) <= 1e-4
+            assert rel_err(hist["rows"][it][0][1:6], c["rows"][it, 0, 1:6]) <= 1e-4
+            assert tuple(hist["cg_iters"][it][0]) == tuple(c["cg_iters"][it, 0])
+            assert hist["rows"][it][0] == res[0][1]["rows"][it][0]
+
+
 @pytest.mark.parametrize("case,world", [("dense_L2_em", 2), ("dense_L4_em_s01", 4), ("dense_K3_L2_em", 3)])
 def test_sharded_dense_rows_trajectory_matches_reference(nat, case, world):
     """Whole runs with every cohort's dense LD partitioned by rows over all ranks (K = 3: cohorts as a batch dimension on
