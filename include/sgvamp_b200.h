@@ -74,6 +74,10 @@ int sgv_set_host_barrier(sgv_handle h, int enable);
 int sgv_device_id(sgv_handle h, char* pci_bus_id, int len);   /* PCI bus id of the handle's GPU */
 int sgv_ld_set_bandwidth_hint(sgv_handle h, int64_t w);   /* common half-bandwidth of the DIA layout across ranks */
 int sgv_partition_info(sgv_handle h, int64_t* M, int64_t* rows, int64_t* row_lo, int* rank, int* world);
+/* Device address of the K x rows block of r1 vectors (cohort k at k * stride doubles).  Rank-per-cohort deployments
+ * (src/sgvamp.py:228-233: every rank broadcasts its cohort's r1 and gam1) all-gather straight into it with one
+ * collective; the caller orders that collective against the handle's stream. */
+int sgv_r1_block(sgv_handle h, void** dev_ptr, int64_t* stride);
 
 /* ---- LD matrices (reference: R argument of VAMP.infer, src/sgvamp.py:196; Rused formed at
  * src/main.py:265).  `s` applies Rused = (1-s) R + s I at upload (pass 0 for an R that is

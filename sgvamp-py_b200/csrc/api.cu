@@ -21,6 +21,16 @@ extern "C" const char* sgv_last_error(void) { return g_err; }
 extern "C" int sgv_version(void) { return 100; }
 
 __global__ void k_resolve(RedCtx rc);
+// Device address of the K x Ml block of r1 vectors (cohort k at k * Ml): the rank-per-cohort mode (src/sgvamp.py:228-233)
+// exchanges the cohorts' r1 with ONE collective straight into this block (shard.TorchComm.allgather_r1) instead of K
+// host round trips.  The caller orders its collective against the handle's stream (sgv_sync / a shared stream).
+extern "C" int sgv_r1_block(sgv_handle c, void** dev_ptr, int64_t* stride) {
+    SGV_CHECK(c != nullptr && c->r1_all != nullptr && dev_ptr != nullptr, "handle not configured");
+    *dev_ptr = c->r1_all;
+    if (stride) *stride = c->Ml;
+    return 0;
+}
+
 __global__ void k_scale_copy(int64_t M, const double* __restrict__ src, double* __restrict__ dst, double scale);
 
 int sgv_reset_cg_state(sgv_ctx* c) {

@@ -30,7 +30,7 @@ SYMBOLS = [
     "sgv_ld_adopt_dsym", "sgv_dsym_extension", "sgv_set_host_barrier", "sgv_device_id", "sgv_ld_upload_dia",
     "sgv_iteration_supported", "sgv_vamp_begin", "sgv_set_truth", "sgv_iteration_probe_buffer", "sgv_iteration_enqueue",
     "sgv_iteration_wait", "sgv_ld_adopt_blockdiag", "sgv_ld_build_banded", "sgv_ld_copy_band", "sgv_vamp_set_alphas",
-    "sgv_ld_upload_dense_rows", "sgv_ld_adopt_dense_colpanel",
+    "sgv_ld_upload_dense_rows", "sgv_ld_adopt_dense_colpanel", "sgv_r1_block",
 ]
 MAX_K, MAX_L, ITER_SLOTS = 8, 8, 4
 
@@ -287,6 +287,12 @@ class Handle:
         out = np.empty(self.M, dtype=np.float64)
         self._ck(self.lib.sgv_get_vec(self.h, C.c_int(cohort), C.c_int(which), _dp(out)))
         return out
+
+    def r1_block(self):
+        """(device pointer, stride in doubles) of the K x rows block of r1 vectors (see sgv_r1_block)."""
+        p, st = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.sgv_r1_block(self.h, C.byref(p), C.byref(st)))
+        return int(p.value), int(st.value)
 
     def set_vec(self, cohort, which, v):
         v = _f64(v).ravel()

@@ -529,12 +529,16 @@ class VAMP:
             t_it = pc()
             gam1s = np.array(gam1, dtype=np.float64)
             if self.rank_mode:                                          # :228-233
-                mine_r1 = h.get_vec(rank, nat.VEC_R1)
-                for i in range(K):
-                    gam1s[i] = self.comm.bcast(gam1s[i], root=i)
-                    got = self.comm.bcast(mine_r1 if i == rank else None, root=i)
-                    if i != rank:
-                        h.set_vec(i, nat.VEC_R1, got)
+                got = self.comm.allgather_r1(h, gam1s[rank]) if hasattr(self.comm, "allgather_r1") else None
+                if got is not None:                                     # device-side: one collective into the r1 block
+                    gam1s = np.array(got, dtype=np.float64)
+                else:                                                   # the reference's 2K broadcasts through the host
+                    mine_r1 = h.get_vec(rank, nat.VEC_R1)
+                    for i in range(K):
+                        gam1s[i] = self.comm.bcast(gam1s[i], root=i)
+                        got_i = self.comm.bcast(mine_r1 if i == rank else None, root=i)
+                        if i != rank:
+                            h.set_vec(i, nat.VEC_R1, got_i)
             # prior update :242-259
             em_steps = 0
             if it >= update_prior_from:

@@ -165,6 +165,36 @@ class TorchComm:
         return t.cpu().numpy()
 
 
+class _DevArray:
+    """A raw device pointer as a CUDA-array-interface object (zero-copy view for torch.as_tensor)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+def _allgather_r1(self, handle, gam1_mine):
+    """Device-side form of the reference's 2K broadcasts (src/sgvamp.py:228-233) for one rank per cohort on GPUs: ONE
+    NCCL all-gather writes every cohort's r1 straight into the library's K x M block of r1 vectors (in place: this rank's
+    slice is already there), a second one collects the K gam1 scalars.  Returns gam1s (host), which also orders the r1
+    gather before the caller's next enqueue.  None when the communicator is not NCCL on GPUs."""
+    if self.dist.get_backend(self.group) != "nccl":
+        return None
+    torch = self.torch
+    ptr, stride = handle.r1_block()
+    K = self.world
+    dev = torch.device("cuda", torch.cuda.current_device())
+    blk = torch.as_tensor(_DevArray(ptr, K * stride), device=dev)
+    handle.sync()                                        # the handle's stream may not be torch's current stream
+    self.dist.all_gather_into_tensor(blk, blk[self.rank * stride:(self.rank + 1) * stride], group=self.group)
+    g = torch.tensor([float(gam1_mine)], dtype=torch.float64, device=dev)
+    out = torch.empty(K, dtype=torch.float64, device=dev)
+    self.dist.all_gather_into_tensor(out, g, group=self.group)
+    return out.cpu().numpy()                             # synchronises: the r1 gather (same stream, earlier) is complete
+
+
+TorchComm.allgather_r1 = _allgather_r1
+
+
 class ThreadShard:
     """In-process ranks (one host thread per GPU) for tests: barrier-based allgather."""
 
