@@ -422,3 +422,18 @@ def test_cli_row_partition_under_torchrun(nat, tmp_path):
     for it in range(its):
         assert os.path.getsize(os.path.join(d, "rp_xhat_it_%d.bin" % it)) == c["M"] * 8
         assert os.path.getsize(os.path.join(d, "rp_r1_cohort_1_it_%d.bin" % it)) == c["M"] * 8
+
+
+def test_rank_per_cohort_under_torchrun(nat):
+    """The reference's own deployment shape on GPUs: K = 2 cohorts, one process per cohort per GPU, the per-iteration
+    r1 / gam1 exchange as one NCCL all-gather into the library's r1 block (rank_mode_worker.py checks against the golden)."""
+    import subprocess
+    import sys
+    if ndev() < 2:
+        pytest.skip("needs 2 GPUs (the in-process rank-mode test in test_gpu_parity.py covers the host exchange on one)")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(here, "rank_mode_worker.py"), "banded_K2_L3_em_s01"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    assert "RANK_MODE_OK 0" in p.stdout and "RANK_MODE_OK 1" in p.stdout
