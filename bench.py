@@ -493,9 +493,13 @@ def main():
         torch.cuda.synchronize()
         t_up = time.perf_counter() - t0
         os.environ.pop("SGV_TIMING", None)
+        t_inf = time.perf_counter()
         xs2 = run(v2, None, iterations, None, write_outputs=False)
+        t_inf = time.perf_counter() - t_inf
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
+        if rank == 0:
+            sys.stderr.write("e2e leg: upload %.4f s, infer %.4f s of which %s\n" % (t_up, t_inf, {k: round(x, 4) for k, x in v2.timers.items()}))
         h2d = sum_over_ranks([(h2d_ld + Ml * 8) / iterations + Ml])[0]
         d2h = M * 8 + 256 * world
         diff = max_over_ranks(max(np.linalg.norm(x1 - x2) / max(np.linalg.norm(x1), 1e-300) for x1, x2 in zip(xs, xs2)))
@@ -509,9 +513,11 @@ def main():
                "its_per_s_excluding_upload": iterations / max(dt - max_over_ranks(t_up), 1e-9),
                "its_per_s_resident_from_it0": iterations / (ms_from0 / 1e3),
                "note": "the upload moves %.1f GB per GPU over the host link once (half of it only to verify symmetry on the "
-                       "device) and is amortised over %d iterations; excluding it, the loop from it=0 runs within a few percent "
-                       "of the resident leg's rate from it=0 (the timed window of `value` starts at it=%d, after the long CG "
-                       "solves of the first iterations)" % (h2d_ld / 1e9, iterations, a.warmup),
+                       "device) and is amortised over %d iterations; the rest is VAMP.infer from it=0: per-run set-up (state "
+                       "reset, pinned log / probe buffers) + the loop, which runs at the resident leg's rate from it=0 (the "
+                       "timed window of `value` starts at it=%d, after the long CG solves of the first iterations)" % (
+                           h2d_ld / 1e9, iterations, a.warmup),
+               "infer_seconds": t_inf, "infer_setup_seconds": v2.timers.get("setup"), "infer_loop_seconds": v2.timers.get("loop"),
                "max_rel_diff_vs_resident": diff,
                "layout": v2.handle.ld_info(0)["layout"], "host_format": a.e2e_format}
         v2.close()

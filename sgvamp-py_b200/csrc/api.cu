@@ -510,6 +510,7 @@ extern "C" int sgv_wait_copies(sgv_handle c) {
 
 extern "C" int sgv_pinned_alloc(sgv_handle c, int64_t bytes, void** out) {
     SGV_CHECK(c != nullptr && out != nullptr, "null argument");
+    SGV_CUDA(cudaSetDevice(c->device));   // callable from any host thread: never touch (and initialise) another device
     SGV_CUDA(cudaMallocHost(out, bytes));
     return 0;
 }

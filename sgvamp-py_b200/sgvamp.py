@@ -202,6 +202,11 @@ class VAMP:
                                        2 if self.rows else int(self.halo))
             shd.attach_peers(self.handle, self.shard)
         self.handle.set_weights(self.a)
+        # the pinned read-back ring of the fused loop (page-locking 4 x 8 MB at M = 1M takes 20-130 ms depending on the
+        # host): allocated in the background from here on, so that it overlaps the LD upload instead of delaying infer()
+        self._pinned_cache = {}
+        self._prefetch = threading.Thread(target=self._prefetch_pinned, daemon=True)
+        self._prefetch.start()
         self._ld_loaded = [False] * self.K
         self._keep = []
         self.stats = {}
@@ -689,6 +694,7 @@ class VAMP:
         worker = _Worker()
         tm = self.timers = dict(enqueue=0.0, wait=0.0, host_tail=0.0)
         pc = time.perf_counter
+        t_enter = pc()
         ck = ck or dict(path=None, every=0)
         it0 = st0["it_next"] if st0 is not None else 0
         probe_src = None
@@ -715,6 +721,8 @@ class VAMP:
             logging.debug(f"a = {self.a}")
         h.sync()
         self.shard.barrier()       # every rank's state is initialised before any kernel touches peer memory
+        tm["setup"] = pc() - t_enter
+        t_loop = pc()
 
         def finish(it):
             slot = it % NS
@@ -813,8 +821,11 @@ class VAMP:
             finish(iterations - 1)
         if iter_hook is not None:
             iter_hook(iterations)
+        tm["loop"] = pc() - t_loop
+        t_end = pc()
         h.sync()
         worker.close()
+        tm["drain"] = pc() - t_end
         if iterations > 0:
             last = self.history["rows"][-1]
             self.gam1_final = [last[k][2] for k in mine]
@@ -910,14 +921,27 @@ class VAMP:
             raise Exception("vector of length %d does not match M=%d (local rows %d)" % (v.shape[0], self.M, self.Ml))
         return v
 
+    def _prefetch_pinned(self):
+        try:
+            key = ("x", nat.ITER_SLOTS, 1)
+            self._pinned_cache[key] = [[self.handle.pinned_array(self.Ml)] for _ in range(nat.ITER_SLOTS)]
+        except Exception:                                               # allocated on demand instead
+            pass
+
     def _pinned_ring(self, tag, depth, width):
+        if self._prefetch is not None:
+            self._prefetch.join()
+            self._prefetch = None
         key = (tag, depth, width)
-        cache = self.__dict__.setdefault("_pinned_cache", {})
+        cache = self._pinned_cache
         if key not in cache:
             cache[key] = [[self.handle.pinned_array(self.Ml) for _ in range(width)] for _ in range(depth)]
         return cache[key]
 
     def close(self):
+        if self._prefetch is not None:
+            self._prefetch.join()
+            self._prefetch = None
         if self.shard.world > 1 and self.handle.h:
             self.handle.sync()
             self.shard.barrier()   # peers may still be reading this rank's arena
