@@ -125,8 +125,9 @@ k_ld_band_gram(const int8_t* __restrict__ G, int64_t ldg, int64_t g0, int64_t nm
 // in tensor memory.  A CTA of 4 warps owns a 128 x 128 tile of S; per chunk of 128 samples its threads copy the 128 A rows
 // and 128 B rows (128 bytes each, K-major) into shared memory in the canonical 128-byte-swizzled UMMA layout (16-byte chunk
 // c of row r at chunk c ^ (r & 7) of the 1 KB atom that holds rows 8*(r/8) .. +7), one elected thread issues four
-// M128 x N128 x K32 MMAs and commits them to an mbarrier, everybody waits for it before the next chunk overwrites the
-// operands.  Epilogue: tcgen05.ld 32 lanes x 32 columns per warp, then the same standardisation / taper / scatter as above.
+// M128 x N128 x K32 MMAs and commits them to the stage's mbarrier.  Two operand stages: while the tensor core works on one,
+// the threads store the next chunk (already in registers, fetched one chunk ahead) into the other and fetch the chunk after
+// it; a stage is refilled once the commit of the chunk that used it has arrived.  Epilogue: tcgen05.ld 32 lanes x 32 columns per warp, then the same standardisation / taper / scatter as above.
 // ---------------------------------------------------------------------------------------------
 #define TC_T 128
 __device__ __forceinline__ unsigned tc_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -142,22 +143,22 @@ k_ld_band_gram_tc(const int8_t* __restrict__ G, int64_t ldg, int64_t g0, int64_t
                   int64_t rows_st, int64_t M, double s, int taper) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem) + 1023) & ~(uintptr_t)1023);
-    unsigned char* sA = base;                 // 128 rows x 128 B
-    unsigned char* sB = base + 16384;
-    __shared__ __align__(8) unsigned long long mbar;
+    // two operand stages of 32 KB (A: 128 rows x 128 B, then B): the tensor core works on one while the threads fill the other
+    __shared__ __align__(8) unsigned long long mbar[2];
     __shared__ unsigned tmem_base_s;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int64_t t0 = (int64_t)blockIdx.x * TC_T;
     const int64_t i0 = row_lo - E + t0;
     const int64_t j0 = i0 + (int64_t)blockIdx.y * TC_T;
     if (j0 - (i0 + TC_T - 1) > w) return;
-    const unsigned bar = tc_smem_u32(&mbar);
+    const unsigned bar0 = tc_smem_u32(&mbar[0]);
     if (wid == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(tc_smem_u32(&tmem_base_s)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -166,22 +167,61 @@ k_ld_band_gram_tc(const int8_t* __restrict__ G, int64_t ldg, int64_t g0, int64_t
     const unsigned tmem_d = tmem_base_s;
     // instruction descriptor: D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
     const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TC_T >> 3) << 17) | ((unsigned)(TC_T >> 4) << 24);
-    const int64_t ia = i0 + tid - g0, jb = j0 + tid - g0;            // this thread's A row / B row in the genotype buffer
-    const bool va = ia >= 0 && ia < nmark, vb = jb >= 0 && jb < nmark;
-    unsigned phase = 0;
-    int nchunk = 0;
-    for (int64_t k0 = 0; k0 < ldg; k0 += 128, ++nchunk) {
+    // Operand fill: 8 consecutive lanes read the 8 16-byte chunks of one 128-byte row segment (a warp instruction covers 4
+    // whole lines), thread tid handles chunk tid % 8 of the rows tid / 8 + 16 * q, q = 0..7, of A and of B
+    const int crow = tid >> 3, cchunk = tid & 7;
+    unsigned vmask_a = 0, vmask_b = 0;
 #pragma unroll
-        for (int cidx = 0; cidx < 8; ++cidx) {
-            int4 a4 = make_int4(0, 0, 0, 0), b4 = a4;
-            if (k0 + cidx * 16 < ldg) {
-                if (va) a4 = *reinterpret_cast<const int4*>(G + ia * ldg + k0 + cidx * 16);
-                if (vb) b4 = *reinterpret_cast<const int4*>(G + jb * ldg + k0 + cidx * 16);
-            }
-            const int off = tid * 128 + ((cidx ^ (tid & 7)) << 4);
-            *reinterpret_cast<int4*>(sA + off) = a4;
-            *reinterpret_cast<int4*>(sB + off) = b4;
+    for (int q = 0; q < 8; ++q) {
+        const int64_t ia = i0 + crow + 16 * q - g0, jb = j0 + crow + 16 * q - g0;
+        if (ia >= 0 && ia < nmark) vmask_a |= 1u << q;
+        if (jb >= 0 && jb < nmark) vmask_b |= 1u << q;
+    }
+    const int8_t* pa = G + (i0 + crow - g0) * ldg + cchunk * 16;
+    const int8_t* pb = G + (j0 + crow - g0) * ldg + cchunk * 16;
+    const int64_t rstep = 16 * ldg;
+    int4 ra[8], rb[8];                                               // the next chunk's operands, in flight from global memory
+    auto fetch = [&](int64_t k0) {
+        const bool kin = k0 + cchunk * 16 < ldg;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            ra[q] = make_int4(0, 0, 0, 0);
+            rb[q] = ra[q];
+            if (kin && ((vmask_a >> q) & 1u)) ra[q] = __ldg(reinterpret_cast<const int4*>(pa + q * rstep + k0));
+            if (kin && ((vmask_b >> q) & 1u)) rb[q] = __ldg(reinterpret_cast<const int4*>(pb + q * rstep + k0));
         }
+    };
+    auto wait_stage = [&](unsigned bar, unsigned parity) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "TC_WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+            "@P1 bra TC_DONE_%=;\n\t"
+            "bra TC_WAIT_%=;\n\t"
+            "TC_DONE_%=:\n\t"
+            "}" ::"r"(bar), "r"(parity)
+            : "memory");
+    };
+    unsigned phase[2] = {0u, 0u};
+    int nchunk = 0;
+    fetch(0);
+    for (int64_t k0 = 0; k0 < ldg; k0 += 128, ++nchunk) {
+        const int st = nchunk & 1;
+        unsigned char* sA = base + st * 32768;
+        unsigned char* sB = sA + 16384;
+        if (nchunk >= 2) {                                            // the MMAs of chunk n-2 have consumed this stage
+            wait_stage(bar0 + 8 * st, phase[st]);
+            phase[st] ^= 1u;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int r = crow + 16 * q;                                 // r & 7 == crow & 7
+            const int off = r * 128 + ((cchunk ^ (r & 7)) << 4);
+            *reinterpret_cast<int4*>(sA + off) = ra[q];
+            *reinterpret_cast<int4*>(sB + off) = rb[q];
+        }
+        if (k0 + 128 < ldg) fetch(k0 + 128);                          // overlaps the MMAs issued below
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
         __syncthreads();
         if (tid == 0) {
@@ -198,20 +238,13 @@ k_ld_band_gram_tc(const int8_t* __restrict__ G, int64_t ldg, int64_t g0, int64_t
                     "}\n" ::"r"(tmem_d), "l"(da + 2ull * kk), "l"(db + 2ull * kk), "r"(idesc), "r"(acc)
                     : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * st) : "memory");
         }
-        // everybody waits until the tensor core has consumed the operands (and, after the last chunk, produced D)
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P1;\n\t"
-            "TC_WAIT:\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-            "@P1 bra TC_DONE;\n\t"
-            "bra TC_WAIT;\n\t"
-            "TC_DONE:\n\t"
-            "}" ::"r"(bar), "r"(phase)
-            : "memory");
-        phase ^= 1u;
+    }
+    // the commit of the last chunk covers every MMA issued before it: D is complete
+    {
+        const int st = (nchunk - 1) & 1;
+        wait_stage(bar0 + 8 * st, phase[st]);
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // epilogue: warp w reads TMEM lanes 32w .. 32w+31 (= rows of the tile), 32 columns at a time
@@ -315,7 +348,12 @@ extern "C" int sgv_ld_build_banded(sgv_handle c, int cohort, const int8_t* G, in
             k_ld_band_gram<<<grid, 256, 0, c->stream>>>(dG, ldg, g0, nmark, N, mu, sd, U, ngr, w, row_lo, E, Ml + E, M, s, taper);
         } else {
             const dim3 grid((unsigned)((Ml + E + TC_T - 1) / TC_T), (unsigned)((w + TC_T - 1) / TC_T + 1));
-            k_ld_band_gram_tc<<<grid, 128, 32768 + 1024, c->stream>>>(dG, ldg, g0, nmark, N, mu, sd, U, ngr, w, row_lo, E, Ml + E, M, s,
+            if (cudaFuncSetAttribute(k_ld_band_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024) != cudaSuccess) {
+                sgv_set_error("cannot raise the dynamic shared memory limit of the LD construction kernel");
+                rc = -2;
+                break;
+            }
+            k_ld_band_gram_tc<<<grid, 128, 65536 + 1024, c->stream>>>(dG, ldg, g0, nmark, N, mu, sd, U, ngr, w, row_lo, E, Ml + E, M, s,
                                                                       taper);
         }
         c->launches++;
