@@ -219,7 +219,9 @@ __global__ void k_resolve(RedCtx rc) {
     // nobody published: the producers exited early too
     if (rc.skip_if_done == SKIP_CG_DONE && rc.st->done[0] && rc.st->done[1]) return;
     if (rc.skip_if_done == SKIP_EM_DONE && rc.st->em.done) return;
-    resolve_warp(rc, threadIdx.x);
+    const unsigned long long seq = red_next_seq(rc);
+    __syncwarp();
+    resolve_warp(rc, threadIdx.x, seq);
 }
 
 RedCtx sgv_red_begin(sgv_ctx* c, int kind, int nv, int off, int maxit, int x0_zero, int is_min) {

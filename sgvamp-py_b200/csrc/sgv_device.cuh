@@ -299,10 +299,8 @@ __device__ __forceinline__ unsigned long long red_next_seq(const RedCtx& rc) {
 // rows in rank order (bit-identical on all ranks) and apply the state transition.  Called by one full
 // warp: lane q collects rank q's row.  On time-out the error flag is raised and the CG / EM loops are
 // marked done, so that nothing hangs.
-__device__ __forceinline__ void resolve_warp(const RedCtx& rc, int lane) {
+__device__ __forceinline__ void resolve_warp(const RedCtx& rc, int lane, unsigned long long seq) {
     Inbox* me = rc.inbox[rc.rank];
-    const unsigned long long seq = red_next_seq(rc);
-    __syncwarp();                                       // every lane has read the counter before lane 0 advances it
     const int slot = (int)(seq % SGV_INBOX_SLOTS);
     const int nv = rc.ap.nv;
     double mine[SGV_MAX_PARTIAL_VALUES];
@@ -361,8 +359,7 @@ __device__ __forceinline__ void resolve_warp(const RedCtx& rc, int lane) {
 // Write this rank's NV partial sums of reduction `seq` into every rank's inbox; called by a full warp, lane e
 // handles entry e = (peer, value) so that the peer stores are issued in parallel.
 template <int NV>
-__device__ __forceinline__ void publish_warp(const double (&acc)[NV], const RedCtx& rc, int lane) {
-    const unsigned long long seq = red_next_seq(rc);
+__device__ __forceinline__ void publish_warp(const double (&acc)[NV], const RedCtx& rc, int lane, unsigned long long seq) {
     const int slot = (int)(seq % SGV_INBOX_SLOTS);
     __threadfence();
     for (int e = lane; e < rc.world * NV; e += 32) {
@@ -416,12 +413,13 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], const RedCtx& rc, d
         // entries) are already ordered: every block fenced at GPU scope before taking its ticket, and peers read
         // this memory through this GPU's L2.  The world x NV entries are written by the 32 lanes in parallel: a
         // single thread issuing them one after the other costs ~0.25 us per peer store (16 us at 8 ranks x 8 sums).
-        publish_warp<NV>(acc, rc, threadIdx.x);
+        const unsigned long long seq = red_next_seq(rc);     // read by every lane before lane 0 advances the counter
+        publish_warp<NV>(acc, rc, threadIdx.x, seq);
         // one GPU per rank: this block completes the cross-rank reduction itself (the kernel ends when every
         // rank has published, which is also the ordering point for the halo reads of the next kernel)
         if (rc.inline_resolve) {
             __syncwarp();
-            resolve_warp(rc, threadIdx.x);
+            resolve_warp(rc, threadIdx.x, seq);
         }
     }
 }

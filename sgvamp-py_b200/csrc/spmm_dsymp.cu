@@ -590,6 +590,8 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
             *g.ticket = 0u;                                     // every CTA has taken its range by now
         }
         if (CG || g.epi != EPI_PLAIN) {
+            // number of the cross-rank exchange that follows: loaded now, in the shadow of the partial sums
+            const unsigned long long xseq = a.rc.world > 1 ? red_next_seq(a.rc) : 0ull;
             double acc[NV];
 #pragma unroll
             for (int k2 = 0; k2 < NV; ++k2) acc[k2] = 0.0;
@@ -607,10 +609,10 @@ k_dsym_persist(SpmmArgs a, DsPersist g, DsSolve sv) {
             }
             if (tid == 0 && rcs.world == 1) apply_totals(rcs.ap, rcs.st, acc);
             if (rcs.world > 1 && tid < 32) {
-                publish_warp<NV>(acc, rcs, tid);
+                publish_warp<NV>(acc, rcs, tid, xseq);
                 if (rcs.inline_resolve) {
                     __syncwarp();
-                    resolve_warp(rcs, tid);
+                    resolve_warp(rcs, tid, xseq);
                 }
             }
         }

@@ -298,9 +298,10 @@ k_em_loop(int64_t M, const double* __restrict__ r1_all, EmConsts kval, RedCtx rc
             block_reduce<16>(tot, red);
             if (threadIdx.x == 0 && rc.world == 1) apply_totals(rc.ap, rc.st, tot);
             if (rc.world > 1 && threadIdx.x < 32) {     // totals are valid in every lane of warp 0
-                publish_warp<16>(tot, rc, threadIdx.x);
+                const unsigned long long seq = red_next_seq(rc);
+                publish_warp<16>(tot, rc, threadIdx.x, seq);
                 __syncwarp();
-                resolve_warp(rc, threadIdx.x);
+                resolve_warp(rc, threadIdx.x, seq);
             }
             __threadfence();
         }
