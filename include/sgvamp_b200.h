@@ -192,6 +192,18 @@ typedef struct {
     int    spmm_passes;      /* SpMM launches that did work */
 } sgv_lmmse_out;
 int sgv_lmmse(sgv_handle h, int cohort, const sgv_lmmse_in* in, const int8_t* probe, sgv_lmmse_out* out);
+/* Additional Hutchinson probes (no reference counterpart: src/sgvamp.py:326-340 draws ONE probe per cohort and iteration;
+ * averaging P probes divides the variance of alpha2 by P).  Solves (gamw R + gam2 I) s = u from s = 0 for u = probe_a and
+ * probe_b (probe_b may be NULL) with the same CG as sgv_lmmse and returns u.s (the trace term of :338) and u^T R s (the
+ * trace term of the gamw update, :359) per probe.  The solver state of the cohort (xhat2, Sigma2_u) is not touched; call
+ * it after sgv_lmmse of the same iteration and average with that call's u_sigma2u / u_R_sigma2u. */
+typedef struct {
+    double u_s[2], u_R_s[2];
+    int    cg_iters[2], cg_info[2];
+    int    spmm_passes;
+} sgv_probe_out;
+int sgv_probe_pair(sgv_handle h, int cohort, double gamw, double gam2, int cg_maxit, const int8_t* probe_a,
+                   const int8_t* probe_b, sgv_probe_out* out);
 /* r1 <- (xhat2 - alpha2*r2)/(1-alpha2)  (src/sgvamp.py:348) */
 int sgv_update_r1(sgv_handle h, int cohort, double alpha2);
 

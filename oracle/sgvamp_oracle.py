@@ -265,7 +265,7 @@ class VAMPOracle:
 
     def infer(self, R_list, r_list, iterations, x0=None, cg_maxit=500, em_prior_maxit=100,
               learn_gamw=True, lmmse_damp=True, prior_update=None, update_prior_from=1,
-              probe_fn=default_probe, per_marker=False, materialise_A=False, timers=None, threads=1):
+              probe_fn=default_probe, per_marker=False, materialise_A=False, timers=None, threads=1, n_probes=1):
         """Follows VAMP.infer, src/sgvamp.py:196-389, for all K cohorts at once.
 
         ``R_list[k]`` is Rused of cohort k (already regularised as in src/main.py:265), as a
@@ -374,7 +374,17 @@ class VAMPOracle:
                 tick("cg", t0)
                 t0 = time.perf_counter()
                 Sig_prev[k] = Sig
-                a2 = gam2 * (u @ Sig) / M                            # :338-340
+                uSu = u @ Sig
+                # n_probes > 1 (an extension the reference does not have; n_probes = 1 is the reference):
+                # further probes probe_fn(k, it, M, p), each solved from x0 = 0, averaged into both trace estimates
+                extra = []
+                for p_ in range(1, n_probes):
+                    up = np.asarray(probe_fn(k, it, M, p_))
+                    sp, _, _ = cg(mv, up, np.zeros(M), cg_maxit)
+                    extra.append((up, sp))
+                    uSu = uSu + up @ sp
+                uSu = uSu / n_probes
+                a2 = gam2 * uSu / M                                  # :338-340
                 if lmmse_damp:
                     a2 = rho * a2 + (1 - rho) * alpha2_prev          # :345-346
                 gam1_new = gam2 * (1 - a2) / a2                      # :347
@@ -385,6 +395,9 @@ class VAMPOracle:
                     if z < 0:
                         z = 0
                     TrRS = u @ apply(R, R_parts[k], Sig)
+                    for up, sp in extra:
+                        TrRS = TrRS + up @ apply(R, R_parts[k], sp)
+                    TrRS = TrRS / n_probes
                     gw_new = float(1 / (z / N + TrRS / N))
                 gamw_raw_it.append(gw_new)
                 gw_new = max(gw_new, 1.0)                            # :374

@@ -115,7 +115,9 @@ static void free_vectors(sgv_ctx* c) {
     cudaFree(c->arena);
     cudaFree(c->bb);
     cudaFree(c->vfull);
+    cudaFree(c->probe_b);
     c->vfull = nullptr;
+    c->probe_b = nullptr;
     c->arena = nullptr;
     c->bb = c->qq = c->xx = c->rr = c->pp[0] = c->pp[1] = c->rr2[0] = c->rr2[1] = c->qq2[0] = c->qq2[1] = nullptr;
     cudaFree(c->r1_all);
@@ -334,6 +336,7 @@ extern "C" int sgv_configure_part(sgv_handle c, int64_t M, int K, int rank, int 
     c->peer[rank].ipc = false;
     SGV_CUDA(cudaMalloc(&c->bb, v2));
     SGV_CUDA(cudaMemsetAsync(c->bb, 0, v2, c->stream));
+    SGV_CUDA(cudaMalloc(&c->probe_b, Ml));
     if (c->rowpart) {
         SGV_CUDA(cudaMalloc(&c->vfull, (size_t)M * sizeof(double2)));
         SGV_CUDA(cudaMemsetAsync(c->vfull, 0, (size_t)M * sizeof(double2), c->stream));

@@ -195,6 +195,7 @@ struct sgv_ctx {
     int64_t      bandwidth_hint = 0; // common half-bandwidth agreed by all ranks (0: detect)
     int          halo = 0;           // banded row partition: SpMM reads w-element halos from the neighbours
     bool         rowpart = false;    // dense row partition (sgv_configure_part halo = 2): every rank holds Ml rows of a dense R
+    int8_t*      probe_b = nullptr;  // second probe of sgv_probe_pair (Ml bytes)
     double2*     vfull = nullptr;    // rows partition: the input vector pair of all ranks, gathered before each product (M entries)
     int          K = 0;
     Cohort       coh[SGV_MAX_K];

@@ -715,6 +715,9 @@ extern "C" int sgv_update_r1(sgv_handle c, int cohort, double alpha2) {
     return 0;
 }
 
+__global__ void k_probe_setup(int64_t M, const int8_t* pa, const int8_t* pb, double2* bb, double2* xx, double2* rr, RedCtx rc);
+__global__ void k_probe_post(int64_t M, const double2* xx, CgBufs cb, const double2* bb, double gamw, double gam2, RedCtx rc);
+
 int sgv_preload_vamp() {
     cudaFuncAttributes fa;
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_denoise));
@@ -730,6 +733,62 @@ int sgv_preload_vamp() {
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_pack_x0));
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_em_loop));
     SGV_CUDA(cudaFuncGetAttributes(&fa, k_em_begin));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_probe_setup));
+    SGV_CUDA(cudaFuncGetAttributes(&fa, k_probe_post));
+    return 0;
+}
+
+// The CG loop of one 2-RHS solve on A = gamw R + gam2 I, enqueued on the handle's stream after a set-up kernel has left
+// b, x0, r_0 and the CG state in place: the whole-solve kernel where it applies, otherwise batches of steps with a state
+// read-back between batches.
+static int cg_enqueue(sgv_ctx* c, Cohort& co, double gamw, double gam2, int cg_maxit, bool dev, int first_batch,
+                      bool* state_fetched) {
+    const int64_t M = c->Ml;
+    const bool fused = co.ld.layout == SGV_LAYOUT_DIA || co.ld.rowpart;
+    const bool fusedcg = co.ld.layout == SGV_LAYOUT_DSYM;
+    const unsigned vgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 8);
+    int launched = 0;
+    int batch = first_batch;   // see sgv_prior_em: counts drift slowly
+    CgState* hs = c->cg_host;
+    if (fusedcg && cg_maxit > 0 && sgv_dsymp_solve_usable(c, co.ld)) {
+        // the whole solve in one cooperative launch: steps separated by a grid barrier, not by launches
+        SGV_TRY(sgv_launch_dsym_solve(c, co, gamw, gam2, cg_maxit));
+        if (!dev) {
+            SGV_TRY(fetch_state(c));
+            *state_fetched = true;
+        }
+        launched = cg_maxit;
+    }
+    while (launched < cg_maxit) {
+        const int nb = std::min(batch, cg_maxit - launched);
+        for (int b = 0; b < nb; ++b) {
+            const int n = launched + b;             // == device step while the solve is active
+            if (fusedcg) {
+                SGV_TRY(sgv_launch_dsym_cg(c, co, n, gamw, gam2));
+                continue;
+            }
+            double2* pcur;
+            if (fused) {
+                pcur = c->pp[n & 1];
+                SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, VEC_PP0 + ((n + 1) & 1), c->qq, gamw, gam2, 1, 1));
+            } else {
+                pcur = c->pp[0];
+                k_p_update<<<vgrid, 256, 0, c->stream>>>(M, c->rr, pcur, c->cg);
+                c->launches++;
+                SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, VEC_PP0, c->qq, gamw, gam2, 1, 0));
+            }
+            RedCtx rc = sgv_red_begin(c, AP_CGUPDATE, 2, 0);
+            rc.skip_if_done = SKIP_CG_DONE;
+            k_cg_update<<<vgrid, 256, 0, c->stream>>>(M, c->xx, c->rr, pcur, c->qq, rc);
+            c->launches++;
+            SGV_TRY(sgv_red_end(c, rc));
+        }
+        launched += nb;
+        SGV_TRY(fetch_state(c));
+        *state_fetched = true;
+        if (hs->done[0] && hs->done[1]) break;
+        batch = 8;
+    }
     return 0;
 }
 
@@ -777,49 +836,9 @@ static int lmmse_enqueue(sgv_ctx* c, int cohort, const sgv_lmmse_in* in, bool de
         c->launches++;
         SGV_TRY(sgv_red_end(c, rc));
     }
-    int launched = 0;
-    int batch = co.last_cg_iters > 0 ? co.last_cg_iters + 2 : 4;   // see sgv_prior_em: counts drift slowly
     CgState* hs = c->cg_host;
     bool state_fetched = false;
-    if (fusedcg && in->cg_maxit > 0 && sgv_dsymp_solve_usable(c, co.ld)) {
-        // the whole solve in one cooperative launch: steps separated by a grid barrier, not by launches
-        SGV_TRY(sgv_launch_dsym_solve(c, co, in->gamw, in->gam2, in->cg_maxit));
-        if (!dev) {
-            SGV_TRY(fetch_state(c));
-            state_fetched = true;
-        }
-        launched = in->cg_maxit;
-    }
-    while (launched < in->cg_maxit) {
-        const int nb = std::min(batch, in->cg_maxit - launched);
-        for (int b = 0; b < nb; ++b) {
-            const int n = launched + b;             // == device step while the solve is active
-            if (fusedcg) {
-                SGV_TRY(sgv_launch_dsym_cg(c, co, n, in->gamw, in->gam2));
-                continue;
-            }
-            double2* pcur;
-            if (fused) {
-                pcur = c->pp[n & 1];
-                SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, VEC_PP0 + ((n + 1) & 1), c->qq, in->gamw, in->gam2, 1, 1));
-            } else {
-                pcur = c->pp[0];
-                k_p_update<<<vgrid, 256, 0, c->stream>>>(M, c->rr, pcur, c->cg);
-                c->launches++;
-                SGV_TRY(sgv_launch_spmm(c, co, EPI_Q, VEC_PP0, c->qq, in->gamw, in->gam2, 1, 0));
-            }
-            RedCtx rc = sgv_red_begin(c, AP_CGUPDATE, 2, 0);
-            rc.skip_if_done = SKIP_CG_DONE;
-            k_cg_update<<<vgrid, 256, 0, c->stream>>>(M, c->xx, c->rr, pcur, c->qq, rc);
-            c->launches++;
-            SGV_TRY(sgv_red_end(c, rc));
-        }
-        launched += nb;
-        SGV_TRY(fetch_state(c));
-        state_fetched = true;
-        if (hs->done[0] && hs->done[1]) break;
-        batch = 8;
-    }
+    SGV_TRY(cg_enqueue(c, co, in->gamw, in->gam2, in->cg_maxit, dev, co.last_cg_iters > 0 ? co.last_cg_iters + 2 : 4, &state_fetched));
     if (state_fetched) co.last_cg_iters = std::max(hs->iters[0], hs->iters[1]);
     {
         RedCtx rc = sgv_red_begin(c, dev ? AP_POST : AP_STATS, 4, 0);
@@ -845,6 +864,110 @@ static int lmmse_enqueue(sgv_ctx* c, int cohort, const sgv_lmmse_in* in, bool de
     c->vs_active = -1;
     SGV_CUDA(cudaGetLastError());
     if (passes_out) *passes_out = passes;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Additional Hutchinson probes (no reference counterpart: src/sgvamp.py:326-340 draws exactly one probe per cohort and
+// iteration).  Two more probes per call ride the two columns of the 2-RHS solver:  A s = u  from x0 = 0
+// for u = probe_a, probe_b; returned are u.s (the trace estimate of :338) and u^T R s (the gamw update's trace, :359),
+// recovered from the recursion as in k_lmmse_post.  Nothing of the solver's state (xhat2, Sigma2_u, R x0) is touched.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_probe_setup(int64_t M, const int8_t* __restrict__ pa, const int8_t* __restrict__ pb, double2* __restrict__ bb,
+              double2* __restrict__ xx, double2* __restrict__ rr, RedCtx rc) {
+    __shared__ double red[4 * 32];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        const double2 b = make_double2((double)pa[j], pb != nullptr ? (double)pb[j] : 0.0);
+        bb[j] = b;
+        xx[j] = make_double2(0.0, 0.0);
+        rr[j] = b;
+        acc[0] += b.x * b.x;
+        acc[1] += b.y * b.y;
+    }
+    acc[2] = acc[0];
+    acc[3] = acc[1];
+    grid_reduce<4>(acc, rc, red);
+}
+
+__global__ void __launch_bounds__(256)
+k_probe_post(int64_t M, const double2* __restrict__ xx, CgBufs cb, const double2* __restrict__ bb, double gamw, double gam2,
+             RedCtx rc) {
+    __shared__ double red[4 * 32];
+    const int z0 = rc.st->zero_b[0], z1 = rc.st->zero_b[1];
+    const double igw = 1.0 / gamw;
+    const int step = rc.st->step;
+    const bool pend = cb.fusedcg && step > 0;
+    const int cur = pend ? ((step - 1) & 1) : 1;
+    const double al0 = pend ? rc.st->alpha[0] : 0.0, al1 = pend ? rc.st->alpha[1] : 0.0;
+    const double2* __restrict__ rr = cb.rr[cur];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+        double2 x = xx[j];
+        const double2 b = bb[j];
+        double2 r = rr[j];
+        if (al0 != 0.0 || al1 != 0.0) {
+            const double2 p = cb.pp[cur][j], q = cb.qq[cur][j];
+            if (al0 != 0.0) { x.x += al0 * p.x; r.x -= al0 * q.x; }
+            if (al1 != 0.0) { x.y += al1 * p.y; r.y -= al1 * q.y; }
+        }
+        const double rx0 = z0 ? 0.0 : (b.x - r.x - gam2 * x.x) * igw;
+        const double rx1 = z1 ? 0.0 : (b.y - r.y - gam2 * x.y) * igw;
+        if (z0) x.x = b.x;
+        if (z1) x.y = b.y;
+        acc[0] += b.x * x.x;       // u_a . s_a
+        acc[1] += b.y * x.y;       // u_b . s_b
+        acc[2] += b.x * rx0;       // u_a^T R s_a
+        acc[3] += b.y * rx1;       // u_b^T R s_b
+    }
+    grid_reduce<4>(acc, rc, red);
+}
+
+extern "C" int sgv_probe_pair(sgv_handle c, int cohort, double gamw, double gam2, int cg_maxit, const int8_t* probe_a,
+                              const int8_t* probe_b, sgv_probe_out* out) {
+    SGV_TRY(check_ready(c));
+    SGV_CHECK(cohort >= 0 && cohort < c->K, "cohort out of range");
+    SGV_CHECK(probe_a && out, "null argument");
+    Cohort& co = c->coh[cohort];
+    SGV_CHECK(co.ld.layout != 0, "cohort %d has no LD matrix", cohort);
+    const int64_t M = c->Ml;
+    SGV_CUDA(cudaMemcpyAsync(co.probe, probe_a, M, cudaMemcpyHostToDevice, c->stream));
+    if (probe_b) SGV_CUDA(cudaMemcpyAsync(c->probe_b, probe_b, M, cudaMemcpyHostToDevice, c->stream));
+    c->vs_active = -1;
+    const unsigned vgrid = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)c->sm_count * 8);
+    SGV_TRY(sgv_ensure_partials(c, vgrid + 1));
+    {
+        RedCtx rc = sgv_red_begin(c, AP_SETUP, 4, 0, cg_maxit, 1);
+        k_probe_setup<<<vgrid, 256, 0, c->stream>>>(M, co.probe, probe_b ? c->probe_b : nullptr, c->bb, c->xx, c->rr, rc);
+        c->launches++;
+        SGV_TRY(sgv_red_end(c, rc));
+    }
+    bool state_fetched = false;
+    SGV_TRY(cg_enqueue(c, co, gamw, gam2, cg_maxit, false, co.last_cg_iters > 0 ? co.last_cg_iters + 2 : 4, &state_fetched));
+    {
+        RedCtx rc = sgv_red_begin(c, AP_STATS, 4, 0);
+        CgBufs cb;
+        for (int i = 0; i < 2; ++i) {
+            cb.rr[i] = c->rr2[i];
+            cb.pp[i] = c->pp[i];
+            cb.qq[i] = c->qq2[i];
+        }
+        cb.fusedcg = co.ld.layout == SGV_LAYOUT_DSYM;
+        k_probe_post<<<vgrid, 256, 0, c->stream>>>(M, c->xx, cb, c->bb, gamw, gam2, rc);
+        c->launches++;
+        SGV_TRY(sgv_red_end(c, rc));
+    }
+    SGV_CUDA(cudaGetLastError());
+    SGV_TRY(fetch_state(c));
+    CgState* hs = c->cg_host;
+    for (int i = 0; i < 2; ++i) {
+        out->u_s[i] = hs->stats[i];
+        out->u_R_s[i] = hs->stats[2 + i];
+        out->cg_iters[i] = hs->iters[i];
+        out->cg_info[i] = hs->done[i] ? hs->info[i] : cg_maxit;
+    }
+    out->spmm_passes = std::max(hs->iters[0], hs->iters[1]);
     return 0;
 }
 

@@ -60,6 +60,8 @@ def build_parser():
     p.add_argument("--probe-seed", help="deterministic Hutchinson probes: the probe of cohort k in iteration it is the it-th draw "
                    "of numpy RandomState(seed + k).binomial(p=1/2, n=1, size=M) (default: the reference's draws from numpy's "
                    "global RNG, src/sgvamp.py:326)", default=None)
+    p.add_argument("--n-probes", help="Rademacher probes averaged in the Hutchinson estimates of alpha2 and of the gamw update "
+                   "(1 = the reference, src/sgvamp.py:326-340)", default=1)
     p.add_argument("--checkpoint-path", help="write a restart file here every --checkpoint-every iterations", default=None)
     p.add_argument("--checkpoint-every", help="iterations between restart files (0: never)", default=0)
     p.add_argument("--resume-from", help="continue the run stored in this restart file", default=None)
@@ -67,16 +69,18 @@ def build_parser():
 
 
 class _SeededProbes:
-    """probes(k, it, M): the it-th draw of RandomState(seed + k), drawn in order and cached."""
+    """probes(k, it, M[, p]): draw number it * n_probes + p of RandomState(seed + k), drawn in order and cached."""
 
-    def __init__(self, seed, K):
+    def __init__(self, seed, K, n_probes=1):
         self.rs = [np.random.RandomState(seed + k) for k in range(K)]
         self.have = [[] for _ in range(K)]
+        self.n_probes = n_probes
 
-    def __call__(self, k, it, M):
-        while len(self.have[k]) <= it:
+    def __call__(self, k, it, M, p=0):
+        idx = it * self.n_probes + p
+        while len(self.have[k]) <= idx:
             self.have[k].append((self.rs[k].binomial(p=1 / 2, n=1, size=M) * 2 - 1).astype(np.int8))
-        return self.have[k][it]
+        return self.have[k][idx]
 
 
 def main(argv=None):
@@ -167,7 +171,8 @@ def main(argv=None):
                          cg_maxit=int(a.cg_maxit), em_prior_maxit=int(a.em_prior_maxit), learn_gamw=learn_gamw,
                          lmmse_damp=lmmse_damp, prior_update=a.prior_update,
                          update_prior_from=int(a.update_prior_from), s=s, layout=a.layout,
-                         probes=_SeededProbes(int(a.probe_seed), K) if a.probe_seed is not None else None,
+                         probes=_SeededProbes(int(a.probe_seed), K, int(a.n_probes)) if a.probe_seed is not None else None,
+                         n_probes=int(a.n_probes),
                          checkpoint_path=a.checkpoint_path, checkpoint_every=int(a.checkpoint_every), resume_from=a.resume_from)
     logging.info(f"sgVAMP inference running time: {(time.time() - ts):0.4f}s\n")
     # README names the dump {out}__xhat_it_{it}.bin, the code writes {out}_xhat_it_{it}.bin: provide both

@@ -30,7 +30,7 @@ SYMBOLS = [
     "sgv_ld_adopt_dsym", "sgv_dsym_extension", "sgv_set_host_barrier", "sgv_device_id", "sgv_ld_upload_dia",
     "sgv_iteration_supported", "sgv_vamp_begin", "sgv_set_truth", "sgv_iteration_probe_buffer", "sgv_iteration_enqueue",
     "sgv_iteration_wait", "sgv_ld_adopt_blockdiag", "sgv_ld_build_banded", "sgv_ld_copy_band", "sgv_vamp_set_alphas",
-    "sgv_ld_upload_dense_rows", "sgv_ld_adopt_dense_colpanel", "sgv_r1_block",
+    "sgv_ld_upload_dense_rows", "sgv_ld_adopt_dense_colpanel", "sgv_r1_block", "sgv_probe_pair",
 ]
 MAX_K, MAX_L, ITER_SLOTS = 8, 8, 4
 
@@ -43,6 +43,11 @@ class LmmseIn(C.Structure):
 class LmmseOut(C.Structure):
     _fields_ = [("u_sigma2u", C.c_double), ("xhat2_r", C.c_double), ("xhat2_R_xhat2", C.c_double),
                 ("u_R_sigma2u", C.c_double), ("cg_iters", C.c_int * 2), ("cg_info", C.c_int * 2),
+                ("spmm_passes", C.c_int)]
+
+
+class ProbeOut(C.Structure):
+    _fields_ = [("u_s", C.c_double * 2), ("u_R_s", C.c_double * 2), ("cg_iters", C.c_int * 2), ("cg_info", C.c_int * 2),
                 ("spmm_passes", C.c_int)]
 
 
@@ -353,6 +358,20 @@ class Handle:
         assert probe.shape[0] == self.M
         self._ck(self.lib.sgv_lmmse(self.h, C.c_int(cohort), C.byref(pin), probe.ctypes.data_as(C.POINTER(C.c_int8)),
                                     C.byref(out)))
+        return out
+
+    def probe_pair(self, cohort, gamw, gam2, cg_maxit, probe_a, probe_b=None):
+        """Two further Hutchinson probes through the 2-RHS solver (see sgv_probe_pair)."""
+        out = ProbeOut()
+        pa = np.ascontiguousarray(probe_a, dtype=np.int8)
+        assert pa.shape[0] == self.M
+        pb = None
+        if probe_b is not None:
+            pb = np.ascontiguousarray(probe_b, dtype=np.int8)
+            assert pb.shape[0] == self.M
+        self._ck(self.lib.sgv_probe_pair(self.h, C.c_int(cohort), C.c_double(gamw), C.c_double(gam2), C.c_int(int(cg_maxit)),
+                                         pa.ctypes.data_as(C.POINTER(C.c_int8)),
+                                         pb.ctypes.data_as(C.POINTER(C.c_int8)) if pb is not None else None, C.byref(out)))
         return out
 
     def update_r1(self, cohort, alpha2):

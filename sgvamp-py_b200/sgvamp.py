@@ -460,12 +460,21 @@ class VAMP:
     # ------------------------------------------------------------------------------------------
     def infer(self, R, r, iterations, x0=None, cg_maxit=500, em_prior_maxit=100, learn_gamw=True, lmmse_damp=True,
               prior_update=None, update_prior_from=1, *, s=0.0, probes=None, layout="auto", write_outputs=True,
-              iter_hook=None, gather_outputs=True, checkpoint_path=None, checkpoint_every=0, resume_from=None):
+              iter_hook=None, gather_outputs=True, checkpoint_path=None, checkpoint_every=0, resume_from=None, n_probes=1):
         """checkpoint_path / checkpoint_every / resume_from (no reference counterpart: the reference cannot restart,
         SURVEY 5.4): every `checkpoint_every` iterations the state needed to continue (r1, xhat1, xhat2, Sigma2_u, the
         scalar chain, the prior, the legacy RNG state of the probe sequence) is written to `checkpoint_path` (one .npz per
         row shard); `resume_from` continues such a run at the iteration after the checkpoint - the entries of the returned
-        list before it are None."""
+        list before it are None.
+
+        n_probes (no reference counterpart; 1 = the reference): number of Rademacher probes averaged in the Hutchinson
+        estimates of alpha2 (src/sgvamp.py:338) and of the gamw update's trace (:359).  Probe 0 is the reference's probe
+        (solved together with xhat2, warm-started); probes 1.. are solved from zero, two per extra 2-RHS solve
+        (sgv_probe_pair).  Injected probes: an array of shape (K, iterations, n_probes, M) or a callable
+        probes(k, it, M, p); the default draws them from numpy's legacy global RNG right after probe 0."""
+        n_probes = int(n_probes)
+        if n_probes < 1:
+            raise Exception("n_probes must be >= 1")
         M, K, Nt, rho = self.M, self.K, self.Nt, self.rho
         h = self.handle
         rank = self.rank if self.shard.world == 1 else self.shard.rank   # only gates logging / rank-per-cohort mode
@@ -488,7 +497,7 @@ class VAMP:
         h.reset_state()                                                 # :199-217
         ck = dict(path=checkpoint_path, every=int(checkpoint_every or 0))
         st0 = self._restore(resume_from) if resume_from is not None else None
-        if (not self.rank_mode and prior_update != "mle" and h.iteration_supported()
+        if (not self.rank_mode and prior_update != "mle" and h.iteration_supported() and n_probes == 1
                 and os.environ.get("SGV_STEPWISE", "0") != "1"):
             return self._infer_fused(rs, Ns, iterations, x0, cg_maxit, em_prior_maxit, learn_gamw, lmmse_damp,
                                      prior_update, update_prior_from, probes, write_outputs, iter_hook, gather_outputs, ck, st0)
@@ -501,7 +510,8 @@ class VAMP:
         if probes is None:
             if st0 is not None and st0.get("rng_state") is not None:
                 np.random.set_state(st0["rng_state"])
-            probe_src = _ProbeSource([(it, k) for it in range(st0["it_next"] if st0 else 0, iterations) for k in mine], M)
+            probe_src = _ProbeSource([key for it in range(st0["it_next"] if st0 else 0, iterations) for k in mine
+                                      for key in [(it, k)] + [(it, k, p) for p in range(1, n_probes)]], M)
         sqrtNt = np.sqrt(Nt)
         truth = None
         if x0 is not None:
@@ -587,20 +597,36 @@ class VAMP:
                 logging.info(f"...LMMSE cohort {k}")
                 alpha2_prev = alpha2[k]
                 gam2 = gam1[k] * (1 - a1) / a1                           # :305
-                if probes is None:
-                    u = probe_src.get((it, k))                           # :326 (same RNG calls, same order)
-                elif callable(probes):
-                    u = probes(k, it, M)
-                else:
-                    u = np.asarray(probes)[k, it]
-                if sharded and len(u) == M:
-                    u = u[self.lo:self.hi]                               # every rank draws the same global probe
+                def probe(p):
+                    if probes is None:
+                        u_ = probe_src.get((it, k) if p == 0 else (it, k, p))    # :326 (same RNG calls, same order)
+                    elif callable(probes):
+                        u_ = probes(k, it, M) if p == 0 else probes(k, it, M, p)
+                    else:
+                        u_ = np.asarray(probes)[k, it] if n_probes == 1 else np.asarray(probes)[k, it, p]
+                    if sharded and len(u_) == M:
+                        u_ = u_[self.lo:self.hi]                          # every rank draws the same global probe
+                    return u_
+
+                u = probe(0)
                 out = h.lmmse(k, float(gamw[k]), float(gam2), float(a1), float(rho), cg_maxit, lmmse_damp, learn_gamw,
                               it == 0, u)
                 for c in range(2):
                     if out.cg_info[c] > 0:
                         logging.info(f"Rank {k} WARNING: CG {c + 1} convergence after {out.cg_info[c]} iterations not achieved!")
-                a2 = gam2 * np.float64(out.u_sigma2u) / M                # :338-340
+                u_sigma2u, u_R_sigma2u = np.float64(out.u_sigma2u), out.u_R_sigma2u
+                if n_probes > 1:                                         # further probes, two per extra solve
+                    extra = [probe(p) for p in range(1, n_probes)]
+                    for i in range(0, len(extra), 2):
+                        ub = extra[i + 1] if i + 1 < len(extra) else None
+                        po = h.probe_pair(k, float(gamw[k]), float(gam2), cg_maxit, extra[i], ub)
+                        for c in range(2 if ub is not None else 1):
+                            u_sigma2u += np.float64(po.u_s[c])
+                            u_R_sigma2u += po.u_R_s[c]
+                        out.spmm_passes += po.spmm_passes
+                    u_sigma2u /= n_probes
+                    u_R_sigma2u /= n_probes
+                a2 = gam2 * u_sigma2u / M                                # :338-340
                 if lmmse_damp:
                     a2 = rho * a2 + (1 - rho) * alpha2_prev              # :345-346
                 alpha2[k] = a2
@@ -612,7 +638,7 @@ class VAMP:
                     z = N - 2 * out.xhat2_r + out.xhat2_R_xhat2
                     if z < 0:
                         z = 0
-                    gw = float(1 / (z / N + out.u_R_sigma2u / N))
+                    gw = float(1 / (z / N + u_R_sigma2u / N))
                 gw = max(gw, 1.0)                                        # :374
                 gamw[k] = gw
                 row = [it, gw, gam1[k], gam2, a1, a2, self.lam]

@@ -686,3 +686,50 @@ def test_full_size_trajectory_properties(nat):
         assert np.all(np.isfinite(xs_a[it]))
     al = float(np.dot(xs_a[-1].ravel(), x0) / (np.linalg.norm(xs_a[-1]) * np.linalg.norm(x0)))
     assert al > 0.5
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-probe Hutchinson (extension): n_probes = 1 is the reference; n_probes > 1 is checked against the
+# oracle extended in the same way (oracle/sgvamp_oracle.py: further probes solved from zero and averaged)
+# ---------------------------------------------------------------------------------------------
+def _run_oracle_probes(c, n_probes, probes):
+    from oracle import sgvamp_oracle as orc
+    K, M = c["K"], c["M"]
+    o = orc.VAMPOracle(c["N_list"], M, c["rho"], c["gamw"], c["gam1"], c["prior_vars"], c["prior_probs"])
+    Rs = [orc.regularise(R, c["s"]) for R in c["R"]]
+    fn = lambda k, it, M_, p=0: probes[k, it, p]
+    x0 = c["x0"] * np.sqrt(c["N_list"][0]) if "x0" in c else None
+    return o.infer(Rs, list(c["r"]), c["iterations"], x0=x0, cg_maxit=c["cg_maxit"], em_prior_maxit=c["em_prior_maxit"],
+                   learn_gamw=c["learn_gamw"], lmmse_damp=c["lmmse_damp"], prior_update=c["prior_update"],
+                   update_prior_from=c["update_prior_from"], probe_fn=fn, n_probes=n_probes)
+
+
+@pytest.mark.parametrize("name,n_probes", [("banded_L2_em_s01", 2), ("banded_L2_em_s01", 4), ("dense_K3_L2_em", 3),
+                                           ("blockdiag_L3_em_s01", 5)])
+def test_multi_probe_hutchinson_matches_oracle(nat, name, n_probes):
+    import sgvamp
+    c = load_case(name)
+    K, M = c["K"], c["M"]
+    rng = np.random.default_rng(n_probes)
+    probes = (rng.integers(0, 2, size=(K, c["iterations"], n_probes, M)) * 2 - 1).astype(np.int8)
+    probes[:, :, 0, :] = c["probes"]                         # probe 0 = the golden run's probe
+    ref = _run_oracle_probes(c, n_probes, probes)
+    N_list = c["N_list"]
+    Nt = sum(N_list)
+    v = sgvamp.VAMP(N=N_list if K > 1 else N_list[0], Nt=Nt, M=M, K=K, rho=c["rho"], gamw=c["gamw"], gam1=c["gam1"],
+                    a=np.array(N_list) / Nt, prior_vars=c["prior_vars"], prior_probs=c["prior_probs"], out_dir=None, out_name="g")
+    x0 = c["x0"] * np.sqrt(N_list[0]) if "x0" in c else None
+    xs = v.infer(c["R"] if K > 1 else c["R"][0], list(c["r"]) if K > 1 else c["r"][0], c["iterations"], x0=x0,
+                 cg_maxit=c["cg_maxit"], em_prior_maxit=c["em_prior_maxit"], learn_gamw=c["learn_gamw"], lmmse_damp=c["lmmse_damp"],
+                 prior_update=c["prior_update"], update_prior_from=c["update_prior_from"], s=c["s"], probes=probes,
+                 n_probes=n_probes)
+    differs = False
+    for it in range(c["iterations"]):
+        # tolerance: the GPU holds LD in fp32 (the oracle in fp64), as in the golden trajectory tests
+        assert rel_l2(xs[it], ref["xhat1"][it]) <= 1e-5, (it, rel_l2(xs[it], ref["xhat1"][it]))
+        for k in range(K):
+            assert rel_err(v.history["rows"][it][k][1:6], np.array(ref["rows"][it][k][1:6])) <= 1e-5
+            assert tuple(v.history["cg_iters"][it][k]) == tuple(ref["cg_iters"][it][k])
+            differs = differs or rel_err(v.history["rows"][it][k][5:6], c["rows"][it, k, 5:6]) > 1e-6
+    assert differs                                            # the extra probes do change alpha2 relative to the 1-probe golden
+    v.close()
