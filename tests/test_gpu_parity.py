@@ -733,3 +733,32 @@ def test_multi_probe_hutchinson_matches_oracle(nat, name, n_probes):
             differs = differs or rel_err(v.history["rows"][it][k][5:6], c["rows"][it, k, 5:6]) > 1e-6
     assert differs                                            # the extra probes do change alpha2 relative to the 1-probe golden
     v.close()
+
+
+def test_outputs_parse_like_reference_plot_script(nat):
+    """scripts/plots.py:34-58 reads the cohort CSV with csv.reader(delimiter='\\t'), skips the header and takes
+    int(row[0]), float(row[1..6]) = it, gamw, gam1, gam2, alpha1, alpha2, lam, and float(row[1]), float(row[2]) =
+    alignment, l2 from the metrics CSV: the files this library writes must go through exactly that reader."""
+    import csv
+    c = load_case("dense_L2_em")
+    with tempfile.TemporaryDirectory() as d:
+        xs, hist, info, fin = run_gpu(c, out_dir=d)
+        its, cols = [], [[] for _ in range(6)]
+        with open(os.path.join(d, "g_cohort_1.csv"), mode="r") as f:
+            rd = csv.reader(f, delimiter="\t")
+            next(rd, None)
+            for row in rd:
+                its.append(int(row[0]))
+                for j in range(6):
+                    cols[j].append(float(row[1 + j]))
+        assert max(its) + 1 == c["iterations"] and its == list(range(c["iterations"]))
+        for it in range(c["iterations"]):
+            assert [cols[j][it] for j in range(6)] == [float(v) for v in hist["rows"][it][0][1:7]]
+        al, l2 = [], []
+        with open(os.path.join(d, "g_metrics.csv"), mode="r") as f:
+            rd = csv.reader(f, delimiter="\t")
+            next(rd, None)
+            for row in rd:
+                al.append(float(row[1]))
+                l2.append(float(row[2]))
+        assert len(al) == c["iterations"] and all(0.0 < a <= 1.0 for a in al) and all(v >= 0.0 for v in l2)
