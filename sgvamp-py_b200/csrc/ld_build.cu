@@ -147,9 +147,10 @@ k_ld_band_gram_tc(const int8_t* __restrict__ G, int64_t ldg, int64_t g0, int64_t
     __shared__ __align__(8) unsigned long long mbar[2];
     __shared__ unsigned tmem_base_s;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const int64_t t0 = (int64_t)blockIdx.x * TC_T;
+    // column-tile offset fastest: the CTAs that share an A tile (and neighbouring B tiles) are resident together and meet in L2
+    const int64_t t0 = (int64_t)blockIdx.y * TC_T;
     const int64_t i0 = row_lo - E + t0;
-    const int64_t j0 = i0 + (int64_t)blockIdx.y * TC_T;
+    const int64_t j0 = i0 + (int64_t)blockIdx.x * TC_T;
     if (j0 - (i0 + TC_T - 1) > w) return;
     const unsigned bar0 = tc_smem_u32(&mbar[0]);
     if (wid == 0) {
@@ -347,7 +348,8 @@ extern "C" int sgv_ld_build_banded(sgv_handle c, int cohort, const int8_t* G, in
             const dim3 grid((unsigned)((Ml + E + LB_T - 1) / LB_T), (unsigned)((w + LB_T - 1) / LB_T + 1));
             k_ld_band_gram<<<grid, 256, 0, c->stream>>>(dG, ldg, g0, nmark, N, mu, sd, U, ngr, w, row_lo, E, Ml + E, M, s, taper);
         } else {
-            const dim3 grid((unsigned)((Ml + E + TC_T - 1) / TC_T), (unsigned)((w + TC_T - 1) / TC_T + 1));
+            const dim3 grid((unsigned)((w + TC_T - 1) / TC_T + 1), (unsigned)((Ml + E + TC_T - 1) / TC_T));
+            if (grid.y > 65535u) { sgv_set_error("too many marker tiles for one launch"); rc = -1; break; }
             if (cudaFuncSetAttribute(k_ld_band_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 1024) != cudaSuccess) {
                 sgv_set_error("cannot raise the dynamic shared memory limit of the LD construction kernel");
                 rc = -2;
