@@ -116,20 +116,35 @@ k_spmm_psym(SpmmArgs a, const float* __restrict__ panels, const SymItem* __restr
                 if (nr > 3) n3 = ldg_stream_f4(p + 3 * (int64_t)it.ld);
             }
             const int jg = it.j0 + jb + jj;                  // global row of c0
-            float4 t0 = c0, t1 = c1, t2 = c2, t3 = c3;
-            if (it.diag && jg + 3 >= it.i0) {                // inside the strip's diagonal tile (warp-uniform)
-                c0 = ps_mask(c0, icol, jg, false);     t0 = ps_mask(t0, icol, jg, true);
-                c1 = ps_mask(c1, icol, jg + 1, false); t1 = ps_mask(t1, icol, jg + 1, true);
-                c2 = ps_mask(c2, icol, jg + 2, false); t2 = ps_mask(t2, icol, jg + 2, true);
-                c3 = ps_mask(c3, icol, jg + 3, false); t3 = ps_mask(t3, icol, jg + 3, true);
-            }
             const double2 x0 = xs[jj], x1 = xs[min(jj + 1, cnt - 1)], x2 = xs[min(jj + 2, cnt - 1)], x3 = xs[min(jj + 3, cnt - 1)];
-            PS_FWD(c0, x0);
-            PS_FWD(c1, x1);
-            PS_FWD(c2, x2);
-            PS_FWD(c3, x3);
-            const double2 d0 = ps_dot(t0, O0, O1, O2, O3), d1 = ps_dot(t1, O0, O1, O2, O3), d2 = ps_dot(t2, O0, O1, O2, O3),
-                          d3 = ps_dot(t3, O0, O1, O2, O3);
+            double2 d0, d1, d2, d3;
+            if (it.diag && jg + 3 >= it.i0) {                // inside the strip's diagonal tile (warp-uniform): masked copies
+                const float4 t0 = ps_mask(c0, icol, jg, true), t1 = ps_mask(c1, icol, jg + 1, true),
+                             t2 = ps_mask(c2, icol, jg + 2, true), t3 = ps_mask(c3, icol, jg + 3, true);
+                c0 = ps_mask(c0, icol, jg, false);
+                c1 = ps_mask(c1, icol, jg + 1, false);
+                c2 = ps_mask(c2, icol, jg + 2, false);
+                c3 = ps_mask(c3, icol, jg + 3, false);
+                PS_FWD(c0, x0);
+                PS_FWD(c1, x1);
+                PS_FWD(c2, x2);
+                PS_FWD(c3, x3);
+                d0 = ps_dot(t0, O0, O1, O2, O3);
+                d1 = ps_dot(t1, O0, O1, O2, O3);
+                d2 = ps_dot(t2, O0, O1, O2, O3);
+                d3 = ps_dot(t3, O0, O1, O2, O3);
+            } else {
+                // the common case: both uses read the SAME registers, so every value is converted to fp64 once
+                // (with separate masked copies the compiler emitted two F2F per value: XU pipe 53 % -> see DESIGN 4)
+                PS_FWD(c0, x0);
+                d0 = ps_dot(c0, O0, O1, O2, O3);
+                PS_FWD(c1, x1);
+                d1 = ps_dot(c1, O0, O1, O2, O3);
+                PS_FWD(c2, x2);
+                d2 = ps_dot(c2, O0, O1, O2, O3);
+                PS_FWD(c3, x3);
+                d3 = ps_dot(c3, O0, O1, O2, O3);
+            }
             // transposing butterfly: 8 values over 32 lanes -> lane L (L % 4 == 0) holds the warp sum of value L / 4
             double v0 = d0.x, v1 = d0.y, v2 = d1.x, v3 = d1.y, v4 = d2.x, v5 = d2.y, v6 = d3.x, v7 = d3.y;
             {
