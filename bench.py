@@ -527,10 +527,12 @@ def main():
             v2 = new_solver()                          # a fresh solver: the first run's learned prior must not carry over
             v2.load_ld(0, Rh, assume_symmetric=True)   # untimed warm-up of the upload path, as above
             barrier()
+            os.environ["SGV_TIMING"] = "1"
             t0s = time.perf_counter()
             v2.load_ld(0, Rh, assume_symmetric=True)
             torch.cuda.synchronize()
             t_up_s = time.perf_counter() - t0s
+            os.environ.pop("SGV_TIMING", None)
             xs3 = run(v2, None, iterations, None, write_outputs=False)
             barrier()
             dt_s = max_over_ranks(time.perf_counter() - t0s)

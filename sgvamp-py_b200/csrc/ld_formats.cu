@@ -956,7 +956,7 @@ static int stream_diagonals(sgv_ctx* c, const void* data, size_t esz, int64_t ld
 
 template <typename T>
 static int upload_dia_t(sgv_ctx* c, LdMatrix& ld, const T* data, int64_t ldd, int64_t col0, const int64_t* offsets, int ndiag,
-                        double s, int layout, int assume_symmetric, int64_t w) {
+                        double s, int layout, int assume_symmetric, int64_t w, PhaseTimer& pt) {
     const int64_t M = c->M, Ml = c->Ml;
     std::vector<int> up, lowr, all;
     for (int k = 0; k < ndiag; ++k) {
@@ -986,7 +986,9 @@ static int upload_dia_t(sgv_ctx* c, LdMatrix& ld, const T* data, int64_t ldd, in
         ld.ldb = n;
         ld.ext = E;
         ld.nnz_stored = (w + 1) * Ml;
+        pt.lap("cudaMalloc half band");
         SGV_CUDA(cudaMemsetAsync(U, 0, (size_t)Dp * n * sizeof(float), c->stream));
+        pt.lap("zero fill");
         const int64_t row_lo = c->row_lo;
         // rows of the buffer beyond the local range (padding to 128) convert to zeros: g + off < M fails or data is zero
         k_dsym_fill_diag<<<592, 256, 0, c->stream>>>(U, Ml, E, ngr, 0.5f * (float)s);
@@ -997,6 +999,7 @@ static int upload_dia_t(sgv_ctx* c, LdMatrix& ld, const T* data, int64_t ldd, in
             return 0;
         };
         SGV_TRY(stream_diagonals(c, data, sizeof(T), ldd, col0, offsets, up, false, g0, n_rows, M, conv));
+        pt.lap("upper diagonals H2D + convert");
         if (!assume_symmetric && !lowr.empty()) {
             unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(c->counter + 8);
             SGV_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
@@ -1017,9 +1020,12 @@ static int upload_dia_t(sgv_ctx* c, LdMatrix& ld, const T* data, int64_t ldd, in
                 sgv_ld_free(ld);
                 return 1;   // not symmetric: the caller falls back to the full band
             }
+            pt.lap("lower diagonals H2D + verify");
         }
         ld.layout = SGV_LAYOUT_DSYM;
-        return sgv_dsym_ensure_scratch(c, ld);
+        const int rcs = sgv_dsym_ensure_scratch(c, ld);
+        pt.lap("kernel scratch");
+        return rcs;
     }
     // full band
     const int64_t ldb = round_up(Ml, 32), g0 = c->row_lo;
@@ -1060,6 +1066,7 @@ extern "C" int sgv_ld_upload_dia(sgv_handle c, int cohort, const void* data, int
     if (c->bandwidth_hint > w) w = c->bandwidth_hint;
     LdMatrix& ld = c->coh[cohort].ld;
     sgv_ld_free(ld);
+    pt.lap("free previous LD");
     int layout = layout_hint;
     bool fallback = false;
     if (layout == SGV_LAYOUT_AUTO) {
@@ -1070,8 +1077,8 @@ extern "C" int sgv_ld_upload_dia(sgv_handle c, int cohort, const void* data, int
     SGV_CHECK(layout != SGV_LAYOUT_DIA || sgv_dia_feasible(w), "DIA layout infeasible for half-bandwidth %lld", (long long)w);
     int rc = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        rc = dtype == SGV_F64 ? upload_dia_t<double>(c, ld, (const double*)data, ldd, col0, offsets, ndiag, s, layout, assume_symmetric, w)
-                              : upload_dia_t<float>(c, ld, (const float*)data, ldd, col0, offsets, ndiag, s, layout, assume_symmetric, w);
+        rc = dtype == SGV_F64 ? upload_dia_t<double>(c, ld, (const double*)data, ldd, col0, offsets, ndiag, s, layout, assume_symmetric, w, pt)
+                              : upload_dia_t<float>(c, ld, (const float*)data, ldd, col0, offsets, ndiag, s, layout, assume_symmetric, w, pt);
         if (rc != 1) break;
         if (fallback && sgv_dia_feasible(w)) {
             layout = SGV_LAYOUT_DIA;
@@ -1082,7 +1089,7 @@ extern "C" int sgv_ld_upload_dia(sgv_handle c, int cohort, const void* data, int
         }
     }
     if (rc != 0) sgv_ld_free(ld);
-    pt.lap("DIA upload + conversion");
+    pt.lap("DIA upload: rest");
     return rc;
 }
 
