@@ -116,6 +116,9 @@ static void free_vectors(sgv_ctx* c) {
     cudaFree(c->bb);
     cudaFree(c->vfull);
     cudaFree(c->probe_b);
+    cudaFree(c->em_cache);
+    c->em_cache = nullptr;
+    c->em_cache_cap = 0;
     c->vfull = nullptr;
     c->probe_b = nullptr;
     c->arena = nullptr;

@@ -232,6 +232,8 @@ struct sgv_ctx {
     double       cg_band_eps = 2.0e-13;   // CgState::band_eps (SGV_CG_BAND overrides: tests force the postponed path)
     bool         coop_ok = false;      // device supports cooperative launches (persistent EM loop kernel)
     int          em_loop_blocks_per_sm = 0;
+    double*      em_cache = nullptr;   // EM loop kernel: the pass-invariant exponentials (Ml x K x L doubles)
+    int64_t      em_cache_cap = 0;
     int          last_em_steps = 0;  // EM passes the previous prior update needed (first batch of the next one)
     double2*     ds_ypart = nullptr; // DSYM kernel: per-row partial sums and per-tile tails
     double2*     ds_tails = nullptr;

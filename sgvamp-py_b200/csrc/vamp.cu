@@ -233,7 +233,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
 
 __global__ void __launch_bounds__(256)
 k_em_loop(int64_t M, const double* __restrict__ r1_all, EmConsts kval, RedCtx rc, unsigned* __restrict__ bar, int maxit,
-          int dev) {
+          int dev, double* __restrict__ cache) {
     __shared__ double red[16 * 32];
     __shared__ EmConsts k;
     if (threadIdx.x == 0) {
@@ -241,6 +241,25 @@ k_em_loop(int64_t M, const double* __restrict__ r1_all, EmConsts kval, RedCtx rc
         else k = kval;
     }
     __syncthreads();
+    // The exponentials of a pass do not depend on (lam, omegas), the only things the passes change: they are evaluated once
+    // per prior update and kept in `cache` (L values per marker and cohort; every thread reads back only what it wrote, so
+    // no barrier is needed).  The passes multiply the same doubles in the same order as the direct evaluation: bit-identical.
+    const int Lc = k.Lm1 + 1;
+    if (cache != nullptr && maxit > 0 && !rc.st->em.done) {
+        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+            for (int q = 0; q < k.K; ++q) {
+                const double r = r1_all[(int64_t)q * M + j];
+                const double r2 = r * r;
+                double e[SGV_MAX_L], emax = 0.0;
+                for (int l = 0; l < k.Lm1; ++l) {
+                    e[l] = r2 * k.ce[q][l];
+                    if (l == 0 || e[l] > emax) emax = e[l];
+                }
+                for (int l = 0; l < k.Lm1; ++l) cache[((int64_t)q * Lc + l) * M + j] = exp(e[l] - emax);
+                cache[((int64_t)q * Lc + k.Lm1) * M + j] = exp(r2 * k.mhg[q] - emax);
+            }
+        }
+    }
     const volatile EmState* em = &rc.st->em;
     const unsigned nblk = gridDim.x;
     unsigned epoch = 0;
@@ -255,19 +274,28 @@ k_em_loop(int64_t M, const double* __restrict__ r1_all, EmConsts kval, RedCtx rc
         const double one_minus_lam = 1.0 - lam;
         for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
             for (int q = 0; q < k.K; ++q) {
-                const double r = r1_all[(int64_t)q * M + j];
-                const double r2 = r * r;
-                double e[SGV_MAX_L], emax = 0.0;
-                for (int l = 0; l < k.Lm1; ++l) {
-                    e[l] = r2 * k.ce[q][l];
-                    if (l == 0 || e[l] > emax) emax = e[l];
+                double xi[SGV_MAX_L], sum_xi = 0.0, es;
+                if (cache != nullptr) {
+                    for (int l = 0; l < k.Lm1; ++l) {
+                        xi[l] = lo[l] * cache[((int64_t)q * Lc + l) * M + j] * k.isq[q][l];
+                        sum_xi += xi[l];
+                    }
+                    es = cache[((int64_t)q * Lc + k.Lm1) * M + j];
+                } else {
+                    const double r = r1_all[(int64_t)q * M + j];
+                    const double r2 = r * r;
+                    double e[SGV_MAX_L], emax = 0.0;
+                    for (int l = 0; l < k.Lm1; ++l) {
+                        e[l] = r2 * k.ce[q][l];
+                        if (l == 0 || e[l] > emax) emax = e[l];
+                    }
+                    for (int l = 0; l < k.Lm1; ++l) {
+                        xi[l] = lo[l] * exp(e[l] - emax) * k.isq[q][l];
+                        sum_xi += xi[l];
+                    }
+                    es = exp(r2 * k.mhg[q] - emax);
                 }
-                double xi[SGV_MAX_L], sum_xi = 0.0;
-                for (int l = 0; l < k.Lm1; ++l) {
-                    xi[l] = lo[l] * exp(e[l] - emax) * k.isq[q][l];
-                    sum_xi += xi[l];
-                }
-                const double t = one_minus_lam * exp(r2 * k.mhg[q] - emax) * k.sqg[q];
+                const double t = one_minus_lam * es * k.sqg[q];
                 const double inv = 1.0 / (sum_xi + t);
                 const double pi = sum_xi * inv;
                 const double ainv = k.a[q] * inv;
@@ -308,6 +336,23 @@ k_em_loop(int64_t M, const double* __restrict__ r1_all, EmConsts kval, RedCtx rc
         ++epoch;
         grid_barrier(bar, epoch * nblk);
     }
+}
+
+// scratch of the EM loop kernel: L exponentials per marker and cohort; optional (without it the kernel re-evaluates them every pass)
+static int ensure_em_cache(sgv_ctx* c) {
+    const int64_t need = c->Ml * (int64_t)c->prior.K * (int64_t)c->prior.L;
+    if (need <= 0 || c->em_cache_cap >= need) return 0;
+    SGV_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->em_cache) cudaFree(c->em_cache);
+    c->em_cache = nullptr;
+    c->em_cache_cap = 0;
+    if (cudaMalloc(&c->em_cache, (size_t)need * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        c->em_cache = nullptr;
+        return 0;
+    }
+    c->em_cache_cap = need;
+    return 0;
 }
 
 extern "C" int sgv_prior_em(sgv_handle c, const double* gam1s, int maxit, double tol, double* lam_out,
@@ -363,7 +408,9 @@ extern "C" int sgv_prior_em(sgv_handle c, const double* gam1s, int maxit, double
         int64_t Ml = c->Ml;
         const double* r1 = c->r1_all;
         int mi = maxit, dev0 = 0;
-        void* args[] = {&Ml, &r1, &k, &rc, &bar, &mi, &dev0};
+        SGV_TRY(ensure_em_cache(c));
+        double* cache = c->em_cache;
+        void* args[] = {&Ml, &r1, &k, &rc, &bar, &mi, &dev0, &cache};
         SGV_CUDA(cudaLaunchCooperativeKernel((const void*)k_em_loop, dim3(lgrid), dim3(256), args, 0, c->stream));
         c->launches++;
         SGV_TRY(fetch_state(c));
@@ -1013,6 +1060,7 @@ extern "C" int sgv_vamp_begin(sgv_handle c, const double* gam1, const double* ga
     const PriorParams& p = c->prior;
     SGV_CHECK(p.L >= 2, "prior not set");
     SGV_CHECK(sgv_iteration_supported(c), "fused iteration needs cooperative launches and one GPU per rank");
+    SGV_TRY(ensure_em_cache(c));
     for (int i = 0; i < sgv_ctx::NLOG; ++i) {
         if (c->log_host[i] == nullptr) {
             SGV_CUDA(cudaMallocHost(&c->log_host[i], sizeof(IterLog)));
@@ -1112,7 +1160,8 @@ extern "C" int sgv_iteration_enqueue(sgv_handle c, const sgv_iter_in* in, double
         EmConsts kdummy;
         memset(&kdummy, 0, sizeof(kdummy));
         int mi = in->em_maxit, dev1 = 1;
-        void* args[] = {&Ml, &r1, &kdummy, &rc, &bar, &mi, &dev1};
+        double* cache = c->em_cache;      // allocated by sgv_vamp_begin
+        void* args[] = {&Ml, &r1, &kdummy, &rc, &bar, &mi, &dev1, &cache};
         SGV_CUDA(cudaLaunchCooperativeKernel((const void*)k_em_loop, dim3(lgrid), dim3(256), args, 0, c->stream));
         c->launches++;
     } else {
